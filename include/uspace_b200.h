@@ -1,0 +1,117 @@
+/* uspace_b200 — C ABI of the Blackwell (sm_100a) U-ViT flow-matching sampler.
+ *
+ * This is the drop-in boundary for the one hot path of dongzhuoyao/uspace: the velocity-field call
+ *     self.net(x, t, y, **kwargs)                 flow_matching.py:34
+ *     self.net(x, t, context=context, **kwargs)   flow_matching_t2i.py:31
+ * and the fixed-grid ODE loops around it
+ *     CNF.decode / CNF.encode                     flow_matching.py:102-151, flow_matching_t2i.py:105-146
+ * The reference has no FFI of its own (it is pure Python); a maintainer binds these symbols with
+ * ctypes from libs/uvit.py / libs/uvit_t2i.py / flow_matching*.py — see INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain C types only; no torch / C++ types cross the boundary;
+ *   - every call returns 0 (USP_OK) or a negative usp_status; usp_last_error() gives the message;
+ *   - all tensors are fp32, contiguous, NCHW for latents; pointers are DEVICE pointers unless the
+ *     function name ends in _host;
+ *   - work is enqueued on the caller's stream (void* == cudaStream_t, may be NULL) and the call
+ *     returns without synchronising, except the *_host entry points which synchronise before returning;
+ *   - a handle is bound to one device and is not thread-safe.
+ */
+#ifndef USPACE_B200_H
+#define USPACE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct usp_handle usp_handle;
+
+typedef enum usp_status {
+    USP_OK = 0,
+    USP_ERR_INVALID = -1,      /* bad argument / unsupported configuration */
+    USP_ERR_CUDA = -2,         /* a CUDA runtime / driver call failed       */
+    USP_ERR_STATE = -3,        /* weights missing or not finalised          */
+    USP_ERR_UNSUPPORTED = -4   /* configuration outside the built path      */
+} usp_status;
+
+/* Mirrors the constructor keywords of libs/uvit.py:183-202 and libs/uvit_t2i.py:193-211. */
+typedef struct usp_config {
+    int32_t img_size;        /* latent side, 32 for the 256^2 models      */
+    int32_t patch_size;      /* 2                                         */
+    int32_t in_chans;        /* 4                                         */
+    int32_t embed_dim;       /* D: multiple of 128 in {256..1536}         */
+    int32_t depth;           /* depth//2 in-blocks + mid + depth//2 out   */
+    int32_t num_heads;       /* D / 64 (head_dim is fixed at 64)          */
+    int32_t mlp_hidden;      /* int(D * mlp_ratio)                        */
+    int32_t num_classes;     /* <= 0: no label token (libs/uvit.py:225)   */
+    int32_t clip_dim;        /* t2i: 768; 0 for the uncond / class model  */
+    int32_t num_clip_token;  /* t2i: 77;  0 for the uncond / class model  */
+    int32_t qkv_bias;        /* 0/1                                       */
+    int32_t conv;            /* final 3x3 conv present                    */
+    int32_t skip;            /* out-blocks carry skip_linear              */
+    int32_t operand_dtype;   /* tensor-core operand type: 0 bf16, 1 fp16  */
+} usp_config;
+
+enum { USP_METHOD_EULER = 0, USP_METHOD_HEUN = 1 };
+enum { USP_EDIT_NONE = 0, USP_EDIT_HEAD = 1, USP_EDIT_TAIL = 2 };
+
+/* Replaces UViT.__init__ (libs/uvit.py:182-291): allocates parameter storage on `device`. */
+int usp_create(const usp_config* cfg, int device, usp_handle** out);
+void usp_destroy(usp_handle* h);
+const char* usp_last_error(const usp_handle* h);  /* h may be NULL: message of the last failed usp_create */
+
+/* Replaces load_state_dict (dissect_lfm.py:70-72): `name` is the reference state_dict key, `data` fp32,
+ * host or device memory. Unknown names or wrong shapes return USP_ERR_INVALID. */
+int usp_set_weight(usp_handle* h, const char* name, const void* data, const int64_t* shape, int ndim);
+/* Packs the GEMM weights to the 16-bit operand type. Must follow the last usp_set_weight. */
+int usp_finalize_weights(usp_handle* h, void* stream);
+/* Number of state_dict entries the configuration expects, and the i-th name (for loaders / tests). */
+int usp_num_weights(const usp_handle* h);
+const char* usp_weight_name(const usp_handle* h, int i);
+
+/* Replaces UViT.forward (libs/uvit.py:306-351, libs/uvit_t2i.py:308-342), inference only.
+ *   x [B,C,S,S], t [B], context [B,n_ctx,clip_dim] or NULL, y int64 [B] or NULL  ->  out [B,C,S,S] */
+int usp_forward(usp_handle* h, const float* x, const float* t, const float* context, const int64_t* y,
+                float* out, int B, void* stream);
+
+/* Replaces odeint(func, z, [t0,t1], method, options=dict(step_size)) as called by CNF.decode (t0=0,t1=1) and
+ * CNF.encode (t0=1,t1=0) (flow_matching.py:118-125,140-147): torchdiffeq fixed-grid semantics, one CUDA graph
+ * per step replayed on `stream`.  z is updated in place.
+ *   delta_table: optional [n_grid, C,S,S] rows indexed by grid point (the delta_{t:.2f}.npy files of
+ *   libs/dissection.py:141-157 pre-gathered by the caller), applied as x + delta*write_scale at edit_loc when
+ *   "0.00" != f"{t:.2f}" <= t_edit (libs/dissection.py:21-26). */
+int usp_sample(usp_handle* h, float* z, const float* context, const int64_t* y, int B, float t0, float t1,
+               float step_size, int method, const float* delta_table, float write_scale, float t_edit,
+               int edit_loc, void* stream);
+/* Same with HOST buffers: copies z (and context / y / delta_table) host->device, samples, copies z back,
+ * and synchronises. This is the end-to-end call bench.py times. */
+int usp_sample_host(usp_handle* h, float* z_host, const float* context_host, const int64_t* y_host, int B, float t0,
+                    float t1, float step_size, int method, const float* delta_table_host, float write_scale,
+                    float t_edit, int edit_loc);
+/* Number of grid points torchdiffeq builds for (t0, t1, step_size): ceil(|t1-t0|/step + 1). */
+int usp_grid_size(float t0, float t1, float step_size);
+
+/* Introspection used by bench.py / tests. */
+size_t usp_workspace_bytes(const usp_handle* h, int B);
+int usp_kernels_per_forward(const usp_handle* h);   /* kernels launched by one velocity evaluation */
+double usp_flops_per_forward(const usp_handle* h);  /* algorithmic FLOPs per image per forward */
+int usp_last_forward_ms(usp_handle* h, float* ms);  /* device time of the most recent usp_forward/usp_sample */
+
+/* Kernel-level entry points (parity tests and micro-benchmarks call the kernels through the ABI).
+ * All pointers are device pointers; a16/w16/q/k/v/out16 hold 16-bit operands of type `operand_dtype`. */
+int usp_op_convert16(const float* in, void* out16, int64_t n, int operand_dtype, void* stream);
+int usp_op_gemm(int epilogue, const void* a16, const void* a16_second, const void* w16, const float* bias,
+                const float* resid, float* out32, void* out16, int M, int N, int K, int K0, int L, int H,
+                int operand_dtype, void* stream);
+int usp_op_attention(const void* q16, const void* k16, const void* v16, void* out16, int B, int H, int L,
+                     int operand_dtype, void* stream);
+int usp_op_layernorm(const float* x, const float* gamma, const float* beta, void* out16, int M, int D,
+                     int operand_dtype, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* USPACE_B200_H */

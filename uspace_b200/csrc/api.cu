@@ -1,0 +1,874 @@
+// C-ABI implementation: handle, weight store, per-batch plans (workspace + TMA descriptors + CUDA graphs),
+// the velocity-field forward (UViT.forward) and the fixed-grid ODE sampler (CNF.decode / CNF.encode).
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/uspace_b200.h"
+#include "kernels.h"
+
+using namespace usp;
+
+namespace usp {
+cudaError_t gemm_configure();
+cudaError_t attention_configure();
+}  // namespace usp
+
+namespace {
+
+thread_local std::string g_create_error;
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn) return fn;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+        return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+    return fn;
+}
+
+// 16-bit row-major [rows, cols] tensor, box = [box_rows, 64 cols], 128B swizzle, OOB -> 0
+bool make_map_2d(CUtensorMap* m, const void* ptr, long long rows, long long cols, int box_rows, int opd) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return false;
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+    cuuint64_t strides[1] = {static_cast<cuuint64_t>(cols) * 2};
+    cuuint32_t box[2] = {64, static_cast<cuuint32_t>(box_rows)};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(m, opd == OPD_FP16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                    const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+// 16-bit [planes, rows, 64] tensor (per-head Q/K/V), box = [1, 128, 64]
+bool make_map_qkv(CUtensorMap* m, const void* ptr, long long planes, long long rows, int opd) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return false;
+    cuuint64_t dims[3] = {64, static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(planes)};
+    cuuint64_t strides[2] = {128, static_cast<cuuint64_t>(rows) * 128};
+    cuuint32_t box[3] = {64, 128, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(m, opd == OPD_FP16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3,
+                    const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+struct Weight {
+    std::string name;
+    std::vector<int64_t> shape;
+    long long numel = 0;
+    float* d32 = nullptr;   // fp32 master copy on device
+    void* d16 = nullptr;    // packed 16-bit GEMM operand (only for GEMM weights)
+    bool gemm = false;
+    bool set = false;
+    CUtensorMap map;        // B-operand map (gemm weights)
+};
+
+struct BlockW {
+    int n1w, n1b, qkvw, qkvb, projw, projb, n2w, n2b, fc1w, fc1b, fc2w, fc2b, skw, skb;
+};
+
+struct Plan {
+    int B = 0, M = 0;
+    void* slab = nullptr;
+    size_t bytes = 0;
+    float* x32 = nullptr;
+    void *h16 = nullptr, *a16 = nullptr, *m16 = nullptr, *xa16 = nullptr, *xb16 = nullptr, *qkv16 = nullptr;
+    std::vector<void*> skip16;
+    float *pf = nullptr, *z = nullptr, *ztmp = nullptr, *k1 = nullptr, *ctxemb = nullptr, *ctx32 = nullptr;
+    void* ctx16 = nullptr;
+    long long* y = nullptr;
+    StepState* st = nullptr;
+    float* grid = nullptr;
+    unsigned char* mask = nullptr;
+    float* delta = nullptr;
+    size_t delta_cap = 0;
+    CUtensorMap m_h, m_a, m_m, m_xa, m_xb, m_q, m_k, m_v, m_ctx;
+    std::vector<CUtensorMap> m_skip;
+    std::map<int, cudaGraphExec_t> graphs;
+};
+
+constexpr int MAX_GRID = 4096;
+
+}  // namespace
+
+struct usp_handle {
+    usp_config cfg;
+    int device = 0;
+    int num_sms = 148;
+    int D = 0, L = 0, extras = 0, n_patch = 0, P = 0, n_in = 0, n_blocks = 0, Hd = 0;
+    std::vector<Weight> w;
+    std::map<std::string, int> widx;
+    std::vector<BlockW> blocks;
+    int i_pos = -1, i_pew = -1, i_peb = -1, i_label = -1, i_ctxw = -1, i_ctxb = -1, i_nw = -1, i_nb = -1,
+        i_dw = -1, i_db = -1, i_fw = -1, i_fb = -1;
+    float* freqs = nullptr;
+    bool finalized = false;
+    std::map<int, std::unique_ptr<Plan>> plans;
+    cudaStream_t cap_stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool ev_valid = false;
+    int kernels_per_forward = 0;
+    std::string err;
+};
+
+namespace {
+
+int fail(usp_handle* h, int code, const std::string& msg) {
+    if (h) h->err = msg;
+    else g_create_error = msg;
+    return code;
+}
+#define CUDA_TRY(h, expr)                                                                         \
+    do {                                                                                          \
+        cudaError_t _e = (expr);                                                                  \
+        if (_e != cudaSuccess)                                                                    \
+            return fail(h, USP_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));     \
+    } while (0)
+
+int add_weight(usp_handle* h, const std::string& name, std::vector<int64_t> shape, bool gemm) {
+    Weight w;
+    w.name = name;
+    w.shape = shape;
+    w.numel = 1;
+    for (auto s : shape) w.numel *= s;
+    w.gemm = gemm;
+    h->w.push_back(w);
+    h->widx[name] = static_cast<int>(h->w.size()) - 1;
+    return static_cast<int>(h->w.size()) - 1;
+}
+
+BlockW add_block(usp_handle* h, const std::string& p, bool skip) {
+    const int64_t D = h->D, Hd = h->Hd;
+    BlockW b;
+    b.n1w = add_weight(h, p + ".norm1.weight", {D}, false);
+    b.n1b = add_weight(h, p + ".norm1.bias", {D}, false);
+    b.qkvw = add_weight(h, p + ".attn.qkv.weight", {3 * D, D}, true);
+    b.qkvb = h->cfg.qkv_bias ? add_weight(h, p + ".attn.qkv.bias", {3 * D}, false) : -1;
+    b.projw = add_weight(h, p + ".attn.proj.weight", {D, D}, true);
+    b.projb = add_weight(h, p + ".attn.proj.bias", {D}, false);
+    b.n2w = add_weight(h, p + ".norm2.weight", {D}, false);
+    b.n2b = add_weight(h, p + ".norm2.bias", {D}, false);
+    b.fc1w = add_weight(h, p + ".mlp.fc1.weight", {Hd, D}, true);
+    b.fc1b = add_weight(h, p + ".mlp.fc1.bias", {Hd}, false);
+    b.fc2w = add_weight(h, p + ".mlp.fc2.weight", {D, Hd}, true);
+    b.fc2b = add_weight(h, p + ".mlp.fc2.bias", {D}, false);
+    b.skw = b.skb = -1;
+    if (skip) {
+        b.skw = add_weight(h, p + ".skip_linear.weight", {D, 2 * D}, true);
+        b.skb = add_weight(h, p + ".skip_linear.bias", {D}, false);
+    }
+    return b;
+}
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+int get_plan(usp_handle* h, int B, Plan** out) {
+    auto it = h->plans.find(B);
+    if (it != h->plans.end()) {
+        *out = it->second.get();
+        return USP_OK;
+    }
+    if (h->plans.size() >= 4) {  // bound the cache: drop everything (graphs included) and start over
+        for (auto& kv : h->plans) {
+            for (auto& g : kv.second->graphs) cudaGraphExecDestroy(g.second);
+            cudaFree(kv.second->slab);
+            cudaFree(kv.second->delta);
+        }
+        h->plans.clear();
+    }
+    std::unique_ptr<Plan> p(new Plan());
+    const int D = h->D, L = h->L, Hd = h->Hd, opd = h->cfg.operand_dtype;
+    const long long M = static_cast<long long>(B) * L;
+    p->B = B;
+    p->M = static_cast<int>(M);
+    const int C = h->cfg.in_chans, S = h->cfg.img_size;
+    const long long zel = static_cast<long long>(B) * C * S * S;
+    const int nctx = h->cfg.num_clip_token, cdim = h->cfg.clip_dim;
+
+    size_t off = 0;
+    auto carve = [&](size_t bytes) {
+        size_t o = off;
+        off = align_up(off + bytes, 1024);
+        return o;
+    };
+    const size_t o_x32 = carve(M * D * 4), o_h = carve(M * D * 2), o_a = carve(M * D * 2),
+                 o_m = carve(M * Hd * 2), o_xa = carve(M * D * 2), o_xb = carve(M * D * 2),
+                 o_qkv = carve(3 * M * D * 2);
+    std::vector<size_t> o_skip(h->n_in);
+    for (int i = 0; i < h->n_in; ++i) o_skip[i] = carve(M * D * 2);
+    const size_t o_pf = carve(static_cast<size_t>(B) * h->n_patch * h->P * 4), o_z = carve(zel * 4),
+                 o_zt = carve(zel * 4), o_k1 = carve(zel * 4);
+    const size_t o_ctxemb = carve(nctx ? static_cast<size_t>(B) * nctx * D * 4 : 16),
+                 o_ctx32 = carve(nctx ? static_cast<size_t>(B) * nctx * cdim * 4 : 16),
+                 o_ctx16 = carve(nctx ? static_cast<size_t>(B) * nctx * cdim * 2 : 16);
+    const size_t o_y = carve(static_cast<size_t>(B) * 8), o_st = carve(sizeof(StepState)),
+                 o_grid = carve(MAX_GRID * 4), o_mask = carve(MAX_GRID);
+    p->bytes = off;
+    CUDA_TRY(h, cudaMalloc(&p->slab, off));
+    CUDA_TRY(h, cudaMemset(p->slab, 0, off));
+    char* base = static_cast<char*>(p->slab);
+    p->x32 = reinterpret_cast<float*>(base + o_x32);
+    p->h16 = base + o_h;
+    p->a16 = base + o_a;
+    p->m16 = base + o_m;
+    p->xa16 = base + o_xa;
+    p->xb16 = base + o_xb;
+    p->qkv16 = base + o_qkv;
+    for (int i = 0; i < h->n_in; ++i) p->skip16.push_back(base + o_skip[i]);
+    p->pf = reinterpret_cast<float*>(base + o_pf);
+    p->z = reinterpret_cast<float*>(base + o_z);
+    p->ztmp = reinterpret_cast<float*>(base + o_zt);
+    p->k1 = reinterpret_cast<float*>(base + o_k1);
+    p->ctxemb = reinterpret_cast<float*>(base + o_ctxemb);
+    p->ctx32 = reinterpret_cast<float*>(base + o_ctx32);
+    p->ctx16 = base + o_ctx16;
+    p->y = reinterpret_cast<long long*>(base + o_y);
+    p->st = reinterpret_cast<StepState*>(base + o_st);
+    p->grid = reinterpret_cast<float*>(base + o_grid);
+    p->mask = reinterpret_cast<unsigned char*>(base + o_mask);
+
+    bool ok = true;
+    ok &= make_map_2d(&p->m_h, p->h16, M, D, GEMM_BM, opd);
+    ok &= make_map_2d(&p->m_a, p->a16, M, D, GEMM_BM, opd);
+    ok &= make_map_2d(&p->m_m, p->m16, M, Hd, GEMM_BM, opd);
+    ok &= make_map_2d(&p->m_xa, p->xa16, M, D, GEMM_BM, opd);
+    ok &= make_map_2d(&p->m_xb, p->xb16, M, D, GEMM_BM, opd);
+    p->m_skip.resize(h->n_in);
+    for (int i = 0; i < h->n_in; ++i) ok &= make_map_2d(&p->m_skip[i], p->skip16[i], M, D, GEMM_BM, opd);
+    const long long BH = static_cast<long long>(B) * h->cfg.num_heads;
+    char* q = static_cast<char*>(p->qkv16);
+    ok &= make_map_qkv(&p->m_q, q, BH, L, opd);
+    ok &= make_map_qkv(&p->m_k, q + M * D * 2, BH, L, opd);
+    ok &= make_map_qkv(&p->m_v, q + 2 * M * D * 2, BH, L, opd);
+    if (nctx) ok &= make_map_2d(&p->m_ctx, p->ctx16, static_cast<long long>(B) * nctx, cdim, GEMM_BM, opd);
+    if (!ok) {
+        cudaFree(p->slab);
+        return fail(h, USP_ERR_CUDA, "cuTensorMapEncodeTiled failed for a plan buffer");
+    }
+    *out = p.get();
+    h->plans[B] = std::move(p);
+    return USP_OK;
+}
+
+struct FwdIO {
+    const float* x;         // latent in
+    const float* tvec;      // per-sample t (forward) or nullptr
+    const StepState* st;    // ODE state or nullptr
+    const long long* y;     // labels or nullptr
+    bool has_ctx;
+    const float* delta;     // edit table or nullptr
+    int edit_loc;
+    // final stage
+    const float* base;
+    const float* aux;
+    float* vstore;
+    float* out;
+    float m1, m2;
+};
+
+#define KTRY(expr)                                                                             \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        ++nk;                                                                                  \
+        if (_e != cudaSuccess)                                                                 \
+            return fail(h, USP_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+    } while (0)
+
+int run_gemm(usp_handle* h, int epi, const CUtensorMap& a0, const CUtensorMap* a1, const Weight& w,
+             const float* bias, const float* resid, float* out32, void* out16, int M, int N, int K, int K0,
+             cudaStream_t s) {
+    GemmMaps maps;
+    maps.a0 = a0;
+    maps.a1 = a1 ? *a1 : a0;
+    maps.b = w.map;
+    GemmArgs g;
+    memset(&g, 0, sizeof(g));
+    g.M = M; g.N = N; g.K = K; g.K0 = K0;
+    g.opd = h->cfg.operand_dtype;
+    g.bias = bias; g.resid = resid; g.out32 = out32; g.out16 = out16;
+    g.L = h->L; g.H = h->cfg.num_heads;
+    g.qkv_stride = static_cast<long long>(M) * h->D;
+    cudaError_t e = launch_gemm(epi, maps, g, h->num_sms, s);
+    if (e != cudaSuccess) return fail(h, USP_ERR_CUDA, std::string("launch_gemm: ") + cudaGetErrorString(e));
+    return USP_OK;
+}
+
+// context_embed (libs/uvit_t2i.py:322): step-invariant, so it runs once per usp_forward / usp_sample call.
+int embed_context(usp_handle* h, Plan* p, const float* ctx_dev, cudaStream_t s) {
+    const int nctx = h->cfg.num_clip_token, cdim = h->cfg.clip_dim;
+    const long long n = static_cast<long long>(p->B) * nctx * cdim;
+    cudaError_t e = launch_convert16(ctx_dev, p->ctx16, n, h->cfg.operand_dtype, s);
+    if (e != cudaSuccess) return fail(h, USP_ERR_CUDA, std::string("convert ctx: ") + cudaGetErrorString(e));
+    return run_gemm(h, EPI_BIAS_F32, p->m_ctx, nullptr, h->w[h->i_ctxw], h->w[h->i_ctxb].d32, nullptr, p->ctxemb,
+                    nullptr, p->B * nctx, h->D, cdim, cdim, s);
+}
+
+// One velocity evaluation: UViT.forward (libs/uvit.py:306-351).
+int enqueue_forward(usp_handle* h, Plan* p, const FwdIO& io, cudaStream_t s) {
+    const int D = h->D, L = h->L, Hd = h->Hd, M = p->M, B = p->B, opd = h->cfg.operand_dtype;
+    int nk = 0;
+    EmbedArgs ea;
+    memset(&ea, 0, sizeof(ea));
+    ea.x = io.x; ea.tvec = io.tvec; ea.st = io.st; ea.y = io.y;
+    ea.ctxemb = io.has_ctx ? p->ctxemb : nullptr;
+    ea.w = h->w[h->i_pew].d32; ea.bias = h->w[h->i_peb].d32; ea.pos = h->w[h->i_pos].d32;
+    ea.label = h->i_label >= 0 ? h->w[h->i_label].d32 : nullptr;
+    ea.freqs = h->freqs;
+    ea.delta = io.edit_loc == USP_EDIT_HEAD ? io.delta : nullptr;
+    ea.out32 = p->x32;
+    ea.B = B; ea.C = h->cfg.in_chans; ea.S = h->cfg.img_size; ea.p = h->cfg.patch_size; ea.D = D; ea.L = L;
+    ea.n_ctx = h->cfg.num_clip_token; ea.has_label = (h->cfg.num_classes > 0 && io.y != nullptr) ? 1 : 0;
+    KTRY(launch_embed(ea, s));
+
+    const CUtensorMap* xprev = nullptr;  // 16-bit copy of the previous block's output
+    for (int bi = 0; bi < h->n_blocks; ++bi) {
+        const BlockW& bw = h->blocks[bi];
+        const bool is_in = bi < h->n_in;
+        const bool is_out = bi > h->n_in;
+        const int oj = bi - h->n_in - 1;
+        int rc;
+        if (is_out && bw.skw >= 0) {
+            // skip_linear(cat[x, skip]) with a two-source K loop; skips are consumed LIFO (libs/uvit.py:340)
+            const int si = h->n_in - 1 - oj;
+            rc = run_gemm(h, EPI_BIAS_F32, *xprev, &p->m_skip[si], h->w[bw.skw], h->w[bw.skb].d32, nullptr, p->x32,
+                          nullptr, M, D, 2 * D, D, s);
+            ++nk;
+            if (rc) return rc;
+        }
+        KTRY(launch_layernorm(p->x32, h->w[bw.n1w].d32, h->w[bw.n1b].d32, p->h16, M, D, opd, s));
+        rc = run_gemm(h, EPI_QKV, p->m_h, nullptr, h->w[bw.qkvw], bw.qkvb >= 0 ? h->w[bw.qkvb].d32 : nullptr,
+                      nullptr, nullptr, p->qkv16, M, 3 * D, D, D, s);
+        ++nk;
+        if (rc) return rc;
+        AttnArgs aa;
+        memset(&aa, 0, sizeof(aa));
+        aa.B = B; aa.H = h->cfg.num_heads; aa.L = L; aa.D = D; aa.opd = opd; aa.out16 = p->a16;
+        KTRY(launch_attention(p->m_q, p->m_k, p->m_v, aa, s));
+        rc = run_gemm(h, EPI_BIAS_RESID, p->m_a, nullptr, h->w[bw.projw], h->w[bw.projb].d32, p->x32, p->x32,
+                      nullptr, M, D, D, D, s);
+        ++nk;
+        if (rc) return rc;
+        KTRY(launch_layernorm(p->x32, h->w[bw.n2w].d32, h->w[bw.n2b].d32, p->h16, M, D, opd, s));
+        rc = run_gemm(h, EPI_BIAS_GELU, p->m_h, nullptr, h->w[bw.fc1w], h->w[bw.fc1b].d32, nullptr, nullptr,
+                      p->m16, M, Hd, D, D, s);
+        ++nk;
+        if (rc) return rc;
+        // 16-bit copy of the block output: a long skip (in-blocks) or the x half of the next skip_linear
+        void* o16 = nullptr;
+        const CUtensorMap* omap = nullptr;
+        if (h->cfg.skip && bi + 1 < h->n_blocks) {
+            if (is_in) { o16 = p->skip16[bi]; omap = &p->m_skip[bi]; }
+            else if (((bi - h->n_in) & 1) == 0) { o16 = p->xa16; omap = &p->m_xa; }
+            else { o16 = p->xb16; omap = &p->m_xb; }
+        }
+        rc = run_gemm(h, EPI_BIAS_RESID, p->m_m, nullptr, h->w[bw.fc2w], h->w[bw.fc2b].d32, p->x32, p->x32, o16, M,
+                      D, Hd, Hd, s);
+        ++nk;
+        if (rc) return rc;
+        // the mid block (and every out block) feeds the next skip_linear through its 16-bit copy
+        xprev = is_in ? nullptr : omap;
+    }
+
+    HeadArgs ha;
+    ha.x32 = p->x32; ha.ng = h->w[h->i_nw].d32; ha.nb = h->w[h->i_nb].d32;
+    ha.w = h->w[h->i_dw].d32; ha.bias = h->w[h->i_db].d32; ha.pf = p->pf;
+    ha.B = B; ha.L = L; ha.D = D; ha.extras = h->extras; ha.P = h->P;
+    KTRY(launch_head(ha, s));
+
+    FinalArgs fa;
+    memset(&fa, 0, sizeof(fa));
+    fa.pf = p->pf;
+    fa.cw = h->i_fw >= 0 ? h->w[h->i_fw].d32 : nullptr;
+    fa.cb = h->i_fb >= 0 ? h->w[h->i_fb].d32 : nullptr;
+    fa.delta = io.edit_loc == USP_EDIT_TAIL ? io.delta : nullptr;
+    fa.st = io.st; fa.base = io.base; fa.aux = io.aux; fa.vstore = io.vstore; fa.out = io.out;
+    fa.m1 = io.m1; fa.m2 = io.m2;
+    fa.B = B; fa.C = h->cfg.in_chans; fa.S = h->cfg.img_size; fa.p = h->cfg.patch_size;
+    KTRY(launch_final(fa, s));
+    h->kernels_per_forward = nk;
+    return USP_OK;
+}
+
+bool is_device_ptr(const void* p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+int check_ready(usp_handle* h, int B) {
+    if (!h) return USP_ERR_INVALID;
+    if (!h->finalized) return fail(h, USP_ERR_STATE, "weights not finalised: call usp_finalize_weights first");
+    if (B < 1 || B > 4096) return fail(h, USP_ERR_INVALID, "batch must be in [1, 4096]");
+    if (static_cast<long long>(B) * h->cfg.num_heads > 65535)
+        return fail(h, USP_ERR_INVALID, "B * num_heads exceeds the attention grid limit (65535)");
+    return USP_OK;
+}
+
+// torchdiffeq FixedGridODESolver grid (_grid_constructor_from_step_size), in fp32 like the reference's
+// torch.tensor([t0, t1], dtype=z.dtype) (flow_matching.py:144).  Decreasing time integrates s = -t.
+int build_grid(float t0, float t1, float h, std::vector<float>* grid) {
+    if (!(h > 0.f) || t0 == t1) return 0;
+    const float sgn = t1 >= t0 ? 1.f : -1.f;
+    const float s0 = sgn * t0, s1 = sgn * t1;
+    volatile float span = (s1 - s0) / h;
+    volatile float nf = ceilf(span + 1.0f);
+    const int n = static_cast<int>(nf);
+    if (n < 2 || n > MAX_GRID) return 0;
+    if (grid) {
+        grid->resize(n);
+        for (int i = 0; i < n; ++i) {
+            volatile float prod = static_cast<float>(i) * h;
+            volatile float v = prod + s0;
+            (*grid)[i] = sgn * v;
+        }
+        (*grid)[n - 1] = t1;
+    }
+    return n;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* usp_last_error(const usp_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int usp_create(const usp_config* cfg, int device, usp_handle** out) {
+    if (!cfg || !out) return fail(nullptr, USP_ERR_INVALID, "null argument");
+    *out = nullptr;
+    const usp_config& c = *cfg;
+    if (c.embed_dim % 128 != 0 || c.embed_dim < 256 || c.embed_dim > 1536 ||
+        !(c.embed_dim == 256 || c.embed_dim == 384 || c.embed_dim == 512 || c.embed_dim == 768 ||
+          c.embed_dim == 1024 || c.embed_dim == 1536))
+        return fail(nullptr, USP_ERR_UNSUPPORTED, "embed_dim must be one of 256, 384, 512, 768, 1024, 1536");
+    if (c.num_heads * 64 != c.embed_dim)
+        return fail(nullptr, USP_ERR_UNSUPPORTED, "head_dim must be 64 (num_heads * 64 == embed_dim)");
+    if (c.mlp_hidden % 128 != 0 || c.mlp_hidden <= 0)
+        return fail(nullptr, USP_ERR_UNSUPPORTED, "mlp_hidden must be a positive multiple of 128");
+    if (c.patch_size < 1 || c.img_size % c.patch_size != 0 || c.in_chans * c.patch_size * c.patch_size > 64)
+        return fail(nullptr, USP_ERR_INVALID, "bad patch geometry");
+    if (c.depth < 2 || c.depth % 2 != 0) return fail(nullptr, USP_ERR_INVALID, "depth must be even and >= 2");
+    if ((c.num_clip_token > 0) != (c.clip_dim > 0) || (c.clip_dim % 64) != 0)
+        return fail(nullptr, USP_ERR_INVALID, "clip_dim / num_clip_token must both be set (clip_dim % 64 == 0)");
+    if (c.num_clip_token > 0 && c.num_classes > 0)
+        return fail(nullptr, USP_ERR_INVALID, "label and context conditioning are separate models in the reference");
+    if (c.operand_dtype != OPD_BF16 && c.operand_dtype != OPD_FP16)
+        return fail(nullptr, USP_ERR_INVALID, "operand_dtype must be 0 (bf16) or 1 (fp16)");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(nullptr, USP_ERR_CUDA, "no CUDA device: the uspace_b200 path has no CPU fallback");
+    }
+    if (device < 0 || device >= ndev) return fail(nullptr, USP_ERR_INVALID, "bad device index");
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return fail(nullptr, USP_ERR_CUDA, "device query failed");
+    if (prop.major != 10)
+        return fail(nullptr, USP_ERR_UNSUPPORTED, "uspace_b200 kernels are built for sm_100a (Blackwell B200) only");
+    if (cudaSetDevice(device) != cudaSuccess) return fail(nullptr, USP_ERR_CUDA, "cudaSetDevice failed");
+    if (!get_encode_fn()) return fail(nullptr, USP_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
+
+    std::unique_ptr<usp_handle> h(new usp_handle());
+    h->cfg = c;
+    h->device = device;
+    h->num_sms = prop.multiProcessorCount;
+    h->D = c.embed_dim;
+    h->Hd = c.mlp_hidden;
+    h->n_patch = (c.img_size / c.patch_size) * (c.img_size / c.patch_size);
+    h->extras = c.num_clip_token > 0 ? 1 + c.num_clip_token : (c.num_classes > 0 ? 2 : 1);
+    h->L = h->extras + h->n_patch;
+    h->P = c.patch_size * c.patch_size * c.in_chans;
+    h->n_in = c.depth / 2;
+    h->n_blocks = 2 * h->n_in + 1;
+    if (h->L > ATTN_MAX_L) return fail(nullptr, USP_ERR_UNSUPPORTED, "sequence length above 384 tokens is not built");
+
+    const int64_t D = h->D;
+    h->i_pos = add_weight(h.get(), "pos_embed", {1, h->L, D}, false);
+    h->i_pew = add_weight(h.get(), "patch_embed.proj.weight", {D, c.in_chans, c.patch_size, c.patch_size}, false);
+    h->i_peb = add_weight(h.get(), "patch_embed.proj.bias", {D}, false);
+    if (c.num_classes > 0) h->i_label = add_weight(h.get(), "label_emb.weight", {c.num_classes, D}, false);
+    if (c.num_clip_token > 0) {
+        h->i_ctxw = add_weight(h.get(), "context_embed.weight", {D, c.clip_dim}, true);
+        h->i_ctxb = add_weight(h.get(), "context_embed.bias", {D}, false);
+    }
+    for (int i = 0; i < h->n_in; ++i) h->blocks.push_back(add_block(h.get(), "in_blocks." + std::to_string(i), false));
+    h->blocks.push_back(add_block(h.get(), "mid_block", false));
+    for (int i = 0; i < h->n_in; ++i)
+        h->blocks.push_back(add_block(h.get(), "out_blocks." + std::to_string(i), c.skip != 0));
+    h->i_nw = add_weight(h.get(), "norm.weight", {D}, false);
+    h->i_nb = add_weight(h.get(), "norm.bias", {D}, false);
+    h->i_dw = add_weight(h.get(), "decoder_pred.weight", {h->P, D}, false);
+    h->i_db = add_weight(h.get(), "decoder_pred.bias", {h->P}, false);
+    if (c.conv) {
+        h->i_fw = add_weight(h.get(), "final_layer.weight", {c.in_chans, c.in_chans, 3, 3}, false);
+        h->i_fb = add_weight(h.get(), "final_layer.bias", {c.in_chans}, false);
+    }
+    usp_handle* hp = h.get();
+    for (auto& w : h->w) {
+        CUDA_TRY(nullptr, cudaMalloc(&w.d32, w.numel * 4));
+        if (w.gemm) CUDA_TRY(nullptr, cudaMalloc(&w.d16, w.numel * 2));
+    }
+    // timestep_embedding frequencies (libs/uvit.py:36-42): exp(-ln(1e4) * i / half) evaluated in fp32
+    {
+        const int half = h->D / 2;
+        std::vector<float> f(half);
+        for (int i = 0; i < half; ++i) {
+            const float a = -logf(10000.0f) * static_cast<float>(i);
+            f[i] = expf(a / static_cast<float>(half));
+        }
+        CUDA_TRY(nullptr, cudaMalloc(&h->freqs, half * 4));
+        CUDA_TRY(nullptr, cudaMemcpy(h->freqs, f.data(), half * 4, cudaMemcpyHostToDevice));
+    }
+    CUDA_TRY(nullptr, cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
+    CUDA_TRY(nullptr, cudaEventCreate(&h->ev0));
+    CUDA_TRY(nullptr, cudaEventCreate(&h->ev1));
+    CUDA_TRY(nullptr, gemm_configure());
+    CUDA_TRY(nullptr, attention_configure());
+    (void)hp;
+    *out = h.release();
+    return USP_OK;
+}
+
+void usp_destroy(usp_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    for (auto& kv : h->plans) {
+        for (auto& g : kv.second->graphs) cudaGraphExecDestroy(g.second);
+        cudaFree(kv.second->slab);
+        cudaFree(kv.second->delta);
+    }
+    for (auto& w : h->w) {
+        cudaFree(w.d32);
+        cudaFree(w.d16);
+    }
+    cudaFree(h->freqs);
+    if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    delete h;
+}
+
+int usp_num_weights(const usp_handle* h) { return h ? static_cast<int>(h->w.size()) : 0; }
+const char* usp_weight_name(const usp_handle* h, int i) {
+    if (!h || i < 0 || i >= static_cast<int>(h->w.size())) return nullptr;
+    return h->w[i].name.c_str();
+}
+
+int usp_set_weight(usp_handle* h, const char* name, const void* data, const int64_t* shape, int ndim) {
+    if (!h || !name || !data || !shape) return fail(h, USP_ERR_INVALID, "null argument");
+    auto it = h->widx.find(name);
+    if (it == h->widx.end()) return fail(h, USP_ERR_INVALID, std::string("unknown weight name: ") + name);
+    Weight& w = h->w[it->second];
+    bool same = static_cast<int>(w.shape.size()) == ndim;
+    for (int i = 0; same && i < ndim; ++i) same = w.shape[i] == shape[i];
+    if (!same) return fail(h, USP_ERR_INVALID, std::string("shape mismatch for ") + name);
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    CUDA_TRY(h, cudaMemcpy(w.d32, data, w.numel * 4, cudaMemcpyDefault));
+    w.set = true;
+    h->finalized = false;
+    return USP_OK;
+}
+
+int usp_finalize_weights(usp_handle* h, void* stream) {
+    if (!h) return USP_ERR_INVALID;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    for (auto& w : h->w)
+        if (!w.set) return fail(h, USP_ERR_STATE, "weight never set: " + w.name);
+    for (auto& w : h->w) {
+        if (!w.gemm) continue;
+        CUDA_TRY(h, launch_convert16(w.d32, w.d16, w.numel, h->cfg.operand_dtype, s));
+        const int N = static_cast<int>(w.shape[0]), K = static_cast<int>(w.shape[1]);
+        if (!make_map_2d(&w.map, w.d16, N, K, gemm_block_n(N), h->cfg.operand_dtype))
+            return fail(h, USP_ERR_CUDA, "cuTensorMapEncodeTiled failed for " + w.name);
+    }
+    CUDA_TRY(h, cudaStreamSynchronize(s));
+    // weights changed: captured graphs stay valid (they reference the same device buffers)
+    h->finalized = true;
+    return USP_OK;
+}
+
+int usp_forward(usp_handle* h, const float* x, const float* t, const float* context, const int64_t* y, float* out,
+                int B, void* stream) {
+    int rc = check_ready(h, B);
+    if (rc) return rc;
+    if (!x || !t || !out) return fail(h, USP_ERR_INVALID, "null tensor");
+    if ((h->cfg.num_clip_token > 0) != (context != nullptr))
+        return fail(h, USP_ERR_INVALID, "context must be given exactly for the t2i model");
+    if ((y != nullptr) != (h->cfg.num_classes > 0))
+        return fail(h, USP_ERR_INVALID, "y must be given exactly for the class-conditional model (num_classes > 0)");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    Plan* p = nullptr;
+    rc = get_plan(h, B, &p);
+    if (rc) return rc;
+    CUDA_TRY(h, cudaEventRecord(h->ev0, s));
+    if (context) {
+        rc = embed_context(h, p, context, s);
+        if (rc) return rc;
+    }
+    FwdIO io;
+    memset(&io, 0, sizeof(io));
+    io.x = x; io.tvec = t; io.y = reinterpret_cast<const long long*>(y); io.has_ctx = context != nullptr;
+    io.out = out; io.m1 = 1.f;
+    rc = enqueue_forward(h, p, io, s);
+    if (rc) return rc;
+    CUDA_TRY(h, cudaEventRecord(h->ev1, s));
+    h->ev_valid = true;
+    return USP_OK;
+}
+
+int usp_grid_size(float t0, float t1, float step_size) { return build_grid(t0, t1, step_size, nullptr); }
+
+int usp_sample(usp_handle* h, float* z, const float* context, const int64_t* y, int B, float t0, float t1,
+               float step_size, int method, const float* delta_table, float write_scale, float t_edit, int edit_loc,
+               void* stream) {
+    int rc = check_ready(h, B);
+    if (rc) return rc;
+    if (!z) return fail(h, USP_ERR_INVALID, "null latent");
+    if ((h->cfg.num_clip_token > 0) != (context != nullptr))
+        return fail(h, USP_ERR_INVALID, "context must be given exactly for the t2i model");
+    if ((y != nullptr) != (h->cfg.num_classes > 0))
+        return fail(h, USP_ERR_INVALID, "y must be given exactly for the class-conditional model (num_classes > 0)");
+    if (method != USP_METHOD_EULER && method != USP_METHOD_HEUN) return fail(h, USP_ERR_INVALID, "unknown method");
+    if (edit_loc != USP_EDIT_NONE && edit_loc != USP_EDIT_HEAD && edit_loc != USP_EDIT_TAIL)
+        return fail(h, USP_ERR_INVALID, "edit_loc must be none, head or tail (\"mid\" is broken in the reference)");
+    if ((edit_loc != USP_EDIT_NONE) != (delta_table != nullptr))
+        return fail(h, USP_ERR_INVALID, "delta_table must be given exactly when edit_loc is head or tail");
+    std::vector<float> grid;
+    const int n = build_grid(t0, t1, step_size, &grid);
+    if (n < 2) return fail(h, USP_ERR_INVALID, "bad time grid (t0 == t1, step_size <= 0 or more than 4096 points)");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    Plan* p = nullptr;
+    rc = get_plan(h, B, &p);
+    if (rc) return rc;
+
+    const int C = h->cfg.in_chans, S = h->cfg.img_size;
+    const size_t zbytes = static_cast<size_t>(B) * C * S * S * 4;
+    // should_edit (libs/dissection.py:21-26): timestep_digit = f"{t:.2f}"; "0.00" never edits; float(digit) <= t_edit
+    std::vector<unsigned char> mask(n, 0);
+    if (edit_loc != USP_EDIT_NONE) {
+        for (int i = 0; i < n; ++i) {
+            char buf[64];
+            snprintf(buf, sizeof(buf), "%.2f", static_cast<double>(grid[i]));
+            mask[i] = (strcmp(buf, "0.00") != 0 && atof(buf) <= static_cast<double>(t_edit)) ? 1 : 0;
+        }
+        const size_t dbytes = static_cast<size_t>(n) * C * S * S * 4;
+        if (p->delta_cap < dbytes) {
+            // growing the table invalidates graphs that captured the old pointer
+            for (auto& g : p->graphs) cudaGraphExecDestroy(g.second);
+            p->graphs.clear();
+            if (p->delta) CUDA_TRY(h, cudaFree(p->delta));
+            p->delta = nullptr;
+            CUDA_TRY(h, cudaMalloc(&p->delta, dbytes));
+            p->delta_cap = dbytes;
+        }
+        CUDA_TRY(h, cudaMemcpyAsync(p->delta, delta_table, dbytes, cudaMemcpyDefault, s));
+    }
+    CUDA_TRY(h, cudaEventRecord(h->ev0, s));
+    CUDA_TRY(h, cudaMemcpyAsync(p->grid, grid.data(), n * 4, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(h, cudaMemcpyAsync(p->mask, mask.data(), n, cudaMemcpyHostToDevice, s));
+    StepState st0;
+    memset(&st0, 0, sizeof(st0));
+    st0.write_scale = write_scale;
+    CUDA_TRY(h, cudaMemcpyAsync(p->st, &st0, sizeof(st0), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(h, cudaMemcpyAsync(p->z, z, zbytes, cudaMemcpyDefault, s));
+    if (y) CUDA_TRY(h, cudaMemcpyAsync(p->y, y, static_cast<size_t>(B) * 8, cudaMemcpyDefault, s));
+    if (context) {
+        rc = embed_context(h, p, context, s);
+        if (rc) return rc;
+    }
+
+    const int key = method | (edit_loc << 2) | ((y ? 1 : 0) << 4);
+    auto git = p->graphs.find(key);
+    if (git == p->graphs.end()) {
+        // capture one ODE step on the private stream; every pointer it touches is plan-owned
+        cudaGraph_t graph = nullptr;
+        CUDA_TRY(h, cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal));
+        auto body = [&]() -> int {
+            cudaError_t e = launch_step(p->st, p->grid, p->mask, 0, h->cap_stream);
+            if (e != cudaSuccess) return fail(h, USP_ERR_CUDA, std::string("launch_step: ") + cudaGetErrorString(e));
+            FwdIO io;
+            memset(&io, 0, sizeof(io));
+            io.st = p->st; io.y = y ? p->y : nullptr; io.has_ctx = context != nullptr;
+            io.delta = edit_loc != USP_EDIT_NONE ? p->delta : nullptr; io.edit_loc = edit_loc;
+            if (method == USP_METHOD_EULER) {
+                io.x = p->z; io.base = p->z; io.out = p->z; io.m1 = 1.f;
+                return enqueue_forward(h, p, io, h->cap_stream);
+            }
+            io.x = p->z; io.base = p->z; io.vstore = p->k1; io.out = p->ztmp; io.m1 = 1.f;
+            int r = enqueue_forward(h, p, io, h->cap_stream);
+            if (r) return r;
+            e = launch_step(p->st, p->grid, p->mask, 1, h->cap_stream);
+            if (e != cudaSuccess) return fail(h, USP_ERR_CUDA, std::string("launch_step: ") + cudaGetErrorString(e));
+            io.x = p->ztmp; io.base = p->z; io.aux = p->k1; io.vstore = nullptr; io.out = p->z;
+            io.m1 = 0.5f; io.m2 = 0.5f;
+            return enqueue_forward(h, p, io, h->cap_stream);
+        };
+        const int brc = body();
+        cudaError_t ce = cudaStreamEndCapture(h->cap_stream, &graph);
+        if (brc) {
+            if (graph) cudaGraphDestroy(graph);
+            return brc;
+        }
+        if (ce != cudaSuccess) return fail(h, USP_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce));
+        cudaGraphExec_t exec = nullptr;
+        ce = cudaGraphInstantiate(&exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ce != cudaSuccess) return fail(h, USP_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ce));
+        p->graphs[key] = exec;
+        git = p->graphs.find(key);
+    }
+    for (int i = 0; i + 1 < n; ++i) CUDA_TRY(h, cudaGraphLaunch(git->second, s));
+    CUDA_TRY(h, cudaMemcpyAsync(z, p->z, zbytes, cudaMemcpyDefault, s));
+    CUDA_TRY(h, cudaEventRecord(h->ev1, s));
+    h->ev_valid = true;
+    return USP_OK;
+}
+
+int usp_sample_host(usp_handle* h, float* z_host, const float* context_host, const int64_t* y_host, int B, float t0,
+                    float t1, float step_size, int method, const float* delta_table_host, float write_scale,
+                    float t_edit, int edit_loc) {
+    int rc = check_ready(h, B);
+    if (rc) return rc;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    Plan* p = nullptr;
+    rc = get_plan(h, B, &p);
+    if (rc) return rc;
+    cudaStream_t s = h->cap_stream;
+    const float* ctx_dev = nullptr;
+    if (context_host) {
+        if (h->cfg.num_clip_token <= 0) return fail(h, USP_ERR_INVALID, "context given to a model without context_embed");
+        CUDA_TRY(h, cudaMemcpyAsync(p->ctx32, context_host,
+                                    static_cast<size_t>(B) * h->cfg.num_clip_token * h->cfg.clip_dim * 4,
+                                    cudaMemcpyHostToDevice, s));
+        ctx_dev = p->ctx32;
+    }
+    // z / y / delta go host->device inside usp_sample (cudaMemcpyDefault handles host sources)
+    rc = usp_sample(h, z_host, ctx_dev, y_host, B, t0, t1, step_size, method, delta_table_host, write_scale, t_edit,
+                    edit_loc, s);
+    if (rc) return rc;
+    CUDA_TRY(h, cudaStreamSynchronize(s));
+    return USP_OK;
+}
+
+size_t usp_workspace_bytes(const usp_handle* h, int B) {
+    if (!h) return 0;
+    auto it = h->plans.find(B);
+    if (it != h->plans.end()) return it->second->bytes;
+    const size_t M = static_cast<size_t>(B) * h->L, D = h->D;
+    return M * D * 4 + M * D * 2 * (4 + h->n_in) + M * h->Hd * 2 + 3 * M * D * 2;
+}
+
+int usp_kernels_per_forward(const usp_handle* h) {
+    if (!h) return 0;
+    if (h->kernels_per_forward) return h->kernels_per_forward;
+    const int n_skip = h->cfg.skip ? h->n_in : 0;
+    return 1 + h->n_blocks * 7 + n_skip + 2;
+}
+
+double usp_flops_per_forward(const usp_handle* h) {
+    if (!h) return 0.0;
+    const double D = h->D, L = h->L, Hd = h->Hd;
+    const double nb = h->n_blocks, ns = h->cfg.skip ? h->n_in : 0;
+    double f = nb * (2.0 * L * D * (3.0 * D) + 2.0 * L * D * D + 4.0 * L * D * Hd + 4.0 * L * L * D);
+    f += ns * 4.0 * L * D * D;
+    f += 2.0 * h->n_patch * h->P * D + 2.0 * L * D * h->P;
+    if (h->cfg.num_clip_token > 0) f += 2.0 * h->cfg.num_clip_token * h->cfg.clip_dim * D;
+    if (h->cfg.conv) f += 2.0 * h->cfg.in_chans * h->cfg.in_chans * 9.0 * h->cfg.img_size * h->cfg.img_size;
+    return f;
+}
+
+int usp_last_forward_ms(usp_handle* h, float* ms) {
+    if (!h || !ms) return USP_ERR_INVALID;
+    if (!h->ev_valid) return fail(h, USP_ERR_STATE, "no forward / sample recorded yet");
+    CUDA_TRY(h, cudaEventSynchronize(h->ev1));
+    CUDA_TRY(h, cudaEventElapsedTime(ms, h->ev0, h->ev1));
+    return USP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernel-level entry points
+// ---------------------------------------------------------------------------------------------
+static int op_fail(const char* what, cudaError_t e) {
+    g_create_error = std::string(what) + ": " + cudaGetErrorString(e);
+    return USP_ERR_CUDA;
+}
+
+int usp_op_convert16(const float* in, void* out16, int64_t n, int operand_dtype, void* stream) {
+    cudaError_t e = launch_convert16(in, out16, n, operand_dtype, static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? USP_OK : op_fail("convert16", e);
+}
+
+int usp_op_gemm(int epilogue, const void* a16, const void* a16_second, const void* w16, const float* bias,
+                const float* resid, float* out32, void* out16, int M, int N, int K, int K0, int L, int H,
+                int operand_dtype, void* stream) {
+    if (!get_encode_fn()) return fail(nullptr, USP_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
+    cudaError_t e = gemm_configure();
+    if (e != cudaSuccess) return op_fail("gemm_configure", e);
+    if (K0 <= 0 || K0 > K || (K0 < K) != (a16_second != nullptr))
+        return fail(nullptr, USP_ERR_INVALID, "K0 / second A source mismatch");
+    GemmMaps maps;
+    bool ok = make_map_2d(&maps.a0, a16, M, K0, GEMM_BM, operand_dtype);
+    if (a16_second) ok &= make_map_2d(&maps.a1, a16_second, M, K - K0, GEMM_BM, operand_dtype);
+    else maps.a1 = maps.a0;
+    ok &= make_map_2d(&maps.b, w16, N, K, gemm_block_n(N), operand_dtype);
+    if (!ok) return fail(nullptr, USP_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+    GemmArgs g;
+    memset(&g, 0, sizeof(g));
+    g.M = M; g.N = N; g.K = K; g.K0 = K0; g.opd = operand_dtype;
+    g.bias = bias; g.resid = resid; g.out32 = out32; g.out16 = out16;
+    g.L = L; g.H = H;
+    g.qkv_stride = static_cast<long long>(M) * (N / 3);
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    e = launch_gemm(epilogue, maps, g, sms, static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? USP_OK : op_fail("launch_gemm", e);
+}
+
+int usp_op_attention(const void* q16, const void* k16, const void* v16, void* out16, int B, int H, int L,
+                     int operand_dtype, void* stream) {
+    if (!get_encode_fn()) return fail(nullptr, USP_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
+    cudaError_t e = attention_configure();
+    if (e != cudaSuccess) return op_fail("attention_configure", e);
+    CUtensorMap mq, mk, mv;
+    const long long BH = static_cast<long long>(B) * H;
+    bool ok = make_map_qkv(&mq, q16, BH, L, operand_dtype) && make_map_qkv(&mk, k16, BH, L, operand_dtype) &&
+              make_map_qkv(&mv, v16, BH, L, operand_dtype);
+    if (!ok) return fail(nullptr, USP_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+    AttnArgs a;
+    memset(&a, 0, sizeof(a));
+    a.B = B; a.H = H; a.L = L; a.D = H * 64; a.opd = operand_dtype; a.out16 = out16;
+    e = launch_attention(mq, mk, mv, a, static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? USP_OK : op_fail("launch_attention", e);
+}
+
+int usp_op_layernorm(const float* x, const float* gamma, const float* beta, void* out16, int M, int D,
+                     int operand_dtype, void* stream) {
+    cudaError_t e = launch_layernorm(x, gamma, beta, out16, M, D, operand_dtype, static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? USP_OK : op_fail("launch_layernorm", e);
+}
+
+}  // extern "C"

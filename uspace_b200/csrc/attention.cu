@@ -1,0 +1,235 @@
+// Whole-row attention on tcgen05/TMEM for short sequences (L <= 384; U-ViT has L = 257 / 258 / 334).
+//
+// Replaces F.scaled_dot_product_attention(q, k, v) at libs/uvit.py:93-95 (and the "math" branch
+// libs/uvit_t2i.py:91-107): O = softmax(Q K^T * hd^-0.5) V, no mask, no dropout, head_dim 64.
+//
+// One CTA per (128-query tile, sample*head).  Because L is short the full score row fits in TMEM
+// (L16 <= 384 fp32 columns), so there is no online-softmax rescaling:
+//   warp 4 (1 thread): TMA loads Q tile, all of K and V (3-D tensor maps, OOB rows zero-filled),
+//                      issues S = Q K^T (tcgen05.mma, K-major operands) into TMEM columns [0, L16),
+//                      later issues O = P V (A = P from swizzled smem, B = V as MN-major) into columns [384, 448).
+//   warps 0-3 (128 threads, thread i <-> query row i <-> TMEM lane i): row max, exp2, row sum in fp32,
+//                      write un-normalised P as 16-bit into the 128B-swizzled K-major smem layout,
+//                      finally scale O by 1/sum and store heads-merged [B*L, H*64].
+#include "common.cuh"
+#include "kernels.h"
+
+namespace usp {
+
+namespace {
+
+constexpr int HD = 64;
+constexpr int QT = 128;                       // query rows per CTA
+constexpr int ATTN_THREADS = 160;
+constexpr int TILE16K = 128 * HD * 2;         // one 128-row x 64-col 16-bit tile
+constexpr int MAX_KCH = ATTN_MAX_L / 128;     // 3 row chunks of K / V
+constexpr int MAX_PCH = ATTN_MAX_L / 64;      // 6 column chunks of P
+constexpr int SQ_OFF = 0;
+constexpr int SK_OFF = SQ_OFF + TILE16K;
+constexpr int SV_OFF = SK_OFF + MAX_KCH * TILE16K;
+constexpr int SP_OFF = SV_OFF + MAX_KCH * TILE16K;
+constexpr int ATTN_SMEM = SP_OFF + MAX_PCH * TILE16K + 1024;
+constexpr int O_COL = 384;
+constexpr int ATTN_TMEM_COLS = 512;
+
+// V tile as the B operand in MN-major form: rows are keys (K dim), 64 head-dim elements contiguous per row
+// (128 B, swizzled), 8-key groups 1024 B apart (SBO).  One 64-wide MN atom, so LBO is unused.
+__device__ __forceinline__ uint64_t umma_desc_v_mn(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((saddr & 0x3FFFF) >> 4);
+    d |= static_cast<uint64_t>(1) << 16;
+    d |= static_cast<uint64_t>(1024 >> 4) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(2) << 61;
+    return d;
+}
+
+__global__ void __launch_bounds__(ATTN_THREADS, 1)
+attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                 const __grid_constant__ CUtensorMap tmV, const AttnArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+    __shared__ __align__(8) uint64_t bar_qk, bar_v, bar_s, bar_p, bar_o;
+    __shared__ uint32_t tmem_base_smem;
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int qt = blockIdx.x;
+    const int bh = blockIdx.y;
+    const int L = a.L;
+    const int L16 = (L + 15) & ~15;
+    const int nkc = (L + 127) / 128;
+
+    if (threadIdx.x == 0) {
+        mbar_init(&bar_qk, 1);
+        mbar_init(&bar_v, 1);
+        mbar_init(&bar_s, 1);
+        mbar_init(&bar_p, 128);
+        mbar_init(&bar_o, 1);
+        fence_barrier_init();
+    }
+    if (warp == 4) tmem_alloc<ATTN_TMEM_COLS>(&tmem_base_smem);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_smem;
+
+    if (warp == 4) {
+        if (lane == 0) {
+            tma_prefetch_desc(&tmQ);
+            tma_prefetch_desc(&tmK);
+            tma_prefetch_desc(&tmV);
+            mbar_expect_tx(&bar_qk, (1 + nkc) * TILE16K);
+            tma_load_3d(&tmQ, &bar_qk, smem + SQ_OFF, 0, qt * QT, bh);
+            for (int c = 0; c < nkc; ++c) tma_load_3d(&tmK, &bar_qk, smem + SK_OFF + c * TILE16K, 0, c * 128, bh);
+            mbar_expect_tx(&bar_v, nkc * TILE16K);
+            for (int c = 0; c < nkc; ++c) tma_load_3d(&tmV, &bar_v, smem + SV_OFF + c * TILE16K, 0, c * 128, bh);
+
+            const int fmt = a.opd == OPD_FP16 ? 0 : 1;
+            // ---- S = Q K^T ----
+            mbar_wait(&bar_qk, 0);
+            tc_fence_after();
+            const uint64_t qdesc = umma_desc_sw128(smem_u32(smem + SQ_OFF));
+            for (int n0 = 0; n0 < L16; n0 += 256) {
+                const int nn = (L16 - n0) < 256 ? (L16 - n0) : 256;
+                const uint32_t idesc = umma_idesc(fmt, QT, nn, 0, 0);
+                const uint64_t kdesc = umma_desc_sw128(smem_u32(smem + SK_OFF + n0 * 128));
+#pragma unroll
+                for (int k = 0; k < HD / 16; ++k)
+                    umma_f16(tmem_base + n0, qdesc + (k * 2), kdesc + (k * 2), idesc, k != 0);
+            }
+            umma_commit(&bar_s);
+            // ---- O = P V ----
+            mbar_wait(&bar_v, 0);
+            mbar_wait(&bar_p, 0);
+            tc_fence_after();
+            const uint32_t idesc_o = umma_idesc(fmt, QT, HD, 0, 1);
+            const int nks = L16 / 16;
+            for (int kk = 0; kk < nks; ++kk) {
+                const uint64_t pdesc =
+                    umma_desc_sw128(smem_u32(smem + SP_OFF + (kk >> 2) * TILE16K)) + ((kk & 3) * 2);
+                const uint64_t vdesc = umma_desc_v_mn(smem_u32(smem + SV_OFF + kk * 16 * 128));
+                umma_f16(tmem_base + O_COL, pdesc, vdesc, idesc_o, kk != 0);
+            }
+            umma_commit(&bar_o);
+        }
+    } else {
+        // ===================== softmax / output warps =====================
+        const int row = threadIdx.x;           // 0..127 == TMEM lane
+        const int l = qt * QT + row;
+        const bool row_ok = l < L;
+        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+        const float c2 = 0.125f * 1.44269504088896340736f;  // hd^-0.5 * log2(e)
+        const int nch = (L + 31) / 32;
+
+        mbar_wait(&bar_s, 0);
+        tc_fence_after();
+
+        float mx = -INFINITY;
+        for (int c = 0; c < nch; ++c) {
+            uint32_t r[32];
+            tmem_ld32(t_row + c * 32, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const float s = __uint_as_float(r[j]);
+                if (c * 32 + j < L) mx = fmaxf(mx, s);
+            }
+        }
+        const float mxs = mx * c2;
+        float sum = 0.f;
+        uint8_t* prow = smem + SP_OFF + (row >> 3) * 1024 + (row & 7) * 128;
+        for (int c = 0; c < nch; ++c) {
+            uint32_t r[32];
+            tmem_ld32(t_row + c * 32, r);
+            tmem_ld_wait();
+            uint32_t pk[16];
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+                float p0 = 0.f, p1 = 0.f;
+                if (c * 32 + j < L) p0 = exp2f(fmaf(__uint_as_float(r[j]), c2, -mxs));
+                if (c * 32 + j + 1 < L) p1 = exp2f(fmaf(__uint_as_float(r[j + 1]), c2, -mxs));
+                // the row sum uses the rounded values that the PV product will see
+                uint32_t u;
+                float2 f;
+                if (a.opd == OPD_FP16) {
+                    u = Op16<OPD_FP16>::pack(p0, p1);
+                    f = Op16<OPD_FP16>::unpack(u);
+                } else {
+                    u = Op16<OPD_BF16>::pack(p0, p1);
+                    f = Op16<OPD_BF16>::unpack(u);
+                }
+                sum += f.x + f.y;
+                pk[j >> 1] = u;
+            }
+            if (row_ok) {
+                // columns [c*32, c*32+32): chunk-of-64 index, then 4 x 16-byte units with the 128B swizzle
+                uint8_t* pc = prow + (c >> 1) * TILE16K;
+                const int u0 = (c & 1) * 4;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int unit = (u0 + u) ^ (row & 7);
+                    *reinterpret_cast<uint4*>(pc + unit * 16) =
+                        make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+                }
+            }
+        }
+        fence_proxy_async();  // make the generic-proxy smem writes visible to the tensor core (async proxy)
+        mbar_arrive(&bar_p);
+
+        mbar_wait(&bar_o, 0);
+        tc_fence_after();
+        const float inv = 1.0f / sum;
+        uint16_t* orow = reinterpret_cast<uint16_t*>(a.out16) +
+                         (static_cast<long long>(bh / a.H) * L + l) * a.D + (bh % a.H) * HD;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            uint32_t r[32];
+            tmem_ld32(t_row + O_COL + c * 32, r);
+            tmem_ld_wait();
+            if (row_ok) {
+                uint4* op = reinterpret_cast<uint4*>(orow + c * 32);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float v[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[8 * j + e]) * inv;
+                    uint4 u;
+                    if (a.opd == OPD_FP16) {
+                        u.x = Op16<OPD_FP16>::pack(v[0], v[1]); u.y = Op16<OPD_FP16>::pack(v[2], v[3]);
+                        u.z = Op16<OPD_FP16>::pack(v[4], v[5]); u.w = Op16<OPD_FP16>::pack(v[6], v[7]);
+                    } else {
+                        u.x = Op16<OPD_BF16>::pack(v[0], v[1]); u.y = Op16<OPD_BF16>::pack(v[2], v[3]);
+                        u.z = Op16<OPD_BF16>::pack(v[4], v[5]); u.w = Op16<OPD_BF16>::pack(v[6], v[7]);
+                    }
+                    op[j] = u;
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) tmem_dealloc<ATTN_TMEM_COLS>(tmem_base);
+}
+
+}  // namespace
+
+cudaError_t attention_configure() {
+    static bool done = false;
+    if (done) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_SMEM);
+    if (e == cudaSuccess) done = true;
+    return e;
+}
+
+cudaError_t launch_attention(const CUtensorMap& q, const CUtensorMap& k, const CUtensorMap& v, const AttnArgs& a,
+                             cudaStream_t s) {
+    if (a.L < 1 || a.L > ATTN_MAX_L || a.D != a.H * HD) return cudaErrorInvalidValue;
+    dim3 grid((a.L + QT - 1) / QT, a.B * a.H);
+    attention_kernel<<<grid, ATTN_THREADS, ATTN_SMEM, s>>>(q, k, v, a);
+    return cudaGetLastError();
+}
+
+}  // namespace usp

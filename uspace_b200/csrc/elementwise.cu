@@ -1,0 +1,323 @@
+// HBM-bound glue kernels around the tensor-core GEMMs: token embedding, LayerNorm -> 16-bit operand,
+// output head (final LN + decoder_pred), unpatchify + 3x3 conv + edit + ODE update, dtype conversion,
+// and the device-side ODE step bookkeeping that lets one captured CUDA graph serve every step.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace usp {
+
+namespace {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// embed: PatchEmbed.forward (libs/uvit.py:175-179) as an explicit (C,p1,p2) gather + [P]x[P,D] product,
+//        timestep_embedding (libs/uvit.py:26-46; t used raw, cos half then sin half),
+//        token order [label?, time, ctx..., patches] (libs/uvit.py:320-327, libs/uvit_t2i.py:320-324), + pos_embed.
+//        Optional "head" edit x + delta[t]*write_scale (libs/dissection.py:157, libs/uvit.py:313-314).
+// grid = (L, B), block = 256
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) embed_kernel(const EmbedArgs a) {
+    const int l = blockIdx.x;
+    const int b = blockIdx.y;
+    const int D = a.D;
+    float* out = a.out32 + (static_cast<long long>(b) * a.L + l) * D;
+    const float* pos = a.pos + static_cast<long long>(l) * D;
+    const int t_tok = a.has_label ? 1 : 0;
+    const int first_patch = t_tok + 1 + a.n_ctx;
+
+    if (a.has_label && l == 0) {
+        const float* e = a.label + a.y[b] * D;
+        for (int d = threadIdx.x; d < D; d += blockDim.x) out[d] = e[d] + pos[d];
+        return;
+    }
+    if (l == t_tok) {
+        const float t = a.st ? a.st->t : a.tvec[b];
+        const int half = D / 2;
+        for (int d = threadIdx.x; d < D; d += blockDim.x) {
+            float v = 0.f;
+            if (d < half) v = cosf(t * a.freqs[d]);
+            else if (d < 2 * half) v = sinf(t * a.freqs[d - half]);
+            out[d] = v + pos[d];
+        }
+        return;
+    }
+    if (l < first_patch) {
+        const float* e = a.ctxemb + (static_cast<long long>(b) * a.n_ctx + (l - t_tok - 1)) * D;
+        for (int d = threadIdx.x; d < D; d += blockDim.x) out[d] = e[d] + pos[d];
+        return;
+    }
+    // patch token
+    __shared__ float feat[64];
+    const int p = a.p, C = a.C, S = a.S;
+    const int P = C * p * p;
+    const int gw = S / p;
+    const int pi = l - first_patch;
+    const int ph = pi / gw, pw = pi % gw;
+    if (threadIdx.x < P) {
+        const int f = threadIdx.x;
+        const int c = f / (p * p);
+        const int p1 = (f / p) % p;
+        const int p2 = f % p;
+        const int idx = (c * S + ph * p + p1) * S + pw * p + p2;
+        float v = a.x[static_cast<long long>(b) * C * S * S + idx];
+        if (a.delta != nullptr && a.st != nullptr) {
+            const float sc = a.st->edit;
+            if (sc != 0.f) v += a.delta[static_cast<long long>(a.st->didx) * C * S * S + idx] * sc;
+        }
+        feat[f] = v;
+    }
+    __syncthreads();
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+        const float* w = a.w + static_cast<long long>(d) * P;
+        float acc = 0.f;
+        for (int f = 0; f < P; ++f) acc = fmaf(w[f], feat[f], acc);
+        out[d] = acc + a.bias[d] + pos[d];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm (eps 1e-5, affine; libs/uvit.py:160-161) fp32 in -> 16-bit GEMM operand out. One warp per row,
+// the row lives in registers (two-pass mean / biased variance in fp32).
+// ------------------------------------------------------------------------------------------------
+template <int V4>  // float4 per lane: D = 128 * V4
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ g,
+                                                        const float* __restrict__ bta, uint16_t* __restrict__ out,
+                                                        int M, int opd) {
+    constexpr int D = 128 * V4;
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= M) return;
+    const float4* xr = reinterpret_cast<const float4*>(x + static_cast<long long>(row) * D);
+    float4 v[V4];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < V4; ++i) {
+        v[i] = xr[i * 32 + lane];
+        s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+    const float mean = warp_sum(s) * (1.0f / D);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < V4; ++i) {
+        const float a0 = v[i].x - mean, a1 = v[i].y - mean, a2 = v[i].z - mean, a3 = v[i].w - mean;
+        q += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
+    }
+    const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + 1e-5f);
+    uint2* orow = reinterpret_cast<uint2*>(out + static_cast<long long>(row) * D);
+#pragma unroll
+    for (int i = 0; i < V4; ++i) {
+        const float4 gg = __ldg(reinterpret_cast<const float4*>(g) + i * 32 + lane);
+        const float4 bb = __ldg(reinterpret_cast<const float4*>(bta) + i * 32 + lane);
+        const float y0 = (v[i].x - mean) * rstd * gg.x + bb.x;
+        const float y1 = (v[i].y - mean) * rstd * gg.y + bb.y;
+        const float y2 = (v[i].z - mean) * rstd * gg.z + bb.z;
+        const float y3 = (v[i].w - mean) * rstd * gg.w + bb.w;
+        uint2 u;
+        if (opd == OPD_FP16) {
+            u.x = Op16<OPD_FP16>::pack(y0, y1);
+            u.y = Op16<OPD_FP16>::pack(y2, y3);
+        } else {
+            u.x = Op16<OPD_BF16>::pack(y0, y1);
+            u.y = Op16<OPD_BF16>::pack(y2, y3);
+        }
+        orow[i * 32 + lane] = u;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// head: final LayerNorm + decoder_pred Linear(D -> P) on the patch tokens only (libs/uvit.py:342-345), fp32 SIMT
+// (P = 16: 0.03 % of the FLOPs, kept exact).  One warp per patch token.
+// ------------------------------------------------------------------------------------------------
+template <int V4>
+__global__ void __launch_bounds__(256) head_kernel(const HeadArgs a) {
+    constexpr int D = 128 * V4;
+    const int n_patch = a.L - a.extras;
+    const int tok = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (tok >= a.B * n_patch) return;
+    const int b = tok / n_patch, pi = tok % n_patch;
+    const float4* xr =
+        reinterpret_cast<const float4*>(a.x32 + (static_cast<long long>(b) * a.L + a.extras + pi) * D);
+    float4 v[V4];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < V4; ++i) {
+        v[i] = xr[i * 32 + lane];
+        s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+    const float mean = warp_sum(s) * (1.0f / D);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < V4; ++i) {
+        const float a0 = v[i].x - mean, a1 = v[i].y - mean, a2 = v[i].z - mean, a3 = v[i].w - mean;
+        q += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
+    }
+    const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + 1e-5f);
+#pragma unroll
+    for (int i = 0; i < V4; ++i) {
+        const float4 gg = __ldg(reinterpret_cast<const float4*>(a.ng) + i * 32 + lane);
+        const float4 bb = __ldg(reinterpret_cast<const float4*>(a.nb) + i * 32 + lane);
+        v[i].x = (v[i].x - mean) * rstd * gg.x + bb.x;
+        v[i].y = (v[i].y - mean) * rstd * gg.y + bb.y;
+        v[i].z = (v[i].z - mean) * rstd * gg.z + bb.z;
+        v[i].w = (v[i].w - mean) * rstd * gg.w + bb.w;
+    }
+    float* o = a.pf + static_cast<long long>(tok) * a.P;
+    for (int j = 0; j < a.P; ++j) {
+        const float4* wr = reinterpret_cast<const float4*>(a.w + static_cast<long long>(j) * D);
+        float acc = 0.f;
+#pragma unroll
+        for (int i = 0; i < V4; ++i) {
+            const float4 w4 = __ldg(wr + i * 32 + lane);
+            acc += (v[i].x * w4.x + v[i].y * w4.y) + (v[i].z * w4.z + v[i].w * w4.w);
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) o[j] = acc + a.bias[j];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// final: unpatchify with feature order (p1,p2,C) (libs/uvit.py:56-63) + final_layer Conv2d 3x3 pad 1
+// (libs/uvit.py:346-347) + optional "tail" edit v + delta[t]*write_scale (libs/uvit.py:349-350) +
+// fixed-grid ODE update (torchdiffeq Euler: y1 = y0 + dt*f; Heun: y0 + dt/2*(k1+k2)).
+// One thread per output element.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) final_kernel(const FinalArgs a) {
+    const int C = a.C, S = a.S, p = a.p;
+    const long long n = static_cast<long long>(a.B) * C * S * S;
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int xw = static_cast<int>(i % S);
+    const int yh = static_cast<int>((i / S) % S);
+    const int co = static_cast<int>((i / (static_cast<long long>(S) * S)) % C);
+    const int b = static_cast<int>(i / (static_cast<long long>(S) * S * C));
+    const int gw = S / p;
+    const int P = C * p * p;
+    const float* pf = a.pf + static_cast<long long>(b) * gw * gw * P;
+    float v;
+    if (a.cw != nullptr) {
+        v = a.cb[co];
+        for (int ci = 0; ci < C; ++ci) {
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky) {
+                const int yy = yh + ky - 1;
+                if (yy < 0 || yy >= S) continue;
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                    const int xx = xw + kx - 1;
+                    if (xx < 0 || xx >= S) continue;
+                    const float img = pf[((yy / p) * gw + (xx / p)) * P + ((yy % p) * p + (xx % p)) * C + ci];
+                    v = fmaf(a.cw[((co * C + ci) * 3 + ky) * 3 + kx], img, v);
+                }
+            }
+        }
+    } else {
+        v = pf[((yh / p) * gw + (xw / p)) * P + ((yh % p) * p + (xw % p)) * C + co];
+    }
+    const int chw = static_cast<int>(i % (static_cast<long long>(C) * S * S));
+    if (a.delta != nullptr && a.st != nullptr) {
+        const float sc = a.st->edit;
+        if (sc != 0.f) v += a.delta[static_cast<long long>(a.st->didx) * C * S * S + chw] * sc;
+    }
+    if (a.st == nullptr) {
+        a.out[i] = v;
+        return;
+    }
+    if (a.vstore != nullptr) a.vstore[i] = v;
+    const float dt = a.st->dt;
+    float inc = a.m1 * v;
+    if (a.aux != nullptr) inc += a.m2 * a.aux[i];
+    a.out[i] = a.base[i] + dt * inc;
+}
+
+__global__ void convert16_kernel(const float* __restrict__ in, uint16_t* __restrict__ out, long long n, int opd) {
+    long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (; i < n; i += stride)
+        out[i] = opd == OPD_FP16 ? Op16<OPD_FP16>::one(in[i]) : Op16<OPD_BF16>::one(in[i]);
+}
+
+__global__ void step_kernel(StepState* st, const float* __restrict__ grid, const unsigned char* __restrict__ mask,
+                            int stage) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (stage == 0) {
+        const int i = st->next;
+        st->cur = i;
+        st->next = i + 1;
+        st->t = grid[i];
+        st->dt = grid[i + 1] - grid[i];
+        st->edit = mask[i] ? st->write_scale : 0.f;
+        st->didx = i;
+    } else {
+        const int i = st->cur;
+        st->t = grid[i + 1];
+        st->edit = mask[i + 1] ? st->write_scale : 0.f;
+        st->didx = i + 1;
+    }
+}
+
+}  // namespace
+
+cudaError_t launch_embed(const EmbedArgs& a, cudaStream_t s) {
+    if (a.C * a.p * a.p > 64) return cudaErrorInvalidValue;
+    embed_kernel<<<dim3(a.L, a.B), 256, 0, s>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_layernorm(const float* x, const float* g, const float* b, void* out16, int M, int D, int opd,
+                             cudaStream_t s) {
+    const int rows_per_block = 8;
+    const int grid = (M + rows_per_block - 1) / rows_per_block;
+    uint16_t* o = reinterpret_cast<uint16_t*>(out16);
+    switch (D) {
+        case 256: layernorm_kernel<2><<<grid, 256, 0, s>>>(x, g, b, o, M, opd); break;
+        case 384: layernorm_kernel<3><<<grid, 256, 0, s>>>(x, g, b, o, M, opd); break;
+        case 512: layernorm_kernel<4><<<grid, 256, 0, s>>>(x, g, b, o, M, opd); break;
+        case 768: layernorm_kernel<6><<<grid, 256, 0, s>>>(x, g, b, o, M, opd); break;
+        case 1024: layernorm_kernel<8><<<grid, 256, 0, s>>>(x, g, b, o, M, opd); break;
+        case 1536: layernorm_kernel<12><<<grid, 256, 0, s>>>(x, g, b, o, M, opd); break;
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_head(const HeadArgs& a, cudaStream_t s) {
+    const int n_tok = a.B * (a.L - a.extras);
+    const int grid = (n_tok + 7) / 8;
+    switch (a.D) {
+        case 256: head_kernel<2><<<grid, 256, 0, s>>>(a); break;
+        case 384: head_kernel<3><<<grid, 256, 0, s>>>(a); break;
+        case 512: head_kernel<4><<<grid, 256, 0, s>>>(a); break;
+        case 768: head_kernel<6><<<grid, 256, 0, s>>>(a); break;
+        case 1024: head_kernel<8><<<grid, 256, 0, s>>>(a); break;
+        case 1536: head_kernel<12><<<grid, 256, 0, s>>>(a); break;
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_final(const FinalArgs& a, cudaStream_t s) {
+    const long long n = static_cast<long long>(a.B) * a.C * a.S * a.S;
+    final_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_convert16(const float* in, void* out16, long long n, int opd, cudaStream_t s) {
+    long long blocks = (n + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks < 1) blocks = 1;
+    convert16_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(in, reinterpret_cast<uint16_t*>(out16), n, opd);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_step(StepState* st, const float* grid, const unsigned char* mask, int stage, cudaStream_t s) {
+    step_kernel<<<1, 32, 0, s>>>(st, grid, mask, stage);
+    return cudaGetLastError();
+}
+
+}  // namespace usp

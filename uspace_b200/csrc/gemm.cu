@@ -1,0 +1,293 @@
+// tcgen05 GEMM for the U-ViT linears: C[M,N] = A[M,K] * W[N,K]^T (+ fused epilogue).
+//
+// Replaces, on the reference path, every nn.Linear inside Block._forward (libs/uvit.py:157-162):
+//   attn.qkv  (libs/uvit.py:81,89)     -> EPI_QKV        (head-major Q/K/V, no rearrange/.float() copies)
+//   attn.proj (libs/uvit.py:116,160)   -> EPI_BIAS_RESID (bias + residual add into the fp32 stream)
+//   mlp.fc1+GELU (libs/timm.py:107-108)-> EPI_BIAS_GELU
+//   mlp.fc2   (libs/timm.py:110)       -> EPI_BIAS_RESID
+//   skip_linear(cat[x,skip]) (libs/uvit.py:158-159) -> EPI_BIAS_F32 with a two-source K loop (no concat)
+//
+// Structure: persistent, warp-specialised CTA per SM.
+//   warp 0    : TMA producer (A and W tiles, 128B-swizzled, 64-wide K blocks) through a STAGES-deep ring
+//   warp 1    : allocates TMEM, single thread issues tcgen05.mma (128 x BN x 16), commits to mbarriers
+//   warps 2-5 : epilogue; tcgen05.ld the fp32 accumulator (double-buffered in TMEM so the next tile's
+//               main loop overlaps this tile's epilogue), fuse bias/GELU/residual, store.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace usp {
+
+namespace {
+
+constexpr int BM = GEMM_BM;
+constexpr int BK = GEMM_BK;
+constexpr int GEMM_THREADS = 192;
+constexpr int A_TILE_BYTES = BM * BK * 2;  // 16 KiB
+
+template <int BN>
+struct GemmCfg {
+    static constexpr int B_TILE_BYTES = BN * BK * 2;
+    static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
+    static constexpr int STAGES = (BN == 256) ? 4 : 6;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;  // + alignment slack
+    static constexpr int TMEM_COLS = 2 * BN;
+};
+
+__device__ __forceinline__ float gelu_erf(float v) { return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f)); }
+
+__device__ __forceinline__ uint32_t pack16(int opd, float a, float b) {
+    return opd == OPD_FP16 ? Op16<OPD_FP16>::pack(a, b) : Op16<OPD_BF16>::pack(a, b);
+}
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+            const __grid_constant__ CUtensorMap tmB, const GemmArgs g) {
+    using Cfg = GemmCfg<BN>;
+    constexpr int STAGES = Cfg::STAGES;
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+    __shared__ __align__(8) uint64_t full_bar[STAGES];
+    __shared__ __align__(8) uint64_t empty_bar[STAGES];
+    __shared__ __align__(8) uint64_t tmem_full_bar[2];
+    __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+    __shared__ uint32_t tmem_base_smem;
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    const int n_tiles_n = g.N / BN;
+    const int n_tiles_m = (g.M + BM - 1) / BM;
+    const int n_tiles = n_tiles_m * n_tiles_n;
+    const int nkb = g.K / BK;
+    const int nkb0 = g.K0 / BK;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA0);
+        tma_prefetch_desc(&tmA1);
+        tma_prefetch_desc(&tmB);
+        for (int i = 0; i < STAGES; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tmem_full_bar[i], 1);
+            mbar_init(&tmem_empty_bar[i], 4);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(&tmem_base_smem);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_smem;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                const int m0 = (tile / n_tiles_n) * BM;
+                const int n0 = (tile % n_tiles_n) * BN;
+                for (int kb = 0; kb < nkb; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+                    uint8_t* sb = sa + A_TILE_BYTES;
+                    mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+                    if (kb < nkb0)
+                        tma_load_2d(&tmA0, &full_bar[stage], sa, kb * BK, m0);
+                    else
+                        tma_load_2d(&tmA1, &full_bar[stage], sa, (kb - nkb0) * BK, m0);
+                    tma_load_2d(&tmB, &full_bar[stage], sb, kb * BK, n0);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc(g.opd == OPD_FP16 ? 0 : 1, BM, BN, 0, 0);
+            int stage = 0;
+            uint32_t phase = 0;
+            int t = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
+                const int as = t & 1;
+                const uint32_t aphase = (t >> 1) & 1;
+                mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + as * BN;
+                for (int kb = 0; kb < nkb; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+                    const uint64_t adesc = umma_desc_sw128(sa);
+                    const uint64_t bdesc = umma_desc_sw128(sa + A_TILE_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k) {
+                        // advance 16 elements (32 B) along K inside the 128B swizzle atom
+                        umma_f16(d_tmem, adesc + (k * 2), bdesc + (k * 2), idesc, (kb | k) != 0);
+                    }
+                    umma_commit(&empty_bar[stage]);  // smem slot is free once these MMAs retire
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&tmem_full_bar[as]);  // accumulator ready for the epilogue
+            }
+        }
+    } else {
+        // ===================== epilogue (warps 2..5) =====================
+        const int lg = warp & 3;  // TMEM lane group this warp may access
+        int t = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
+            const int as = t & 1;
+            const uint32_t aphase = (t >> 1) & 1;
+            const int m0 = (tile / n_tiles_n) * BM;
+            const int n0 = (tile % n_tiles_n) * BN;
+            const int m = m0 + lg * 32 + lane;
+            const bool row_ok = m < g.M;
+
+            mbar_wait(&tmem_full_bar[as], aphase);
+            tc_fence_after();
+
+            // per-row destination bookkeeping
+            long long qkv_row = 0;
+            if (EPI == EPI_QKV) {
+                const int b = m / g.L;
+                const int l = m - b * g.L;
+                qkv_row = (static_cast<long long>(b) * g.H * g.L + l) * 64;  // + h*L*64 + which*stride + d
+            }
+
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                uint32_t r[32];
+                tmem_ld32(tmem_base + (static_cast<uint32_t>(lg * 32) << 16) + as * BN + c * 32, r);
+                tmem_ld_wait();
+                const int n = n0 + c * 32;
+                if (row_ok) {
+                    float v[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                    if (EPI != EPI_QKV || g.bias != nullptr) {
+                        if (g.bias != nullptr) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4) {
+                                const float4 b4 = __ldg(reinterpret_cast<const float4*>(g.bias + n + j));
+                                v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+                            }
+                        }
+                    }
+                    if (EPI == EPI_BIAS_GELU) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+                    }
+                    if (EPI == EPI_BIAS_RESID) {
+                        const float4* rp = reinterpret_cast<const float4*>(g.resid + static_cast<long long>(m) * g.N + n);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 x4 = rp[j];
+                            v[4 * j] += x4.x; v[4 * j + 1] += x4.y; v[4 * j + 2] += x4.z; v[4 * j + 3] += x4.w;
+                        }
+                    }
+                    if (EPI == EPI_BIAS_RESID || EPI == EPI_BIAS_F32) {
+                        if (g.out32 != nullptr) {
+                            float4* op = reinterpret_cast<float4*>(g.out32 + static_cast<long long>(m) * g.N + n);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                        }
+                    }
+                    // 16-bit output
+                    uint16_t* o16 = nullptr;
+                    if (EPI == EPI_QKV) {
+                        const int Dm = g.H * 64;
+                        const int which = n / Dm;
+                        const int rem = n - which * Dm;
+                        const int h = rem >> 6;
+                        const int d = rem & 63;
+                        o16 = reinterpret_cast<uint16_t*>(g.out16) + which * g.qkv_stride + qkv_row +
+                              static_cast<long long>(h) * g.L * 64 + d;
+                    } else if (g.out16 != nullptr) {
+                        o16 = reinterpret_cast<uint16_t*>(g.out16) + static_cast<long long>(m) * g.N + n;
+                    }
+                    if (o16 != nullptr) {
+                        uint4* op = reinterpret_cast<uint4*>(o16);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            uint4 u;
+                            u.x = pack16(g.opd, v[8 * j], v[8 * j + 1]);
+                            u.y = pack16(g.opd, v[8 * j + 2], v[8 * j + 3]);
+                            u.z = pack16(g.opd, v[8 * j + 4], v[8 * j + 5]);
+                            u.w = pack16(g.opd, v[8 * j + 6], v[8 * j + 7]);
+                            op[j] = u;
+                        }
+                    }
+                }
+            }
+            // release this accumulator buffer back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+}
+
+template <int BN, int EPI>
+cudaError_t launch_one(const GemmMaps& maps, const GemmArgs& a, int num_sms, cudaStream_t s) {
+    using Cfg = GemmCfg<BN>;
+    const int n_tiles = ((a.M + BM - 1) / BM) * (a.N / BN);
+    const int grid = n_tiles < num_sms ? n_tiles : num_sms;
+    gemm_kernel<BN, EPI><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, s>>>(maps.a0, maps.a1, maps.b, a);
+    return cudaGetLastError();
+}
+
+template <int BN>
+cudaError_t launch_bn(int epi, const GemmMaps& maps, const GemmArgs& a, int num_sms, cudaStream_t s) {
+    switch (epi) {
+        case EPI_QKV: return launch_one<BN, EPI_QKV>(maps, a, num_sms, s);
+        case EPI_BIAS_GELU: return launch_one<BN, EPI_BIAS_GELU>(maps, a, num_sms, s);
+        case EPI_BIAS_RESID: return launch_one<BN, EPI_BIAS_RESID>(maps, a, num_sms, s);
+        case EPI_BIAS_F32: return launch_one<BN, EPI_BIAS_F32>(maps, a, num_sms, s);
+    }
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace
+
+template <int BN, int EPI>
+cudaError_t configure_one() {
+    return cudaFuncSetAttribute(gemm_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                GemmCfg<BN>::SMEM_BYTES);
+}
+
+// opt every instantiation into its dynamic shared memory size (done once, outside any graph capture)
+cudaError_t gemm_configure() {
+    static bool done = false;
+    if (done) return cudaSuccess;
+    cudaError_t e;
+    if ((e = configure_one<256, EPI_QKV>()) != cudaSuccess) return e;
+    if ((e = configure_one<256, EPI_BIAS_GELU>()) != cudaSuccess) return e;
+    if ((e = configure_one<256, EPI_BIAS_RESID>()) != cudaSuccess) return e;
+    if ((e = configure_one<256, EPI_BIAS_F32>()) != cudaSuccess) return e;
+    if ((e = configure_one<128, EPI_QKV>()) != cudaSuccess) return e;
+    if ((e = configure_one<128, EPI_BIAS_GELU>()) != cudaSuccess) return e;
+    if ((e = configure_one<128, EPI_BIAS_RESID>()) != cudaSuccess) return e;
+    if ((e = configure_one<128, EPI_BIAS_F32>()) != cudaSuccess) return e;
+    done = true;
+    return cudaSuccess;
+}
+
+int gemm_block_n(int N) { return (N % 256 == 0) ? 256 : 128; }
+
+cudaError_t launch_gemm(int epi, const GemmMaps& maps, const GemmArgs& a, int num_sms, cudaStream_t s) {
+    if (a.M <= 0 || a.N % 128 != 0 || a.K % BK != 0 || a.K0 % BK != 0 || a.K0 > a.K) return cudaErrorInvalidValue;
+    if (gemm_block_n(a.N) == 256) return launch_bn<256>(epi, maps, a, num_sms, s);
+    return launch_bn<128>(epi, maps, a, num_sms, s);
+}
+
+}  // namespace usp

@@ -1,0 +1,117 @@
+// Internal (C++) launcher interface between api.cu and the kernel translation units.
+// Nothing here is part of the public ABI (see include/uspace_b200.h).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace usp {
+
+// tensor-core operand type (both run at the same tcgen05 kind::f16 rate)
+enum OperandDtype : int { OPD_BF16 = 0, OPD_FP16 = 1 };
+
+// ---- GEMM: C[M,N] = A[M,K] * W[N,K]^T with fused epilogues ------------------------------------
+enum GemmEpilogue : int {
+    EPI_QKV = 0,        // 16-bit head-major scatter: out16[which][b*H+h][l][d]      (libs/uvit.py:89-94)
+    EPI_BIAS_GELU = 1,  // out16[m,n] = gelu_erf(acc + bias[n])                       (libs/timm.py:107-108)
+    EPI_BIAS_RESID = 2, // out32[m,n] = resid[m,n] + acc + bias[n]; optional 16-bit copy (libs/uvit.py:160-161)
+    EPI_BIAS_F32 = 3,   // out32[m,n] = acc + bias[n]; optional 16-bit copy            (libs/uvit.py:158-159)
+};
+
+struct GemmArgs {
+    int M, N, K;         // K = total reduction length
+    int K0;              // columns [0,K0) come from A0, [K0,K) from A1 (K0 == K: single source)
+    int opd;             // OperandDtype
+    const float* bias;   // [N] or nullptr
+    const float* resid;  // [M,N] fp32 or nullptr
+    float* out32;        // [M,N] fp32 or nullptr
+    void* out16;         // [M,N] 16-bit (or QKV base) or nullptr
+    int L, H;            // EPI_QKV: tokens per sample, heads (head_dim = 64)
+    long long qkv_stride;  // EPI_QKV: elements between the q, k and v planes
+};
+
+struct GemmMaps {
+    CUtensorMap a0, a1, b;
+};
+
+// Box sizes the GEMM expects in its tensor maps.
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_BK = 64;
+int gemm_block_n(int N);  // 256 or 128
+cudaError_t launch_gemm(int epi, const GemmMaps& maps, const GemmArgs& args, int num_sms, cudaStream_t s);
+
+// ---- attention: softmax(Q K^T / sqrt(64)) V per (sample, head) ---------------------------------
+struct AttnArgs {
+    int B, H, L;       // head_dim fixed at 64
+    int D;             // H*64 (row pitch of out16)
+    int opd;
+    void* out16;       // [B*L, D] 16-bit, heads merged "(H hd)"
+    const float* vscale;  // optional per-(sample,key) V-row scale [B, L] (p2p re-weighting), or nullptr
+};
+constexpr int ATTN_MAX_L = 384;
+cudaError_t launch_attention(const CUtensorMap& q, const CUtensorMap& k, const CUtensorMap& v,
+                             const AttnArgs& args, cudaStream_t s);
+
+// ---- small fused kernels ---------------------------------------------------------------------
+struct StepState {       // lives in device memory; advanced by step_kernel inside the captured graph
+    int next;            // index of the next grid interval
+    int cur;             // interval being integrated
+    float t;             // time fed to the velocity field for the current stage
+    float dt;            // signed step (t_{i+1} - t_i)
+    float edit;          // write_scale if the edit is active at `t`, else 0
+    float write_scale;
+    int didx;            // row of the edit table that belongs to `t`
+    int pad;
+};
+
+struct EmbedArgs {
+    const float* x;        // [B,C,S,S] latent
+    const float* tvec;     // [B] per-sample time (forward) ...
+    const StepState* st;   // ... or the shared ODE time (sampling); exactly one is non-null
+    const long long* y;    // [B] labels or nullptr
+    const float* ctxemb;   // [B*n_ctx, D] fp32 context tokens or nullptr
+    const float* w;        // patch_embed.proj.weight [D, C*p*p]
+    const float* bias;     // [D]
+    const float* pos;      // [L, D]
+    const float* label;    // label_emb.weight [num_classes, D] or nullptr
+    const float* freqs;    // [D/2]
+    const float* delta;    // head edit table [nsteps+1, C*S*S] or nullptr
+    float* out32;          // [B*L, D]
+    int B, C, S, p, D, L, n_ctx, has_label;
+};
+cudaError_t launch_embed(const EmbedArgs& a, cudaStream_t s);
+
+cudaError_t launch_layernorm(const float* x, const float* g, const float* b, void* out16, int M, int D, int opd,
+                             cudaStream_t s);
+
+struct HeadArgs {
+    const float* x32;     // [B*L, D]
+    const float* ng;      // norm.weight
+    const float* nb;      // norm.bias
+    const float* w;       // decoder_pred.weight [P, D]
+    const float* bias;    // [P]
+    float* pf;            // [B, n_patches, P]
+    int B, L, D, extras, P;
+};
+cudaError_t launch_head(const HeadArgs& a, cudaStream_t s);
+
+struct FinalArgs {
+    const float* pf;       // [B, n_patches, P] with P ordered (p1, p2, C)
+    const float* cw;       // final_layer.weight [C,C,3,3] or nullptr (conv=False)
+    const float* cb;       // [C]
+    const float* delta;    // tail edit table [nsteps+1, C*S*S] or nullptr
+    const StepState* st;   // nullptr for a plain forward
+    const float* base;     // ODE: state the update starts from
+    const float* aux;      // Heun stage 2: k1
+    float* vstore;         // Heun stage 1: where to keep k1 (or nullptr)
+    float* out;            // forward: v;  ODE: base + dt*(m1*v + m2*aux)
+    float m1, m2;
+    int B, C, S, p;
+};
+cudaError_t launch_final(const FinalArgs& a, cudaStream_t s);
+
+cudaError_t launch_convert16(const float* in, void* out16, long long n, int opd, cudaStream_t s);
+// stage 0: start interval `next` (t = grid[next]) and advance; stage 1: second Heun stage (t = grid[cur+1])
+cudaError_t launch_step(StepState* st, const float* grid, const unsigned char* mask, int stage, cudaStream_t s);
+
+}  // namespace usp
