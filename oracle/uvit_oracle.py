@@ -1,0 +1,258 @@
+"""CPU oracle for the U-ViT velocity field and the fixed-grid ODE loop.  TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this
+module; the product path (uspace_b200/) never does.
+
+It is a restatement (not a copy) of the reference algorithm in plain torch fp32/fp64 tensor arithmetic
+with explicit index maps, working on a flat ``state_dict`` (same keys as the reference modules):
+
+  timestep_embedding   libs/uvit.py:26-46
+  patch embedding      libs/uvit.py:165-179   (Conv2d k=s=p == (C,p1,p2) gather + matmul)
+  token assembly       libs/uvit.py:316-327, libs/uvit_t2i.py:316-324
+  attention            libs/uvit.py:86-118    (qkv split "(K H D)", softmax(QK^T/sqrt(hd))V, merge "(H D)")
+  mlp                  libs/timm.py:96-112    (fc1 -> exact-erf GELU -> fc2)
+  block                libs/uvit.py:157-162   (skip_linear(cat[x, skip]); pre-LN residuals, eps 1e-5)
+  output head          libs/uvit.py:342-347   (LN, decoder_pred, drop extras, unpatchify (p1,p2,C), conv3x3)
+  edit hook            libs/dissection.py:21-34,115-157 ("write_attr"/"write_pca": x + delta[t]*write_scale)
+  ODE                  flow_matching.py:102-151 + torchdiffeq's documented FixedGridODESolver semantics
+                       (torchdiffeq is an un-vendored, unpinned dependency: README.md:121)
+
+Pinning: the reference ships no tests or golden vectors.  The model part is pinned against
+the reference modules themselves (imported from /root/reference by tests/golden/make_golden.py, outputs
+committed under tests/golden/).  The ODE loop is "parity unpinned": torchdiffeq is not installed anywhere
+in this environment, so its fixed-grid algorithm is restated from its published behaviour (grid lengths
+51/101/41 probe-verified in SURVEY.md §8c).
+"""
+from __future__ import annotations
+
+import math
+from typing import Callable, Dict, List, Optional
+
+import torch
+import torch.nn.functional as F
+
+Tensor = torch.Tensor
+
+
+# ----------------------------------------------------------------------------------------------
+# configuration helpers
+# ----------------------------------------------------------------------------------------------
+def model_dims(cfg: dict) -> dict:
+    """Derived sizes for a reference ctor-kwargs dict (libs/uvit.py:183-202 / libs/uvit_t2i.py:193-211)."""
+    D = cfg["embed_dim"]
+    p = cfg["patch_size"]
+    n_patch = (cfg["img_size"] // p) ** 2
+    n_ctx = cfg.get("num_clip_token", 0) if "clip_dim" in cfg else 0
+    if n_ctx:
+        extras = 1 + n_ctx
+    else:
+        extras = 2 if cfg.get("num_classes", -1) > 0 else 1
+    return dict(
+        D=D, p=p, C=cfg["in_chans"], S=cfg["img_size"], n_patch=n_patch, extras=extras, L=extras + n_patch,
+        H=cfg["num_heads"], hidden=int(D * cfg.get("mlp_ratio", 4.0)), n_in=cfg["depth"] // 2,
+        n_ctx=n_ctx, P=p * p * cfg["in_chans"],
+    )
+
+
+def flops_per_forward(cfg: dict) -> float:
+    """algorithmic FLOPs per image per forward (multiply-add = 2)."""
+    d = model_dims(cfg)
+    D, L = d["D"], d["L"]
+    n_blk = 2 * d["n_in"] + 1
+    n_skip = d["n_in"] if cfg.get("skip", True) else 0
+    f = n_blk * (2 * L * D * 3 * D + 2 * L * D * D + 4 * L * D * d["hidden"] + 4 * L * L * D)
+    f += n_skip * 4 * L * D * D
+    f += 2 * d["n_patch"] * d["P"] * D + 2 * L * D * d["P"]
+    if d["n_ctx"]:
+        f += 2 * d["n_ctx"] * cfg["clip_dim"] * D
+    if cfg.get("conv", True):
+        f += 2 * d["C"] * d["C"] * 9 * d["S"] * d["S"]
+    return float(f)
+
+
+# ----------------------------------------------------------------------------------------------
+# index maps (integer work: bit-exact targets)
+# ----------------------------------------------------------------------------------------------
+def patchify_index(C: int, S: int, p: int) -> Tensor:
+    """[n_patch, C*p*p] flat indices into a [C,S,S] image; feature order (C, p1, p2), token = h*gw + w."""
+    gw = S // p
+    idx = torch.empty(gw * gw, C * p * p, dtype=torch.long)
+    for ph in range(gw):
+        for pw in range(gw):
+            f = 0
+            for c in range(C):
+                for p1 in range(p):
+                    for p2 in range(p):
+                        idx[ph * gw + pw, f] = (c * S + ph * p + p1) * S + pw * p + p2
+                        f += 1
+    return idx
+
+
+def unpatchify_index(C: int, S: int, p: int) -> Tensor:
+    """[C*S*S] flat indices into a [n_patch, p*p*C] token matrix; feature order (p1, p2, C)."""
+    gw = S // p
+    P = p * p * C
+    idx = torch.empty(C * S * S, dtype=torch.long)
+    for c in range(C):
+        for y in range(S):
+            for x in range(S):
+                tok = (y // p) * gw + (x // p)
+                feat = ((y % p) * p + (x % p)) * C + c
+                idx[(c * S + y) * S + x] = tok * P + feat
+    return idx
+
+
+# ----------------------------------------------------------------------------------------------
+# model pieces
+# ----------------------------------------------------------------------------------------------
+def timestep_embedding(t: Tensor, dim: int, max_period: float = 10000.0) -> Tensor:
+    half = dim // 2
+    freqs = torch.exp(-math.log(max_period) * torch.arange(half, dtype=torch.float32) / half).to(t.dtype)
+    args = t[:, None] * freqs[None]
+    emb = torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
+    if dim % 2:
+        emb = torch.cat([emb, torch.zeros_like(emb[:, :1])], dim=-1)
+    return emb
+
+
+def layer_norm(x: Tensor, w: Tensor, b: Tensor, eps: float = 1e-5) -> Tensor:
+    mu = x.mean(dim=-1, keepdim=True)
+    var = ((x - mu) ** 2).mean(dim=-1, keepdim=True)
+    return (x - mu) / torch.sqrt(var + eps) * w + b
+
+
+def gelu_erf(x: Tensor) -> Tensor:
+    return 0.5 * x * (1.0 + torch.erf(x / math.sqrt(2.0)))
+
+
+def attention(x: Tensor, sd: Dict[str, Tensor], pre: str, H: int, vscale: Optional[Tensor] = None) -> Tensor:
+    B, L, D = x.shape
+    hd = D // H
+    qkv = x @ sd[pre + ".attn.qkv.weight"].T
+    if pre + ".attn.qkv.bias" in sd:
+        qkv = qkv + sd[pre + ".attn.qkv.bias"]
+    q, k, v = (qkv[..., i * D:(i + 1) * D].reshape(B, L, H, hd).permute(0, 2, 1, 3) for i in range(3))
+    s = (q @ k.transpose(-1, -2)) * (hd ** -0.5)
+    pr = torch.softmax(s, dim=-1)
+    if vscale is not None:  # post-softmax column re-weighting == scaling rows of V (tools/utils_t2i.py:196-224)
+        v = v * vscale[:, None, :, None]
+    o = (pr @ v).permute(0, 2, 1, 3).reshape(B, L, D)
+    return o @ sd[pre + ".attn.proj.weight"].T + sd[pre + ".attn.proj.bias"]
+
+
+def mlp(x: Tensor, sd: Dict[str, Tensor], pre: str) -> Tensor:
+    h = gelu_erf(x @ sd[pre + ".mlp.fc1.weight"].T + sd[pre + ".mlp.fc1.bias"])
+    return h @ sd[pre + ".mlp.fc2.weight"].T + sd[pre + ".mlp.fc2.bias"]
+
+
+def block(x: Tensor, sd: Dict[str, Tensor], pre: str, H: int, skip: Optional[Tensor] = None) -> Tensor:
+    if pre + ".skip_linear.weight" in sd:
+        x = torch.cat([x, skip], dim=-1) @ sd[pre + ".skip_linear.weight"].T + sd[pre + ".skip_linear.bias"]
+    x = x + attention(layer_norm(x, sd[pre + ".norm1.weight"], sd[pre + ".norm1.bias"]), sd, pre, H)
+    x = x + mlp(layer_norm(x, sd[pre + ".norm2.weight"], sd[pre + ".norm2.bias"]), sd, pre)
+    return x
+
+
+def should_edit(t: float, t_edit) -> bool:
+    digit = f"{t:.2f}"
+    if digit == "0.00":
+        return False
+    if isinstance(t_edit, (int, float)):
+        return float(digit) <= t_edit
+    if isinstance(t_edit, str) and t_edit.startswith("every_"):
+        return float(digit) % float(t_edit.replace("every_", "")) == 0.0
+    raise ValueError(t_edit)
+
+
+def uvit_forward(sd: Dict[str, Tensor], cfg: dict, x: Tensor, t: Tensor, y: Optional[Tensor] = None,
+                 context: Optional[Tensor] = None, head_delta: Optional[Tensor] = None,
+                 tail_delta: Optional[Tensor] = None) -> Tensor:
+    """UViT.forward on a flat state_dict.  head_delta / tail_delta are already scaled [C,S,S] edits or None."""
+    d = model_dims(cfg)
+    dt = x.dtype
+    sd = {k: v.to(dt) for k, v in sd.items()}
+    B = x.shape[0]
+    C, S, p, D = d["C"], d["S"], d["p"], d["D"]
+    if head_delta is not None:
+        x = x + head_delta.to(dt)
+    pidx = patchify_index(C, S, p)
+    feats = x.reshape(B, C * S * S)[:, pidx.reshape(-1)].reshape(B, d["n_patch"], d["P"])
+    tok = feats @ sd["patch_embed.proj.weight"].reshape(D, d["P"]).T + sd["patch_embed.proj.bias"]
+    time_tok = timestep_embedding(t.to(dt), D)[:, None, :]
+    if d["n_ctx"]:
+        ctx = context.to(dt) @ sd["context_embed.weight"].T + sd["context_embed.bias"]
+        h = torch.cat([time_tok, ctx, tok], dim=1)
+    else:
+        h = torch.cat([time_tok, tok], dim=1)
+        if y is not None:
+            h = torch.cat([sd["label_emb.weight"][y][:, None, :], h], dim=1)
+    h = h + sd["pos_embed"]
+    skips: List[Tensor] = []
+    for i in range(d["n_in"]):
+        h = block(h, sd, f"in_blocks.{i}", d["H"])
+        skips.append(h)
+    h = block(h, sd, "mid_block", d["H"])
+    for i in range(d["n_in"]):
+        h = block(h, sd, f"out_blocks.{i}", d["H"], skips.pop())
+    h = layer_norm(h, sd["norm.weight"], sd["norm.bias"])
+    h = h @ sd["decoder_pred.weight"].T + sd["decoder_pred.bias"]
+    h = h[:, d["extras"]:, :]
+    uidx = unpatchify_index(C, S, p)
+    img = h.reshape(B, -1)[:, uidx].reshape(B, C, S, S)
+    if "final_layer.weight" in sd:
+        img = F.conv2d(img, sd["final_layer.weight"], sd["final_layer.bias"], padding=1)
+    if tail_delta is not None:
+        img = img + tail_delta.to(dt)
+    return img
+
+
+# ----------------------------------------------------------------------------------------------
+# fixed-grid ODE (torchdiffeq FixedGridODESolver semantics, restated)
+# ----------------------------------------------------------------------------------------------
+def fixed_grid(t0: float, t1: float, step_size: float, dtype=torch.float32) -> Tensor:
+    """grid = arange(ceil((t1-t0)/h + 1)) * h + t0, last point clamped to t1; decreasing time via s = -t."""
+    sgn = 1.0 if t1 >= t0 else -1.0
+    s0 = torch.tensor(sgn * t0, dtype=dtype)
+    s1 = torch.tensor(sgn * t1, dtype=dtype)
+    h = torch.tensor(step_size, dtype=dtype)
+    niters = int(torch.ceil((s1 - s0) / h + 1).item())
+    grid = torch.arange(0, niters, dtype=dtype) * h + s0
+    grid[-1] = s1
+    return grid * sgn
+
+
+def odeint_fixed(func: Callable[[Tensor, Tensor], Tensor], z: Tensor, t0: float, t1: float, step_size: float,
+                 method: str = "euler") -> Tensor:
+    grid = fixed_grid(t0, t1, step_size, torch.float32)
+    y = z
+    for i in range(len(grid) - 1):
+        ta, tb = grid[i], grid[i + 1]
+        dt = (tb - ta).to(z.dtype)
+        if method == "euler":
+            y = y + dt * func(ta, y)
+        elif method == "heun":
+            k1 = func(ta, y)
+            k2 = func(tb, y + dt * k1)
+            y = y + dt * 0.5 * (k1 + k2)
+        else:
+            raise NotImplementedError(method)
+    return y
+
+
+def sample(sd: Dict[str, Tensor], cfg: dict, z: Tensor, t0: float = 0.0, t1: float = 1.0, step_size: float = 0.02,
+           method: str = "euler", y: Optional[Tensor] = None, context: Optional[Tensor] = None,
+           delta_table: Optional[Tensor] = None, write_scale: float = 0.0, t_edit: float = 0.0,
+           edit_loc: Optional[str] = None) -> Tensor:
+    """CNF.decode / CNF.encode (flow_matching.py:102-151) with the write_attr edit hook; delta_table rows are
+    indexed by grid point (== the delta_{t:.2f}.npy file the reference would load at that time)."""
+    grid = fixed_grid(t0, t1, step_size, torch.float32)
+    lookup = {float(g): i for i, g in enumerate(grid.tolist())}
+
+    def func(t: Tensor, x: Tensor) -> Tensor:
+        hd = td = None
+        if edit_loc is not None and delta_table is not None and should_edit(float(t), t_edit):
+            dlt = delta_table[lookup[float(t)]] * write_scale
+            hd, td = (dlt, None) if edit_loc == "head" else (None, dlt)
+        return uvit_forward(sd, cfg, x, t.expand(x.shape[0]), y=y, context=context, head_delta=hd, tail_delta=td)
+
+    return odeint_fixed(func, z, t0, t1, step_size, method)

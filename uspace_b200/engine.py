@@ -1,0 +1,150 @@
+"""Thin owner of a ``usp_handle``: loads reference-format weights and enqueues forward / sample on the
+caller's CUDA stream.  PyTorch is only used for device memory and streams here."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional
+
+import torch
+
+from . import _lib
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def config_from_kwargs(kw: dict, operand_dtype: str = "fp16") -> _lib.UspConfig:
+    """Map the reference ctor kwargs (libs/uvit.py:183-202, libs/uvit_t2i.py:193-211) to usp_config."""
+    if kw.get("mlp_time_embed", False):
+        raise NotImplementedError("mlp_time_embed=True is not used by any reference config and is not built")
+    if kw.get("qk_scale") is not None:
+        raise NotImplementedError("qk_scale override is not built (reference configs use head_dim**-0.5)")
+    t2i = "clip_dim" in kw or "num_clip_token" in kw
+    c = _lib.UspConfig()
+    c.img_size = kw.get("img_size", 224)
+    c.patch_size = kw.get("patch_size", 16)
+    c.in_chans = kw.get("in_chans", 3)
+    c.embed_dim = kw.get("embed_dim", 768)
+    c.depth = kw.get("depth", 12)
+    c.num_heads = kw.get("num_heads", 12)
+    c.mlp_hidden = int(c.embed_dim * kw.get("mlp_ratio", 4.0))
+    c.num_classes = 0 if t2i else max(0, kw.get("num_classes", -1))
+    c.clip_dim = kw.get("clip_dim", 768) if t2i else 0
+    c.num_clip_token = kw.get("num_clip_token", 77) if t2i else 0
+    c.qkv_bias = int(bool(kw.get("qkv_bias", False)))
+    c.conv = int(bool(kw.get("conv", True)))
+    c.skip = int(bool(kw.get("skip", True)))
+    c.operand_dtype = _lib.OPERAND[operand_dtype]
+    return c
+
+
+class Engine:
+    def __init__(self, ctor_kwargs: dict, device: torch.device, operand_dtype: str = "fp16"):
+        if device.type != "cuda":
+            raise RuntimeError("uspace_b200 runs on CUDA (sm_100a) only; there is no CPU path")
+        self.lib = _lib.load()
+        self.device = device
+        self.cfg = config_from_kwargs(ctor_kwargs, operand_dtype)
+        self.operand_dtype = operand_dtype
+        self.handle = C.c_void_p()
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        _lib.check(self.lib.usp_create(C.byref(self.cfg), idx, C.byref(self.handle)), None, "usp_create")
+        self.names = [self.lib.usp_weight_name(self.handle, i).decode()
+                      for i in range(self.lib.usp_num_weights(self.handle))]
+        self.C, self.S = self.cfg.in_chans, self.cfg.img_size
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.usp_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- weights -------------------------------------------------------------------------------
+    def load_state_dict(self, sd: Dict[str, torch.Tensor]):
+        missing = [n for n in self.names if n not in sd]
+        if missing:
+            raise KeyError(f"state_dict is missing {len(missing)} tensors, e.g. {missing[:3]}")
+        for n in self.names:
+            t = sd[n].detach().to(dtype=torch.float32).contiguous()
+            shape = (C.c_int64 * t.dim())(*t.shape)
+            _lib.check(self.lib.usp_set_weight(self.handle, n.encode(), _ptr(t), shape, t.dim()), self.handle,
+                       f"usp_set_weight({n})")
+        _lib.check(self.lib.usp_finalize_weights(self.handle, self._stream()), self.handle, "usp_finalize_weights")
+
+    # ---- compute -------------------------------------------------------------------------------
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _check_latent(self, x: torch.Tensor):
+        if x.device != self.device and x.device.type == "cuda" and x.device.index != self.device.index:
+            raise RuntimeError(f"latent on {x.device}, engine on {self.device}")
+        if x.dim() != 4 or x.shape[1:] != (self.C, self.S, self.S):
+            raise ValueError(f"latent must be [B,{self.C},{self.S},{self.S}], got {tuple(x.shape)}")
+
+    def forward(self, x, t, y=None, context=None) -> torch.Tensor:
+        self._check_latent(x)
+        B = x.shape[0]
+        x = x.to(self.device, torch.float32).contiguous()
+        t = t.to(self.device, torch.float32).expand(B).contiguous()
+        if y is not None:
+            y = y.to(self.device, torch.int64).contiguous()
+        if context is not None:
+            context = context.to(self.device, torch.float32).contiguous()
+        out = torch.empty_like(x)
+        _lib.check(self.lib.usp_forward(self.handle, _ptr(x), _ptr(t), _ptr(context), _ptr(y), _ptr(out), B,
+                                        self._stream()), self.handle, "usp_forward")
+        return out
+
+    def sample(self, z, t0=0.0, t1=1.0, step_size=0.02, method="euler", y=None, context=None, delta_table=None,
+               write_scale=0.0, t_edit=0.0, edit_loc=None) -> torch.Tensor:
+        """Device-resident fixed-grid integration; returns a new tensor (z is not modified)."""
+        self._check_latent(z)
+        B = z.shape[0]
+        zz = z.to(self.device, torch.float32).contiguous().clone()
+        if y is not None:
+            y = y.to(self.device, torch.int64).contiguous()
+        if context is not None:
+            context = context.to(self.device, torch.float32).contiguous()
+        if delta_table is not None:
+            delta_table = delta_table.to(self.device, torch.float32).contiguous()
+            n = self.lib.usp_grid_size(t0, t1, step_size)
+            if delta_table.shape != (n, self.C, self.S, self.S):
+                raise ValueError(f"delta_table must be [{n},{self.C},{self.S},{self.S}]")
+        _lib.check(self.lib.usp_sample(self.handle, _ptr(zz), _ptr(context), _ptr(y), B, t0, t1, step_size,
+                                       _lib.METHOD[method], _ptr(delta_table), write_scale, t_edit,
+                                       _lib.EDIT_LOC[edit_loc], self._stream()), self.handle, "usp_sample")
+        return zz
+
+    def sample_host(self, z_host, t0=0.0, t1=1.0, step_size=0.02, method="euler", y=None, context=None,
+                    delta_table=None, write_scale=0.0, t_edit=0.0, edit_loc=None) -> torch.Tensor:
+        """End-to-end call on HOST tensors (ideally pinned): H2D, sample, D2H, synchronise. In place on z_host."""
+        for tns in (z_host, y, context, delta_table):
+            if tns is not None and (tns.device.type != "cpu" or not tns.is_contiguous()):
+                raise ValueError("sample_host takes contiguous CPU tensors")
+        self._check_latent(z_host)
+        _lib.check(self.lib.usp_sample_host(self.handle, _ptr(z_host), _ptr(context), _ptr(y), z_host.shape[0],
+                                            t0, t1, step_size, _lib.METHOD[method], _ptr(delta_table),
+                                            write_scale, t_edit, _lib.EDIT_LOC[edit_loc]), self.handle,
+                   "usp_sample_host")
+        return z_host
+
+    # ---- introspection ---------------------------------------------------------------------------
+    def last_ms(self) -> float:
+        ms = C.c_float()
+        _lib.check(self.lib.usp_last_forward_ms(self.handle, C.byref(ms)), self.handle, "usp_last_forward_ms")
+        return ms.value
+
+    def kernels_per_forward(self) -> int:
+        return self.lib.usp_kernels_per_forward(self.handle)
+
+    def flops_per_forward(self) -> float:
+        return self.lib.usp_flops_per_forward(self.handle)
+
+    def grid_size(self, t0, t1, step_size) -> int:
+        return self.lib.usp_grid_size(t0, t1, step_size)
