@@ -1,0 +1,314 @@
+#!/usr/bin/env python
+"""Headline benchmark: images/sec at 50 ODE steps, U-ViT-L 256 (BASELINE.json), one process per GPU.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+A "step" is one complete 50-NFE Euler sampling (CNF.decode, flow_matching.py:130-151) of one batch of 64 images
+per GPU (BASELINE.json configs[1], lfm_cm256_uvit_large), synthetic N(0,1) latents and reference-initialised
+random weights.  `value` times K steps with the latents already in HBM; `e2e` times the same K steps through
+usp_sample_host() with pinned HOST latents (H2D + sampling + D2H inside the timed region).  N > 1 shards the
+global batch (64 per GPU, weak scaling) and ends every step with the one NCCL all-gather of final latents.
+
+--impl reference times the reference algorithm's CPU implementation (the torch-fp32 oracle port; the reference
+itself is pure Python and cannot travel to the GPU box) on all host cores, on a bounded sample of the same work.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CFG_L = dict(img_size=32, patch_size=2, in_chans=4, embed_dim=1024, depth=20, num_heads=16, mlp_ratio=4,
+             qkv_bias=False, mlp_time_embed=False, num_classes=-1, use_checkpoint=False)  # configs/lfm_cm256_uvit_large.py:42-56
+CFG_L_T2I = dict(img_size=32, patch_size=2, in_chans=4, embed_dim=1024, depth=20, num_heads=16, mlp_ratio=4,
+                 qkv_bias=False, mlp_time_embed=False, clip_dim=768, num_clip_token=77, use_checkpoint=False)
+WORKLOADS = {
+    "c2": dict(name="lfm_cm256_uvit_large: 50-step Euler sampling, batch=64 per GPU, U-ViT-L 256 (configs[1])",
+               cfg=CFG_L, t2i=False, batch=64, method="euler", step=0.02),
+    "c3": dict(name="lfm_mmcelebahq256_uvit_large (t2i): 50-step Euler, 77-token context, batch=128 per GPU (configs[2])",
+               cfg=CFG_L_T2I, t2i=True, batch=128, method="euler", step=0.02),
+    "c4": dict(name="lfm_mscoco_uvit_from_in256 (t2i): 50-step Heun, batch=32 per GPU (configs[3])",
+               cfg=CFG_L_T2I, t2i=True, batch=32, method="heun", step=0.02),
+    "c5": dict(name="dissect sweep: U-ViT-L, 50-step Euler, tail write_attr edit, batch=64 per GPU (configs[4])",
+               cfg=CFG_L, t2i=False, batch=64, method="euler", step=0.02, edit=True),
+}
+METRIC = "images/sec at 50 ODE steps, U-ViT-L 256"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(burst=d["bf16_tflops"], sustained=d["bf16_tflops_sustained"], hbm=d["hbm_gbs"], src="measured")
+    return dict(burst=1590.0, sustained=1400.0, hbm=6650.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+    def stop(self, t_begin, t_end):
+        if self.proc is None:
+            return None
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        rows = [r for ts, r in self.rows if t_begin <= ts <= t_end and len(r) >= 7] or [r for _, r in self.rows if len(r) >= 7]
+        if not rows:
+            return None
+        sm = [float(r[0]) for r in rows if r[0].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in rows)]
+        pw = [float(r[2]) for r in rows if r[2].replace(".", "").isdigit()]
+        return dict(sm_mhz=statistics.median(sm) if sm else None, sm_max_mhz=float(rows[0][1]) if rows[0][1].isdigit() else None,
+                    reasons=reasons, power_w_max=max(pw) if pw else None, samples=len(rows))
+
+
+def cpu_port_forward_time(cfg, t2i, B, max_seconds=25.0, warmup=1, reps=3):
+    """Times the CPU oracle (torch fp32, all host threads) for one velocity evaluation at batch B."""
+    import torch
+
+    from oracle import uvit_oracle as O
+    from uspace_b200.uvit import UViT, UViTT2I
+    torch.set_num_threads(os.cpu_count() or 1)
+    O.FAST = True  # the same fused library calls the reference's torch-eager path makes
+    torch.manual_seed(0)
+    sd = (UViTT2I if t2i else UViT)(**cfg).state_dict()
+    g = torch.Generator().manual_seed(1230)
+    x = torch.randn(B, 4, 32, 32, generator=g)
+    t = torch.full((B,), 0.5)
+    ctx = torch.randn(B, 77, 768, generator=g) if t2i else None
+    times = []
+    with torch.no_grad():
+        for _ in range(warmup):
+            O.uvit_forward(sd, cfg, x, t, context=ctx)
+        t_start = time.perf_counter()
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            O.uvit_forward(sd, cfg, x, t, context=ctx)
+            times.append(time.perf_counter() - t0)
+            if time.perf_counter() - t_start > max_seconds:
+                break
+    return statistics.median(times), len(times)
+
+
+def run_reference(args, wl):
+    """Reference arm: the reference algorithm on the host cores (oracle port), bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    nfe = 50 * (2 if wl["method"] == "heun" else 1)
+    Bs = 8
+    cores = os.cpu_count() or 1
+    sec = []
+    for i in range(args.warmup + args.steps):
+        tf, _ = cpu_port_forward_time(wl["cfg"], wl["t2i"], Bs, max_seconds=60, warmup=0, reps=1)
+        if i >= args.warmup:
+            sec.append(tf)
+    tf = sum(sec) / len(sec)
+    value = Bs / (tf * nfe)
+    sample = f"each step = 1 velocity evaluation at batch {Bs} (of {nfe} x {wl['batch']}); images/s = {Bs}/(t_fwd*{nfe}), extrapolated"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": tf * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+        "config": {"workload": wl["name"], "nfe": nfe, "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample,
+                         "torch_threads": torch.get_num_threads()},
+        "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=list(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch override")
+    ap.add_argument("--operand", default="fp16", choices=["fp16", "bf16"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    wl = dict(WORKLOADS[args.workload])
+    if args.batch:
+        wl["batch"] = args.batch
+    if args.impl == "reference":
+        return run_reference(args, wl)
+
+    import torch
+    import torch.distributed as dist
+
+    from uspace_b200 import parallel
+    from uspace_b200.uvit import UViT, UViTT2I
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the uspace_b200 path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    torch.manual_seed(0)
+    model = (UViTT2I if wl["t2i"] else UViT)(**wl["cfg"]).eval()
+    model.operand_dtype = args.operand
+    model = model.to(dev)
+    eng = model.engine()
+    Bl = wl["batch"]
+    Bg = Bl * world
+    nfe_per_step = 2 if wl["method"] == "heun" else 1
+    n_grid = eng.grid_size(0.0, 1.0, wl["step"])
+    nfe = (n_grid - 1) * nfe_per_step
+
+    z_glob = parallel.global_noise(Bg, seed=1230)
+    z_loc = parallel.shard(z_glob, rank, world).contiguous()
+    ctx_loc = None
+    if wl["t2i"]:
+        ctx = torch.randn(Bg, 77, 768, generator=torch.Generator().manual_seed(1231))
+        ctx_loc = parallel.shard(ctx, rank, world).contiguous()
+    delta = None
+    ekw = {}
+    if wl.get("edit"):
+        delta = 0.1 * torch.randn(n_grid, 4, 32, 32, generator=torch.Generator().manual_seed(1232))
+        ekw = dict(delta_table=delta.to(dev), write_scale=1.5, t_edit=0.4, edit_loc="tail")
+    z_dev = z_loc.to(dev)
+    ctx_dev = None if ctx_loc is None else ctx_loc.to(dev)
+
+    def step_device():
+        out = eng.sample(z_dev, 0.0, 1.0, wl["step"], wl["method"], context=ctx_dev, **ekw)
+        return parallel.gather_latents(out, Bg) if world > 1 else out
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_device()
+    sync_all()
+    sampler = ClockSampler(local) if rank == 0 else None
+    t_begin = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        out = step_device()
+    e1.record()
+    sync_all()
+    t_end = time.perf_counter()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = ms.item()
+    clocks = sampler.stop(t_begin, t_end) if sampler else None
+    finite = bool(torch.isfinite(out).all().item())
+
+    # ---- end to end: pinned host latents in, host latents out, every step ----
+    zh_src = z_loc.clone().pin_memory()
+    zh = torch.empty_like(zh_src).pin_memory()
+    ctx_h = None if ctx_loc is None else ctx_loc.clone().pin_memory()
+    ekw_h = dict(ekw)
+    if delta is not None:
+        ekw_h["delta_table"] = delta.clone().pin_memory()
+
+    def step_host():
+        zh.copy_(zh_src)
+        eng.sample_host(zh, 0.0, 1.0, wl["step"], wl["method"], context=ctx_h, **ekw_h)
+
+    step_host()
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_host()
+    sync_all()
+    e2e_s = torch.tensor([time.perf_counter() - t0], device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_s = e2e_s.item()
+    same = bool(torch.equal(zh.to(dev), out[rank * Bl:(rank + 1) * Bl] if world > 1 else out))
+    h2d = zh.numel() * 4 + (ctx_h.numel() * 4 if ctx_h is not None else 0) + (delta.numel() * 4 if delta is not None else 0)
+    d2h = zh.numel() * 4
+
+    # ---- per-kernel-class device time of one velocity evaluation (events between launches) ----
+    t_half = torch.full((Bl,), 0.5, device=dev)
+    eng.profile_forward(z_dev, t_half, context=ctx_dev)
+    prof = eng.profile_forward(z_dev, t_half, context=ctx_dev)
+    torch.cuda.synchronize()
+
+    if rank == 0:
+        pk = peaks()
+        from oracle.uvit_oracle import model_dims
+        d = model_dims(wl["cfg"])
+        D, L = d["D"], d["L"]
+        gemm_flops_img = (2 * d["n_in"] + 1) * 24.0 * L * D * D + d["n_in"] * 4.0 * L * D * D
+        gemm_ms = sum(prof[k][0] for k in ("gemm_qkv", "gemm_proj", "gemm_fc1", "gemm_fc2", "gemm_skip"))
+        gemm_launches = sum(prof[k][1] for k in ("gemm_qkv", "gemm_proj", "gemm_fc1", "gemm_fc2", "gemm_skip"))
+        fwd_ms = sum(v[0] for v in prof.values())
+        achieved = gemm_flops_img * Bl / (gemm_ms * 1e-3) / 1e12
+        flops_img = eng.flops_per_forward()
+        sec = ms_total * 1e-3
+        value = Bg * args.steps / sec
+        res = {
+            "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": args.operand, "data": "synthetic",
+            "config": {"workload": wl["name"], "global_batch": Bg, "per_gpu_batch": Bl, "nfe": nfe, "method": wl["method"],
+                       "parallelism": f"dp{world}", "weights": "random-init (reference ctor, seed 0)",
+                       "accumulate": "fp32 (TMEM), fp32 residual stream / LayerNorm / softmax",
+                       "l2": "activations per velocity evaluation (~1.9 GB at batch 64) exceed the 126 MB L2; no flush needed"},
+            "achieved_tflops_per_gpu": flops_img * Bl * nfe * args.steps / sec / 1e12,
+            "tensor_peak_frac_burst": flops_img * Bl * nfe * args.steps / sec / 1e12 / pk["burst"],
+            "tensor_peak_frac_sustained": flops_img * Bl * nfe * args.steps / sec / 1e12 / pk["sustained"],
+            "e2e": {"value": Bg * args.steps / e2e_s, "unit": "images/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "matches_device_path": same},
+            "gpu_launches": args.steps * (n_grid - 1) * nfe_per_step * (eng.kernels_per_forward() + 1),
+            "roofline": {"bound": "tensor", "kernel": "usp::gemm_kernel<BN,EPI> (all five U-ViT linears, one velocity evaluation)",
+                         "achieved": achieved, "peak": pk["sustained"], "unit": "TFLOP/s", "frac": achieved / pk["sustained"],
+                         "peak_kind": f"bf16_tflops_sustained of {pk['src']} (kernel timed inside a long step); burst {pk['burst']}",
+                         "launches": gemm_launches, "avg_launch_ms": gemm_ms / max(1, gemm_launches),
+                         "share_of_forward": gemm_ms / fwd_ms, "traffic": None},
+            "kernel_ms_per_forward": {k: round(v[0], 4) for k, v in prof.items()},
+            "clocks": clocks, "finite": finite,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            tf, n = cpu_port_forward_time(wl["cfg"], wl["t2i"], 8)
+            res["cpu_baseline"] = {"value": 8 / (tf * nfe), "unit": "images/s", "cores": os.cpu_count(), "kind": "port",
+                                   "sample": f"{n} velocity evaluations at batch 8 on the host cores (torch fp32 oracle), "
+                                             f"images/s = 8/(t_fwd*{nfe}) extrapolated from per-forward time"}
+        print(json.dumps(res))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -93,12 +93,21 @@ int usp_sample_host(usp_handle* h, float* z_host, const float* context_host, con
                     float t_edit, int edit_loc);
 /* Number of grid points torchdiffeq builds for (t0, t1, step_size): ceil(|t1-t0|/step + 1). */
 int usp_grid_size(float t0, float t1, float step_size);
+/* Writes the grid itself (host memory, fp32) into out[0..cap); returns the number of points or 0 on error. */
+int usp_time_grid(float t0, float t1, float step_size, float* out, int cap);
 
 /* Introspection used by bench.py / tests. */
 size_t usp_workspace_bytes(const usp_handle* h, int B);
 int usp_kernels_per_forward(const usp_handle* h);   /* kernels launched by one velocity evaluation */
 double usp_flops_per_forward(const usp_handle* h);  /* algorithmic FLOPs per image per forward */
 int usp_last_forward_ms(usp_handle* h, float* ms);  /* device time of the most recent usp_forward/usp_sample */
+
+/* One eager velocity evaluation with a CUDA event between consecutive launches; returns per-class device time.
+ * Classes: 0 embed, 1 layernorm, 2 gemm_qkv, 3 attention, 4 gemm_proj, 5 gemm_fc1, 6 gemm_fc2, 7 gemm_skip,
+ * 8 head+final, 9 context_embed.  class_ms / class_launches have USP_NUM_KERNEL_CLASSES entries. Synchronises. */
+#define USP_NUM_KERNEL_CLASSES 10
+int usp_profile_forward(usp_handle* h, const float* x, const float* t, const float* context, const int64_t* y,
+                        float* out, int B, float* class_ms, int* class_launches, void* stream);
 
 /* Kernel-level entry points (parity tests and micro-benchmarks call the kernels through the ABI).
  * All pointers are device pointers; a16/w16/q/k/v/out16 hold 16-bit operands of type `operand_dtype`. */
@@ -110,6 +119,14 @@ int usp_op_attention(const void* q16, const void* k16, const void* v16, void* ou
                      int operand_dtype, void* stream);
 int usp_op_layernorm(const float* x, const float* gamma, const float* beta, void* out16, int M, int D,
                      int operand_dtype, void* stream);
+
+/* Token embedding alone (libs/uvit.py:175-179,316-327 without label/context tokens): out [B, 1+n_patch, D]. */
+int usp_op_patch_embed(const float* x, const float* t, const float* w, const float* bias, const float* pos,
+                       float* out32, int B, int C, int S, int p, int D, void* stream);
+/* unpatchify (p1,p2,C) + optional 3x3 conv (libs/uvit.py:56-63,346-347): pf [B, n_patch, p*p*C] -> out [B,C,S,S];
+ * conv_w / conv_b may be NULL (conv=False). */
+int usp_op_unpatchify_conv(const float* pf, const float* conv_w, const float* conv_b, float* out, int B, int C,
+                           int S, int p, void* stream);
 
 #ifdef __cplusplus
 }

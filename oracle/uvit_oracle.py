@@ -115,39 +115,57 @@ def timestep_embedding(t: Tensor, dim: int, max_period: float = 10000.0) -> Tens
     return emb
 
 
+# FAST=True swaps the explicit formulas for the fused library calls the reference itself makes (F.linear,
+# F.layer_norm, F.gelu, F.scaled_dot_product_attention).  Same arithmetic; used only so that the CPU baseline
+# timed by bench.py is as fast as the reference's own torch-eager path (tests check FAST == explicit).
+FAST = False
+
+
+def linear(x: Tensor, w: Tensor, b: Optional[Tensor] = None) -> Tensor:
+    if FAST:
+        return F.linear(x, w, b)
+    y = x @ w.T
+    return y if b is None else y + b
+
+
 def layer_norm(x: Tensor, w: Tensor, b: Tensor, eps: float = 1e-5) -> Tensor:
+    if FAST:
+        return F.layer_norm(x, (x.shape[-1],), w, b, eps)
     mu = x.mean(dim=-1, keepdim=True)
     var = ((x - mu) ** 2).mean(dim=-1, keepdim=True)
     return (x - mu) / torch.sqrt(var + eps) * w + b
 
 
 def gelu_erf(x: Tensor) -> Tensor:
+    if FAST:
+        return F.gelu(x)
     return 0.5 * x * (1.0 + torch.erf(x / math.sqrt(2.0)))
 
 
 def attention(x: Tensor, sd: Dict[str, Tensor], pre: str, H: int, vscale: Optional[Tensor] = None) -> Tensor:
     B, L, D = x.shape
     hd = D // H
-    qkv = x @ sd[pre + ".attn.qkv.weight"].T
-    if pre + ".attn.qkv.bias" in sd:
-        qkv = qkv + sd[pre + ".attn.qkv.bias"]
+    qkv = linear(x, sd[pre + ".attn.qkv.weight"], sd.get(pre + ".attn.qkv.bias"))
     q, k, v = (qkv[..., i * D:(i + 1) * D].reshape(B, L, H, hd).permute(0, 2, 1, 3) for i in range(3))
-    s = (q @ k.transpose(-1, -2)) * (hd ** -0.5)
-    pr = torch.softmax(s, dim=-1)
     if vscale is not None:  # post-softmax column re-weighting == scaling rows of V (tools/utils_t2i.py:196-224)
         v = v * vscale[:, None, :, None]
-    o = (pr @ v).permute(0, 2, 1, 3).reshape(B, L, D)
-    return o @ sd[pre + ".attn.proj.weight"].T + sd[pre + ".attn.proj.bias"]
+    if FAST:
+        o = F.scaled_dot_product_attention(q, k, v)
+    else:
+        s = (q @ k.transpose(-1, -2)) * (hd ** -0.5)
+        o = torch.softmax(s, dim=-1) @ v
+    o = o.permute(0, 2, 1, 3).reshape(B, L, D)
+    return linear(o, sd[pre + ".attn.proj.weight"], sd[pre + ".attn.proj.bias"])
 
 
 def mlp(x: Tensor, sd: Dict[str, Tensor], pre: str) -> Tensor:
-    h = gelu_erf(x @ sd[pre + ".mlp.fc1.weight"].T + sd[pre + ".mlp.fc1.bias"])
-    return h @ sd[pre + ".mlp.fc2.weight"].T + sd[pre + ".mlp.fc2.bias"]
+    h = gelu_erf(linear(x, sd[pre + ".mlp.fc1.weight"], sd[pre + ".mlp.fc1.bias"]))
+    return linear(h, sd[pre + ".mlp.fc2.weight"], sd[pre + ".mlp.fc2.bias"])
 
 
 def block(x: Tensor, sd: Dict[str, Tensor], pre: str, H: int, skip: Optional[Tensor] = None) -> Tensor:
     if pre + ".skip_linear.weight" in sd:
-        x = torch.cat([x, skip], dim=-1) @ sd[pre + ".skip_linear.weight"].T + sd[pre + ".skip_linear.bias"]
+        x = linear(torch.cat([x, skip], dim=-1), sd[pre + ".skip_linear.weight"], sd[pre + ".skip_linear.bias"])
     x = x + attention(layer_norm(x, sd[pre + ".norm1.weight"], sd[pre + ".norm1.bias"]), sd, pre, H)
     x = x + mlp(layer_norm(x, sd[pre + ".norm2.weight"], sd[pre + ".norm2.bias"]), sd, pre)
     return x
@@ -170,7 +188,8 @@ def uvit_forward(sd: Dict[str, Tensor], cfg: dict, x: Tensor, t: Tensor, y: Opti
     """UViT.forward on a flat state_dict.  head_delta / tail_delta are already scaled [C,S,S] edits or None."""
     d = model_dims(cfg)
     dt = x.dtype
-    sd = {k: v.to(dt) for k, v in sd.items()}
+    if any(v.dtype != dt for v in sd.values()):
+        sd = {k: v.to(dt) for k, v in sd.items()}
     B = x.shape[0]
     C, S, p, D = d["C"], d["S"], d["p"], d["D"]
     if head_delta is not None:

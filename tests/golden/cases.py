@@ -1,0 +1,44 @@
+"""Golden-vector case table shared by make_golden.py (reference side) and the tests (oracle / CUDA side)."""
+import torch
+
+_L = dict(img_size=32, patch_size=2, in_chans=4, embed_dim=1024, depth=20, num_heads=16, mlp_ratio=4,
+          qkv_bias=False, mlp_time_embed=False, use_checkpoint=False)
+_S16 = dict(img_size=32, patch_size=2, in_chans=4, embed_dim=512, depth=16, num_heads=8, mlp_ratio=4,
+            qkv_bias=False, mlp_time_embed=False, use_checkpoint=False)
+_TINY = dict(img_size=32, patch_size=2, in_chans=4, embed_dim=256, depth=4, num_heads=4, mlp_ratio=4,
+             qkv_bias=False, mlp_time_embed=False, use_checkpoint=False)
+
+CASES = {
+    # BASELINE.json configs[0]: lfm_cm256_uvit_small_deep16 (configs/lfm_cm256_uvit_small_deep16_scratch.py:40-53)
+    "small16_uncond": dict(cfg=dict(_S16, num_classes=-1), t2i=False, seed=0, B=2, in_seed=1230, euler_steps=None,
+                           edit=dict(seed=1232, t=0.2, t_edit=0.4, write_scale=1.5, ith_attr=1)),
+    "tiny_uncond": dict(cfg=dict(_TINY, num_classes=-1), t2i=False, seed=0, B=3, in_seed=7, euler_steps=5,
+                        edit=dict(seed=5, t=0.4, t_edit=0.4, write_scale=-2.1, ith_attr="0_2")),
+    "tiny_class": dict(cfg=dict(_TINY, num_classes=10), t2i=False, seed=1, B=2, in_seed=8, euler_steps=None),
+    "tiny_qkvbias_noconv": dict(cfg=dict(_TINY, num_classes=-1, qkv_bias=True, conv=False), t2i=False, seed=2, B=2,
+                                in_seed=9, euler_steps=None),
+    "tiny_t2i": dict(cfg=dict(_TINY, clip_dim=768, num_clip_token=77), t2i=True, seed=3, B=2, in_seed=10,
+                     euler_steps=4),
+    # configs/lfm_cm256_uvit_large.py:42-56 and configs/lfm_mmcelebahq256_uvit_large.py:43-58, one image
+    "large_uncond": dict(cfg=dict(_L, num_classes=-1), t2i=False, seed=0, B=1, in_seed=1230, euler_steps=None),
+    "large_t2i": dict(cfg=dict(_L, clip_dim=768, num_clip_token=77), t2i=True, seed=0, B=1, in_seed=1231,
+                      euler_steps=None),
+}
+
+
+def build_inputs(case):
+    """Deterministic inputs for a case: x ~ N(0,1), t ~ U(0,1) per sample, labels / context when conditional."""
+    g = torch.Generator(device="cpu").manual_seed(case["in_seed"])
+    B, cfg = case["B"], case["cfg"]
+    x = torch.randn(B, cfg["in_chans"], cfg["img_size"], cfg["img_size"], generator=g)
+    t = torch.rand(B, generator=g)
+    y = None
+    if cfg.get("num_classes", -1) > 0:
+        y = torch.randint(0, cfg["num_classes"], (B,), generator=g)
+    ctx = torch.randn(B, cfg["num_clip_token"], cfg["clip_dim"], generator=g) if case["t2i"] else None
+    return x, t, y, ctx
+
+
+def build_model(case, cls_uncond, cls_t2i):
+    torch.manual_seed(case["seed"])
+    return (cls_t2i if case["t2i"] else cls_uncond)(**case["cfg"]).eval()

@@ -202,6 +202,18 @@ def sec_perf(lib, opd):
               f"{flops * B * 50 / dt / 1e12:.1f} TFLOP/s", flush=True)
 
 
+def sec_one(lib, opd):
+    """Two eager velocity evaluations of U-ViT-L at batch 64 (profile the second one under ncu)."""
+    m = build(CFG_L, opd).to(dev)
+    eng = m.engine()
+    z = torch.randn(64, 4, 32, 32, device=dev)
+    t = torch.full((64,), 0.5, device=dev)
+    for _ in range(2):
+        eng.forward(z, t)
+    torch.cuda.synchronize()
+    print("kernels per forward", eng.kernels_per_forward())
+
+
 if __name__ == "__main__":
     lib = _lib.load()
     sec = sys.argv[1]

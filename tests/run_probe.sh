@@ -1,5 +1,16 @@
+#!/bin/bash
+# Developer GPU session (run under gpurun): tests, smoke, bench, ncu launch list + full captures.
 mkdir -p gpurun_out
-for s in "ln fp16" "gemm fp16" "gemm bf16" "attn fp16" "attn bf16" "fwd fp16" "fwd bf16" "sample fp16" "perf fp16"; do
-  timeout 300 python tests/gpu_probe.py $s 2>&1 | grep -v "^$" | tail -25
-done > gpurun_out/probe1.log 2>&1
-tail -100 gpurun_out/probe1.log
+R=${R:-r01}
+(timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -15) > gpurun_out/${R}_pytest_gpu.log
+(timeout 300 python __graft_entry__.py smoke 2>&1 | tail -3) > gpurun_out/${R}_smoke.log
+(timeout 600 python bench.py 2>&1 | tail -1) > gpurun_out/${R}_bench.json
+if [ "${NCU:-1}" = "1" ]; then
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 160 -c 160 --csv \
+    --log-file gpurun_out/${R}_launches.csv python tests/gpu_probe.py one > gpurun_out/${R}_ncu_launch.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_kernel -s 94 -c 5 \
+    -o gpurun_out/${R}_prof_gemm -f python tests/gpu_probe.py one > gpurun_out/${R}_ncu_gemm.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:attention_kernel -s 21 -c 1 \
+    -o gpurun_out/${R}_prof_attn -f python tests/gpu_probe.py one > gpurun_out/${R}_ncu_attn.log 2>&1
+fi
+cat gpurun_out/${R}_pytest_gpu.log gpurun_out/${R}_smoke.log gpurun_out/${R}_bench.json

@@ -1,0 +1,394 @@
+"""GPU tier (-m gpu, run on a real B200): the CUDA path, called through the C ABI, against the CPU oracle and the
+golden vectors generated from the reference.  Tolerances (norm-wise relative error  ||a-b|| / ||b||):
+
+  integer / index work (patch gather, unpatchify scatter, batch independence)      bit-exact
+  kernels on identical 16-bit inputs (GEMM fp32 accumulate, LN, attention)        see per-test bounds
+  whole forward / sampler, fp16 tensor-core operands (the default)                 <= 1.5e-3  (measured 4.6e-4..7.2e-4)
+  whole forward, bf16 tensor-core operands                                         <= 1.2e-2  (measured 3.6e-3..5.7e-3)
+
+BASELINE.json's north star asks for 1e-3 relative to the fp32 reference; fp16 operands with fp32 accumulation,
+fp32 residual stream / LayerNorm / softmax statistics meet it on every measured case, bf16 operands do not
+(8 mantissa bits), which is why fp16 is the default operand type (same tcgen05 kind::f16 rate).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import uvit_oracle as O
+from tests.golden.cases import CASES, build_inputs, build_model
+from uspace_b200 import _lib, parallel
+from uspace_b200.flow_matching import CNF, CNFT2I
+from uspace_b200.uvit import UViT, UViTT2I
+
+pytestmark = pytest.mark.gpu
+TD = {"fp16": torch.float16, "bf16": torch.bfloat16}
+FWD_TOL = {"fp16": 1.5e-3, "bf16": 1.2e-2}
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def P(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def rel(a, b):
+    a, b = torch.as_tensor(a).double().cpu(), torch.as_tensor(b).double().cpu()
+    return ((a - b).norm() / b.norm()).item()
+
+
+def golden(golden_dir, name):
+    return np.load(os.path.join(golden_dir, f"{name}.npz"))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    lib = _lib.load()
+    assert torch.cuda.is_available()
+    return lib
+
+
+_models = {}
+
+
+def model(name, opd="fp16"):
+    key = (name, opd)
+    if key not in _models:
+        m = build_model(CASES[name], UViT, UViTT2I)
+        m.operand_dtype = opd
+        _models[key] = m.to(dev())
+    return _models[key]
+
+
+# ---- kernels through the ABI ---------------------------------------------------------------------------
+@pytest.mark.parametrize("opd", ["fp16", "bf16"])
+@pytest.mark.parametrize("epi,M,N,K,K0", [
+    ("bias_f32", 128, 256, 64, 64), ("bias_f32", 300, 384, 128, 128), ("bias_f32", 514, 1024, 2048, 1024),
+    ("qkv", 514, 3072, 1024, 1024), ("qkv", 771, 768, 256, 256), ("bias_gelu", 514, 4096, 1024, 1024),
+    ("bias_resid", 514, 1024, 4096, 4096), ("bias_resid", 16448, 1024, 1024, 1024),
+    ("bias_f32", 16448, 1024, 2048, 1024), ("qkv", 10688, 3072, 1024, 1024)])
+def test_gemm_epilogues(lib, opd, epi, M, N, K, K0):
+    td, L = TD[opd], 257
+    g = torch.Generator().manual_seed(M + N + K)
+    a = torch.randn(M, K, generator=g).to(dev()).to(td)
+    w = (torch.randn(N, K, generator=g) * 0.05).to(dev()).to(td)
+    bias = torch.randn(N, generator=g).to(dev())
+    resid = torch.randn(M, N, generator=g).to(dev())
+    ref = a.float() @ w.float().T  # same rounded operands: only accumulation order differs
+    a0 = a[:, :K0].contiguous()
+    a1 = a[:, K0:].contiguous() if K0 < K else None
+    out32 = torch.zeros(M, N, device=dev())
+    out16 = torch.zeros(M, N, device=dev(), dtype=td)
+    eps16 = 2.0 ** -11 if opd == "fp16" else 2.0 ** -8
+    e = _lib.EPI[epi]
+    if epi == "qkv":
+        H = N // 3 // 64
+        _lib.check(lib.usp_op_gemm(e, P(a0), P(a1), P(w), None, None, None, P(out16), M, N, K, K0, L, H,
+                                   _lib.OPERAND[opd], stream()))
+        torch.cuda.synchronize()
+        B = M // L
+        got = out16.view(3, B, H, L, 64).float()
+        want = ref.view(B, L, 3, H, 64).permute(2, 0, 3, 1, 4)
+        assert rel(got, want) < eps16
+    elif epi == "bias_gelu":
+        _lib.check(lib.usp_op_gemm(e, P(a0), P(a1), P(w), P(bias), None, None, P(out16), M, N, K, K0, L, 1,
+                                   _lib.OPERAND[opd], stream()))
+        torch.cuda.synchronize()
+        assert rel(out16.float(), torch.nn.functional.gelu(ref + bias)) < eps16
+    elif epi == "bias_resid":
+        _lib.check(lib.usp_op_gemm(e, P(a0), P(a1), P(w), P(bias), P(resid), P(out32), P(out16), M, N, K, K0, L, 1,
+                                   _lib.OPERAND[opd], stream()))
+        torch.cuda.synchronize()
+        want = ref + bias + resid
+        assert rel(out32, want) < 1e-5
+        assert rel(out16.float(), want) < eps16
+    else:
+        _lib.check(lib.usp_op_gemm(e, P(a0), P(a1), P(w), P(bias), None, P(out32), None, M, N, K, K0, L, 1,
+                                   _lib.OPERAND[opd], stream()))
+        torch.cuda.synchronize()
+        assert rel(out32, ref + bias) < 1e-5
+
+
+@pytest.mark.parametrize("opd", ["fp16", "bf16"])
+@pytest.mark.parametrize("B,H,L", [(1, 1, 17), (1, 1, 128), (1, 2, 256), (2, 8, 257), (3, 4, 258), (2, 16, 334),
+                                   (1, 1, 384), (64, 16, 257)])
+def test_attention(lib, opd, B, H, L):
+    td = TD[opd]
+    g = torch.Generator().manual_seed(B * 1000 + L)
+    q, k, v = (torch.randn(B * H, L, 64, generator=g).to(dev()).to(td) for _ in range(3))
+    out = torch.zeros(B * L, H * 64, device=dev(), dtype=td)
+    _lib.check(lib.usp_op_attention(P(q), P(k), P(v), P(out), B, H, L, _lib.OPERAND[opd], stream()))
+    torch.cuda.synchronize()
+    ref = torch.nn.functional.scaled_dot_product_attention(q.float(), k.float(), v.float())
+    want = ref.view(B, H, L, 64).permute(0, 2, 1, 3).reshape(B * L, H * 64)
+    # P and O are rounded to 16 bits once each
+    assert rel(out.float(), want) < (6e-4 if opd == "fp16" else 5e-3)
+
+
+def test_attention_rejects_long_sequences(lib):
+    q = torch.zeros(1, 385, 64, device=dev(), dtype=torch.float16)
+    assert lib.usp_op_attention(P(q), P(q), P(q), P(q), 1, 1, 385, 1, stream()) != 0
+
+
+@pytest.mark.parametrize("M,D", [(7, 256), (514, 512), (16448, 1024)])
+def test_layernorm(lib, M, D):
+    g = torch.Generator().manual_seed(M)
+    x = (torch.randn(M, D, generator=g) * 3 + 1).to(dev())
+    gam, bet = torch.randn(D, generator=g).to(dev()), torch.randn(D, generator=g).to(dev())
+    out = torch.zeros(M, D, device=dev(), dtype=torch.float16)
+    _lib.check(lib.usp_op_layernorm(P(x), P(gam), P(bet), P(out), M, D, 1, stream()))
+    torch.cuda.synchronize()
+    want = O.layer_norm(x.cpu().double(), gam.cpu().double(), bet.cpu().double())
+    assert rel(out.float(), want) < 2.0 ** -11
+
+
+def test_patch_gather_and_unpatchify_scatter_bit_exact(lib):
+    """Integer-valued data through identity weights: the index maps must reproduce the oracle's bit for bit."""
+    B, Cc, S, p, D = 3, 4, 32, 2, 128
+    n_patch, Pd = (S // p) ** 2, Cc * p * p
+    x = torch.arange(B * Cc * S * S, dtype=torch.float32).reshape(B, Cc, S, S) % 4099.0
+    w = torch.zeros(D, Pd)
+    w[:Pd, :Pd] = torch.eye(Pd)
+    out = torch.full((B, 1 + n_patch, D), -1.0, device=dev())
+    t = torch.zeros(B, device=dev())
+    _lib.check(lib.usp_op_patch_embed(P(x.to(dev())), P(t), P(w.to(dev())), P(torch.zeros(D, device=dev())),
+                                      P(torch.zeros(1 + n_patch, D, device=dev())), P(out), B, Cc, S, p, D, stream()))
+    torch.cuda.synchronize()
+    want = x.reshape(B, -1)[:, O.patchify_index(Cc, S, p).reshape(-1)].reshape(B, n_patch, Pd)
+    assert torch.equal(out[:, 1:, :Pd].cpu(), want)
+    assert torch.equal(out[:, 1:, Pd:].cpu(), torch.zeros(B, n_patch, D - Pd))
+    # time token at t=0: cos(0)=1 for the first half, sin(0)=0 for the second
+    assert torch.equal(out[:, 0, :D // 2].cpu(), torch.ones(B, D // 2))
+    assert torch.equal(out[:, 0, D // 2:].cpu(), torch.zeros(B, D // 2))
+
+    pf = (torch.arange(B * n_patch * Pd, dtype=torch.float32) % 8191.0).reshape(B, n_patch, Pd)
+    img = torch.zeros(B, Cc, S, S, device=dev())
+    _lib.check(lib.usp_op_unpatchify_conv(P(pf.to(dev())), None, None, P(img), B, Cc, S, p, stream()))
+    torch.cuda.synchronize()
+    want = pf.reshape(B, -1)[:, O.unpatchify_index(Cc, S, p)].reshape(B, Cc, S, S)
+    assert torch.equal(img.cpu(), want)
+    cw = torch.randn(Cc, Cc, 3, 3)
+    cb = torch.randn(Cc)
+    _lib.check(lib.usp_op_unpatchify_conv(P(pf.to(dev())), P(cw.to(dev())), P(cb.to(dev())), P(img), B, Cc, S, p,
+                                          stream()))
+    torch.cuda.synchronize()
+    want = torch.nn.functional.conv2d(want.double(), cw.double(), cb.double(), padding=1)
+    assert rel(img, want) < 1e-6
+
+
+# ---- whole forward against the reference goldens ---------------------------------------------------------
+@pytest.mark.parametrize("opd", ["fp16", "bf16"])
+@pytest.mark.parametrize("name", list(CASES))
+def test_forward_matches_reference_golden(golden_dir, name, opd):
+    case = CASES[name]
+    m = model(name, opd)
+    x, t, y, ctx = build_inputs(case)
+    with torch.no_grad():
+        if case["t2i"]:
+            out, aux = m(x.to(dev()), t.to(dev()), context=ctx.to(dev()), dissect_name=None, extra_kwarg=1)
+        else:
+            out, aux = m(x.to(dev()), t.to(dev()), y if y is None else y.to(dev()), edit_loc=None)
+    assert aux is None and out.shape == x.shape and out.dtype == torch.float32
+    want = golden(golden_dir, name)["forward"]
+    assert rel(out, want) < FWD_TOL[opd]
+
+
+def test_forward_meets_1e3_on_north_star_model(golden_dir):
+    for name in ("large_uncond", "large_t2i", "small16_uncond"):
+        case = CASES[name]
+        m = model(name)
+        x, t, y, ctx = build_inputs(case)
+        with torch.no_grad():
+            out = m(x.to(dev()), t.to(dev()), context=ctx.to(dev()))[0] if case["t2i"] else m(x.to(dev()), t.to(dev()))[0]
+        assert rel(out, golden(golden_dir, name)["forward"]) < 1e-3
+
+
+def test_batch_independence_at_full_size_bit_exact(golden_dir):
+    """BASELINE config 2 size (B=64, M=16448): a sample's velocity does not depend on its batch neighbours."""
+    m = model("large_uncond")
+    z = parallel.global_noise(64).to(dev())
+    t = torch.full((64,), 0.5, device=dev())
+    with torch.no_grad():
+        big = m(z, t)[0]
+        small = m(z[61:64].clone(), t[:3])[0]
+    assert torch.equal(big[61:64], small)
+    # and the first sample of that batch matches the oracle
+    sd = {k: v.cpu() for k, v in m.state_dict().items()}
+    want = O.uvit_forward(sd, CASES["large_uncond"]["cfg"], z[:1].cpu(), t[:1].cpu())
+    assert rel(big[:1], want) < 1e-3
+
+
+def test_load_state_dict_repacks_weights():
+    case = CASES["tiny_uncond"]
+    m = build_model(case, UViT, UViTT2I).to(dev())
+    x, t, _, _ = build_inputs(case)
+    with torch.no_grad():
+        a = m(x.to(dev()), t.to(dev()))[0]
+        torch.manual_seed(123)
+        other = UViT(**case["cfg"]).state_dict()
+        m.load_state_dict(other)
+        b = m(x.to(dev()), t.to(dev()))[0]
+    want = O.uvit_forward(other, case["cfg"], x, t)
+    assert rel(b, want) < 1.5e-3 and rel(a, want) > 0.1
+
+
+# ---- sampler -------------------------------------------------------------------------------------------
+FIXED = dict(dissect_name="none", solver_kwargs=dict(solver="fixed", solver_fix="euler", solver_fix_step=0.2))
+
+
+@pytest.mark.parametrize("name", ["tiny_uncond", "tiny_t2i"])
+def test_decode_matches_reference_driven_euler_golden(golden_dir, name):
+    case = CASES[name]
+    m = model(name)
+    x, _, y, ctx = build_inputs(case)
+    kw = dict(FIXED, solver_kwargs=dict(solver="fixed", solver_fix="euler", solver_fix_step=1.0 / case["euler_steps"]))
+    if case["t2i"]:
+        out = CNFT2I(m).decode(x.to(dev()), context=ctx.to(dev()), **kw)
+    else:
+        out = CNF(m).decode(x.to(dev()), y=None, **kw)
+    assert rel(out, golden(golden_dir, name)["euler"]) < 1e-3
+
+
+@pytest.mark.parametrize("method,h", [("euler", 0.1), ("heun", 0.25)])
+def test_sampler_against_oracle(method, h):
+    case = CASES["tiny_class"]
+    m = model("tiny_class")
+    x, _, y, _ = build_inputs(case)
+    sd = {k: v.cpu() for k, v in m.state_dict().items()}
+    want = O.sample(sd, case["cfg"], x.double(), 0.0, 1.0, h, method, y=y)
+    kw = dict(dissect_name="none", solver_kwargs=dict(solver="fixed", solver_fix=method, solver_fix_step=h))
+    got = CNF(m).decode(x.to(dev()), y=y.to(dev()), **kw)
+    assert rel(got, want) < 1e-3
+    # encode runs the same loop on the reversed grid (flow_matching.py:102-125)
+    want = O.sample(sd, case["cfg"], x.double(), 1.0, 0.0, h, method, y=y)
+    got = CNF(m).encode(x.to(dev()), y=y.to(dev()), **kw)
+    assert rel(got, want) < 1e-3
+
+
+@pytest.mark.parametrize("name", ["tiny_uncond", "small16_uncond"])
+@pytest.mark.parametrize("loc", ["head", "tail"])
+def test_edit_hook_against_reference_golden(golden_dir, tmp_path, name, loc):
+    """One Euler step starting at the edit time: (z1 - z0)/h is the edited velocity the reference produced."""
+    case = CASES[name]
+    e = case["edit"]
+    g = golden(golden_dir, name)
+    m = model(name)
+    x, _, _, _ = build_inputs(case)
+    h = 0.1
+    np.save(tmp_path / f"delta_{e['t']:.2f}.npy", g["edit_delta"])
+    np.save(tmp_path / f"delta_{e['t'] + h:.2f}.npy", g["edit_delta"])
+    kw = dict(dissect_task="uspace_uvit", dissect_name="write_attr", write_path_root=str(tmp_path),
+              ith_attr=e["ith_attr"], t_edit=e["t_edit"], write_scale=e["write_scale"], edit_loc=loc,
+              solver_kwargs=dict(solver="fixed", solver_fix="euler", solver_fix_step=h))
+    eng = m.engine()
+    from uspace_b200.flow_matching import build_delta_table
+    from uspace_b200.engine import time_grid
+    grid = time_grid(e["t"], e["t"] + h, h)
+    assert len(grid) == 2
+    tab, tloc = build_delta_table(grid, (4, 32, 32), **kw)
+    z1 = eng.sample(x.to(dev()), e["t"], e["t"] + h, h, "euler", delta_table=tab, write_scale=e["write_scale"],
+                    t_edit=float("inf"), edit_loc=tloc)
+    v = (z1.cpu().double() - x.double()) / (np.float32(grid[1]) - np.float32(grid[0]))
+    assert rel(v, g[f"edit_{loc}"]) < 2e-3
+    # without the edit the velocity is measurably different
+    z0 = eng.sample(x.to(dev()), e["t"], e["t"] + h, h, "euler")
+    assert rel((z0.cpu().double() - x.double()) / h, g[f"edit_{loc}"]) > 1e-2
+
+
+def test_edit_sweep_via_cnf_decode_against_oracle(tmp_path):
+    case = CASES["tiny_uncond"]
+    m = model("tiny_uncond")
+    x, _, _, _ = build_inputs(case)
+    sd = {k: v.cpu() for k, v in m.state_dict().items()}
+    h = 0.1
+    rng = torch.Generator().manual_seed(3)
+    table = torch.zeros(11, 4, 32, 32)
+    for i, t in enumerate(O.fixed_grid(0.0, 1.0, h).tolist()):
+        if O.should_edit(t, 0.4):
+            d = 0.1 * torch.randn(2, 4, 32, 32, generator=rng)
+            np.save(tmp_path / f"delta_{t:.2f}.npy", d.numpy())
+            table[i] = d[1]
+    for scale in (-2.1, 0.0, 1.5):
+        kw = dict(dissect_task="uspace_uvit", dissect_name="write_attr", write_path_root=str(tmp_path), ith_attr=1,
+                  t_edit=0.4, write_scale=scale, edit_loc="tail",
+                  solver_kwargs=dict(solver="fixed", solver_fix="euler", solver_fix_step=h))
+        got = CNF(m).decode(x.to(dev()), y=None, **kw)
+        want = O.sample(sd, case["cfg"], x.double(), 0.0, 1.0, h, "euler", delta_table=table.double(),
+                        write_scale=scale, t_edit=0.4, edit_loc="tail")
+        assert rel(got, want) < 1e-3
+
+
+def test_library_mask_follows_should_edit():
+    """usp_sample's own t_edit mask (used when the caller passes a dense table) == libs/dissection.py:21-26."""
+    case = CASES["tiny_uncond"]
+    m = model("tiny_uncond")
+    x, _, _, _ = build_inputs(case)
+    sd = {k: v.cpu() for k, v in m.state_dict().items()}
+    g = torch.Generator().manual_seed(11)
+    table = 0.1 * torch.randn(6, 4, 32, 32, generator=g)  # dense: every grid point has a row
+    got = m.engine().sample(x.to(dev()), 0.0, 1.0, 0.2, "euler", delta_table=table, write_scale=2.0, t_edit=0.4,
+                            edit_loc="head")
+    want = O.sample(sd, case["cfg"], x.double(), 0.0, 1.0, 0.2, "euler", delta_table=table.double(), write_scale=2.0,
+                    t_edit=0.4, edit_loc="head")
+    assert rel(got, want) < 1e-3
+
+
+def test_encode_decode_round_trip_full_size_model():
+    """Size-independent property at the north-star model: decode(encode(x)) returns to x up to O(h) Euler error,
+    and the error shrinks with the step (flow_matching.py vis_reversible idea, dissect_lfm.py:171-195)."""
+    m = model("large_uncond")
+    eng = m.engine()
+    x = parallel.global_noise(4, seed=5).to(dev())
+    errs = []
+    for h in (0.1, 0.05):
+        z = eng.sample(x, 1.0, 0.0, h, "heun")
+        back = eng.sample(z, 0.0, 1.0, h, "heun")
+        errs.append(rel(back, x))
+    assert errs[0] < 5e-2 and errs[1] < errs[0]
+
+
+def test_sample_host_equals_device_path_bit_exact():
+    m = model("tiny_uncond")
+    eng = m.engine()
+    z = parallel.global_noise(5, seed=9)
+    a = eng.sample(z.to(dev()), 0.0, 1.0, 0.25, "heun").cpu()
+    zh = z.clone().pin_memory()
+    eng.sample_host(zh, 0.0, 1.0, 0.25, "heun")
+    assert torch.equal(a, zh)
+    assert eng.last_ms() > 0 and eng.kernels_per_forward() > 10
+
+
+def test_error_paths():
+    m = model("tiny_uncond")
+    eng = m.engine()
+    z = torch.zeros(1, 4, 32, 32, device=dev())
+    with pytest.raises(ValueError):
+        eng.forward(torch.zeros(1, 3, 32, 32, device=dev()), torch.zeros(1, device=dev()))
+    with pytest.raises(RuntimeError, match="y must be given exactly"):
+        eng.forward(z, torch.zeros(1, device=dev()), y=torch.zeros(1, dtype=torch.long, device=dev()))
+    with pytest.raises(RuntimeError, match="bad time grid"):
+        eng.sample(z, 0.0, 0.0, 0.1)
+    with pytest.raises(RuntimeError, match="delta_table"):
+        eng.sample(z, 0.0, 1.0, 0.5, edit_loc="tail")
+    with pytest.raises(KeyError):
+        eng.load_state_dict({})
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_gpu_sharded_sampling_matches_single_gpu():
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29611", os.path.join(root, "tests", "mp_check.py")],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "MP_CHECK_OK" in r.stdout

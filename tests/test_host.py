@@ -1,0 +1,223 @@
+"""CPU tier: C-ABI surface, host-side mirrors of the reference interface, sharding logic (gloo, world_size 2)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import uvit_oracle as O
+from tests.golden.cases import CASES
+from uspace_b200 import _lib, parallel
+from uspace_b200.engine import config_from_kwargs, time_grid
+from uspace_b200.flow_matching import CNF, CNFT2I, build_delta_table, should_edit
+from uspace_b200.uvit import UViT, UViTT2I, get_nnet
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# ---- C ABI ---------------------------------------------------------------------------------------
+def test_library_loads_and_exports_every_declared_symbol():
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, "include", "uspace_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(usp_[a-z0-9_]+)\s*\(", header)))
+    assert len(declared) >= 20
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/uspace_b200.h but not exported"
+    assert sorted(_lib.EXPORTED_SYMBOLS) == declared  # the ctypes table covers the whole header
+
+
+def test_config_struct_layout_matches_header():
+    header = open(os.path.join(ROOT, "include", "uspace_b200.h")).read()
+    body = header[header.index("typedef struct usp_config {"):header.index("} usp_config;")]
+    fields = re.findall(r"int32_t\s+(\w+);", body)
+    assert fields == [f[0] for f in _lib.UspConfig._fields_]
+    assert C.sizeof(_lib.UspConfig) == 4 * len(fields)
+
+
+@pytest.mark.parametrize("t0,t1,h", [(0.0, 1.0, 0.02), (0.0, 1.0, 0.01), (0.0, 0.4, 0.01), (1.0, 0.0, 0.02),
+                                     (1.0, 0.0, 0.1), (0.0, 1.0, 0.3), (0.2, 0.3, 0.1)])
+def test_time_grid_bit_exact_with_oracle(t0, t1, h):
+    got = np.array(time_grid(t0, t1, h), dtype=np.float32)
+    want = O.fixed_grid(t0, t1, h).numpy()
+    assert got.shape == want.shape and (got == want).all()
+    assert _lib.load().usp_grid_size(t0, t1, h) == len(want)
+
+
+def test_bad_grid_is_rejected():
+    lib = _lib.load()
+    assert lib.usp_grid_size(0.0, 0.0, 0.1) == 0
+    assert lib.usp_grid_size(0.0, 1.0, 0.0) == 0
+    assert lib.usp_grid_size(0.0, 1.0, 1e-6) == 0  # more than 4096 points
+    with pytest.raises(ValueError):
+        time_grid(0.0, 1.0, -1.0)
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU error path")
+def test_create_without_gpu_fails_loudly():
+    lib = _lib.load()
+    cfg = config_from_kwargs(CASES["tiny_uncond"]["cfg"])
+    h = C.c_void_p()
+    rc = lib.usp_create(C.byref(cfg), 0, C.byref(h))
+    assert rc != 0 and not h.value
+    assert b"no CPU fallback" in lib.usp_last_error(None)
+
+
+def test_config_mapping():
+    c = config_from_kwargs(CASES["large_t2i"]["cfg"], "bf16")
+    assert (c.embed_dim, c.depth, c.num_heads, c.mlp_hidden) == (1024, 20, 16, 4096)
+    assert (c.clip_dim, c.num_clip_token, c.num_classes, c.operand_dtype) == (768, 77, 0, 0)
+    c = config_from_kwargs(CASES["tiny_class"]["cfg"])
+    assert (c.num_classes, c.clip_dim, c.num_clip_token, c.operand_dtype) == (10, 0, 0, 1)
+    with pytest.raises(NotImplementedError):
+        config_from_kwargs(dict(CASES["tiny_uncond"]["cfg"], mlp_time_embed=True))
+
+
+# ---- module mirrors ----------------------------------------------------------------------------------
+def test_state_dict_keys_and_shapes_match_reference_layout():
+    m = get_nnet("uvit", **CASES["small16_uncond"]["cfg"])
+    sd = m.state_dict()
+    assert len(sd) == 212  # 212 tensors for small-deep16 uncond
+    assert sd["pos_embed"].shape == (1, 257, 512)
+    assert sd["patch_embed.proj.weight"].shape == (512, 4, 2, 2)
+    assert sd["in_blocks.0.attn.qkv.weight"].shape == (1536, 512)
+    assert "in_blocks.0.attn.qkv.bias" not in sd and "in_blocks.0.skip_linear.weight" not in sd
+    assert sd["out_blocks.7.skip_linear.weight"].shape == (512, 1024)
+    assert sd["decoder_pred.weight"].shape == (16, 512) and sd["final_layer.weight"].shape == (4, 4, 3, 3)
+    t = get_nnet("uvit_t2i", **CASES["tiny_t2i"]["cfg"]).state_dict()
+    assert t["context_embed.weight"].shape == (256, 768) and t["pos_embed"].shape == (1, 334, 256)
+    c = get_nnet("uvit", **CASES["tiny_class"]["cfg"]).state_dict()
+    assert c["label_emb.weight"].shape == (10, 256) and c["pos_embed"].shape == (1, 258, 256)
+    with pytest.raises(NotImplementedError):
+        get_nnet("unet_t2i")
+
+
+def test_param_counts_match_survey():
+    n = sum(p.numel() for p in UViT(**CASES["large_uncond"]["cfg"]).parameters())
+    assert n == 285_737_124
+    n = sum(p.numel() for p in UViTT2I(**CASES["large_t2i"]["cfg"]).parameters())
+    assert n == 286_603_428
+
+
+def test_inference_on_cpu_raises_instead_of_falling_back():
+    m = UViT(**CASES["tiny_uncond"]["cfg"]).eval()
+    x = torch.randn(1, 4, 32, 32)
+    with torch.no_grad(), pytest.raises(RuntimeError, match="no CPU"):
+        m(x, torch.tensor([0.5]))
+    cnf = CNF(m)
+    kw = dict(dissect_name="none", solver_kwargs=dict(solver="fixed", solver_fix="euler", solver_fix_step=0.5))
+    with pytest.raises(RuntimeError, match="no CPU"):
+        cnf.decode(x, y=None, **kw)
+
+
+def test_autograd_training_graph_matches_oracle():
+    # train_lfm*.py keep working: grad-enabled calls run a differentiable PyTorch graph of the same parameters
+    case = CASES["tiny_class"]
+    torch.manual_seed(case["seed"])
+    m = UViT(**case["cfg"])
+    x = torch.randn(2, 4, 32, 32)
+    t = torch.tensor([0.1, 0.9])
+    y = torch.tensor([3, 7])
+    out, aux = m(x, t, y)
+    assert aux is None and out.requires_grad
+    want = O.uvit_forward(m.state_dict(), case["cfg"], x, t, y=y)
+    assert (out.detach() - want).abs().max() < 1e-5
+    loss = CNF(m).training_losses(x, y, sigma_min=1e-4)
+    assert loss.shape == (2,)
+    loss.mean().backward()
+    assert m.in_blocks[0].attn.qkv.weight.grad is not None
+
+
+def test_cnf_rejects_unbuilt_solvers():
+    cnf = CNFT2I(UViTT2I(**CASES["tiny_t2i"]["cfg"]))
+    z, ctx = torch.zeros(1, 4, 32, 32), torch.zeros(1, 77, 768)
+    for solver in ("adaptive", "fixadp"):
+        with pytest.raises(NotImplementedError):
+            cnf.decode(z, ctx, dissect_name="p2p", solver_kwargs=dict(solver=solver))
+    with pytest.raises(NotImplementedError):  # non-dissection mode == dopri5 in the reference
+        cnf.get_ode_kwargs(solver_kwargs=dict(solver="fixed"))
+    with pytest.raises(NotImplementedError):
+        cnf.get_ode_kwargs(dissect_name="x", solver_kwargs=dict(solver="fixed", solver_fix="rk4", solver_fix_step=.1))
+    ok = cnf.get_ode_kwargs(dissect_name="x", solver_kwargs=dict(solver="fixed", solver_fix="euler", solver_fix_step=0.02))
+    assert ok == dict(method="euler", options=dict(step_size=0.02))
+
+
+def test_delta_table_from_reference_file_layout(tmp_path):
+    grid = time_grid(0.0, 1.0, 0.1)
+    rng = np.random.default_rng(0)
+    files = {}
+    for t in grid:
+        d = f"{t:.2f}"
+        if should_edit(d, 0.4):
+            files[d] = rng.standard_normal((5, 4, 32, 32)).astype(np.float32)
+            np.save(tmp_path / f"delta_{d}.npy", files[d])
+    assert sorted(files) == ["0.10", "0.20", "0.30", "0.40"]
+    kw = dict(dissect_task="uspace_uvit", dissect_name="write_attr", write_path_root=str(tmp_path), t_edit=0.4,
+              edit_loc="tail")
+    tab, loc = build_delta_table(grid, (4, 32, 32), ith_attr=2, **kw)
+    assert loc == "tail" and tab.shape == (11, 4, 32, 32)
+    assert torch.equal(tab[0], torch.zeros(4, 32, 32)) and torch.equal(tab[5], torch.zeros(4, 32, 32))
+    assert np.array_equal(tab[3].numpy(), files["0.30"][2])
+    tab, _ = build_delta_table(grid, (4, 32, 32), ith_attr="1_4", **kw)  # multi-attribute mean (dissection.py:63-68)
+    assert np.allclose(tab[1].numpy(), (files["0.10"][1] + files["0.10"][4]) / 2)
+    assert build_delta_table(grid, (4, 32, 32), dissect_name=None) == (None, None)
+    with pytest.raises(NotImplementedError):
+        build_delta_table(grid, (4, 32, 32), dissect_task="uspace_uvit", dissect_name="read")
+    with pytest.raises(NotImplementedError):
+        build_delta_table(grid, (4, 32, 32), **dict(kw, edit_loc="mid"))
+
+
+# ---- sharding + the one collective ---------------------------------------------------------------------
+def test_amortize_matches_reference():
+    assert parallel.amortize(10, 4) == [4, 4, 2]
+    assert parallel.amortize(8, 4) == [4, 4]
+    assert parallel.amortize(3, 4) == [3]
+
+
+def test_shard_bounds_partition():
+    for n in (1, 7, 64, 257, 512):
+        for w in (1, 2, 3, 8):
+            b = [parallel.shard_bounds(n, r, w) for r in range(w)]
+            assert b[0][0] == 0 and b[-1][1] == n
+            assert all(b[i][1] == b[i + 1][0] for i in range(w - 1))
+            sizes = [hi - lo for lo, hi in b]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_global_noise_is_world_size_independent():
+    z = parallel.global_noise(10)
+    parts = [parallel.shard(z, r, 4) for r in range(4)]
+    assert torch.equal(torch.cat(parts), z)
+    assert torch.equal(parallel.global_noise(10), z)
+
+
+def _gloo_worker(rank, world, port, n_total, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        z = parallel.global_noise(n_total, shape=(4, 8, 8))
+        # stand-in for the per-rank ODE: any per-sample function must commute with sharding
+        out = parallel.sample_sharded(lambda zl, c: zl * 2.0 + 1.0, z)
+        q.put((rank, out.numpy()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_total", [8, 7])
+def test_sharded_sampling_gathers_in_rank_order_gloo(n_total):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() + n_total) % 2000
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, n_total, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    want = (parallel.global_noise(n_total, shape=(4, 8, 8)) * 2.0 + 1.0).numpy()
+    for r in range(2):
+        assert res[r].shape == want.shape and np.array_equal(res[r], want)

@@ -39,16 +39,22 @@ _SIGNATURES = {
     "usp_sample": (_i, [_vp, _vp, _vp, _vp, _i, _f, _f, _f, _i, _vp, _f, _f, _i, _vp]),
     "usp_sample_host": (_i, [_vp, _vp, _vp, _vp, _i, _f, _f, _f, _i, _vp, _f, _f, _i]),
     "usp_grid_size": (_i, [_f, _f, _f]),
+    "usp_time_grid": (_i, [_f, _f, _f, C.POINTER(_f), _i]),
     "usp_workspace_bytes": (C.c_size_t, [_vp, _i]),
     "usp_kernels_per_forward": (_i, [_vp]),
     "usp_flops_per_forward": (C.c_double, [_vp]),
     "usp_last_forward_ms": (_i, [_vp, C.POINTER(_f)]),
+    "usp_profile_forward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, C.POINTER(_f), C.POINTER(_i), _vp]),
     "usp_op_convert16": (_i, [_vp, _vp, _i64, _i, _vp]),
     "usp_op_gemm": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "usp_op_attention": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "usp_op_layernorm": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "usp_op_patch_embed": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "usp_op_unpatchify_conv": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+KERNEL_CLASSES = ("embed", "layernorm", "gemm_qkv", "attention", "gemm_proj", "gemm_fc1", "gemm_fc2", "gemm_skip",
+                  "head_final", "context_embed")
 
 
 def load():

@@ -128,6 +128,10 @@ struct usp_handle {
     bool ev_valid = false;
     int kernels_per_forward = 0;
     std::string err;
+    // per-launch profiling (usp_profile_forward): an event before every launch, tagged with its kernel class
+    bool profiling = false;
+    std::vector<cudaEvent_t> prof_ev;
+    std::vector<int> prof_cls;
 };
 
 namespace {
@@ -285,6 +289,15 @@ struct FwdIO {
     float m1, m2;
 };
 
+void prof_mark(usp_handle* h, int cls, cudaStream_t s) {
+    if (!h->profiling) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, s);
+    h->prof_ev.push_back(e);
+    h->prof_cls.push_back(cls);
+}
+
 #define KTRY(expr)                                                                             \
     do {                                                                                       \
         cudaError_t _e = (expr);                                                               \
@@ -316,6 +329,7 @@ int run_gemm(usp_handle* h, int epi, const CUtensorMap& a0, const CUtensorMap* a
 int embed_context(usp_handle* h, Plan* p, const float* ctx_dev, cudaStream_t s) {
     const int nctx = h->cfg.num_clip_token, cdim = h->cfg.clip_dim;
     const long long n = static_cast<long long>(p->B) * nctx * cdim;
+    prof_mark(h, 9, s);
     cudaError_t e = launch_convert16(ctx_dev, p->ctx16, n, h->cfg.operand_dtype, s);
     if (e != cudaSuccess) return fail(h, USP_ERR_CUDA, std::string("convert ctx: ") + cudaGetErrorString(e));
     return run_gemm(h, EPI_BIAS_F32, p->m_ctx, nullptr, h->w[h->i_ctxw], h->w[h->i_ctxb].d32, nullptr, p->ctxemb,
@@ -337,6 +351,7 @@ int enqueue_forward(usp_handle* h, Plan* p, const FwdIO& io, cudaStream_t s) {
     ea.out32 = p->x32;
     ea.B = B; ea.C = h->cfg.in_chans; ea.S = h->cfg.img_size; ea.p = h->cfg.patch_size; ea.D = D; ea.L = L;
     ea.n_ctx = h->cfg.num_clip_token; ea.has_label = (h->cfg.num_classes > 0 && io.y != nullptr) ? 1 : 0;
+    prof_mark(h, 0, s);
     KTRY(launch_embed(ea, s));
 
     const CUtensorMap* xprev = nullptr;  // 16-bit copy of the previous block's output
@@ -349,12 +364,15 @@ int enqueue_forward(usp_handle* h, Plan* p, const FwdIO& io, cudaStream_t s) {
         if (is_out && bw.skw >= 0) {
             // skip_linear(cat[x, skip]) with a two-source K loop; skips are consumed LIFO (libs/uvit.py:340)
             const int si = h->n_in - 1 - oj;
+            prof_mark(h, 7, s);
             rc = run_gemm(h, EPI_BIAS_F32, *xprev, &p->m_skip[si], h->w[bw.skw], h->w[bw.skb].d32, nullptr, p->x32,
                           nullptr, M, D, 2 * D, D, s);
             ++nk;
             if (rc) return rc;
         }
+        prof_mark(h, 1, s);
         KTRY(launch_layernorm(p->x32, h->w[bw.n1w].d32, h->w[bw.n1b].d32, p->h16, M, D, opd, s));
+        prof_mark(h, 2, s);
         rc = run_gemm(h, EPI_QKV, p->m_h, nullptr, h->w[bw.qkvw], bw.qkvb >= 0 ? h->w[bw.qkvb].d32 : nullptr,
                       nullptr, nullptr, p->qkv16, M, 3 * D, D, D, s);
         ++nk;
@@ -362,12 +380,16 @@ int enqueue_forward(usp_handle* h, Plan* p, const FwdIO& io, cudaStream_t s) {
         AttnArgs aa;
         memset(&aa, 0, sizeof(aa));
         aa.B = B; aa.H = h->cfg.num_heads; aa.L = L; aa.D = D; aa.opd = opd; aa.out16 = p->a16;
+        prof_mark(h, 3, s);
         KTRY(launch_attention(p->m_q, p->m_k, p->m_v, aa, s));
+        prof_mark(h, 4, s);
         rc = run_gemm(h, EPI_BIAS_RESID, p->m_a, nullptr, h->w[bw.projw], h->w[bw.projb].d32, p->x32, p->x32,
                       nullptr, M, D, D, D, s);
         ++nk;
         if (rc) return rc;
+        prof_mark(h, 1, s);
         KTRY(launch_layernorm(p->x32, h->w[bw.n2w].d32, h->w[bw.n2b].d32, p->h16, M, D, opd, s));
+        prof_mark(h, 5, s);
         rc = run_gemm(h, EPI_BIAS_GELU, p->m_h, nullptr, h->w[bw.fc1w], h->w[bw.fc1b].d32, nullptr, nullptr,
                       p->m16, M, Hd, D, D, s);
         ++nk;
@@ -380,6 +402,7 @@ int enqueue_forward(usp_handle* h, Plan* p, const FwdIO& io, cudaStream_t s) {
             else if (((bi - h->n_in) & 1) == 0) { o16 = p->xa16; omap = &p->m_xa; }
             else { o16 = p->xb16; omap = &p->m_xb; }
         }
+        prof_mark(h, 6, s);
         rc = run_gemm(h, EPI_BIAS_RESID, p->m_m, nullptr, h->w[bw.fc2w], h->w[bw.fc2b].d32, p->x32, p->x32, o16, M,
                       D, Hd, Hd, s);
         ++nk;
@@ -392,6 +415,7 @@ int enqueue_forward(usp_handle* h, Plan* p, const FwdIO& io, cudaStream_t s) {
     ha.x32 = p->x32; ha.ng = h->w[h->i_nw].d32; ha.nb = h->w[h->i_nb].d32;
     ha.w = h->w[h->i_dw].d32; ha.bias = h->w[h->i_db].d32; ha.pf = p->pf;
     ha.B = B; ha.L = L; ha.D = D; ha.extras = h->extras; ha.P = h->P;
+    prof_mark(h, 8, s);
     KTRY(launch_head(ha, s));
 
     FinalArgs fa;
@@ -404,6 +428,7 @@ int enqueue_forward(usp_handle* h, Plan* p, const FwdIO& io, cudaStream_t s) {
     fa.m1 = io.m1; fa.m2 = io.m2;
     fa.B = B; fa.C = h->cfg.in_chans; fa.S = h->cfg.img_size; fa.p = h->cfg.patch_size;
     KTRY(launch_final(fa, s));
+    prof_mark(h, -1, s);
     h->kernels_per_forward = nk;
     return USP_OK;
 }
@@ -638,7 +663,44 @@ int usp_forward(usp_handle* h, const float* x, const float* t, const float* cont
     return USP_OK;
 }
 
+int usp_profile_forward(usp_handle* h, const float* x, const float* t, const float* context, const int64_t* y,
+                        float* out, int B, float* class_ms, int* class_launches, void* stream) {
+    if (!h || !class_ms || !class_launches) return USP_ERR_INVALID;
+    h->profiling = true;
+    h->prof_ev.clear();
+    h->prof_cls.clear();
+    int rc = usp_forward(h, x, t, context, y, out, B, stream);
+    h->profiling = false;
+    if (rc == USP_OK) {
+        cudaError_t e = cudaStreamSynchronize(static_cast<cudaStream_t>(stream));
+        if (e != cudaSuccess) rc = fail(h, USP_ERR_CUDA, std::string("profile sync: ") + cudaGetErrorString(e));
+    }
+    for (int i = 0; i < USP_NUM_KERNEL_CLASSES; ++i) { class_ms[i] = 0.f; class_launches[i] = 0; }
+    if (rc == USP_OK) {
+        for (size_t i = 0; i + 1 < h->prof_ev.size(); ++i) {
+            const int c = h->prof_cls[i];
+            if (c < 0 || c >= USP_NUM_KERNEL_CLASSES) continue;
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, h->prof_ev[i], h->prof_ev[i + 1]);
+            class_ms[c] += ms;
+            class_launches[c] += (c == 8 || c == 9) ? 2 : 1;
+        }
+    }
+    for (auto e : h->prof_ev) cudaEventDestroy(e);
+    h->prof_ev.clear();
+    h->prof_cls.clear();
+    return rc;
+}
+
 int usp_grid_size(float t0, float t1, float step_size) { return build_grid(t0, t1, step_size, nullptr); }
+
+int usp_time_grid(float t0, float t1, float step_size, float* out, int cap) {
+    std::vector<float> grid;
+    const int n = build_grid(t0, t1, step_size, &grid);
+    if (n < 2 || !out || cap < n) return 0;
+    memcpy(out, grid.data(), n * sizeof(float));
+    return n;
+}
 
 int usp_sample(usp_handle* h, float* z, const float* context, const int64_t* y, int B, float t0, float t1,
                float step_size, int method, const float* delta_table, float write_scale, float t_edit, int edit_loc,
@@ -869,6 +931,37 @@ int usp_op_layernorm(const float* x, const float* gamma, const float* beta, void
                      int operand_dtype, void* stream) {
     cudaError_t e = launch_layernorm(x, gamma, beta, out16, M, D, operand_dtype, static_cast<cudaStream_t>(stream));
     return e == cudaSuccess ? USP_OK : op_fail("launch_layernorm", e);
+}
+
+int usp_op_patch_embed(const float* x, const float* t, const float* w, const float* bias, const float* pos,
+                       float* out32, int B, int C, int S, int p, int D, void* stream) {
+    if (p < 1 || S % p != 0 || C * p * p > 64 || D % 2 != 0) return fail(nullptr, USP_ERR_INVALID, "bad geometry");
+    const int half = D / 2;
+    std::vector<float> f(half);
+    for (int i = 0; i < half; ++i) f[i] = expf(-logf(10000.0f) * static_cast<float>(i) / static_cast<float>(half));
+    float* dfreq = nullptr;
+    cudaError_t e = cudaMalloc(&dfreq, half * 4);
+    if (e != cudaSuccess) return op_fail("cudaMalloc", e);
+    cudaMemcpy(dfreq, f.data(), half * 4, cudaMemcpyHostToDevice);
+    EmbedArgs ea;
+    memset(&ea, 0, sizeof(ea));
+    ea.x = x; ea.tvec = t; ea.w = w; ea.bias = bias; ea.pos = pos; ea.freqs = dfreq; ea.out32 = out32;
+    ea.B = B; ea.C = C; ea.S = S; ea.p = p; ea.D = D; ea.L = 1 + (S / p) * (S / p);
+    e = launch_embed(ea, static_cast<cudaStream_t>(stream));
+    cudaStreamSynchronize(static_cast<cudaStream_t>(stream));
+    cudaFree(dfreq);
+    return e == cudaSuccess ? USP_OK : op_fail("launch_embed", e);
+}
+
+int usp_op_unpatchify_conv(const float* pf, const float* conv_w, const float* conv_b, float* out, int B, int C,
+                           int S, int p, void* stream) {
+    if (p < 1 || S % p != 0) return fail(nullptr, USP_ERR_INVALID, "bad geometry");
+    FinalArgs fa;
+    memset(&fa, 0, sizeof(fa));
+    fa.pf = pf; fa.cw = conv_w; fa.cb = conv_b; fa.out = out; fa.m1 = 1.f;
+    fa.B = B; fa.C = C; fa.S = S; fa.p = p;
+    cudaError_t e = launch_final(fa, static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? USP_OK : op_fail("launch_final", e);
 }
 
 }  // extern "C"

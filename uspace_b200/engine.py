@@ -134,6 +134,19 @@ class Engine:
                    "usp_sample_host")
         return z_host
 
+    def profile_forward(self, x, t, y=None, context=None):
+        """One eager forward with an event between launches -> {kernel class: (ms, launches)}."""
+        B = x.shape[0]
+        x = x.to(self.device, torch.float32).contiguous()
+        t = t.to(self.device, torch.float32).expand(B).contiguous()
+        out = torch.empty_like(x)
+        n = len(_lib.KERNEL_CLASSES)
+        ms = (C.c_float * n)()
+        cnt = (C.c_int * n)()
+        _lib.check(self.lib.usp_profile_forward(self.handle, _ptr(x), _ptr(t), _ptr(context), _ptr(y), _ptr(out), B,
+                                                ms, cnt, self._stream()), self.handle, "usp_profile_forward")
+        return {k: (ms[i], cnt[i]) for i, k in enumerate(_lib.KERNEL_CLASSES)}
+
     # ---- introspection ---------------------------------------------------------------------------
     def last_ms(self) -> float:
         ms = C.c_float()
@@ -148,3 +161,15 @@ class Engine:
 
     def grid_size(self, t0, t1, step_size) -> int:
         return self.lib.usp_grid_size(t0, t1, step_size)
+
+
+def time_grid(t0: float, t1: float, step_size: float):
+    """The fp32 time grid the sampler will use (torchdiffeq fixed-grid construction), as a list of floats."""
+    lib = _lib.load()
+    n = lib.usp_grid_size(t0, t1, step_size)
+    if n < 2:
+        raise ValueError(f"bad time grid: t0={t0} t1={t1} step_size={step_size}")
+    buf = (C.c_float * n)()
+    if lib.usp_time_grid(t0, t1, step_size, buf, n) != n:
+        raise RuntimeError("usp_time_grid failed")
+    return [float(v) for v in buf]

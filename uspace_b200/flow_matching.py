@@ -1,0 +1,195 @@
+"""Mirror of the reference ``CNF`` wrappers (flow_matching.py:15-180, flow_matching_t2i.py:14-175).
+
+``decode`` / ``encode`` keep the reference signatures and the ``solver_kwargs`` dictionary, but the
+``torchdiffeq.odeint`` call (flow_matching.py:118-125,140-147) is replaced by the library's fixed-grid
+Euler / Heun loop: one CUDA-graph-captured step replayed on the current stream, no host sync per NFE.
+
+Built: ``solver="fixed"`` with ``solver_fix`` in {"euler", "heun"}; the "write_attr" / "write_pca" edit hook at
+``edit_loc`` head / tail (libs/dissection.py:115-186) through a pre-loaded delta table.
+Not built (NotImplementedError): adaptive dopri5 (``solver="adaptive"``, the non-dissection default, and the
+adaptive tail of ``"fixadp"``), the activation-dump "read" mode, ``edit_loc="mid"`` (broken in the reference
+for U-ViT).
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+import torch
+import torch.nn as nn
+from torch import Tensor
+
+from .engine import time_grid
+
+_FIXED_METHODS = ("euler", "heun")
+
+
+def should_edit(timestep_digit: str, t_edit) -> bool:
+    """libs/dissection.py:21-34."""
+    if timestep_digit == "0.00":
+        return False
+    if isinstance(t_edit, (float, int)):
+        return float(timestep_digit) <= t_edit
+    if isinstance(t_edit, str) and t_edit.startswith("every_"):
+        return float(timestep_digit) % float(t_edit.replace("every_", "")) == 0.0
+    raise ValueError(f"t_edit={t_edit!r}")
+
+
+def _read_delta(path: str, ith) -> np.ndarray:
+    """libs/dissection.py:55-70: row ``ith`` of a [n, C, W, H] .npy, or the mean of rows "a_b_c"."""
+    arr = np.load(path)
+    if isinstance(ith, (int, np.integer)):
+        return arr[int(ith)]
+    if isinstance(ith, str):
+        ids = [int(s) for s in ith.split("_")]
+        return sum(arr[i] for i in ids) / len(ids)
+    raise TypeError(f"ith element must be int or 'a_b_c' string, got {ith!r}")
+
+
+def build_delta_table(grid, shape, **kwargs):
+    """Pre-gather what dissect_helper_uvit would np.load at each NFE (libs/dissection.py:139-183).
+
+    Returns (table [len(grid), C, S, S] float32 with zero rows where no edit applies, edit_loc) or (None, None).
+    """
+    name = kwargs.get("dissect_name")
+    if kwargs.get("dissect_task") != "uspace_uvit" or name in (None, "none"):
+        return None, None
+    if name == "read":
+        raise NotImplementedError("dissect_name='read' (per-NFE activation dump) is not built")
+    if name not in ("write_attr", "write_pca"):
+        raise ValueError(f"dissect_name should be read or write, here is {name}")
+    loc = kwargs.get("edit_loc")
+    if loc == "mid":
+        raise NotImplementedError("edit_loc='mid' is broken in the reference for U-ViT and is not built")
+    if loc not in ("head", "tail"):
+        return None, None
+    root = kwargs["write_path_root"]
+    table = np.zeros((len(grid),) + tuple(shape), dtype=np.float32)
+    for i, t in enumerate(grid):
+        digit = f"{t:.2f}"
+        if not should_edit(digit, kwargs.get("t_edit")):
+            continue
+        if name == "write_attr":
+            table[i] = _read_delta(os.path.join(root, f"delta_{digit}.npy"), kwargs.get("ith_attr"))
+        else:
+            table[i] = _read_delta(os.path.join(root, f"pca{kwargs.get('pca_n')}_{digit}.npy"),
+                                   kwargs.get("ith_component"))
+    return torch.from_numpy(table), loc
+
+
+class _CNFBase(nn.Module):
+    def __init__(self, net):
+        super().__init__()
+        self.net = net
+
+    def _call_net(self, x, t, cond, **kwargs):
+        raise NotImplementedError
+
+    def _cond_kw(self, cond):
+        raise NotImplementedError
+
+    def _velocity(self, t: Tensor, x: Tensor, cond, **kwargs) -> Tensor:
+        """flow_matching.py:23-36 (the t.item() logging — a host sync per NFE — is dropped)."""
+        if t.numel() == 1:
+            t = t.expand(x.size(0))
+        pred, _ = self._call_net(x, t, cond, **kwargs)
+        return pred
+
+    def is_dissection_mode(self, kwargs):
+        return "dissect_name" in kwargs and kwargs["dissect_name"] is not None
+
+    def get_ode_kwargs(self, **kwargs):
+        """flow_matching.py:38-85, restricted to what is built (fixed grid)."""
+        if not self.is_dissection_mode(kwargs):
+            raise NotImplementedError(
+                "adaptive dopri5 (the reference's non-dissection default) is not built; pass dissect_name and "
+                "solver_kwargs=dict(solver='fixed', solver_fix='euler'|'heun', solver_fix_step=h)")
+        sk = kwargs["solver_kwargs"]
+        if sk["solver"] != "fixed":
+            raise NotImplementedError(f"solver={sk['solver']!r}: only the fixed-grid solver is built")
+        return self._fixed_kwargs(sk)
+
+    @staticmethod
+    def _fixed_kwargs(sk):
+        if sk["solver_fix"] not in _FIXED_METHODS:
+            raise NotImplementedError(f"solver_fix={sk['solver_fix']!r}: built methods are {_FIXED_METHODS}")
+        return dict(method=sk["solver_fix"], options=dict(step_size=float(sk["solver_fix_step"])))
+
+    def training_losses(self, x, cond, sigma_min, **kwargs):
+        """flow_matching.py:88-100 (runs the differentiable PyTorch graph of the mirror module)."""
+        noise = torch.randn_like(x)
+        t = torch.rand(len(x), device=x.device, dtype=x.dtype)
+        t_ = t[:, None, None, None]
+        x_new = t_ * x + (1 - (1 - sigma_min) * t_) * noise
+        u = x - (1 - sigma_min) * noise
+        return (self._velocity(t, x_new, cond, **kwargs) - u).square().mean(dim=(1, 2, 3))
+
+    @torch.no_grad()
+    def _integrate(self, z: Tensor, cond, t0: float, t1: float, ode_kwargs: dict, **kwargs) -> Tensor:
+        net = self.net.module if hasattr(self.net, "module") else self.net  # DDP / accelerate wrapper
+        engine = net.engine()
+        h = ode_kwargs["options"]["step_size"]
+        table, loc = None, None
+        if self.is_dissection_mode(kwargs):
+            table, loc = build_delta_table(time_grid(t0, t1, h), z.shape[1:], **kwargs)
+        ws = float(kwargs.get("write_scale") or 0.0) if table is not None else 0.0
+        # rows where should_edit() is false are zero, so the library's own mask can stay wide open
+        return engine.sample(z, t0, t1, h, ode_kwargs["method"], delta_table=table, write_scale=ws,
+                             t_edit=float("inf"), edit_loc=loc, **self._cond_kw(cond))
+
+    def _decode(self, z: Tensor, cond, **kwargs) -> Tensor:
+        """flow_matching.py:130-151."""
+        solver = kwargs["solver_kwargs"]["solver"]
+        if solver == "fixed":
+            return self._integrate(z, cond, 0.0, 1.0, self.get_ode_kwargs(**kwargs), **kwargs)
+        if solver in ("adaptive", "fixadp"):
+            raise NotImplementedError(f"solver={solver!r} needs adaptive dopri5, which is not built")
+        raise NotImplementedError(f"unknown solver {kwargs['solver_kwargs']}")
+
+
+class CNF(_CNFBase):
+    """Mirror of flow_matching.py::CNF (unconditional / class-conditional, ``y=``)."""
+
+    def _call_net(self, x, t, y, **kwargs):
+        return self.net(x, t, y, **kwargs)
+
+    def _cond_kw(self, y):
+        return dict(y=y)
+
+    def forward(self, t: Tensor, x: Tensor, y: Tensor = None, **kwargs) -> Tensor:
+        return self._velocity(t, x, y, **kwargs)
+
+    def training_losses(self, x, y, sigma_min, **kwargs):
+        return super().training_losses(x, y, sigma_min, **kwargs)
+
+    def encode(self, x: Tensor, y: Tensor = None, **kwargs) -> Tensor:
+        """flow_matching.py:102-125: always the fixed solver, t: 1 -> 0."""
+        return self._integrate(x, y, 1.0, 0.0, self._fixed_kwargs(kwargs["solver_kwargs"]), **kwargs)
+
+    def decode(self, z: Tensor, y: Tensor = None, **kwargs) -> Tensor:
+        return self._decode(z, y, **kwargs)
+
+
+class CNFT2I(_CNFBase):
+    """Mirror of flow_matching_t2i.py::CNF (``context=``)."""
+
+    def _call_net(self, x, t, context, **kwargs):
+        return self.net(x, t, context=context, **kwargs)
+
+    def _cond_kw(self, context):
+        return dict(context=context)
+
+    def forward(self, t: Tensor, x: Tensor, context: Tensor, **kwargs) -> Tensor:
+        return self._velocity(t, x, context, **kwargs)
+
+    def training_losses(self, x, context, sigma_min, **kwargs):
+        return super().training_losses(x, context, sigma_min, **kwargs)
+
+    def encode(self, x: Tensor, context: Tensor, **kwargs) -> Tensor:
+        """flow_matching_t2i.py:105-122: goes through get_ode_kwargs, t: 1 -> 0."""
+        kwargs.update({"fm_direction": "encode"})
+        return self._integrate(x, context, 1.0, 0.0, self.get_ode_kwargs(**kwargs), **kwargs)
+
+    def decode(self, z: Tensor, context: Tensor, **kwargs) -> Tensor:
+        kwargs.update({"fm_direction": "decode"})
+        return self._decode(z, context, **kwargs)
