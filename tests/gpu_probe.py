@@ -202,6 +202,22 @@ def sec_perf(lib, opd):
               f"{flops * B * 50 / dt / 1e12:.1f} TFLOP/s", flush=True)
 
 
+def sec_prof(lib, opd):
+    """Per-kernel-class device time of one U-ViT-L velocity evaluation (events between launches)."""
+    for cfg, t2i, B in [(CFG_L, False, 64), (CFG_L_T2I, True, 128)]:
+        m = build(cfg, opd, t2i).to(dev)
+        eng = m.engine()
+        z = torch.randn(B, 4, 32, 32, device=dev)
+        t = torch.full((B,), 0.5, device=dev)
+        ctx = torch.randn(B, 77, 768, device=dev) if t2i else None
+        for _ in range(3):
+            p = eng.profile_forward(z, t, context=ctx)
+        tot = sum(v[0] for v in p.values())
+        print(f"prof {'t2i' if t2i else 'uncond'} B{B} total {tot:.3f} ms: " +
+              " ".join(f"{k}={v[0]:.3f}/{v[1]}" for k, v in p.items()), flush=True)
+        del m, eng
+
+
 def sec_one(lib, opd):
     """Two eager velocity evaluations of U-ViT-L at batch 64 (profile the second one under ncu)."""
     m = build(CFG_L, opd).to(dev)

@@ -624,7 +624,7 @@ int usp_finalize_weights(usp_handle* h, void* stream) {
         if (!w.gemm) continue;
         CUDA_TRY(h, launch_convert16(w.d32, w.d16, w.numel, h->cfg.operand_dtype, s));
         const int N = static_cast<int>(w.shape[0]), K = static_cast<int>(w.shape[1]);
-        if (!make_map_2d(&w.map, w.d16, N, K, gemm_block_n(N), h->cfg.operand_dtype))
+        if (!make_map_2d(&w.map, w.d16, N, K, gemm_weight_box_rows(), h->cfg.operand_dtype))
             return fail(h, USP_ERR_CUDA, "cuTensorMapEncodeTiled failed for " + w.name);
     }
     CUDA_TRY(h, cudaStreamSynchronize(s));
@@ -895,7 +895,7 @@ int usp_op_gemm(int epilogue, const void* a16, const void* a16_second, const voi
     bool ok = make_map_2d(&maps.a0, a16, M, K0, GEMM_BM, operand_dtype);
     if (a16_second) ok &= make_map_2d(&maps.a1, a16_second, M, K - K0, GEMM_BM, operand_dtype);
     else maps.a1 = maps.a0;
-    ok &= make_map_2d(&maps.b, w16, N, K, gemm_block_n(N), operand_dtype);
+    ok &= make_map_2d(&maps.b, w16, N, K, gemm_weight_box_rows(), operand_dtype);
     if (!ok) return fail(nullptr, USP_ERR_CUDA, "cuTensorMapEncodeTiled failed");
     GemmArgs g;
     memset(&g, 0, sizeof(g));

@@ -5,10 +5,11 @@
 //
 // One CTA per (128-query tile, sample*head).  Because L is short the full score row fits in TMEM
 // (L16 <= 384 fp32 columns), so there is no online-softmax rescaling:
-//   warp 4 (1 thread): TMA loads Q tile, all of K and V (3-D tensor maps, OOB rows zero-filled),
+//   warp 8 (1 thread): TMA loads Q tile, all of K and V (3-D tensor maps, OOB rows zero-filled),
 //                      issues S = Q K^T (tcgen05.mma, K-major operands) into TMEM columns [0, L16),
 //                      later issues O = P V (A = P from swizzled smem, B = V as MN-major) into columns [384, 448).
-//   warps 0-3 (128 threads, thread i <-> query row i <-> TMEM lane i): row max, exp2, row sum in fp32,
+//   warps 0-7 (256 threads; warps w and w+4 share TMEM lane group w, i.e. two threads per query row, each
+//                      taking half of the key columns and half of the output columns): row max, exp2, row sum in fp32,
 //                      write un-normalised P as 16-bit into the 128B-swizzled K-major smem layout,
 //                      finally scale O by 1/sum and store heads-merged [B*L, H*64].
 #include "common.cuh"
@@ -20,7 +21,8 @@ namespace {
 
 constexpr int HD = 64;
 constexpr int QT = 128;                       // query rows per CTA
-constexpr int ATTN_THREADS = 160;
+constexpr int ATTN_THREADS = 288;          // 8 softmax warps + 1 control warp
+constexpr int CTRL_WARP = 8;
 constexpr int TILE16K = 128 * HD * 2;         // one 128-row x 64-col 16-bit tile
 constexpr int MAX_KCH = ATTN_MAX_L / 128;     // 3 row chunks of K / V
 constexpr int MAX_PCH = ATTN_MAX_L / 64;      // 6 column chunks of P
@@ -44,6 +46,12 @@ __device__ __forceinline__ uint64_t umma_desc_v_mn(uint32_t saddr) {
     return d;
 }
 
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 __global__ void __launch_bounds__(ATTN_THREADS, 1)
 attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                  const __grid_constant__ CUtensorMap tmV, const AttnArgs a) {
@@ -52,6 +60,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 
     __shared__ __align__(8) uint64_t bar_qk, bar_v, bar_s, bar_p, bar_o;
     __shared__ uint32_t tmem_base_smem;
+    __shared__ float s_max[2][QT], s_sum[2][QT];
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -65,17 +74,18 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         mbar_init(&bar_qk, 1);
         mbar_init(&bar_v, 1);
         mbar_init(&bar_s, 1);
-        mbar_init(&bar_p, 128);
+        mbar_init(&bar_p, 256);
         mbar_init(&bar_o, 1);
         fence_barrier_init();
     }
-    if (warp == 4) tmem_alloc<ATTN_TMEM_COLS>(&tmem_base_smem);
+    __syncwarp();
+    if (warp == CTRL_WARP) tmem_alloc<ATTN_TMEM_COLS>(&tmem_base_smem);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
 
-    if (warp == 4) {
+    if (warp == CTRL_WARP) {
         if (lane == 0) {
             tma_prefetch_desc(&tmQ);
             tma_prefetch_desc(&tmK);
@@ -114,104 +124,118 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             }
             umma_commit(&bar_o);
         }
+        __syncwarp();
     } else {
-        // ===================== softmax / output warps =====================
-        const int row = threadIdx.x;           // 0..127 == TMEM lane
+        // ===================== softmax / output warps (8 warps, two threads per query row) =====================
+        const int lg = warp & 3;               // TMEM lane group of this warp
+        const int part = warp >> 2;            // which half of the key columns / output columns
+        const int row = lg * 32 + lane;        // 0..127 == TMEM lane
         const int l = qt * QT + row;
         const bool row_ok = l < L;
-        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+        // tcgen05.ld is warp-collective (.sync.aligned): skip work only when the WHOLE warp has no valid row
+        const bool warp_ok = __any_sync(0xffffffffu, row_ok);
+        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(lg * 32) << 16);
         const float c2 = 0.125f * 1.44269504088896340736f;  // hd^-0.5 * log2(e)
         const int nch = (L + 31) / 32;
+        const int c_lo = part == 0 ? 0 : (nch + 1) / 2;
+        const int c_hi = part == 0 ? (nch + 1) / 2 : nch;
 
         mbar_wait(&bar_s, 0);
         tc_fence_after();
 
         float mx = -INFINITY;
-        for (int c = 0; c < nch; ++c) {
-            uint32_t r[32];
-            tmem_ld32(t_row + c * 32, r);
-            tmem_ld_wait();
+        if (warp_ok) {
+            for (int c = c_lo; c < c_hi; ++c) {
+                uint32_t r[32];
+                tmem_ld32(t_row + c * 32, r);
+                tmem_ld_wait();
+                if (c * 32 + 32 <= L) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const float s = __uint_as_float(r[j]);
-                if (c * 32 + j < L) mx = fmaxf(mx, s);
+                    for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(r[j]));
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (c * 32 + j < L) mx = fmaxf(mx, __uint_as_float(r[j]));
+                }
             }
         }
+        s_max[part][row] = mx;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        mx = fmaxf(s_max[0][row], s_max[1][row]);
         const float mxs = mx * c2;
         float sum = 0.f;
-        uint8_t* prow = smem + SP_OFF + (row >> 3) * 1024 + (row & 7) * 128;
-        for (int c = 0; c < nch; ++c) {
-            uint32_t r[32];
-            tmem_ld32(t_row + c * 32, r);
-            tmem_ld_wait();
-            uint32_t pk[16];
+        if (warp_ok) {
+            uint8_t* prow = smem + SP_OFF + (row >> 3) * 1024 + (row & 7) * 128;
+            for (int c = c_lo; c < c_hi; ++c) {
+                uint32_t r[32];
+                tmem_ld32(t_row + c * 32, r);
+                tmem_ld_wait();
+                float p[32];
+                if (c * 32 + 32 <= L) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 2) {
-                float p0 = 0.f, p1 = 0.f;
-                if (c * 32 + j < L) p0 = exp2f(fmaf(__uint_as_float(r[j]), c2, -mxs));
-                if (c * 32 + j + 1 < L) p1 = exp2f(fmaf(__uint_as_float(r[j + 1]), c2, -mxs));
-                // the row sum uses the rounded values that the PV product will see
-                uint32_t u;
-                float2 f;
-                if (a.opd == OPD_FP16) {
-                    u = Op16<OPD_FP16>::pack(p0, p1);
-                    f = Op16<OPD_FP16>::unpack(u);
+                    for (int j = 0; j < 32; ++j) p[j] = ex2_approx(fmaf(__uint_as_float(r[j]), c2, -mxs));
                 } else {
-                    u = Op16<OPD_BF16>::pack(p0, p1);
-                    f = Op16<OPD_BF16>::unpack(u);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        p[j] = (c * 32 + j < L) ? ex2_approx(fmaf(__uint_as_float(r[j]), c2, -mxs)) : 0.f;
                 }
-                sum += f.x + f.y;
-                pk[j >> 1] = u;
-            }
-            if (row_ok) {
+                // (the row sum is taken before the 16-bit rounding of P: the difference is ~2^-12/sqrt(L) relative)
+#pragma unroll
+                for (int j = 0; j < 32; ++j) sum += p[j];
                 // columns [c*32, c*32+32): chunk-of-64 index, then 4 x 16-byte units with the 128B swizzle
                 uint8_t* pc = prow + (c >> 1) * TILE16K;
                 const int u0 = (c & 1) * 4;
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     const int unit = (u0 + u) ^ (row & 7);
-                    *reinterpret_cast<uint4*>(pc + unit * 16) =
-                        make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+                    uint4 w;
+                    if (a.opd == OPD_FP16) {
+                        w.x = Op16<OPD_FP16>::pack(p[8 * u], p[8 * u + 1]); w.y = Op16<OPD_FP16>::pack(p[8 * u + 2], p[8 * u + 3]);
+                        w.z = Op16<OPD_FP16>::pack(p[8 * u + 4], p[8 * u + 5]); w.w = Op16<OPD_FP16>::pack(p[8 * u + 6], p[8 * u + 7]);
+                    } else {
+                        w.x = Op16<OPD_BF16>::pack(p[8 * u], p[8 * u + 1]); w.y = Op16<OPD_BF16>::pack(p[8 * u + 2], p[8 * u + 3]);
+                        w.z = Op16<OPD_BF16>::pack(p[8 * u + 4], p[8 * u + 5]); w.w = Op16<OPD_BF16>::pack(p[8 * u + 6], p[8 * u + 7]);
+                    }
+                    if (row_ok) *reinterpret_cast<uint4*>(pc + unit * 16) = w;
                 }
             }
         }
+        s_sum[part][row] = sum;
         fence_proxy_async();  // make the generic-proxy smem writes visible to the tensor core (async proxy)
         mbar_arrive(&bar_p);
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const float inv = 1.0f / (s_sum[0][row] + s_sum[1][row]);
 
         mbar_wait(&bar_o, 0);
         tc_fence_after();
-        const float inv = 1.0f / sum;
-        uint16_t* orow = reinterpret_cast<uint16_t*>(a.out16) +
-                         (static_cast<long long>(bh / a.H) * L + l) * a.D + (bh % a.H) * HD;
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
+        if (warp_ok) {
+            uint16_t* orow = reinterpret_cast<uint16_t*>(a.out16) +
+                             (static_cast<long long>(bh / a.H) * L + l) * a.D + (bh % a.H) * HD + part * 32;
             uint32_t r[32];
-            tmem_ld32(t_row + O_COL + c * 32, r);
+            tmem_ld32(t_row + O_COL + part * 32, r);
             tmem_ld_wait();
-            if (row_ok) {
-                uint4* op = reinterpret_cast<uint4*>(orow + c * 32);
+            uint4* op = reinterpret_cast<uint4*>(orow);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    float v[8];
+            for (int j = 0; j < 4; ++j) {
+                float v[8];
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[8 * j + e]) * inv;
-                    uint4 u;
-                    if (a.opd == OPD_FP16) {
-                        u.x = Op16<OPD_FP16>::pack(v[0], v[1]); u.y = Op16<OPD_FP16>::pack(v[2], v[3]);
-                        u.z = Op16<OPD_FP16>::pack(v[4], v[5]); u.w = Op16<OPD_FP16>::pack(v[6], v[7]);
-                    } else {
-                        u.x = Op16<OPD_BF16>::pack(v[0], v[1]); u.y = Op16<OPD_BF16>::pack(v[2], v[3]);
-                        u.z = Op16<OPD_BF16>::pack(v[4], v[5]); u.w = Op16<OPD_BF16>::pack(v[6], v[7]);
-                    }
-                    op[j] = u;
+                for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[8 * j + e]) * inv;
+                uint4 u;
+                if (a.opd == OPD_FP16) {
+                    u.x = Op16<OPD_FP16>::pack(v[0], v[1]); u.y = Op16<OPD_FP16>::pack(v[2], v[3]);
+                    u.z = Op16<OPD_FP16>::pack(v[4], v[5]); u.w = Op16<OPD_FP16>::pack(v[6], v[7]);
+                } else {
+                    u.x = Op16<OPD_BF16>::pack(v[0], v[1]); u.y = Op16<OPD_BF16>::pack(v[2], v[3]);
+                    u.z = Op16<OPD_BF16>::pack(v[4], v[5]); u.w = Op16<OPD_BF16>::pack(v[6], v[7]);
                 }
+                if (row_ok) op[j] = u;
             }
         }
     }
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 4) tmem_dealloc<ATTN_TMEM_COLS>(tmem_base);
+    if (warp == CTRL_WARP) tmem_dealloc<ATTN_TMEM_COLS>(tmem_base);
 }
 
 }  // namespace

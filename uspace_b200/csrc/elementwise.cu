@@ -19,64 +19,69 @@ __device__ __forceinline__ float warp_sum(float v) {
 //        timestep_embedding (libs/uvit.py:26-46; t used raw, cos half then sin half),
 //        token order [label?, time, ctx..., patches] (libs/uvit.py:320-327, libs/uvit_t2i.py:320-324), + pos_embed.
 //        Optional "head" edit x + delta[t]*write_scale (libs/dissection.py:157, libs/uvit.py:313-314).
-// grid = (L, B), block = 256
+// grid = (ceil(L / EMB_TOK), B), block = 256.  Each block handles EMB_TOK consecutive tokens of one sample so
+// that the [D, P] projection weights are read once per block (registers), not once per token.
 // ------------------------------------------------------------------------------------------------
+constexpr int EMB_TOK = 16;
+constexpr int EMB_MAXP = 64;   // C*p*p upper bound
+
 __global__ void __launch_bounds__(256) embed_kernel(const EmbedArgs a) {
-    const int l = blockIdx.x;
+    const int l0 = blockIdx.x * EMB_TOK;
     const int b = blockIdx.y;
     const int D = a.D;
-    float* out = a.out32 + (static_cast<long long>(b) * a.L + l) * D;
-    const float* pos = a.pos + static_cast<long long>(l) * D;
     const int t_tok = a.has_label ? 1 : 0;
     const int first_patch = t_tok + 1 + a.n_ctx;
-
-    if (a.has_label && l == 0) {
-        const float* e = a.label + a.y[b] * D;
-        for (int d = threadIdx.x; d < D; d += blockDim.x) out[d] = e[d] + pos[d];
-        return;
-    }
-    if (l == t_tok) {
-        const float t = a.st ? a.st->t : a.tvec[b];
-        const int half = D / 2;
-        for (int d = threadIdx.x; d < D; d += blockDim.x) {
-            float v = 0.f;
-            if (d < half) v = cosf(t * a.freqs[d]);
-            else if (d < 2 * half) v = sinf(t * a.freqs[d - half]);
-            out[d] = v + pos[d];
-        }
-        return;
-    }
-    if (l < first_patch) {
-        const float* e = a.ctxemb + (static_cast<long long>(b) * a.n_ctx + (l - t_tok - 1)) * D;
-        for (int d = threadIdx.x; d < D; d += blockDim.x) out[d] = e[d] + pos[d];
-        return;
-    }
-    // patch token
-    __shared__ float feat[64];
     const int p = a.p, C = a.C, S = a.S;
     const int P = C * p * p;
     const int gw = S / p;
-    const int pi = l - first_patch;
-    const int ph = pi / gw, pw = pi % gw;
-    if (threadIdx.x < P) {
-        const int f = threadIdx.x;
-        const int c = f / (p * p);
-        const int p1 = (f / p) % p;
-        const int p2 = f % p;
-        const int idx = (c * S + ph * p + p1) * S + pw * p + p2;
-        float v = a.x[static_cast<long long>(b) * C * S * S + idx];
-        if (a.delta != nullptr && a.st != nullptr) {
-            const float sc = a.st->edit;
-            if (sc != 0.f) v += a.delta[static_cast<long long>(a.st->didx) * C * S * S + idx] * sc;
+    const int l1 = min(l0 + EMB_TOK, a.L);
+
+    __shared__ float feat[EMB_TOK][EMB_MAXP];
+    // gather the (C,p1,p2) features of every patch token in this block
+    for (int i = threadIdx.x; i < EMB_TOK * P; i += blockDim.x) {
+        const int tk = i / P, f = i % P;
+        const int l = l0 + tk;
+        if (l >= first_patch && l < a.L) {
+            const int pi = l - first_patch;
+            const int ph = pi / gw, pw = pi % gw;
+            const int c = f / (p * p);
+            const int p1 = (f / p) % p;
+            const int p2 = f % p;
+            const int idx = (c * S + ph * p + p1) * S + pw * p + p2;
+            float v = a.x[static_cast<long long>(b) * C * S * S + idx];
+            if (a.delta != nullptr && a.st != nullptr) {
+                const float sc = a.st->edit;
+                if (sc != 0.f) v += a.delta[static_cast<long long>(a.st->didx) * C * S * S + idx] * sc;
+            }
+            feat[tk][f] = v;
         }
-        feat[f] = v;
     }
     __syncthreads();
+
     for (int d = threadIdx.x; d < D; d += blockDim.x) {
-        const float* w = a.w + static_cast<long long>(d) * P;
-        float acc = 0.f;
-        for (int f = 0; f < P; ++f) acc = fmaf(w[f], feat[f], acc);
-        out[d] = acc + a.bias[d] + pos[d];
+        const float* wrow = a.w + static_cast<long long>(d) * P;
+        const float bias = a.bias[d];
+        for (int l = l0; l < l1; ++l) {
+            float* out = a.out32 + (static_cast<long long>(b) * a.L + l) * D;
+            const float pos = a.pos[static_cast<long long>(l) * D + d];
+            float v;
+            if (a.has_label && l == 0) {
+                v = a.label[a.y[b] * D + d];
+            } else if (l == t_tok) {
+                const float t = a.st ? a.st->t : a.tvec[b];
+                const int half = D / 2;
+                v = 0.f;
+                if (d < half) v = cosf(t * a.freqs[d]);
+                else if (d < 2 * half) v = sinf(t * a.freqs[d - half]);
+            } else if (l < first_patch) {
+                v = a.ctxemb[(static_cast<long long>(b) * a.n_ctx + (l - t_tok - 1)) * D + d];
+            } else {
+                float acc = 0.f;
+                for (int f = 0; f < P; ++f) acc = fmaf(__ldg(wrow + f), feat[l - l0][f], acc);
+                v = acc + bias;
+            }
+            out[d] = v + pos;
+        }
     }
 }
 
@@ -265,7 +270,7 @@ __global__ void step_kernel(StepState* st, const float* __restrict__ grid, const
 
 cudaError_t launch_embed(const EmbedArgs& a, cudaStream_t s) {
     if (a.C * a.p * a.p > 64) return cudaErrorInvalidValue;
-    embed_kernel<<<dim3(a.L, a.B), 256, 0, s>>>(a);
+    embed_kernel<<<dim3((a.L + EMB_TOK - 1) / EMB_TOK, a.B), 256, 0, s>>>(a);
     return cudaGetLastError();
 }
 

@@ -12,7 +12,10 @@
 //   warp 1    : allocates TMEM, single thread issues tcgen05.mma (128 x BN x 16), commits to mbarriers
 //   warps 2-5 : epilogue; tcgen05.ld the fp32 accumulator (double-buffered in TMEM so the next tile's
 //               main loop overlaps this tile's epilogue), fuse bias/GELU/residual, store.
+#include <stdlib.h>
+
 #include "common.cuh"
+#include "gemm_epilogue.cuh"
 #include "kernels.h"
 
 namespace usp {
@@ -32,12 +35,6 @@ struct GemmCfg {
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;  // + alignment slack
     static constexpr int TMEM_COLS = 2 * BN;
 };
-
-__device__ __forceinline__ float gelu_erf(float v) { return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f)); }
-
-__device__ __forceinline__ uint32_t pack16(int opd, float a, float b) {
-    return opd == OPD_FP16 ? Op16<OPD_FP16>::pack(a, b) : Op16<OPD_BF16>::pack(a, b);
-}
 
 template <int BN, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
@@ -78,6 +75,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
         }
         fence_barrier_init();
     }
+    __syncwarp();
     if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(&tmem_base_smem);
     tc_fence_before();
     __syncthreads();
@@ -102,10 +100,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
                     else
                         tma_load_2d(&tmA1, &full_bar[stage], sa, (kb - nkb0) * BK, m0);
                     tma_load_2d(&tmB, &full_bar[stage], sb, kb * BK, n0);
+                    if (BN == 256) tma_load_2d(&tmB, &full_bar[stage], sb + 128 * BK * 2, kb * BK, n0 + 128);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
+        __syncwarp();
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
@@ -136,6 +136,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
                 umma_commit(&tmem_full_bar[as]);  // accumulator ready for the epilogue
             }
         }
+        __syncwarp();
     } else {
         // ===================== epilogue (warps 2..5) =====================
         const int lg = warp & 3;  // TMEM lane group this warp may access
@@ -146,84 +147,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
             const int m0 = (tile / n_tiles_n) * BM;
             const int n0 = (tile % n_tiles_n) * BN;
             const int m = m0 + lg * 32 + lane;
-            const bool row_ok = m < g.M;
 
             mbar_wait(&tmem_full_bar[as], aphase);
             tc_fence_after();
 
-            // per-row destination bookkeeping
-            long long qkv_row = 0;
-            if (EPI == EPI_QKV) {
-                const int b = m / g.L;
-                const int l = m - b * g.L;
-                qkv_row = (static_cast<long long>(b) * g.H * g.L + l) * 64;  // + h*L*64 + which*stride + d
-            }
-
+            const EpiRow row = epi_row(g, EPI, m);
 #pragma unroll 1
             for (int c = 0; c < BN / 32; ++c) {
                 uint32_t r[32];
+                float4 rb[8];
+                if (EPI == EPI_BIAS_RESID) epi_load_resid(g, row, n0 + c * 32, rb);
                 tmem_ld32(tmem_base + (static_cast<uint32_t>(lg * 32) << 16) + as * BN + c * 32, r);
                 tmem_ld_wait();
-                const int n = n0 + c * 32;
-                if (row_ok) {
-                    float v[32];
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-                    if (EPI != EPI_QKV || g.bias != nullptr) {
-                        if (g.bias != nullptr) {
-#pragma unroll
-                            for (int j = 0; j < 32; j += 4) {
-                                const float4 b4 = __ldg(reinterpret_cast<const float4*>(g.bias + n + j));
-                                v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
-                            }
-                        }
-                    }
-                    if (EPI == EPI_BIAS_GELU) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
-                    }
-                    if (EPI == EPI_BIAS_RESID) {
-                        const float4* rp = reinterpret_cast<const float4*>(g.resid + static_cast<long long>(m) * g.N + n);
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const float4 x4 = rp[j];
-                            v[4 * j] += x4.x; v[4 * j + 1] += x4.y; v[4 * j + 2] += x4.z; v[4 * j + 3] += x4.w;
-                        }
-                    }
-                    if (EPI == EPI_BIAS_RESID || EPI == EPI_BIAS_F32) {
-                        if (g.out32 != nullptr) {
-                            float4* op = reinterpret_cast<float4*>(g.out32 + static_cast<long long>(m) * g.N + n);
-#pragma unroll
-                            for (int j = 0; j < 8; ++j)
-                                op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                        }
-                    }
-                    // 16-bit output
-                    uint16_t* o16 = nullptr;
-                    if (EPI == EPI_QKV) {
-                        const int Dm = g.H * 64;
-                        const int which = n / Dm;
-                        const int rem = n - which * Dm;
-                        const int h = rem >> 6;
-                        const int d = rem & 63;
-                        o16 = reinterpret_cast<uint16_t*>(g.out16) + which * g.qkv_stride + qkv_row +
-                              static_cast<long long>(h) * g.L * 64 + d;
-                    } else if (g.out16 != nullptr) {
-                        o16 = reinterpret_cast<uint16_t*>(g.out16) + static_cast<long long>(m) * g.N + n;
-                    }
-                    if (o16 != nullptr) {
-                        uint4* op = reinterpret_cast<uint4*>(o16);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            uint4 u;
-                            u.x = pack16(g.opd, v[8 * j], v[8 * j + 1]);
-                            u.y = pack16(g.opd, v[8 * j + 2], v[8 * j + 3]);
-                            u.z = pack16(g.opd, v[8 * j + 4], v[8 * j + 5]);
-                            u.w = pack16(g.opd, v[8 * j + 6], v[8 * j + 7]);
-                            op[j] = u;
-                        }
-                    }
-                }
+                epi_chunk<EPI>(g, row, n0 + c * 32, r, rb);
             }
             // release this accumulator buffer back to the MMA warp
             tc_fence_before();
@@ -266,6 +202,8 @@ cudaError_t configure_one() {
 }
 
 // opt every instantiation into its dynamic shared memory size (done once, outside any graph capture)
+cudaError_t gemm2_configure();
+
 cudaError_t gemm_configure() {
     static bool done = false;
     if (done) return cudaSuccess;
@@ -278,14 +216,31 @@ cudaError_t gemm_configure() {
     if ((e = configure_one<128, EPI_BIAS_GELU>()) != cudaSuccess) return e;
     if ((e = configure_one<128, EPI_BIAS_RESID>()) != cudaSuccess) return e;
     if ((e = configure_one<128, EPI_BIAS_F32>()) != cudaSuccess) return e;
+    if ((e = gemm2_configure()) != cudaSuccess) return e;
     done = true;
     return cudaSuccess;
 }
 
 int gemm_block_n(int N) { return (N % 256 == 0) ? 256 : 128; }
+int gemm_weight_box_rows() { return 128; }
+
+cudaError_t gemm2_configure();
+bool gemm2_supported(const GemmArgs& a);
+cudaError_t launch_gemm2(int epi, const GemmMaps& maps, const GemmArgs& a, int num_sms, cudaStream_t s);
+
+// USP_GEMM_1CTA=1 forces the single-CTA kernel (A/B comparison, debugging)
+static bool force_1cta() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("USP_GEMM_1CTA");
+        v = (e && e[0] == '1') ? 1 : 0;
+    }
+    return v == 1;
+}
 
 cudaError_t launch_gemm(int epi, const GemmMaps& maps, const GemmArgs& a, int num_sms, cudaStream_t s) {
     if (a.M <= 0 || a.N % 128 != 0 || a.K % BK != 0 || a.K0 % BK != 0 || a.K0 > a.K) return cudaErrorInvalidValue;
+    if (!force_1cta() && gemm2_supported(a)) return launch_gemm2(epi, maps, a, num_sms, s);
     if (gemm_block_n(a.N) == 256) return launch_bn<256>(epi, maps, a, num_sms, s);
     return launch_bn<128>(epi, maps, a, num_sms, s);
 }

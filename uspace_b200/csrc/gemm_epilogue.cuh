@@ -1,0 +1,116 @@
+// Fused GEMM epilogues shared by the 1-CTA and 2-CTA tcgen05 GEMM kernels.
+// A thread owns one accumulator row (TMEM lane) and works on 32 consecutive columns at a time.
+#pragma once
+#include "common.cuh"
+#include "kernels.h"
+
+namespace usp {
+
+// exact-erf GELU (nn.GELU() default, libs/timm.py:101-108).  erf via Abramowitz-Stegun 7.1.26
+// (|abs err| <= 1.5e-7, far below the 16-bit rounding of the stored activation); 2 MUFU + ~12 FMA-class ops,
+// about half the instruction count of erff(), which matters because fc1's epilogue is issue-bound.
+__device__ __forceinline__ float gelu_erf_fast(float v) {
+    const float x = fabsf(v) * 0.70710678118654752440f;
+    float t;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, x, 1.0f)));
+    float p = fmaf(1.061405429f, t, -1.453152027f);
+    p = fmaf(p, t, 1.421413741f);
+    p = fmaf(p, t, -0.284496736f);
+    p = fmaf(p, t, 0.254829592f);
+    p *= t;
+    float e;
+    const float a = -x * x * 1.44269504088896340736f;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(a));
+    const float erf_abs = fmaf(-p, e, 1.0f);      // erf(|v|/sqrt2)
+    const float hv = 0.5f * v;
+    return fmaf(fabsf(hv), erf_abs, hv);          // 0.5*v*(1 + sign(v)*erf_abs) == hv + |hv|*erf_abs
+}
+
+__device__ __forceinline__ uint32_t pack16(int opd, float a, float b) {
+    return opd == OPD_FP16 ? Op16<OPD_FP16>::pack(a, b) : Op16<OPD_BF16>::pack(a, b);
+}
+
+struct EpiRow {          // per-row bookkeeping, computed once per tile
+    int m;               // global row
+    bool ok;             // m < M
+    long long qkv_row;   // EPI_QKV: (b*H*L + l) * 64
+};
+
+__device__ __forceinline__ EpiRow epi_row(const GemmArgs& g, int epi, int m) {
+    EpiRow r;
+    r.m = m;
+    r.ok = m < g.M;
+    r.qkv_row = 0;
+    if (epi == EPI_QKV) {
+        const int b = m / g.L;
+        const int l = m - b * g.L;
+        r.qkv_row = (static_cast<long long>(b) * g.H * g.L + l) * 64;
+    }
+    return r;
+}
+
+// residual prefetch for EPI_BIAS_RESID: 32 fp32 = 8 x float4 of row m, columns [n, n+32)
+__device__ __forceinline__ void epi_load_resid(const GemmArgs& g, const EpiRow& row, int n, float4* buf) {
+    if (row.ok) {
+        const float4* rp = reinterpret_cast<const float4*>(g.resid + static_cast<long long>(row.m) * g.N + n);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) buf[j] = rp[j];
+    }
+}
+
+template <int EPI>
+__device__ __forceinline__ void epi_chunk(const GemmArgs& g, const EpiRow& row, int n, const uint32_t* r,
+                                          const float4* resid) {
+    if (!row.ok) return;
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+    if (g.bias != nullptr) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(g.bias + n + j));
+            v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+        }
+    }
+    if (EPI == EPI_BIAS_GELU) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = gelu_erf_fast(v[j]);
+    }
+    if (EPI == EPI_BIAS_RESID) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            v[4 * j] += resid[j].x; v[4 * j + 1] += resid[j].y; v[4 * j + 2] += resid[j].z; v[4 * j + 3] += resid[j].w;
+        }
+    }
+    if (EPI == EPI_BIAS_RESID || EPI == EPI_BIAS_F32) {
+        if (g.out32 != nullptr) {
+            float4* op = reinterpret_cast<float4*>(g.out32 + static_cast<long long>(row.m) * g.N + n);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
+    }
+    uint16_t* o16 = nullptr;
+    if (EPI == EPI_QKV) {
+        const int Dm = g.H * 64;
+        const int which = n / Dm;
+        const int rem = n - which * Dm;
+        o16 = reinterpret_cast<uint16_t*>(g.out16) + which * g.qkv_stride + row.qkv_row +
+              static_cast<long long>(rem >> 6) * g.L * 64 + (rem & 63);
+    } else if (g.out16 != nullptr) {
+        o16 = reinterpret_cast<uint16_t*>(g.out16) + static_cast<long long>(row.m) * g.N + n;
+    }
+    if (o16 != nullptr) {
+        uint4* op = reinterpret_cast<uint4*>(o16);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            uint4 u;
+            u.x = pack16(g.opd, v[8 * j], v[8 * j + 1]);
+            u.y = pack16(g.opd, v[8 * j + 2], v[8 * j + 3]);
+            u.z = pack16(g.opd, v[8 * j + 4], v[8 * j + 5]);
+            u.w = pack16(g.opd, v[8 * j + 6], v[8 * j + 7]);
+            op[j] = u;
+        }
+    }
+}
+
+}  // namespace usp

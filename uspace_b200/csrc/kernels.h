@@ -38,6 +38,7 @@ struct GemmMaps {
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
 int gemm_block_n(int N);  // 256 or 128
+int gemm_weight_box_rows();  // rows of the TMA box the W[N,K] tensor map must use (128)
 cudaError_t launch_gemm(int epi, const GemmMaps& maps, const GemmArgs& args, int num_sms, cudaStream_t s);
 
 // ---- attention: softmax(Q K^T / sqrt(64)) V per (sample, head) ---------------------------------
