@@ -1,0 +1,93 @@
+"""Turn gpurun_out ncu artefacts into small tracked summaries under profiles/.
+
+    python profiles/summarize.py <tag>      # e.g. r01 -> reads gpurun_out/<tag>_launches.csv, <tag>_prof_*.ncu-rep
+"""
+import collections
+import csv
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OUT = os.path.join(ROOT, "profiles")
+GO = os.path.join(ROOT, "gpurun_out")
+
+RAW_METRICS = [
+    "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+    "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+    "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
+    "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "sm__cycles_elapsed.avg",
+    "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "lts__t_bytes.sum",
+]
+
+
+def launches(tag):
+    p = os.path.join(GO, f"{tag}_launches.csv")
+    if not os.path.exists(p):
+        return
+    rows = list(csv.reader(open(p)))
+    hi = [i for i, r in enumerate(rows) if "Kernel Name" in r][0]
+    h = rows[hi]
+    kn, mv = h.index("Kernel Name"), h.index("Metric Value")
+    agg = collections.OrderedDict()
+    for r in rows[hi + 1:]:
+        if len(r) > mv:
+            agg.setdefault(r[kn].split("(")[0].replace("void ", "").replace("usp::<unnamed>::", "")[-48:], []).append(
+                float(r[mv].replace(",", "")))
+    tot = sum(sum(v) for v in agg.values())
+    with open(os.path.join(OUT, f"{tag}_launch_list.md"), "w") as f:
+        f.write(f"# {tag}: ncu launch list of ONE U-ViT-L velocity evaluation at batch 64 "
+                "(`--metrics gpu__time_duration.sum --clock-control none`, cold-cache, serialised: compare shares)\n\n")
+        f.write("| kernel | launches | total us | avg us | share |\n|---|---:|---:|---:|---:|\n")
+        for k, v in agg.items():
+            f.write(f"| `{k}` | {len(v)} | {sum(v) / 1e3:.1f} | {sum(v) / len(v) / 1e3:.1f} | {100 * sum(v) / tot:.1f} % |\n")
+        f.write(f"| **total** | {sum(len(v) for v in agg.values())} | {tot / 1e3:.1f} | | |\n")
+
+
+def rep(tag, name):
+    p = os.path.join(GO, f"{tag}_prof_{name}.ncu-rep")
+    if not os.path.exists(p):
+        return
+    raw = subprocess.run(["ncu", "-i", p, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    h = rows[0]
+    with open(os.path.join(OUT, f"{tag}_ncu_{name}.md"), "w") as f:
+        f.write(f"# {tag}: `ncu --set full --clock-control none` capture, {name} kernel(s), U-ViT-L batch 64\n\n")
+        for r in rows[2:]:
+            f.write(f"## {r[h.index('Kernel Name')][:100]}\n\n| metric | value | unit |\n|---|---:|---|\n")
+            for m in RAW_METRICS:
+                if m in h:
+                    i = h.index(m)
+                    f.write(f"| {m} | {r[i]} | {rows[1][i]} |\n")
+            f.write("\n")
+    src = subprocess.run(["ncu", "-i", p, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+    ks, cur = [], None
+    for r in csv.reader(src.splitlines()):
+        if r and r[0] == "Kernel Name":
+            cur = dict(name=r[1], rows=[])
+            ks.append(cur)
+        elif r and r[0] == "Address" and cur is not None:
+            cur["hdr"] = r
+        elif cur is not None and len(r) > 10:
+            cur["rows"].append(r)
+    with open(os.path.join(OUT, f"{tag}_ncu_{name}.md"), "a") as f:
+        for k in ks:
+            if "hdr" not in k:
+                continue
+            h2 = k["hdr"]
+            si = h2.index("# Samples")
+            tot = sum(int(r[si]) for r in k["rows"]) or 1
+            sc = [i for i, c in enumerate(h2) if c.startswith("stall_") and "Not Issued" not in c]
+            f.write(f"### top stall sites: {k['name'][:90]}\n\n| % samples | SASS | top stall reasons |\n|---:|---|---|\n")
+            for r in sorted(k["rows"], key=lambda r: -int(r[si]))[:10]:
+                st = sorted(((h2[i][6:], int(r[i])) for i in sc if int(r[i]) > 0), key=lambda x: -x[1])[:3]
+                f.write(f"| {100 * int(r[si]) / tot:.1f} | `{r[1].strip()[:70]}` | {st} |\n")
+            f.write("\n")
+
+
+if __name__ == "__main__":
+    tag = sys.argv[1]
+    launches(tag)
+    for n in ("gemm", "attn"):
+        rep(tag, n)
