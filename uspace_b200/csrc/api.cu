@@ -57,16 +57,30 @@ bool make_map_2d(CUtensorMap* m, const void* ptr, long long rows, long long cols
     return r == CUDA_SUCCESS;
 }
 // 16-bit [planes, rows, 64] tensor (per-head Q/K/V), box = [1, 128, 64]
-bool make_map_qkv(CUtensorMap* m, const void* ptr, long long planes, long long rows, int opd) {
+bool make_map_qkv(CUtensorMap* m, const void* ptr, long long planes, long long rows, int opd, int box_rows) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) return false;
     cuuint64_t dims[3] = {64, static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(planes)};
     cuuint64_t strides[2] = {128, static_cast<cuuint64_t>(rows) * 128};
-    cuuint32_t box[3] = {64, 128, 1};
+    cuuint32_t box[3] = {64, static_cast<cuuint32_t>(box_rows), 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = fn(m, opd == OPD_FP16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3,
                     const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+// fp32 row-major [rows, cols] tensor, box = [128 rows, 32 cols] (128 B), 128B swizzle: GEMM epilogue staging
+bool make_map_f32(CUtensorMap* m, const void* ptr, long long rows, long long cols) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return false;
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+    cuuint64_t strides[1] = {static_cast<cuuint64_t>(cols) * 4};
+    cuuint32_t box[2] = {32, 128};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS;
 }
@@ -260,9 +274,9 @@ int get_plan(usp_handle* h, int B, Plan** out) {
     for (int i = 0; i < h->n_in; ++i) ok &= make_map_2d(&p->m_skip[i], p->skip16[i], M, D, GEMM_BM, opd);
     const long long BH = static_cast<long long>(B) * h->cfg.num_heads;
     char* q = static_cast<char*>(p->qkv16);
-    ok &= make_map_qkv(&p->m_q, q, BH, L, opd);
-    ok &= make_map_qkv(&p->m_k, q + M * D * 2, BH, L, opd);
-    ok &= make_map_qkv(&p->m_v, q + 2 * M * D * 2, BH, L, opd);
+    ok &= make_map_qkv(&p->m_q, q, BH, L, opd, 128);
+    ok &= make_map_qkv(&p->m_k, q + M * D * 2, BH, L, opd, attn_kv_box_rows(L));
+    ok &= make_map_qkv(&p->m_v, q + 2 * M * D * 2, BH, L, opd, attn_kv_box_rows(L));
     if (nctx) ok &= make_map_2d(&p->m_ctx, p->ctx16, static_cast<long long>(B) * nctx, cdim, GEMM_BM, opd);
     if (!ok) {
         cudaFree(p->slab);
@@ -313,6 +327,11 @@ int run_gemm(usp_handle* h, int epi, const CUtensorMap& a0, const CUtensorMap* a
     maps.a0 = a0;
     maps.a1 = a1 ? *a1 : a0;
     maps.b = w.map;
+    if (out32 != nullptr) {
+        maps.has_f32 = make_map_f32(&maps.o32, out32, M, N);
+        if (resid != nullptr) maps.has_f32 = maps.has_f32 && make_map_f32(&maps.r32, resid, M, N);
+        else maps.r32 = maps.o32;
+    }
     GemmArgs g;
     memset(&g, 0, sizeof(g));
     g.M = M; g.N = N; g.K = K; g.K0 = K0;
@@ -379,7 +398,7 @@ int enqueue_forward(usp_handle* h, Plan* p, const FwdIO& io, cudaStream_t s) {
         if (rc) return rc;
         AttnArgs aa;
         memset(&aa, 0, sizeof(aa));
-        aa.B = B; aa.H = h->cfg.num_heads; aa.L = L; aa.D = D; aa.opd = opd; aa.out16 = p->a16;
+        aa.B = B; aa.H = h->cfg.num_heads; aa.L = L; aa.D = D; aa.opd = opd; aa.out16 = p->a16; aa.num_sms = h->num_sms;
         prof_mark(h, 3, s);
         KTRY(launch_attention(p->m_q, p->m_k, p->m_v, aa, s));
         prof_mark(h, 4, s);
@@ -896,6 +915,11 @@ int usp_op_gemm(int epilogue, const void* a16, const void* a16_second, const voi
     if (a16_second) ok &= make_map_2d(&maps.a1, a16_second, M, K - K0, GEMM_BM, operand_dtype);
     else maps.a1 = maps.a0;
     ok &= make_map_2d(&maps.b, w16, N, K, gemm_weight_box_rows(), operand_dtype);
+    if (out32 != nullptr) {
+        maps.has_f32 = make_map_f32(&maps.o32, out32, M, N);
+        if (resid != nullptr) maps.has_f32 = maps.has_f32 && make_map_f32(&maps.r32, resid, M, N);
+        else maps.r32 = maps.o32;
+    }
     if (!ok) return fail(nullptr, USP_ERR_CUDA, "cuTensorMapEncodeTiled failed");
     GemmArgs g;
     memset(&g, 0, sizeof(g));
@@ -917,12 +941,18 @@ int usp_op_attention(const void* q16, const void* k16, const void* v16, void* ou
     if (e != cudaSuccess) return op_fail("attention_configure", e);
     CUtensorMap mq, mk, mv;
     const long long BH = static_cast<long long>(B) * H;
-    bool ok = make_map_qkv(&mq, q16, BH, L, operand_dtype) && make_map_qkv(&mk, k16, BH, L, operand_dtype) &&
-              make_map_qkv(&mv, v16, BH, L, operand_dtype);
+    bool ok = make_map_qkv(&mq, q16, BH, L, operand_dtype, 128) && make_map_qkv(&mk, k16, BH, L, operand_dtype, attn_kv_box_rows(L)) &&
+              make_map_qkv(&mv, v16, BH, L, operand_dtype, attn_kv_box_rows(L));
     if (!ok) return fail(nullptr, USP_ERR_CUDA, "cuTensorMapEncodeTiled failed");
     AttnArgs a;
     memset(&a, 0, sizeof(a));
     a.B = B; a.H = H; a.L = L; a.D = H * 64; a.opd = operand_dtype; a.out16 = out16;
+    {
+        int dev = 0;
+        a.num_sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&a.num_sms, cudaDevAttrMultiProcessorCount, dev);
+    }
     e = launch_attention(mq, mk, mv, a, static_cast<cudaStream_t>(stream));
     return e == cudaSuccess ? USP_OK : op_fail("launch_attention", e);
 }

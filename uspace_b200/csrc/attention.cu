@@ -12,6 +12,8 @@
 //                      taking half of the key columns and half of the output columns): row max, exp2, row sum in fp32,
 //                      write un-normalised P as 16-bit into the 128B-swizzled K-major smem layout,
 //                      finally scale O by 1/sum and store heads-merged [B*L, H*64].
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -68,7 +70,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const int bh = blockIdx.y;
     const int L = a.L;
     const int L16 = (L + 15) & ~15;
-    const int nkc = (L + 127) / 128;
+    const int hrows = L16 / 2;           // K / V arrive as two TMA boxes of L16/2 rows each
 
     if (threadIdx.x == 0) {
         mbar_init(&bar_qk, 1);
@@ -90,11 +92,13 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             tma_prefetch_desc(&tmQ);
             tma_prefetch_desc(&tmK);
             tma_prefetch_desc(&tmV);
-            mbar_expect_tx(&bar_qk, (1 + nkc) * TILE16K);
+            mbar_expect_tx(&bar_qk, TILE16K + L16 * 128);
             tma_load_3d(&tmQ, &bar_qk, smem + SQ_OFF, 0, qt * QT, bh);
-            for (int c = 0; c < nkc; ++c) tma_load_3d(&tmK, &bar_qk, smem + SK_OFF + c * TILE16K, 0, c * 128, bh);
-            mbar_expect_tx(&bar_v, nkc * TILE16K);
-            for (int c = 0; c < nkc; ++c) tma_load_3d(&tmV, &bar_v, smem + SV_OFF + c * TILE16K, 0, c * 128, bh);
+            for (int c = 0; c < 2; ++c)
+                tma_load_3d(&tmK, &bar_qk, smem + SK_OFF + c * hrows * 128, 0, c * hrows, bh);
+            mbar_expect_tx(&bar_v, L16 * 128);
+            for (int c = 0; c < 2; ++c)
+                tma_load_3d(&tmV, &bar_v, smem + SV_OFF + c * hrows * 128, 0, c * hrows, bh);
 
             const int fmt = a.opd == OPD_FP16 ? 0 : 1;
             // ---- S = Q K^T ----
@@ -240,17 +244,34 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 
 }  // namespace
 
+cudaError_t attention2_configure();
+bool attention2_supported(const AttnArgs& a);
+cudaError_t launch_attention2(const CUtensorMap& q, const CUtensorMap& k, const CUtensorMap& v, const AttnArgs& a,
+                              int num_sms, cudaStream_t s);
+
 cudaError_t attention_configure() {
     static bool done = false;
     if (done) return cudaSuccess;
     cudaError_t e = cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_SMEM);
+    if (e == cudaSuccess) e = attention2_configure();
     if (e == cudaSuccess) done = true;
     return e;
+}
+
+// USP_ATTN_V1=1 forces the one-CTA-per-tile kernel (A/B comparison, debugging)
+static bool force_v1() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("USP_ATTN_V1");
+        v = (e && e[0] == '1') ? 1 : 0;
+    }
+    return v == 1;
 }
 
 cudaError_t launch_attention(const CUtensorMap& q, const CUtensorMap& k, const CUtensorMap& v, const AttnArgs& a,
                              cudaStream_t s) {
     if (a.L < 1 || a.L > ATTN_MAX_L || a.D != a.H * HD) return cudaErrorInvalidValue;
+    if (!force_v1() && attention2_supported(a)) return launch_attention2(q, k, v, a, a.num_sms, s);
     dim3 grid((a.L + QT - 1) / QT, a.B * a.H);
     attention_kernel<<<grid, ATTN_THREADS, ATTN_SMEM, s>>>(q, k, v, a);
     return cudaGetLastError();

@@ -1,0 +1,334 @@
+// Persistent whole-row attention (v2): one CTA per SM loops over (sample, head) items.
+//
+// Same math as attention.cu (softmax(Q K^T / 8) V, L <= 352, head_dim 64) with the three costs the round-1
+// ncu capture showed removed:
+//   * K and V of an item are TMA-loaded ONCE (two boxes of L16/2 rows, 128B swizzle) and reused by all of its query tiles,
+//     and the NEXT item's K/V are prefetched into the other shared-memory buffer while this item computes
+//     (v1 reloaded K/V per 128-query tile and exposed the full load latency in every CTA);
+//   * P never goes through shared memory: the softmax warps write 16-bit P straight into TMEM (tcgen05.st) and
+//     O = P V runs as a TMEM-A-operand UMMA (`tcgen05.mma [d], [a_tmem], b_desc`), V consumed MN-major from its
+//     natural [L,64] layout;
+//   * TMEM is allocated once per CTA, barriers are initialised once, the control warp issues from warp-uniform code.
+//
+// TMEM columns (512): S fp32 [0, L16) | O fp32 [L16, L16+64) | P words of column-part 1 [L16+64, ...).
+// The P words of column-part 0 alias the S columns that the same thread has already consumed (chunk c's 16 packed
+// words land in S columns [16c, 16c+16), i.e. inside chunk c/2 <= c of the same thread), so no cross-thread hazard.
+//
+// Per query tile: S-MMA -> (8 warps) max / exp2 / sum, P -> TMEM -> PV-MMA -> O * 1/sum -> global.
+// S-MMA of tile g+1 overlaps the O read-out of tile g (disjoint TMEM columns).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace usp {
+
+namespace {
+
+constexpr int HD = 64;
+constexpr int QT = 128;
+constexpr int THREADS = 288;            // 8 softmax warps + 1 control warp
+constexpr int CTRL_WARP = 8;
+constexpr int QTILE_BYTES = QT * HD * 2;   // 16 KiB
+constexpr int MAX_L2 = 352;
+constexpr int TMEM_COLS = 512;
+
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// A operand from TMEM (M=128 lanes x 16 K-elements = 8 packed 32-bit columns), B from smem descriptor
+__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+          "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// V rows as the B operand in MN-major form (see attention.cu): 64 head-dim elements contiguous per key row
+__device__ __forceinline__ uint64_t umma_desc_v_mn(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((saddr & 0x3FFFF) >> 4);
+    d |= static_cast<uint64_t>(1) << 16;
+    d |= static_cast<uint64_t>(1024 >> 4) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(2) << 61;
+    return d;
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
+attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                  const __grid_constant__ CUtensorMap tmV, const AttnArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+    __shared__ __align__(8) uint64_t q_full[2], kv_full[2], bar_s, bar_p, bar_o;
+    __shared__ uint32_t tmem_base_smem;
+    __shared__ float s_max[2][QT], s_sum[2][QT];
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int L = a.L;
+    const int L16 = (L + 15) & ~15;
+    const int hrows = L16 / 2;              // K / V arrive as two TMA boxes of L16/2 rows (multiple of 8)
+    const int kv_bytes = L16 * 128;
+    const int n_qt = (L + QT - 1) / QT;
+    const int n_items = a.B * a.H;
+    const int nch = (L + 31) / 32;          // 32-column score chunks
+    const int n0 = (nch + 1) / 2;           // chunks handled by column-part 0
+    const int S_COL = 0, O_COL = L16, P1_COL = L16 + 64;
+
+    // smem: Q[2] | K[2] | V[2]
+    uint8_t* sQ = smem;
+    uint8_t* sK = smem + 2 * QTILE_BYTES;
+    uint8_t* sV = sK + 2 * kv_bytes;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&q_full[i], 1);
+            mbar_init(&kv_full[i], 1);
+        }
+        mbar_init(&bar_s, 1);
+        mbar_init(&bar_p, 256);
+        mbar_init(&bar_o, 1);
+        fence_barrier_init();
+    }
+    __syncwarp();
+    if (warp == CTRL_WARP) tmem_alloc<TMEM_COLS>(&tmem_base_smem);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_smem;
+
+    if (warp == CTRL_WARP) {
+        // ===================== control warp: TMA + MMA issue (warp-uniform, one elected lane acts) ============
+        const int fmt = a.opd == OPD_FP16 ? 0 : 1;
+        const uint32_t idesc_o = umma_idesc(fmt, QT, HD, 0, 1);
+        if (lane == 0) {
+            tma_prefetch_desc(&tmQ);
+            tma_prefetch_desc(&tmK);
+            tma_prefetch_desc(&tmV);
+        }
+        __syncwarp();
+        // prologue: first item's K/V and first Q tile
+        if (static_cast<int>(blockIdx.x) < n_items) {
+            if (elect_one()) {
+                const int bh = blockIdx.x;
+                mbar_expect_tx(&kv_full[0], 2 * kv_bytes);
+                for (int c = 0; c < 2; ++c) {
+                    tma_load_3d(&tmK, &kv_full[0], sK + c * hrows * 128, 0, c * hrows, bh);
+                    tma_load_3d(&tmV, &kv_full[0], sV + c * hrows * 128, 0, c * hrows, bh);
+                }
+                mbar_expect_tx(&q_full[0], QTILE_BYTES);
+                tma_load_3d(&tmQ, &q_full[0], sQ, 0, 0, bh);
+            }
+            __syncwarp();
+        }
+        int g = 0;  // global tile counter of this CTA
+        int n = 0;  // item counter of this CTA
+        for (int bh = blockIdx.x; bh < n_items; bh += gridDim.x, ++n) {
+            const int kb = n & 1;
+            for (int t = 0; t < n_qt; ++t, ++g) {
+                // previous tile's PV finished: S / P columns and (at t == 0) the other K/V buffer are free
+                if (g > 0) mbar_wait(&bar_o, (g - 1) & 1);
+                if (elect_one()) {
+                    if (t == 0 && bh + static_cast<int>(gridDim.x) < n_items) {   // prefetch next item's K/V
+                        const int nb = kb ^ 1;
+                        const int bh2 = bh + gridDim.x;
+                        mbar_expect_tx(&kv_full[nb], 2 * kv_bytes);
+                        for (int c = 0; c < 2; ++c) {
+                            tma_load_3d(&tmK, &kv_full[nb], sK + nb * kv_bytes + c * hrows * 128, 0, c * hrows, bh2);
+                            tma_load_3d(&tmV, &kv_full[nb], sV + nb * kv_bytes + c * hrows * 128, 0, c * hrows, bh2);
+                        }
+                    }
+                    // next Q tile (this item's next tile, or the next item's first tile)
+                    const bool last_t = (t + 1 == n_qt);
+                    const int bhq = last_t ? bh + static_cast<int>(gridDim.x) : bh;
+                    if (bhq < n_items) {
+                        const int qb = (g + 1) & 1;
+                        mbar_expect_tx(&q_full[qb], QTILE_BYTES);
+                        tma_load_3d(&tmQ, &q_full[qb], sQ + qb * QTILE_BYTES, 0, last_t ? 0 : (t + 1) * QT, bhq);
+                    }
+                }
+                __syncwarp();
+                mbar_wait(&q_full[g & 1], (g >> 1) & 1);
+                if (t == 0) mbar_wait(&kv_full[kb], (n >> 1) & 1);
+                tc_fence_after();
+                // ---- S = Q K^T ----
+                const uint64_t qdesc = umma_desc_sw128(smem_u32(sQ + (g & 1) * QTILE_BYTES));
+                const uint32_t kbase = smem_u32(sK + kb * kv_bytes);
+                if (elect_one()) {
+                    for (int c0 = 0; c0 < L16; c0 += 256) {
+                        const int nn = (L16 - c0) < 256 ? (L16 - c0) : 256;
+                        const uint32_t idesc = umma_idesc(fmt, QT, nn, 0, 0);
+                        const uint64_t kdesc = umma_desc_sw128(kbase + c0 * 128);
+#pragma unroll
+                        for (int k = 0; k < HD / 16; ++k)
+                            umma_f16(tmem_base + S_COL + c0, qdesc + (k * 2), kdesc + (k * 2), idesc, k != 0);
+                    }
+                    umma_commit(&bar_s);
+                }
+                __syncwarp();
+                // ---- O = P V (A = P in TMEM) ----
+                mbar_wait(&bar_p, g & 1);
+                tc_fence_after();
+                const uint32_t vbase = smem_u32(sV + kb * kv_bytes);
+                if (elect_one()) {
+                    const int nks = L16 / 16;
+                    for (int kk = 0; kk < nks; ++kk) {
+                        const int c = kk >> 1;
+                        const uint32_t pcol = (c < n0 ? S_COL + 16 * c : P1_COL + 16 * (c - n0)) + 8 * (kk & 1);
+                        const uint64_t vdesc = umma_desc_v_mn(vbase + kk * 16 * 128);
+                        umma_f16_ts(tmem_base + O_COL, tmem_base + pcol, vdesc, idesc_o, kk != 0);
+                    }
+                    umma_commit(&bar_o);
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // ===================== softmax / output warps (two threads per query row) =====================
+        const int lg = warp & 3;
+        const int part = warp >> 2;
+        const int row = lg * 32 + lane;
+        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(lg * 32) << 16);
+        const float c2 = 0.125f * 1.44269504088896340736f;  // hd^-0.5 * log2(e)
+        const int c_lo = part == 0 ? 0 : n0;
+        const int c_hi = part == 0 ? n0 : nch;
+        int g = 0;
+        for (int bh = blockIdx.x; bh < n_items; bh += gridDim.x) {
+            for (int t = 0; t < n_qt; ++t, ++g) {
+                const int l = t * QT + row;
+                const bool row_ok = l < L;
+                const bool warp_ok = __any_sync(0xffffffffu, row_ok);   // tcgen05.ld/st are warp-collective
+
+                mbar_wait(&bar_s, g & 1);
+                tc_fence_after();
+                float mx = -INFINITY;
+                if (warp_ok) {
+                    for (int c = c_lo; c < c_hi; ++c) {
+                        uint32_t r[32];
+                        tmem_ld32(t_row + S_COL + c * 32, r);
+                        tmem_ld_wait();
+                        if (c * 32 + 32 <= L) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(r[j]));
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (c * 32 + j < L) mx = fmaxf(mx, __uint_as_float(r[j]));
+                        }
+                    }
+                }
+                s_max[part][row] = mx;
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                mx = fmaxf(s_max[0][row], s_max[1][row]);
+                const float mxs = mx * c2;
+                float sum = 0.f;
+                if (warp_ok) {
+                    for (int c = c_lo; c < c_hi; ++c) {
+                        uint32_t r[32];
+                        tmem_ld32(t_row + S_COL + c * 32, r);
+                        tmem_ld_wait();
+                        float p[32];
+                        if (c * 32 + 32 <= L) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) p[j] = ex2_approx(fmaf(__uint_as_float(r[j]), c2, -mxs));
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                p[j] = (c * 32 + j < L) ? ex2_approx(fmaf(__uint_as_float(r[j]), c2, -mxs)) : 0.f;
+                        }
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) sum += p[j];
+                        uint32_t w[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            w[j] = a.opd == OPD_FP16 ? Op16<OPD_FP16>::pack(p[2 * j], p[2 * j + 1])
+                                                     : Op16<OPD_BF16>::pack(p[2 * j], p[2 * j + 1]);
+                        const uint32_t pcol = c < n0 ? S_COL + 16 * c : P1_COL + 16 * (c - n0);
+                        tmem_st16(t_row + pcol, w);
+                    }
+                    tmem_st_wait();
+                }
+                s_sum[part][row] = sum;
+                tc_fence_before();
+                mbar_arrive(&bar_p);
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                const float inv = 1.0f / (s_sum[0][row] + s_sum[1][row]);
+
+                mbar_wait(&bar_o, g & 1);
+                tc_fence_after();
+                if (warp_ok) {
+                    uint32_t r[32];
+                    tmem_ld32(t_row + O_COL + part * 32, r);
+                    tmem_ld_wait();
+                    uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(a.out16) +
+                                                         (static_cast<long long>(bh / a.H) * L + l) * a.D +
+                                                         (bh % a.H) * HD + part * 32);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        float v[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[8 * j + e]) * inv;
+                        uint4 u;
+                        if (a.opd == OPD_FP16) {
+                            u.x = Op16<OPD_FP16>::pack(v[0], v[1]); u.y = Op16<OPD_FP16>::pack(v[2], v[3]);
+                            u.z = Op16<OPD_FP16>::pack(v[4], v[5]); u.w = Op16<OPD_FP16>::pack(v[6], v[7]);
+                        } else {
+                            u.x = Op16<OPD_BF16>::pack(v[0], v[1]); u.y = Op16<OPD_BF16>::pack(v[2], v[3]);
+                            u.z = Op16<OPD_BF16>::pack(v[4], v[5]); u.w = Op16<OPD_BF16>::pack(v[6], v[7]);
+                        }
+                        if (row_ok) op[j] = u;
+                    }
+                }
+                // the O read-out above must retire before the next tile's PV-MMA overwrites O: that MMA is only
+                // issued after this thread's next bar_p arrival, which follows in program order
+                tc_fence_before();
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == CTRL_WARP) tmem_dealloc<TMEM_COLS>(tmem_base);
+}
+
+int smem_bytes_for(int L) {
+    const int L16 = (L + 15) & ~15;
+    return 2 * QTILE_BYTES + 4 * L16 * 128 + 1024;
+}
+
+}  // namespace
+
+cudaError_t attention2_configure() {
+    return cudaFuncSetAttribute(attention2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes_for(MAX_L2));
+}
+
+bool attention2_supported(const AttnArgs& a) {
+    if (a.L > MAX_L2) return false;
+    const int L16 = (a.L + 15) & ~15;
+    const int nch = (a.L + 31) / 32;
+    return L16 + 64 + 16 * (nch - (nch + 1) / 2) <= TMEM_COLS;
+}
+
+cudaError_t launch_attention2(const CUtensorMap& q, const CUtensorMap& k, const CUtensorMap& v, const AttnArgs& a,
+                              int num_sms, cudaStream_t s) {
+    const int items = a.B * a.H;
+    const int grid = items < num_sms ? items : num_sms;
+    attention2_kernel<<<grid, THREADS, smem_bytes_for(a.L), s>>>(q, k, v, a);
+    return cudaGetLastError();
+}
+
+}  // namespace usp

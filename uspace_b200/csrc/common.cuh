@@ -56,6 +56,14 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
+// One lane of a fully converged warp.  Keeping the surrounding loop warp-uniform and electing only around the
+// single-thread instructions (TMA / tcgen05.mma / commit) lets ptxas keep descriptors and addresses in uniform
+// registers; an `if (lane == 0)` around the whole loop forces an R2UR waterfall loop per instruction instead.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P1;\n\telect.sync _|P1, 0xffffffff;\n\tselp.u32 %0, 1, 0, P1;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 
 // ----------------------------------------------------------------------------------------------
 // mbarrier

@@ -61,6 +61,17 @@ __global__ void __launch_bounds__(256) embed_kernel(const EmbedArgs a) {
     for (int d = threadIdx.x; d < D; d += blockDim.x) {
         const float* wrow = a.w + static_cast<long long>(d) * P;
         const float bias = a.bias[d];
+        // P == 16 (patch 2, 4 channels: every reference config): keep this row of W in registers, read once as
+        // 4 x 128-bit (scalar per-token re-reads cost 32 L1 sectors per warp instruction and dominated the kernel)
+        float wr[16];
+        const bool p16 = (P == 16);
+        if (p16) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float4 w4 = __ldg(reinterpret_cast<const float4*>(wrow) + q);
+                wr[4 * q] = w4.x; wr[4 * q + 1] = w4.y; wr[4 * q + 2] = w4.z; wr[4 * q + 3] = w4.w;
+            }
+        }
         for (int l = l0; l < l1; ++l) {
             float* out = a.out32 + (static_cast<long long>(b) * a.L + l) * D;
             const float pos = a.pos[static_cast<long long>(l) * D + d];
@@ -77,7 +88,12 @@ __global__ void __launch_bounds__(256) embed_kernel(const EmbedArgs a) {
                 v = a.ctxemb[(static_cast<long long>(b) * a.n_ctx + (l - t_tok - 1)) * D + d];
             } else {
                 float acc = 0.f;
-                for (int f = 0; f < P; ++f) acc = fmaf(__ldg(wrow + f), feat[l - l0][f], acc);
+                if (p16) {
+#pragma unroll
+                    for (int f = 0; f < 16; ++f) acc = fmaf(wr[f], feat[l - l0][f], acc);
+                } else {
+                    for (int f = 0; f < P; ++f) acc = fmaf(__ldg(wrow + f), feat[l - l0][f], acc);
+                }
                 v = acc + bias;
             }
             out[d] = v + pos;

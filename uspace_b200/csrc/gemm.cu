@@ -83,8 +83,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
     const uint32_t tmem_base = tmem_base_smem;
 
     if (warp == 0) {
-        // ===================== TMA producer =====================
-        if (lane == 0) {
+        // ===================== TMA producer (warp-uniform loop, one elected lane issues) =====================
+        {
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -94,13 +94,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
                     uint8_t* sb = sa + A_TILE_BYTES;
-                    mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-                    if (kb < nkb0)
-                        tma_load_2d(&tmA0, &full_bar[stage], sa, kb * BK, m0);
-                    else
-                        tma_load_2d(&tmA1, &full_bar[stage], sa, (kb - nkb0) * BK, m0);
-                    tma_load_2d(&tmB, &full_bar[stage], sb, kb * BK, n0);
-                    if (BN == 256) tma_load_2d(&tmB, &full_bar[stage], sb + 128 * BK * 2, kb * BK, n0 + 128);
+                    if (elect_one()) {
+                        mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+                        if (kb < nkb0)
+                            tma_load_2d(&tmA0, &full_bar[stage], sa, kb * BK, m0);
+                        else
+                            tma_load_2d(&tmA1, &full_bar[stage], sa, (kb - nkb0) * BK, m0);
+                        tma_load_2d(&tmB, &full_bar[stage], sb, kb * BK, n0);
+                        if (BN == 256) tma_load_2d(&tmB, &full_bar[stage], sb + 128 * BK * 2, kb * BK, n0 + 128);
+                    }
+                    __syncwarp();
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -108,7 +111,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
         __syncwarp();
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
+        {
             const uint32_t idesc = umma_idesc(g.opd == OPD_FP16 ? 0 : 1, BM, BN, 0, 0);
             int stage = 0;
             uint32_t phase = 0;
@@ -125,15 +128,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
                     const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
                     const uint64_t adesc = umma_desc_sw128(sa);
                     const uint64_t bdesc = umma_desc_sw128(sa + A_TILE_BYTES);
+                    if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k) {
-                        // advance 16 elements (32 B) along K inside the 128B swizzle atom
-                        umma_f16(d_tmem, adesc + (k * 2), bdesc + (k * 2), idesc, (kb | k) != 0);
+                        for (int k = 0; k < BK / 16; ++k) {
+                            // advance 16 elements (32 B) along K inside the 128B swizzle atom
+                            umma_f16(d_tmem, adesc + (k * 2), bdesc + (k * 2), idesc, (kb | k) != 0);
+                        }
+                        umma_commit(&empty_bar[stage]);  // smem slot is free once these MMAs retire
+                        if (kb == nkb - 1) umma_commit(&tmem_full_bar[as]);  // accumulator ready for the epilogue
                     }
-                    umma_commit(&empty_bar[stage]);  // smem slot is free once these MMAs retire
+                    __syncwarp();
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(&tmem_full_bar[as]);  // accumulator ready for the epilogue
             }
         }
         __syncwarp();
@@ -225,7 +231,7 @@ int gemm_block_n(int N) { return (N % 256 == 0) ? 256 : 128; }
 int gemm_weight_box_rows() { return 128; }
 
 cudaError_t gemm2_configure();
-bool gemm2_supported(const GemmArgs& a);
+bool gemm2_supported(int epi, const GemmMaps& maps, const GemmArgs& a);
 cudaError_t launch_gemm2(int epi, const GemmMaps& maps, const GemmArgs& a, int num_sms, cudaStream_t s);
 
 // USP_GEMM_1CTA=1 forces the single-CTA kernel (A/B comparison, debugging)
@@ -240,7 +246,7 @@ static bool force_1cta() {
 
 cudaError_t launch_gemm(int epi, const GemmMaps& maps, const GemmArgs& a, int num_sms, cudaStream_t s) {
     if (a.M <= 0 || a.N % 128 != 0 || a.K % BK != 0 || a.K0 % BK != 0 || a.K0 > a.K) return cudaErrorInvalidValue;
-    if (!force_1cta() && gemm2_supported(a)) return launch_gemm2(epi, maps, a, num_sms, s);
+    if (!force_1cta() && gemm2_supported(epi, maps, a)) return launch_gemm2(epi, maps, a, num_sms, s);
     if (gemm_block_n(a.N) == 256) return launch_bn<256>(epi, maps, a, num_sms, s);
     return launch_bn<128>(epi, maps, a, num_sms, s);
 }

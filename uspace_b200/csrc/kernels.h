@@ -32,6 +32,8 @@ struct GemmArgs {
 
 struct GemmMaps {
     CUtensorMap a0, a1, b;
+    CUtensorMap r32, o32;   // fp32 [M,N] residual-in / output maps (box 32 cols x 128 rows, 128B swizzle)
+    bool has_f32 = false;
 };
 
 // Box sizes the GEMM expects in its tensor maps.
@@ -46,10 +48,13 @@ struct AttnArgs {
     int B, H, L;       // head_dim fixed at 64
     int D;             // H*64 (row pitch of out16)
     int opd;
+    int num_sms;       // persistent grid size
     void* out16;       // [B*L, D] 16-bit, heads merged "(H hd)"
     const float* vscale;  // optional per-(sample,key) V-row scale [B, L] (p2p re-weighting), or nullptr
 };
 constexpr int ATTN_MAX_L = 384;
+// tensor maps: q = [planes, L, 64] with 128-row boxes; k, v = same tensors with attn_kv_box_rows(L)-row boxes
+inline int attn_kv_box_rows(int L) { return ((L + 15) & ~15) / 2; }
 cudaError_t launch_attention(const CUtensorMap& q, const CUtensorMap& k, const CUtensorMap& v,
                              const AttnArgs& args, cudaStream_t s);
 
