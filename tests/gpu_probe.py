@@ -218,6 +218,39 @@ def sec_prof(lib, opd):
         del m, eng
 
 
+def sec_gemmperf(lib, opd):
+    """Stand-alone timing of the five U-ViT-L GEMM shapes (M = 64*257), 20 back-to-back launches each."""
+    td = TD[opd]
+    M, D = 16448, 1024
+    shapes = [("qkv", 3 * D, D, D), ("bias_resid", D, D, D), ("bias_gelu", 4 * D, D, D),
+              ("bias_resid", D, 4 * D, 4 * D), ("bias_f32", D, 2 * D, D)]
+    s = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for epi, N, K, K0 in shapes:
+        a0 = torch.randn(M, K0, device=dev).to(td)
+        a1 = torch.randn(M, K - K0, device=dev).to(td) if K0 < K else None
+        w = (torch.randn(N, K, device=dev) * 0.05).to(td)
+        bias = torch.randn(N, device=dev)
+        x32 = torch.randn(M, N, device=dev) if epi in ("bias_resid", "bias_f32") else None
+        o16 = torch.empty(M, N, device=dev, dtype=td) if epi in ("qkv", "bias_gelu", "bias_resid") else None
+        H = D // 64 if epi == "qkv" else 1
+
+        def run():
+            return lib.usp_op_gemm(_lib.EPI[epi], P(a0), P(a1), P(w), None if epi == "qkv" else P(bias),
+                                   P(x32) if epi == "bias_resid" else None, P(x32), P(o16), M, N, K, K0, 257, H,
+                                   _lib.OPERAND[opd], s)
+        for _ in range(3):
+            rc = run()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+        e0.record()
+        for _ in range(20):
+            run()
+        e1.record()
+        torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) / 20 * 1e3
+        print(f"gemmperf {epi:10s} N={N} K={K}: rc={rc} {us:7.1f} us  {2.0 * M * N * K / us / 1e6:7.1f} TFLOP/s", flush=True)
+
+
 def sec_one(lib, opd):
     """Two eager velocity evaluations of U-ViT-L at batch 64 (profile the second one under ncu)."""
     m = build(CFG_L, opd).to(dev)

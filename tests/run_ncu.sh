@@ -1,16 +1,11 @@
 #!/bin/bash
-# Developer GPU session (run under gpurun): tests, smoke, bench, ncu launch list + full captures.
+# ncu captures only (run under gpurun): R=tag bash tests/run_ncu.sh
 mkdir -p gpurun_out
-R=${R:-r01}
-(timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -15) > gpurun_out/${R}_pytest_gpu.log
-(timeout 300 python __graft_entry__.py smoke 2>&1 | tail -3) > gpurun_out/${R}_smoke.log
-(timeout 600 python bench.py 2>&1 | tail -1) > gpurun_out/${R}_bench.json
-if [ "${NCU:-1}" = "1" ]; then
+R=${R:-ncu}
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 160 -c 160 --csv \
     --log-file gpurun_out/${R}_launches.csv python tests/gpu_probe.py one > gpurun_out/${R}_ncu_launch.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm2_kernel -s 94 -c 5 \
     -o gpurun_out/${R}_prof_gemm -f python tests/gpu_probe.py one > gpurun_out/${R}_ncu_gemm.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:attention2_kernel -s 21 -c 1 \
     -o gpurun_out/${R}_prof_attn -f python tests/gpu_probe.py one > gpurun_out/${R}_ncu_attn.log 2>&1
-fi
-cat gpurun_out/${R}_pytest_gpu.log gpurun_out/${R}_smoke.log gpurun_out/${R}_bench.json
+tail -3 gpurun_out/${R}_ncu_gemm.log gpurun_out/${R}_ncu_attn.log

@@ -159,8 +159,9 @@ def test_patch_gather_and_unpatchify_scatter_bit_exact(lib):
     w[:Pd, :Pd] = torch.eye(Pd)
     out = torch.full((B, 1 + n_patch, D), -1.0, device=dev())
     t = torch.zeros(B, device=dev())
-    _lib.check(lib.usp_op_patch_embed(P(x.to(dev())), P(t), P(w.to(dev())), P(torch.zeros(D, device=dev())),
-                                      P(torch.zeros(1 + n_patch, D, device=dev())), P(out), B, Cc, S, p, D, stream()))
+    xd, wd = x.to(dev()), w.to(dev())   # keep every device buffer alive across the asynchronous launch
+    bd, pd = torch.zeros(D, device=dev()), torch.zeros(1 + n_patch, D, device=dev())
+    _lib.check(lib.usp_op_patch_embed(P(xd), P(t), P(wd), P(bd), P(pd), P(out), B, Cc, S, p, D, stream()))
     torch.cuda.synchronize()
     want = x.reshape(B, -1)[:, O.patchify_index(Cc, S, p).reshape(-1)].reshape(B, n_patch, Pd)
     assert torch.equal(out[:, 1:, :Pd].cpu(), want)
@@ -171,14 +172,15 @@ def test_patch_gather_and_unpatchify_scatter_bit_exact(lib):
 
     pf = (torch.arange(B * n_patch * Pd, dtype=torch.float32) % 8191.0).reshape(B, n_patch, Pd)
     img = torch.zeros(B, Cc, S, S, device=dev())
-    _lib.check(lib.usp_op_unpatchify_conv(P(pf.to(dev())), None, None, P(img), B, Cc, S, p, stream()))
+    pfd = pf.to(dev())
+    _lib.check(lib.usp_op_unpatchify_conv(P(pfd), None, None, P(img), B, Cc, S, p, stream()))
     torch.cuda.synchronize()
     want = pf.reshape(B, -1)[:, O.unpatchify_index(Cc, S, p)].reshape(B, Cc, S, S)
     assert torch.equal(img.cpu(), want)
     cw = torch.randn(Cc, Cc, 3, 3)
     cb = torch.randn(Cc)
-    _lib.check(lib.usp_op_unpatchify_conv(P(pf.to(dev())), P(cw.to(dev())), P(cb.to(dev())), P(img), B, Cc, S, p,
-                                          stream()))
+    cwd, cbd = cw.to(dev()), cb.to(dev())
+    _lib.check(lib.usp_op_unpatchify_conv(P(pfd), P(cwd), P(cbd), P(img), B, Cc, S, p, stream()))
     torch.cuda.synchronize()
     want = torch.nn.functional.conv2d(want.double(), cw.double(), cb.double(), padding=1)
     assert rel(img, want) < 1e-6

@@ -25,7 +25,7 @@ namespace {
 
 constexpr int HD = 64;
 constexpr int QT = 128;
-constexpr int THREADS = 288;            // 8 softmax warps + 1 control warp
+constexpr int THREADS = 384;            // 2 softmax warpgroups + 1 control warpgroup (only its first warp works)
 constexpr int CTRL_WARP = 8;
 constexpr int QTILE_BYTES = QT * HD * 2;   // 16 KiB
 constexpr int MAX_L2 = 352;
@@ -67,6 +67,7 @@ __device__ __forceinline__ uint64_t umma_desc_v_mn(uint32_t saddr) {
     return d;
 }
 
+template <bool REGS>
 __global__ void __launch_bounds__(THREADS, 1)
 attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                   const __grid_constant__ CUtensorMap tmV, const AttnArgs a) {
@@ -111,7 +112,12 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
 
-    if (warp == CTRL_WARP) {
+    // Register re-balancing between warpgroups (setmaxnreg): the control warpgroup needs almost nothing, the softmax
+    // warpgroups keep a whole score-row share (160 fp32) in registers.  8*32*216 + 4*32*64 = 63488 <= 65536.
+    if (warp > CTRL_WARP) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");   // idle warps of the control warpgroup
+    } else if (warp == CTRL_WARP) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
         // ===================== control warp: TMA + MMA issue (warp-uniform, one elected lane acts) ============
         const int fmt = a.opd == OPD_FP16 ? 0 : 1;
         const uint32_t idesc_o = umma_idesc(fmt, QT, HD, 0, 1);
@@ -199,6 +205,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         }
     } else {
         // ===================== softmax / output warps (two threads per query row) =====================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
         const int lg = warp & 3;
         const int part = warp >> 2;
         const int row = lg * 32 + lane;
@@ -216,6 +223,61 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                 mbar_wait(&bar_s, g & 1);
                 tc_fence_after();
                 float mx = -INFINITY;
+                float sum = 0.f;
+                if (REGS) {
+                    // this thread's whole share of the score row (<= 5 chunks of 32) stays in registers across the
+                    // max exchange: one TMEM round trip instead of two passes of per-chunk load/wait
+                    uint32_t r[5][32];
+                    const int cnt = c_hi - c_lo;
+                    if (warp_ok) {
+#pragma unroll
+                        for (int k = 0; k < 5; ++k)
+                            if (k < cnt) tmem_ld32(t_row + S_COL + (c_lo + k) * 32, r[k]);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int k = 0; k < 5; ++k) {
+                            if (k < cnt) {
+                                const int c = c_lo + k;
+                                if (c * 32 + 32 <= L) {
+#pragma unroll
+                                    for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(r[k][j]));
+                                } else {
+#pragma unroll
+                                    for (int j = 0; j < 32; ++j)
+                                        if (c * 32 + j < L) mx = fmaxf(mx, __uint_as_float(r[k][j]));
+                                }
+                            }
+                        }
+                    }
+                    s_max[part][row] = mx;
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                    mx = fmaxf(s_max[0][row], s_max[1][row]);
+                    const float mxs = mx * c2;
+                    if (warp_ok) {
+#pragma unroll
+                        for (int k = 0; k < 5; ++k) {
+                            if (k < cnt) {
+                                const int c = c_lo + k;
+                                uint32_t w[16];
+                                const bool full = (c * 32 + 32 <= L);
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) {
+                                    float p0 = ex2_approx(fmaf(__uint_as_float(r[k][2 * j]), c2, -mxs));
+                                    float p1 = ex2_approx(fmaf(__uint_as_float(r[k][2 * j + 1]), c2, -mxs));
+                                    if (!full) {
+                                        if (c * 32 + 2 * j >= L) p0 = 0.f;
+                                        if (c * 32 + 2 * j + 1 >= L) p1 = 0.f;
+                                    }
+                                    sum += p0 + p1;
+                                    w[j] = a.opd == OPD_FP16 ? Op16<OPD_FP16>::pack(p0, p1) : Op16<OPD_BF16>::pack(p0, p1);
+                                }
+                                const uint32_t pcol = c < n0 ? S_COL + 16 * c : P1_COL + 16 * (c - n0);
+                                tmem_st16(t_row + pcol, w);
+                            }
+                        }
+                        tmem_st_wait();
+                    }
+                } else {
                 if (warp_ok) {
                     for (int c = c_lo; c < c_hi; ++c) {
                         uint32_t r[32];
@@ -235,7 +297,6 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                 asm volatile("bar.sync 1, 256;" ::: "memory");
                 mx = fmaxf(s_max[0][row], s_max[1][row]);
                 const float mxs = mx * c2;
-                float sum = 0.f;
                 if (warp_ok) {
                     for (int c = c_lo; c < c_hi; ++c) {
                         uint32_t r[32];
@@ -261,6 +322,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                         tmem_st16(t_row + pcol, w);
                     }
                     tmem_st_wait();
+                }
                 }
                 s_sum[part][row] = sum;
                 tc_fence_before();
@@ -313,7 +375,11 @@ int smem_bytes_for(int L) {
 }  // namespace
 
 cudaError_t attention2_configure() {
-    return cudaFuncSetAttribute(attention2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes_for(MAX_L2));
+    cudaError_t e = cudaFuncSetAttribute(attention2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         smem_bytes_for(MAX_L2));
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(attention2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                smem_bytes_for(MAX_L2));
 }
 
 bool attention2_supported(const AttnArgs& a) {
@@ -327,7 +393,11 @@ cudaError_t launch_attention2(const CUtensorMap& q, const CUtensorMap& k, const 
                               int num_sms, cudaStream_t s) {
     const int items = a.B * a.H;
     const int grid = items < num_sms ? items : num_sms;
-    attention2_kernel<<<grid, THREADS, smem_bytes_for(a.L), s>>>(q, k, v, a);
+    const int nch = (a.L + 31) / 32;
+    if ((nch + 1) / 2 <= 5)   // each thread's share of a score row fits in registers (L <= 320)
+        attention2_kernel<true><<<grid, THREADS, smem_bytes_for(a.L), s>>>(q, k, v, a);
+    else
+        attention2_kernel<false><<<grid, THREADS, smem_bytes_for(a.L), s>>>(q, k, v, a);
     return cudaGetLastError();
 }
 

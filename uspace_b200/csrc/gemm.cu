@@ -246,7 +246,16 @@ static bool force_1cta() {
 
 cudaError_t launch_gemm(int epi, const GemmMaps& maps, const GemmArgs& a, int num_sms, cudaStream_t s) {
     if (a.M <= 0 || a.N % 128 != 0 || a.K % BK != 0 || a.K0 % BK != 0 || a.K0 > a.K) return cudaErrorInvalidValue;
-    if (!force_1cta() && gemm2_supported(epi, maps, a)) return launch_gemm2(epi, maps, a, num_sms, s);
+    if (!force_1cta() && gemm2_supported(epi, maps, a)) {
+        static int diag = -1;
+        if (diag < 0) {
+            const char* e = getenv("USP_GEMM_DIAG");
+            diag = e ? atoi(e) : 0;
+        }
+        GemmArgs a2 = a;
+        a2.diag = diag;
+        return launch_gemm2(epi, maps, a2, num_sms, s);
+    }
     if (gemm_block_n(a.N) == 256) return launch_bn<256>(epi, maps, a, num_sms, s);
     return launch_bn<128>(epi, maps, a, num_sms, s);
 }

@@ -9,11 +9,11 @@
 //   warp 1    : TMEM allocator (both CTAs); in the leader one thread issues tcgen05.mma.cta_group::2 and
 //               multicasts its commits to both CTAs' empty / tmem_full barriers
 //   warps 2-9 : epilogue, two warps per TMEM lane group (each takes 128 of the 256 accumulator columns)
-//   warp 10   : fp32 epilogues only: TMA-prefetches the residual tile chunks (128 rows x 32 fp32, 128B swizzle)
-//               three chunks ahead, so the epilogue never waits on DRAM latency (ncu r01: the direct-load epilogue
-//               spent 60 % of its samples in long-scoreboard stalls on the residual and ran `proj` at 28 % tensor
-//               activity).  The epilogue adds accumulator + bias in place in that smem chunk and one thread TMA-stores
-//               it (coalesced 128-byte rows, OOB rows clipped by the tensor map).
+//   warp 10   : residual epilogue only: TMA-prefetches the residual tile in chunks (128 rows x 32 fp32, 128B swizzle)
+//               three chunks ahead per column half, so the epilogue never waits on DRAM latency (ncu r01: the
+//               direct-load epilogue spent 60 % of its samples in long-scoreboard stalls on the residual and ran
+//               `proj` at 28 % tensor activity).  A chunk is released back to the loader as soon as its rows are in
+//               registers; results leave through full 128-byte per-row global stores.
 #include "common.cuh"
 #include "gemm_epilogue.cuh"
 #include "kernels.h"
@@ -33,12 +33,14 @@ constexpr int B_BYTES = (BN / 2) * BK * 2;
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;   // 32 KiB per CTA per stage
 constexpr int TMEM_COLS = 2 * BN;                // double-buffered accumulator
 constexpr int CHUNK_BYTES = BM * 32 * 4;         // 128 rows x 32 fp32 = 16 KiB staging chunk
-constexpr int NBUF = 3;                          // staging chunks in flight per column half
 
-template <int EPI>
+// LONGK (K >= 2048: fc2): the main loop per tile is long, so the residual prefetch needs little depth and the
+// operand ring keeps 6 stages; short K (proj) trades two ring stages for a 3-deep residual prefetch per column half.
+template <int EPI, bool LONGK>
 struct Cfg2 {
-    static constexpr bool STAGED = (EPI == EPI_BIAS_RESID || EPI == EPI_BIAS_F32);
-    static constexpr int STAGES = STAGED ? 4 : 6;
+    static constexpr bool STAGED = (EPI == EPI_BIAS_RESID);   // residual chunks are TMA-prefetched into smem
+    static constexpr int NBUF = LONGK ? 1 : 3;                // staging chunks in flight per column half
+    static constexpr int STAGES = STAGED ? (LONGK ? 6 : 4) : 6;
     static constexpr int EPI_BYTES = STAGED ? 2 * NBUF * CHUNK_BYTES : 0;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024;
 };
@@ -63,14 +65,15 @@ __device__ __forceinline__ void bulk_wait() {
     asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
 }
 
-template <int EPI>
+template <int EPI, bool LONGK>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
              const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmR,
              const __grid_constant__ CUtensorMap tmO, const GemmArgs g) {
-    using Cfg = Cfg2<EPI>;
+    using Cfg = Cfg2<EPI, LONGK>;
     constexpr int STAGES = Cfg::STAGES;
     constexpr bool STAGED = Cfg::STAGED;
+    constexpr int NBUF = Cfg::NBUF;
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -80,8 +83,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
     __shared__ __align__(8) uint64_t empty_bar[STAGES];      // one per CTA, arrived by the leader's multicast commit
     __shared__ __align__(8) uint64_t tmem_full_bar[2];       // one per CTA, multicast commit
     __shared__ __align__(8) uint64_t tmem_empty_bar[2];      // leader only: 2 CTAs x 8 epilogue warps
-    __shared__ __align__(8) uint64_t rfull_bar[2][NBUF];     // staging chunk holds the residual (or is writable)
-    __shared__ __align__(8) uint64_t rfree_bar[2][NBUF];     // staging chunk's TMA store has finished reading smem
+    __shared__ __align__(8) uint64_t rfull_bar[2][3];     // staging chunk holds the residual (or is writable)
+    __shared__ __align__(8) uint64_t rfree_bar[2][3];     // staging chunk's TMA store has finished reading smem
     __shared__ uint32_t tmem_base_smem;
 
     const int warp = threadIdx.x >> 5;
@@ -101,10 +104,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
         tma_prefetch_desc(&tmA0);
         tma_prefetch_desc(&tmA1);
         tma_prefetch_desc(&tmB);
-        if (STAGED) {
-            tma_prefetch_desc(&tmR);
-            tma_prefetch_desc(&tmO);
-        }
+        if (STAGED) tma_prefetch_desc(&tmR);
         for (int i = 0; i < STAGES; ++i) {
             mbar_init(&full_bar[i], 1);
             mbar_init(&empty_bar[i], 1);
@@ -114,7 +114,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
             mbar_init(&tmem_empty_bar[i], 2 * EPI_WARPS);
             for (int j = 0; j < NBUF; ++j) {
                 mbar_init(&rfull_bar[i][j], 1);
-                mbar_init(&rfree_bar[i][j], 1);
+                mbar_init(&rfree_bar[i][j], 4);   // one arrive per epilogue warp of that column half
             }
         }
         fence_barrier_init();
@@ -139,7 +139,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
                     uint8_t* sa = smem + stage * STAGE_BYTES;
                     uint8_t* sb = sa + A_BYTES;
                     const uint32_t lead_full = mapa_rank(smem_u32(&full_bar[stage]), 0);
-                    if (elect_one()) {
+                    if (g.diag == 1 && (tile != cluster_id || kb >= STAGES)) {
+                        // diagnostic: no operand traffic at all, the MMAs re-read whatever the ring holds
+                        if (leader && elect_one()) mbar_arrive(&full_bar[stage]);
+                    } else if (elect_one()) {
                         if (leader) mbar_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);
                         if (kb < nkb0)
                             tma_load_2d_cg2(&tmA0, lead_full, sa, kb * BK, m0);
@@ -198,12 +201,12 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
                     for (int half = 0; half < 2; ++half) {
                         mbar_wait(&rfree_bar[half][b], ph ^ 1);
                         if (elect_one()) {
-                            if (EPI == EPI_BIAS_RESID) {
+                            if (g.diag & 2) {   // diagnostic: no residual traffic
+                                mbar_arrive(&rfull_bar[half][b]);
+                            } else {
                                 mbar_expect_tx(&rfull_bar[half][b], CHUNK_BYTES);
                                 tma_load_2d(&tmR, &rfull_bar[half][b], ebuf + (half * NBUF + b) * CHUNK_BYTES,
-                                            n0 + half * (BN / 2) + c * 32, m0);
-                            } else {
-                                mbar_arrive(&rfull_bar[half][b]);
+                                            n0 + (2 * c + half) * 32, m0);
                             }
                         }
                         __syncwarp();
@@ -217,7 +220,6 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
         const int lg = warp & 3;                 // TMEM lane group this warp may access
         const int half = (warp - 2) >> 2;        // which 128 accumulator columns
         constexpr int NCH = BN / 2 / 32;         // 4 chunks of 32 columns per warp
-        const bool storer = (lg == 0 && lane == 0);
         const int rloc = lg * 32 + lane;         // row inside the CTA's 128-row slab
         int t = 0;
         int i = 0;                               // staging chunk counter (matches the loader's)
@@ -225,69 +227,47 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
             const int as = t & 1;
             const uint32_t aphase = (t >> 1) & 1;
             const int m0 = (tile / n_tiles_n) * (2 * BM) + static_cast<int>(rank) * BM;
-            const int n0 = (tile % n_tiles_n) * BN + half * (BN / 2);
+            const int n0 = (tile % n_tiles_n) * BN;   // the two column halves take interleaved chunks, so that at
+                                                      // any moment the CTA touches 256 B contiguous per output row
             const EpiRow row = epi_row(g, EPI, m0 + rloc);
 
             mbar_wait(&tmem_full_bar[as], aphase);
             tc_fence_after();
-            const uint32_t t_row = tmem_base + (static_cast<uint32_t>(lg * 32) << 16) + as * BN + half * (BN / 2);
+            const uint32_t t_row = tmem_base + (static_cast<uint32_t>(lg * 32) << 16) + as * BN;
+            if (!STAGED) {
+                // two TMEM loads in flight per wait: halves the number of exposed TMEM round trips
 #pragma unroll 1
-            for (int c = 0; c < NCH; ++c) {
-                uint32_t r[32];
-                tmem_ld32(t_row + c * 32, r);
-                if (!STAGED) {
+                for (int c = 0; c < NCH; c += 2) {
+                    const int col = (c + half) * 64;       // 64-column pieces: half 0 -> 0,128; half 1 -> 64,192
+                    uint32_t r0[32], r1[32];
+                    tmem_ld32(t_row + col, r0);
+                    tmem_ld32(t_row + col + 32, r1);
                     tmem_ld_wait();
-                    epi_chunk<EPI>(g, row, n0 + c * 32, r, nullptr);
-                } else {
+                    epi_chunk<EPI>(g, row, n0 + col, r0, nullptr);
+                    epi_chunk<EPI>(g, row, n0 + col + 32, r1, nullptr);
+                }
+            } else {
+#pragma unroll 1
+                for (int c = 0; c < NCH; ++c) {
+                    const int col = (2 * c + half) * 32;   // interleaved 32-column chunks (matches the loader)
+                    uint32_t r[32];
+                    tmem_ld32(t_row + col, r);
+                    {
                     const int b = i % NBUF;
                     const uint32_t ph = (i / NBUF) & 1;
                     ++i;
                     uint8_t* buf = ebuf + (half * NBUF + b) * CHUNK_BYTES + rloc * 128;
                     mbar_wait(&rfull_bar[half][b], ph);
+                    // residual row out of the prefetched chunk: 128-byte rows, 16-byte units XOR-swizzled by
+                    // (row & 7) -> conflict-free 128-bit reads; the chunk is handed back to the loader right away
+                    float4 x4[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) x4[u] = *reinterpret_cast<const float4*>(buf + ((u ^ (rloc & 7)) << 4));
+                    fence_proxy_async();   // generic-proxy reads above vs. the async-proxy (TMA) refill of this chunk
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&rfree_bar[half][b]);
                     tmem_ld_wait();
-                    const int n = n0 + c * 32;
-                    float v[32];
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-                    if (g.bias != nullptr) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            const float4 b4 = __ldg(reinterpret_cast<const float4*>(g.bias + n + j));
-                            v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
-                        }
-                    }
-                    // 128-byte rows, 16-byte units XOR-swizzled by (row & 7): conflict-free 128-bit accesses
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        float4* p4 = reinterpret_cast<float4*>(buf + ((u ^ (rloc & 7)) << 4));
-                        float4 o = make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
-                        if (EPI == EPI_BIAS_RESID) {
-                            const float4 x4 = *p4;
-                            o.x += x4.x; o.y += x4.y; o.z += x4.z; o.w += x4.w;
-                            v[4 * u] = o.x; v[4 * u + 1] = o.y; v[4 * u + 2] = o.z; v[4 * u + 3] = o.w;
-                        }
-                        *p4 = o;
-                    }
-                    if (g.out16 != nullptr && row.ok) {   // 16-bit copy of the new residual stream (next skip_linear operand)
-                        uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(g.out16) +
-                                                             static_cast<long long>(row.m) * g.N + n);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            uint4 q;
-                            q.x = pack16(g.opd, v[8 * j], v[8 * j + 1]);
-                            q.y = pack16(g.opd, v[8 * j + 2], v[8 * j + 3]);
-                            q.z = pack16(g.opd, v[8 * j + 4], v[8 * j + 5]);
-                            q.w = pack16(g.opd, v[8 * j + 6], v[8 * j + 7]);
-                            op[j] = q;
-                        }
-                    }
-                    fence_proxy_async();                               // smem writes -> visible to the TMA store
-                    asm volatile("bar.sync %0, 128;" ::"r"(2 + half) : "memory");
-                    if (storer) {
-                        tma_store_2d(&tmO, ebuf + (half * NBUF + b) * CHUNK_BYTES, n, m0);
-                        bulk_commit();
-                        bulk_wait_read<1>();                           // the previous chunk's store has drained its smem
-                        if (i >= 2) mbar_arrive(&rfree_bar[half][(i - 2) % NBUF]);
+                    epi_chunk<EPI>(g, row, n0 + col, r, x4);
                     }
                 }
             }
@@ -296,7 +276,6 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(&tmem_empty_bar[as], 0);
         }
-        if (STAGED && storer) bulk_wait<0>();   // all output tiles are in global memory before the CTA exits
     }
 
     // no CTA may exit (or free TMEM) while its peer can still touch its shared memory / barriers
@@ -305,20 +284,29 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
     if (warp == 1) tmem_dealloc_cg2<TMEM_COLS>(tmem_base);
 }
 
-template <int EPI>
-cudaError_t launch2(const GemmMaps& maps, const GemmArgs& a, int num_sms, cudaStream_t s) {
+template <int EPI, bool LONGK>
+cudaError_t launch2k(const GemmMaps& maps, const GemmArgs& a, int num_sms, cudaStream_t s) {
     const int n_tiles = ((a.M + 2 * BM - 1) / (2 * BM)) * (a.N / BN);
     int clusters = num_sms / 2;
     if (n_tiles < clusters) clusters = n_tiles;
-    gemm2_kernel<EPI><<<2 * clusters, THREADS, Cfg2<EPI>::SMEM_BYTES, s>>>(maps.a0, maps.a1, maps.b, maps.r32,
-                                                                          maps.o32, a);
+    gemm2_kernel<EPI, LONGK><<<2 * clusters, THREADS, Cfg2<EPI, LONGK>::SMEM_BYTES, s>>>(
+        maps.a0, maps.a1, maps.b, maps.r32, maps.o32, a);
     return cudaGetLastError();
 }
 
 template <int EPI>
+cudaError_t launch2(const GemmMaps& maps, const GemmArgs& a, int num_sms, cudaStream_t s) {
+    if (EPI == EPI_BIAS_RESID && a.K >= 2048) return launch2k<EPI, true>(maps, a, num_sms, s);
+    return launch2k<EPI, false>(maps, a, num_sms, s);
+}
+
+template <int EPI>
 cudaError_t configure2() {
-    return cudaFuncSetAttribute(gemm2_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                Cfg2<EPI>::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(gemm2_kernel<EPI, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg2<EPI, false>::SMEM_BYTES);
+    if (e != cudaSuccess || EPI != EPI_BIAS_RESID) return e;
+    return cudaFuncSetAttribute(gemm2_kernel<EPI, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                Cfg2<EPI, true>::SMEM_BYTES);
 }
 
 }  // namespace
@@ -335,10 +323,10 @@ cudaError_t gemm2_configure() {
     return cudaSuccess;
 }
 
-// fp32-output epilogues need the fp32 tensor maps (GemmMaps::has_f32) and write fp32 through them
+// the residual epilogue needs the fp32 residual tensor map (GemmMaps::r32, has_f32)
 bool gemm2_supported(int epi, const GemmMaps& maps, const GemmArgs& a) {
     if (a.N % BN != 0 || a.M <= BM) return false;
-    if (epi == EPI_BIAS_RESID || epi == EPI_BIAS_F32) return maps.has_f32 && a.out32 != nullptr;
+    if (epi == EPI_BIAS_RESID) return maps.has_f32 && a.resid != nullptr && a.out32 != nullptr;
     return true;
 }
 

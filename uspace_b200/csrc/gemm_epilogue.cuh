@@ -83,10 +83,10 @@ __device__ __forceinline__ void epi_chunk(const GemmArgs& g, const EpiRow& row, 
         }
     }
     if (EPI == EPI_BIAS_RESID || EPI == EPI_BIAS_F32) {
-        if (g.out32 != nullptr) {
-            float4* op = reinterpret_cast<float4*>(g.out32 + static_cast<long long>(row.m) * g.N + n);
+        if (g.out32 != nullptr && !(g.diag & 4)) {   // diag 4: skip the fp32 store (diagnostic)
+            float* op = g.out32 + static_cast<long long>(row.m) * g.N + n;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            for (int j = 0; j < 4; ++j) st_global_v8_f32(op + 8 * j, v + 8 * j);
         }
     }
     uint16_t* o16 = nullptr;
@@ -100,16 +100,11 @@ __device__ __forceinline__ void epi_chunk(const GemmArgs& g, const EpiRow& row, 
         o16 = reinterpret_cast<uint16_t*>(g.out16) + static_cast<long long>(row.m) * g.N + n;
     }
     if (o16 != nullptr) {
-        uint4* op = reinterpret_cast<uint4*>(o16);
+        uint32_t u[16];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            uint4 u;
-            u.x = pack16(g.opd, v[8 * j], v[8 * j + 1]);
-            u.y = pack16(g.opd, v[8 * j + 2], v[8 * j + 3]);
-            u.z = pack16(g.opd, v[8 * j + 4], v[8 * j + 5]);
-            u.w = pack16(g.opd, v[8 * j + 6], v[8 * j + 7]);
-            op[j] = u;
-        }
+        for (int j = 0; j < 16; ++j) u[j] = pack16(g.opd, v[2 * j], v[2 * j + 1]);
+        st_global_v8_b32(o16, u);
+        st_global_v8_b32(o16 + 16, u + 8);
     }
 }
 

@@ -28,6 +28,7 @@ struct GemmArgs {
     void* out16;         // [M,N] 16-bit (or QKV base) or nullptr
     int L, H;            // EPI_QKV: tokens per sample, heads (head_dim = 64)
     long long qkv_stride;  // EPI_QKV: elements between the q, k and v planes
+    int diag;              // diagnostics (env USP_GEMM_DIAG): 1 = skip TMA loads after the first ring fill (results invalid)
 };
 
 struct GemmMaps {
