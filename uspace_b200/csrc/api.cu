@@ -398,7 +398,7 @@ int enqueue_forward(usp_handle* h, Plan* p, const FwdIO& io, cudaStream_t s) {
         if (rc) return rc;
         AttnArgs aa;
         memset(&aa, 0, sizeof(aa));
-        aa.B = B; aa.H = h->cfg.num_heads; aa.L = L; aa.D = D; aa.opd = opd; aa.out16 = p->a16; aa.num_sms = h->num_sms;
+        aa.B = B; aa.H = h->cfg.num_heads; aa.L = L; aa.D = D; aa.opd = opd; aa.out16 = p->a16; aa.num_sms = h->num_sms; aa.q16 = p->qkv16;
         prof_mark(h, 3, s);
         KTRY(launch_attention(p->m_q, p->m_k, p->m_v, aa, s));
         prof_mark(h, 4, s);
@@ -946,7 +946,7 @@ int usp_op_attention(const void* q16, const void* k16, const void* v16, void* ou
     if (!ok) return fail(nullptr, USP_ERR_CUDA, "cuTensorMapEncodeTiled failed");
     AttnArgs a;
     memset(&a, 0, sizeof(a));
-    a.B = B; a.H = H; a.L = L; a.D = H * 64; a.opd = operand_dtype; a.out16 = out16;
+    a.B = B; a.H = H; a.L = L; a.D = H * 64; a.opd = operand_dtype; a.out16 = out16; a.q16 = q16;
     {
         int dev = 0;
         a.num_sms = 148;

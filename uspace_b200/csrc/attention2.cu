@@ -30,6 +30,8 @@ constexpr int CTRL_WARP = 8;
 constexpr int QTILE_BYTES = QT * HD * 2;   // 16 KiB
 constexpr int MAX_L2 = 352;
 constexpr int TMEM_COLS = 512;
+constexpr int TAIL_MAX = 2;             // leftover query rows handled on CUDA cores
+constexpr int TAIL_THREADS = 96;        // warps 9-11
 
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
@@ -74,7 +76,8 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
-    __shared__ __align__(8) uint64_t q_full[2], kv_full[2], bar_s, bar_p, bar_o;
+    __shared__ __align__(8) uint64_t q_full[2], kv_full[2], bar_s, bar_p, bar_o, tail_done, tail_go;
+    __shared__ float t_q[HD], t_p[MAX_L2], t_red[2][4], t_o[3][HD];
     __shared__ uint32_t tmem_base_smem;
     __shared__ float s_max[2][QT], s_sum[2][QT];
 
@@ -84,7 +87,11 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     const int L16 = (L + 15) & ~15;
     const int hrows = L16 / 2;              // K / V arrive as two TMA boxes of L16/2 rows (multiple of 8)
     const int kv_bytes = L16 * 128;
-    const int n_qt = (L + QT - 1) / QT;
+    // 1-2 leftover query rows (L = 257 / 258) would cost a whole extra MMA tile per item in the serial
+    // S-MMA -> softmax -> PV-MMA chain; they are computed by the otherwise idle warps 9-11 on CUDA cores instead,
+    // from the K / V tiles already in shared memory, concurrently with the tensor-core pipeline.
+    const bool tail_simt = (L >= QT) && (L % QT != 0) && (L % QT <= TAIL_MAX);
+    const int n_qt = tail_simt ? L / QT : (L + QT - 1) / QT;
     const int n_items = a.B * a.H;
     const int nch = (L + 31) / 32;          // 32-column score chunks
     const int n0 = (nch + 1) / 2;           // chunks handled by column-part 0
@@ -103,6 +110,8 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         mbar_init(&bar_s, 1);
         mbar_init(&bar_p, 256);
         mbar_init(&bar_o, 1);
+        mbar_init(&tail_done, 3);
+        mbar_init(&tail_go, 1);
         fence_barrier_init();
     }
     __syncwarp();
@@ -113,11 +122,104 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     const uint32_t tmem_base = tmem_base_smem;
 
     // Register re-balancing between warpgroups (setmaxnreg): the control warpgroup needs almost nothing, the softmax
-    // warpgroups keep a whole score-row share (160 fp32) in registers.  8*32*216 + 4*32*64 = 63488 <= 65536.
+    // warpgroups keep a whole score-row share (160 fp32) in registers.  (168-72)*128 regs released == (216-168)*256 regs acquired <= 65536.
     if (warp > CTRL_WARP) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");   // idle warps of the control warpgroup
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
+        // ===================== tail warps (9-11): leftover query rows on CUDA cores =====================
+        if (tail_simt) {
+            const int tt = threadIdx.x - (CTRL_WARP + 1) * 32;   // 0..95
+            const float c2 = 0.125f * 1.44269504088896340736f;
+            int n = 0;
+            for (int bh = blockIdx.x; bh < n_items; bh += gridDim.x, ++n) {
+                const uint8_t* kbuf = sK + (n & 1) * kv_bytes;
+                const uint8_t* vbuf = sV + (n & 1) * kv_bytes;
+                mbar_wait(&tail_go, n & 1);
+                mbar_wait(&kv_full[n & 1], (n >> 1) & 1);
+                for (int l = n_qt * QT; l < L; ++l) {
+                    // query row -> fp32 in smem
+                    if (tt < HD / 2) {
+                        const uint32_t w = reinterpret_cast<const uint32_t*>(a.q16)[(static_cast<long long>(bh) * L + l) * (HD / 2) + tt];
+                        const float2 f = a.opd == OPD_FP16 ? Op16<OPD_FP16>::unpack(w) : Op16<OPD_BF16>::unpack(w);
+                        t_q[2 * tt] = f.x;
+                        t_q[2 * tt + 1] = f.y;
+                    }
+                    asm volatile("bar.sync 2, 96;" ::: "memory");
+                    // scores for keys tt, tt+96, tt+192 (log2 domain)
+                    float x[3];
+                    float mx = -INFINITY;
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) {
+                        const int j = tt + i * TAIL_THREADS;
+                        x[i] = -INFINITY;
+                        if (j < L) {
+                            const uint8_t* krow = kbuf + (j >> 3) * 1024 + (j & 7) * 128;
+                            float acc = 0.f;
+#pragma unroll 1
+                            for (int u = 0; u < 8; ++u) {
+                                const uint4 kk = *reinterpret_cast<const uint4*>(krow + ((u ^ (j & 7)) << 4));
+                                const uint32_t kw[4] = {kk.x, kk.y, kk.z, kk.w};
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    const float2 f = a.opd == OPD_FP16 ? Op16<OPD_FP16>::unpack(kw[e]) : Op16<OPD_BF16>::unpack(kw[e]);
+                                    acc = fmaf(t_q[u * 8 + 2 * e], f.x, acc);
+                                    acc = fmaf(t_q[u * 8 + 2 * e + 1], f.y, acc);
+                                }
+                            }
+                            x[i] = acc * c2;
+                            mx = fmaxf(mx, x[i]);
+                        }
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+                    if (lane == 0) t_red[0][warp - CTRL_WARP - 1] = mx;
+                    asm volatile("bar.sync 2, 96;" ::: "memory");
+                    mx = fmaxf(fmaxf(t_red[0][0], t_red[0][1]), t_red[0][2]);
+                    float sum = 0.f;
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) {
+                        const int j = tt + i * TAIL_THREADS;
+                        if (j < L) {
+                            // P is rounded to the 16-bit operand type exactly like the tensor-core path
+                            float p = ex2_approx(x[i] - mx);
+                            const uint32_t w = a.opd == OPD_FP16 ? Op16<OPD_FP16>::pack(p, 0.f) : Op16<OPD_BF16>::pack(p, 0.f);
+                            sum += p;
+                            p = (a.opd == OPD_FP16 ? Op16<OPD_FP16>::unpack(w) : Op16<OPD_BF16>::unpack(w)).x;
+                            t_p[j] = p;
+                        }
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+                    if (lane == 0) t_red[1][warp - CTRL_WARP - 1] = sum;
+                    asm volatile("bar.sync 2, 96;" ::: "memory");
+                    const float inv = 1.0f / (t_red[1][0] + t_red[1][1] + t_red[1][2]);
+                    // O[d] = sum_j p_j V[j][d]: thread = (pair of d, one third of the keys)
+                    const int dp = tt & 31, seg = tt >> 5;
+                    float o0 = 0.f, o1 = 0.f;
+                    for (int j = seg; j < L; j += 3) {
+                        const uint8_t* vrow = vbuf + (j >> 3) * 1024 + (j & 7) * 128;
+                        const uint32_t w = *reinterpret_cast<const uint32_t*>(vrow + ((((dp >> 2) ^ (j & 7))) << 4) + (dp & 3) * 4);
+                        const float2 f = a.opd == OPD_FP16 ? Op16<OPD_FP16>::unpack(w) : Op16<OPD_BF16>::unpack(w);
+                        const float p = t_p[j];
+                        o0 = fmaf(p, f.x, o0);
+                        o1 = fmaf(p, f.y, o1);
+                    }
+                    t_o[seg][2 * dp] = o0;
+                    t_o[seg][2 * dp + 1] = o1;
+                    asm volatile("bar.sync 2, 96;" ::: "memory");
+                    if (tt < HD / 2) {
+                        const float r0 = (t_o[0][2 * tt] + t_o[1][2 * tt] + t_o[2][2 * tt]) * inv;
+                        const float r1 = (t_o[0][2 * tt + 1] + t_o[1][2 * tt + 1] + t_o[2][2 * tt + 1]) * inv;
+                        const uint32_t w = a.opd == OPD_FP16 ? Op16<OPD_FP16>::pack(r0, r1) : Op16<OPD_BF16>::pack(r0, r1);
+                        reinterpret_cast<uint32_t*>(a.out16)[((static_cast<long long>(bh / a.H) * L + l) * a.D + (bh % a.H) * HD) / 2 + tt] = w;
+                    }
+                    asm volatile("bar.sync 2, 96;" ::: "memory");   // t_q / t_p / t_o are reused by the next row
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tail_done);
+            }
+        }
     } else if (warp == CTRL_WARP) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
         // ===================== control warp: TMA + MMA issue (warp-uniform, one elected lane acts) ============
         const int fmt = a.opd == OPD_FP16 ? 0 : 1;
         const uint32_t idesc_o = umma_idesc(fmt, QT, HD, 0, 1);
@@ -149,6 +251,12 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                 // previous tile's PV finished: S / P columns and (at t == 0) the other K/V buffer are free
                 if (g > 0) mbar_wait(&bar_o, (g - 1) & 1);
                 if (elect_one()) {
+                    if (t == 0 && tail_simt) {
+                        // two-way handshake with the tail warps: neither side can get a full mbarrier phase ahead
+                        // (a one-way tail_done could complete two phases before it is polled and alias its parity)
+                        if (n > 0) mbar_wait(&tail_done, (n - 1) & 1);   // tail warps have left the other K/V buffer
+                        mbar_arrive(&tail_go);
+                    }
                     if (t == 0 && bh + static_cast<int>(gridDim.x) < n_items) {   // prefetch next item's K/V
                         const int nb = kb ^ 1;
                         const int bh2 = bh + gridDim.x;
