@@ -291,7 +291,7 @@ def main():
             "e2e": {"value": Bg * args.steps / e2e_s, "unit": "images/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "matches_device_path": same},
             "gpu_launches": args.steps * (n_grid - 1) * nfe_per_step * (eng.kernels_per_forward() + 1),
-            "roofline": {"bound": "tensor", "kernel": "usp::gemm_kernel<BN,EPI> (all five U-ViT linears, one velocity evaluation)",
+            "roofline": {"bound": "tensor", "kernel": "usp::gemm2_kernel<EPI,LONGK> (2-CTA tcgen05 GEMM: all five U-ViT linears of one velocity evaluation)",
                          "achieved": achieved, "peak": pk["sustained"], "unit": "TFLOP/s", "frac": achieved / pk["sustained"],
                          "peak_kind": f"bf16_tflops_sustained of {pk['src']} (kernel timed inside a long step); burst {pk['burst']}",
                          "launches": gemm_launches, "avg_launch_ms": gemm_ms / max(1, gemm_launches),

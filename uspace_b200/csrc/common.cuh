@@ -110,6 +110,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         if (++spins > (1u << 24)) __trap();
     }
 }
+// Same, for waits that are expected to be long (an epilogue waiting for a whole main loop): back off with
+// nanosleep between polls so that idle warps do not burn issue slots / power while the tensor pipe is busy.
+__device__ __forceinline__ void mbar_wait_idle(uint64_t* bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++spins > 2) __nanosleep(spins > 64 ? 256 : 64);
+        if (spins > (1u << 22)) __trap();
+    }
+}
 
 // ----------------------------------------------------------------------------------------------
 // TMA (cp.async.bulk.tensor) loads into swizzled shared memory

@@ -199,7 +199,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
                     const int b = i % NBUF;
                     const uint32_t ph = (i / NBUF) & 1;
                     for (int half = 0; half < 2; ++half) {
-                        mbar_wait(&rfree_bar[half][b], ph ^ 1);
+                        mbar_wait_idle(&rfree_bar[half][b], ph ^ 1);
                         if (elect_one()) {
                             if (g.diag & 2) {   // diagnostic: no residual traffic
                                 mbar_arrive(&rfull_bar[half][b]);
@@ -231,7 +231,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
                                                       // any moment the CTA touches 256 B contiguous per output row
             const EpiRow row = epi_row(g, EPI, m0 + rloc);
 
-            mbar_wait(&tmem_full_bar[as], aphase);
+            mbar_wait_idle(&tmem_full_bar[as], aphase);
             tc_fence_after();
             const uint32_t t_row = tmem_base + (static_cast<uint32_t>(lg * 32) << 16) + as * BN;
             if (!STAGED) {
