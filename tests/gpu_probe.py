@@ -251,6 +251,26 @@ def sec_gemmperf(lib, opd):
         print(f"gemmperf {epi:10s} N={N} K={K}: rc={rc} {us:7.1f} us  {2.0 * M * N * K / us / 1e6:7.1f} TFLOP/s", flush=True)
 
 
+def sec_attnperf(lib, opd):
+    """Stand-alone timing of the attention kernel at the U-ViT-L shapes."""
+    td = TD[opd]
+    s = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for (B, H, L) in [(64, 16, 257), (128, 16, 334), (64, 16, 256)]:
+        q, k, v = (torch.randn(B * H, L, 64, device=dev).to(td) for _ in range(3))
+        out = torch.zeros(B * L, H * 64, device=dev, dtype=td)
+        for _ in range(3):
+            rc = lib.usp_op_attention(P(q), P(k), P(v), P(out), B, H, L, _lib.OPERAND[opd], s)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+        e0.record()
+        for _ in range(20):
+            lib.usp_op_attention(P(q), P(k), P(v), P(out), B, H, L, _lib.OPERAND[opd], s)
+        e1.record()
+        torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) / 20 * 1e3
+        print(f"attnperf B{B} H{H} L{L}: rc={rc} {us:7.1f} us  {4.0 * B * H * L * L * 64 / us / 1e6:7.1f} TFLOP/s", flush=True)
+
+
 def sec_one(lib, opd):
     """Two eager velocity evaluations of U-ViT-L at batch 64 (profile the second one under ncu)."""
     m = build(CFG_L, opd).to(dev)

@@ -86,6 +86,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
+    pdl_wait();
+    pdl_launch();
 
     if (warp == CTRL_WARP) {
         if (lane == 0) {
@@ -273,8 +275,7 @@ cudaError_t launch_attention(const CUtensorMap& q, const CUtensorMap& k, const C
     if (a.L < 1 || a.L > ATTN_MAX_L || a.D != a.H * HD) return cudaErrorInvalidValue;
     if (!force_v1() && attention2_supported(a)) return launch_attention2(q, k, v, a, a.num_sms, s);
     dim3 grid((a.L + QT - 1) / QT, a.B * a.H);
-    attention_kernel<<<grid, ATTN_THREADS, ATTN_SMEM, s>>>(q, k, v, a);
-    return cudaGetLastError();
+    return launch_pdl(attention_kernel, grid, dim3(ATTN_THREADS), ATTN_SMEM, s, q, k, v, a);
 }
 
 }  // namespace usp

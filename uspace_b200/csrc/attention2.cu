@@ -16,6 +16,8 @@
 //
 // Per query tile: S-MMA -> (8 warps) max / exp2 / sum, P -> TMEM -> PV-MMA -> O * 1/sum -> global.
 // S-MMA of tile g+1 overlaps the O read-out of tile g (disjoint TMEM columns).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -76,7 +78,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
-    __shared__ __align__(8) uint64_t q_full[2], kv_full[2], bar_s, bar_p, bar_o, tail_done, tail_go;
+    __shared__ __align__(8) uint64_t q_full[2], kv_full[2], bar_s, p_stage[6], bar_o, tail_done, tail_go;
     __shared__ float t_q[HD], t_p[MAX_L2], t_red[2][4], t_o[3][HD];
     __shared__ uint32_t tmem_base_smem;
     __shared__ float s_max[2][QT], s_sum[2][QT];
@@ -108,7 +110,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
             mbar_init(&kv_full[i], 1);
         }
         mbar_init(&bar_s, 1);
-        mbar_init(&bar_p, 256);
+        for (int i = 0; i < 6; ++i) mbar_init(&p_stage[i], 256);
         mbar_init(&bar_o, 1);
         mbar_init(&tail_done, 3);
         mbar_init(&tail_go, 1);
@@ -120,6 +122,8 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
+    pdl_wait();
+    pdl_launch();
 
     // Register re-balancing between warpgroups (setmaxnreg): the control warpgroup needs almost nothing, the softmax
     // warpgroups keep a whole score-row share (160 fp32) in registers.  (168-72)*128 regs released == (216-168)*256 regs acquired <= 65536.
@@ -283,7 +287,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                 const uint64_t qdesc = umma_desc_sw128(smem_u32(sQ + (g & 1) * QTILE_BYTES));
                 const uint32_t kbase = smem_u32(sK + kb * kv_bytes);
                 if (elect_one()) {
-                    for (int c0 = 0; c0 < L16; c0 += 256) {
+                    for (int c0 = 0; c0 < ((a.diag & 8) ? 0 : L16); c0 += 256) {
                         const int nn = (L16 - c0) < 256 ? (L16 - c0) : 256;
                         const uint32_t idesc = umma_idesc(fmt, QT, nn, 0, 0);
                         const uint64_t kdesc = umma_desc_sw128(kbase + c0 * 128);
@@ -294,21 +298,33 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                     umma_commit(&bar_s);
                 }
                 __syncwarp();
-                // ---- O = P V (A = P in TMEM) ----
-                mbar_wait(&bar_p, g & 1);
-                tc_fence_after();
+                // ---- O = P V (A = P in TMEM), issued stage by stage as the softmax warps publish P chunks:
+                //      stage s = chunk s of column-part 0 and chunk n0+s of column-part 1, so the PV MMAs of the
+                //      early chunks run underneath the exponentials of the later ones ----
                 const uint32_t vbase = smem_u32(sV + kb * kv_bytes);
-                if (elect_one()) {
-                    const int nks = L16 / 16;
-                    for (int kk = 0; kk < nks; ++kk) {
-                        const int c = kk >> 1;
-                        const uint32_t pcol = (c < n0 ? S_COL + 16 * c : P1_COL + 16 * (c - n0)) + 8 * (kk & 1);
-                        const uint64_t vdesc = umma_desc_v_mn(vbase + kk * 16 * 128);
-                        umma_f16_ts(tmem_base + O_COL, tmem_base + pcol, vdesc, idesc_o, kk != 0);
+                const int nks = L16 / 16;
+                for (int st = 0; st < n0; ++st) {
+                    mbar_wait(&p_stage[st], g & 1);
+                    tc_fence_after();
+                    if (elect_one()) {
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const int c = h == 0 ? st : n0 + st;
+                            if (c >= nch) continue;
+                            const uint32_t pbase = h == 0 ? S_COL + 16 * c : P1_COL + 16 * (c - n0);
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) {
+                                const int kk = 2 * c + e;
+                                if (kk >= nks || (a.diag & 4)) continue;
+                                const uint64_t vdesc = umma_desc_v_mn(vbase + kk * 16 * 128);
+                                umma_f16_ts(tmem_base + O_COL, tmem_base + pbase + 8 * e, vdesc, idesc_o,
+                                            !(st == 0 && h == 0 && e == 0));
+                            }
+                        }
+                        if (st == n0 - 1) umma_commit(&bar_o);
                     }
-                    umma_commit(&bar_o);
+                    __syncwarp();
                 }
-                __syncwarp();
             }
         }
     } else {
@@ -337,7 +353,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                     // max exchange: one TMEM round trip instead of two passes of per-chunk load/wait
                     uint32_t r[5][32];
                     const int cnt = c_hi - c_lo;
-                    if (warp_ok) {
+                    if (warp_ok && !(a.diag & 16)) {
 #pragma unroll
                         for (int k = 0; k < 5; ++k)
                             if (k < cnt) tmem_ld32(t_row + S_COL + (c_lo + k) * 32, r[k]);
@@ -361,17 +377,21 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                     asm volatile("bar.sync 1, 256;" ::: "memory");
                     mx = fmaxf(s_max[0][row], s_max[1][row]);
                     const float mxs = mx * c2;
-                    if (warp_ok) {
 #pragma unroll
-                        for (int k = 0; k < 5; ++k) {
-                            if (k < cnt) {
+                    for (int k = 0; k < 5; ++k) {
+                        if (k < n0) {
+                            if (warp_ok && k < cnt && !(a.diag & 2)) {
                                 const int c = c_lo + k;
                                 uint32_t w[16];
                                 const bool full = (c * 32 + 32 <= L);
 #pragma unroll
                                 for (int j = 0; j < 16; ++j) {
-                                    float p0 = ex2_approx(fmaf(__uint_as_float(r[k][2 * j]), c2, -mxs));
-                                    float p1 = ex2_approx(fmaf(__uint_as_float(r[k][2 * j + 1]), c2, -mxs));
+                                    float p0 = fmaf(__uint_as_float(r[k][2 * j]), c2, -mxs);
+                                    float p1 = fmaf(__uint_as_float(r[k][2 * j + 1]), c2, -mxs);
+                                    if (!(a.diag & 3)) {
+                                        p0 = ex2_approx(p0);
+                                        p1 = ex2_approx(p1);
+                                    }
                                     if (!full) {
                                         if (c * 32 + 2 * j >= L) p0 = 0.f;
                                         if (c * 32 + 2 * j + 1 >= L) p1 = 0.f;
@@ -381,9 +401,11 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                                 }
                                 const uint32_t pcol = c < n0 ? S_COL + 16 * c : P1_COL + 16 * (c - n0);
                                 tmem_st16(t_row + pcol, w);
+                                tmem_st_wait();
                             }
+                            tc_fence_before();
+                            mbar_arrive(&p_stage[k]);   // every thread publishes every stage (with or without work)
                         }
-                        tmem_st_wait();
                     }
                 } else {
                 if (warp_ok) {
@@ -405,8 +427,9 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                 asm volatile("bar.sync 1, 256;" ::: "memory");
                 mx = fmaxf(s_max[0][row], s_max[1][row]);
                 const float mxs = mx * c2;
-                if (warp_ok) {
-                    for (int c = c_lo; c < c_hi; ++c) {
+                for (int k = 0; k < n0; ++k) {
+                    const int c = c_lo + k;
+                    if (warp_ok && c < c_hi) {
                         uint32_t r[32];
                         tmem_ld32(t_row + S_COL + c * 32, r);
                         tmem_ld_wait();
@@ -428,19 +451,19 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                                                      : Op16<OPD_BF16>::pack(p[2 * j], p[2 * j + 1]);
                         const uint32_t pcol = c < n0 ? S_COL + 16 * c : P1_COL + 16 * (c - n0);
                         tmem_st16(t_row + pcol, w);
+                        tmem_st_wait();
                     }
-                    tmem_st_wait();
+                    tc_fence_before();
+                    mbar_arrive(&p_stage[k]);
                 }
                 }
                 s_sum[part][row] = sum;
-                tc_fence_before();
-                mbar_arrive(&bar_p);
                 asm volatile("bar.sync 1, 256;" ::: "memory");
                 const float inv = 1.0f / (s_sum[0][row] + s_sum[1][row]);
 
                 mbar_wait(&bar_o, g & 1);
                 tc_fence_after();
-                if (warp_ok) {
+                if (warp_ok && !(a.diag & 16)) {
                     uint32_t r[32];
                     tmem_ld32(t_row + O_COL + part * 32, r);
                     tmem_ld_wait();
@@ -464,7 +487,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                     }
                 }
                 // the O read-out above must retire before the next tile's PV-MMA overwrites O: that MMA is only
-                // issued after this thread's next bar_p arrival, which follows in program order
+                // issued after this thread's next p_stage arrival, which follows in program order
                 tc_fence_before();
             }
         }
@@ -501,12 +524,17 @@ cudaError_t launch_attention2(const CUtensorMap& q, const CUtensorMap& k, const 
                               int num_sms, cudaStream_t s) {
     const int items = a.B * a.H;
     const int grid = items < num_sms ? items : num_sms;
+    static int diag = -1;
+    if (diag < 0) {
+        const char* e = getenv("USP_ATTN_DIAG");
+        diag = e ? atoi(e) : 0;
+    }
+    AttnArgs a2 = a;
+    a2.diag = diag;
     const int nch = (a.L + 31) / 32;
     if ((nch + 1) / 2 <= 5)   // each thread's share of a score row fits in registers (L <= 320)
-        attention2_kernel<true><<<grid, THREADS, smem_bytes_for(a.L), s>>>(q, k, v, a);
-    else
-        attention2_kernel<false><<<grid, THREADS, smem_bytes_for(a.L), s>>>(q, k, v, a);
-    return cudaGetLastError();
+        return launch_pdl(attention2_kernel<true>, dim3(grid), dim3(THREADS), smem_bytes_for(a.L), s, q, k, v, a2);
+    return launch_pdl(attention2_kernel<false>, dim3(grid), dim3(THREADS), smem_bytes_for(a.L), s, q, k, v, a2);
 }
 
 }  // namespace usp

@@ -255,6 +255,12 @@ __device__ __forceinline__ void st_global_v8_b32(void* p, const uint32_t* v) {
                  : "memory");
 }
 
+// Programmatic dependent launch: a kernel's prologue (barrier init, TMEM allocation, descriptor prefetch) may run
+// while its predecessor in the stream / graph is still draining; pdl_wait() blocks until the predecessor's memory
+// is visible, pdl_launch() lets the successor start its own prologue.  No global memory is touched before pdl_wait().
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
@@ -264,4 +270,32 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
     return r;
 }
 
+}  // namespace usp
+
+#include <stdlib.h>
+namespace usp {
+// USP_PDL=1 enables programmatic dependent launch (measured: no gain, the kernels fill every SM, so the
+// successor cannot become resident early); default is plain stream order
+inline bool pdl_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("USP_PDL");
+        v = (e && e[0] == '1') ? 1 : 0;
+    }
+    return v == 1;
+}
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
 }  // namespace usp

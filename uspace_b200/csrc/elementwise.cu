@@ -26,6 +26,8 @@ constexpr int EMB_TOK = 16;
 constexpr int EMB_MAXP = 64;   // C*p*p upper bound
 
 __global__ void __launch_bounds__(256) embed_kernel(const EmbedArgs a) {
+    pdl_wait();
+    pdl_launch();
     const int l0 = blockIdx.x * EMB_TOK;
     const int b = blockIdx.y;
     const int D = a.D;
@@ -110,6 +112,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
                                                         const float* __restrict__ bta, uint16_t* __restrict__ out,
                                                         int M, int opd) {
     constexpr int D = 128 * V4;
+    pdl_wait();
+    pdl_launch();
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= M) return;
@@ -157,6 +161,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
 template <int V4>
 __global__ void __launch_bounds__(256) head_kernel(const HeadArgs a) {
     constexpr int D = 128 * V4;
+    pdl_wait();
+    pdl_launch();
     const int n_patch = a.L - a.extras;
     const int tok = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
@@ -209,6 +215,8 @@ __global__ void __launch_bounds__(256) head_kernel(const HeadArgs a) {
 // One thread per output element.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) final_kernel(const FinalArgs a) {
+    pdl_wait();
+    pdl_launch();
     const int C = a.C, S = a.S, p = a.p;
     const long long n = static_cast<long long>(a.B) * C * S * S;
     const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -257,6 +265,8 @@ __global__ void __launch_bounds__(256) final_kernel(const FinalArgs a) {
 }
 
 __global__ void convert16_kernel(const float* __restrict__ in, uint16_t* __restrict__ out, long long n, int opd) {
+    pdl_wait();
+    pdl_launch();
     long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
     for (; i < n; i += stride)
@@ -265,6 +275,8 @@ __global__ void convert16_kernel(const float* __restrict__ in, uint16_t* __restr
 
 __global__ void step_kernel(StepState* st, const float* __restrict__ grid, const unsigned char* __restrict__ mask,
                             int stage) {
+    pdl_wait();
+    pdl_launch();
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     if (stage == 0) {
         const int i = st->next;
@@ -286,8 +298,7 @@ __global__ void step_kernel(StepState* st, const float* __restrict__ grid, const
 
 cudaError_t launch_embed(const EmbedArgs& a, cudaStream_t s) {
     if (a.C * a.p * a.p > 64) return cudaErrorInvalidValue;
-    embed_kernel<<<dim3((a.L + EMB_TOK - 1) / EMB_TOK, a.B), 256, 0, s>>>(a);
-    return cudaGetLastError();
+    return launch_pdl(embed_kernel, dim3((a.L + EMB_TOK - 1) / EMB_TOK, a.B), dim3(256), 0, s, a);
 }
 
 cudaError_t launch_layernorm(const float* x, const float* g, const float* b, void* out16, int M, int D, int opd,
@@ -296,12 +307,12 @@ cudaError_t launch_layernorm(const float* x, const float* g, const float* b, voi
     const int grid = (M + rows_per_block - 1) / rows_per_block;
     uint16_t* o = reinterpret_cast<uint16_t*>(out16);
     switch (D) {
-        case 256: layernorm_kernel<2><<<grid, 256, 0, s>>>(x, g, b, o, M, opd); break;
-        case 384: layernorm_kernel<3><<<grid, 256, 0, s>>>(x, g, b, o, M, opd); break;
-        case 512: layernorm_kernel<4><<<grid, 256, 0, s>>>(x, g, b, o, M, opd); break;
-        case 768: layernorm_kernel<6><<<grid, 256, 0, s>>>(x, g, b, o, M, opd); break;
-        case 1024: layernorm_kernel<8><<<grid, 256, 0, s>>>(x, g, b, o, M, opd); break;
-        case 1536: layernorm_kernel<12><<<grid, 256, 0, s>>>(x, g, b, o, M, opd); break;
+        case 256: return launch_pdl(layernorm_kernel<2>, dim3(grid), dim3(256), 0, s, x, g, b, o, M, opd);
+        case 384: return launch_pdl(layernorm_kernel<3>, dim3(grid), dim3(256), 0, s, x, g, b, o, M, opd);
+        case 512: return launch_pdl(layernorm_kernel<4>, dim3(grid), dim3(256), 0, s, x, g, b, o, M, opd);
+        case 768: return launch_pdl(layernorm_kernel<6>, dim3(grid), dim3(256), 0, s, x, g, b, o, M, opd);
+        case 1024: return launch_pdl(layernorm_kernel<8>, dim3(grid), dim3(256), 0, s, x, g, b, o, M, opd);
+        case 1536: return launch_pdl(layernorm_kernel<12>, dim3(grid), dim3(256), 0, s, x, g, b, o, M, opd);
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();
@@ -311,12 +322,12 @@ cudaError_t launch_head(const HeadArgs& a, cudaStream_t s) {
     const int n_tok = a.B * (a.L - a.extras);
     const int grid = (n_tok + 7) / 8;
     switch (a.D) {
-        case 256: head_kernel<2><<<grid, 256, 0, s>>>(a); break;
-        case 384: head_kernel<3><<<grid, 256, 0, s>>>(a); break;
-        case 512: head_kernel<4><<<grid, 256, 0, s>>>(a); break;
-        case 768: head_kernel<6><<<grid, 256, 0, s>>>(a); break;
-        case 1024: head_kernel<8><<<grid, 256, 0, s>>>(a); break;
-        case 1536: head_kernel<12><<<grid, 256, 0, s>>>(a); break;
+        case 256: return launch_pdl(head_kernel<2>, dim3(grid), dim3(256), 0, s, a);
+        case 384: return launch_pdl(head_kernel<3>, dim3(grid), dim3(256), 0, s, a);
+        case 512: return launch_pdl(head_kernel<4>, dim3(grid), dim3(256), 0, s, a);
+        case 768: return launch_pdl(head_kernel<6>, dim3(grid), dim3(256), 0, s, a);
+        case 1024: return launch_pdl(head_kernel<8>, dim3(grid), dim3(256), 0, s, a);
+        case 1536: return launch_pdl(head_kernel<12>, dim3(grid), dim3(256), 0, s, a);
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();
@@ -324,21 +335,19 @@ cudaError_t launch_head(const HeadArgs& a, cudaStream_t s) {
 
 cudaError_t launch_final(const FinalArgs& a, cudaStream_t s) {
     const long long n = static_cast<long long>(a.B) * a.C * a.S * a.S;
-    final_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(a);
-    return cudaGetLastError();
+    return launch_pdl(final_kernel, dim3(static_cast<unsigned>((n + 255) / 256)), dim3(256), 0, s, a);
 }
 
 cudaError_t launch_convert16(const float* in, void* out16, long long n, int opd, cudaStream_t s) {
     long long blocks = (n + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
     if (blocks < 1) blocks = 1;
-    convert16_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(in, reinterpret_cast<uint16_t*>(out16), n, opd);
-    return cudaGetLastError();
+    return launch_pdl(convert16_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, s, in,
+                      reinterpret_cast<uint16_t*>(out16), n, opd);
 }
 
 cudaError_t launch_step(StepState* st, const float* grid, const unsigned char* mask, int stage, cudaStream_t s) {
-    step_kernel<<<1, 32, 0, s>>>(st, grid, mask, stage);
-    return cudaGetLastError();
+    return launch_pdl(step_kernel, dim3(1), dim3(32), 0, s, st, grid, mask, stage);
 }
 
 }  // namespace usp

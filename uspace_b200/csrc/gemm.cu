@@ -81,6 +81,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
+    pdl_wait();
+    pdl_launch();
 
     if (warp == 0) {
         // ===================== TMA producer (warp-uniform loop, one elected lane issues) =====================
@@ -184,8 +186,8 @@ cudaError_t launch_one(const GemmMaps& maps, const GemmArgs& a, int num_sms, cud
     using Cfg = GemmCfg<BN>;
     const int n_tiles = ((a.M + BM - 1) / BM) * (a.N / BN);
     const int grid = n_tiles < num_sms ? n_tiles : num_sms;
-    gemm_kernel<BN, EPI><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, s>>>(maps.a0, maps.a1, maps.b, a);
-    return cudaGetLastError();
+    return launch_pdl(gemm_kernel<BN, EPI>, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, s, maps.a0, maps.a1, maps.b,
+                      a);
 }
 
 template <int BN>

@@ -125,6 +125,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
     cluster_sync_all();   // peer barriers initialised, both TMEM allocations done
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
+    pdl_wait();     // everything above overlapped the previous kernel's tail
+    pdl_launch();
 
     if (warp == 0) {
         // ===================== TMA producer (both CTAs; warp-uniform loop, one elected lane issues) =====
@@ -289,9 +291,8 @@ cudaError_t launch2k(const GemmMaps& maps, const GemmArgs& a, int num_sms, cudaS
     const int n_tiles = ((a.M + 2 * BM - 1) / (2 * BM)) * (a.N / BN);
     int clusters = num_sms / 2;
     if (n_tiles < clusters) clusters = n_tiles;
-    gemm2_kernel<EPI, LONGK><<<2 * clusters, THREADS, Cfg2<EPI, LONGK>::SMEM_BYTES, s>>>(
-        maps.a0, maps.a1, maps.b, maps.r32, maps.o32, a);
-    return cudaGetLastError();
+    return launch_pdl(gemm2_kernel<EPI, LONGK>, dim3(2 * clusters), dim3(THREADS), Cfg2<EPI, LONGK>::SMEM_BYTES, s,
+                      maps.a0, maps.a1, maps.b, maps.r32, maps.o32, a);
 }
 
 template <int EPI>

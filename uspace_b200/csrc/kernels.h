@@ -52,6 +52,7 @@ struct AttnArgs {
     int num_sms;       // persistent grid size
     void* out16;       // [B*L, D] 16-bit, heads merged "(H hd)"
     const float* vscale;  // optional per-(sample,key) V-row scale [B, L] (p2p re-weighting), or nullptr
+    int diag;             // diagnostics (env USP_ATTN_DIAG): 1 = no MUFU, 2 = no softmax arithmetic at all (results invalid)
     const void* q16;      // raw pointer to Q [B*H, L, 64] (the SIMT tail-row path reads its query rows directly)
 };
 constexpr int ATTN_MAX_L = 384;
