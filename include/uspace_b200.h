@@ -53,6 +53,7 @@ typedef struct usp_config {
     int32_t conv;            /* final 3x3 conv present                    */
     int32_t skip;            /* out-blocks carry skip_linear              */
     int32_t operand_dtype;   /* tensor-core operand type: 0 bf16, 1 fp16  */
+    int32_t fuse_layernorm;  /* 1: fold norm1/norm2 into the qkv / fc1 GEMMs (no LayerNorm kernels) */
 } usp_config;
 
 enum { USP_METHOD_EULER = 0, USP_METHOD_HEUN = 1 };

@@ -203,6 +203,23 @@ def test_forward_matches_reference_golden(golden_dir, name, opd):
     assert rel(out, want) < FWD_TOL[opd]
 
 
+@pytest.mark.parametrize("name", ["small16_uncond", "tiny_class", "tiny_t2i", "large_uncond"])
+def test_forward_with_layernorm_folded_into_gemms(golden_dir, name):
+    """usp_config.fuse_layernorm: norm1 / norm2 applied algebraically in the qkv / fc1 epilogues."""
+    case = CASES[name]
+    m = build_model(case, UViT, UViTT2I)
+    m.fuse_layernorm = True
+    m = m.to(dev())
+    x, t, y, ctx = build_inputs(case)
+    with torch.no_grad():
+        if case["t2i"]:
+            out = m(x.to(dev()), t.to(dev()), context=ctx.to(dev()))[0]
+        else:
+            out = m(x.to(dev()), t.to(dev()), y if y is None else y.to(dev()))[0]
+    assert m.engine().kernels_per_forward() < model(name).engine().kernels_per_forward()  # no LayerNorm launches
+    assert rel(out, golden(golden_dir, name)["forward"]) < 1e-3
+
+
 def test_forward_meets_1e3_on_north_star_model(golden_dir):
     for name in ("large_uncond", "large_t2i", "small16_uncond"):
         case = CASES[name]

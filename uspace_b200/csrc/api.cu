@@ -98,6 +98,8 @@ struct Weight {
 
 struct BlockW {
     int n1w, n1b, qkvw, qkvb, projw, projb, n2w, n2b, fc1w, fc1b, fc2w, fc2b, skw, skb;
+    // folded LayerNorm (fuse_layernorm): per-output-column vectors of the qkv / fc1 GEMMs
+    float *qkv_c = nullptr, *qkv_d = nullptr, *fc1_c = nullptr, *fc1_d = nullptr;
 };
 
 struct Plan {
@@ -106,6 +108,8 @@ struct Plan {
     size_t bytes = 0;
     float* x32 = nullptr;
     void *h16 = nullptr, *a16 = nullptr, *m16 = nullptr, *xa16 = nullptr, *xb16 = nullptr, *qkv16 = nullptr;
+    void *xe16 = nullptr, *xp16 = nullptr, *xs16 = nullptr;   // fused-LN path: 16-bit copies after embed / proj / skip
+    float* stats = nullptr;                                    // [M, max(8, D/128), 2] partial row statistics
     std::vector<void*> skip16;
     float *pf = nullptr, *z = nullptr, *ztmp = nullptr, *k1 = nullptr, *ctxemb = nullptr, *ctx32 = nullptr;
     void* ctx16 = nullptr;
@@ -115,7 +119,7 @@ struct Plan {
     unsigned char* mask = nullptr;
     float* delta = nullptr;
     size_t delta_cap = 0;
-    CUtensorMap m_h, m_a, m_m, m_xa, m_xb, m_q, m_k, m_v, m_ctx;
+    CUtensorMap m_h, m_a, m_m, m_xa, m_xb, m_q, m_k, m_v, m_ctx, m_xe, m_xp, m_xs;
     std::vector<CUtensorMap> m_skip;
     std::map<int, cudaGraphExec_t> graphs;
 };
@@ -136,6 +140,7 @@ struct usp_handle {
         i_dw = -1, i_db = -1, i_fw = -1, i_fb = -1;
     float* freqs = nullptr;
     bool finalized = false;
+    bool fuse_ln = false;   // cfg.fuse_layernorm and every GEMM shape is served by the pair kernel
     std::map<int, std::unique_ptr<Plan>> plans;
     cudaStream_t cap_stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -231,6 +236,9 @@ int get_plan(usp_handle* h, int B, Plan** out) {
     const size_t o_x32 = carve(M * D * 4), o_h = carve(M * D * 2), o_a = carve(M * D * 2),
                  o_m = carve(M * Hd * 2), o_xa = carve(M * D * 2), o_xb = carve(M * D * 2),
                  o_qkv = carve(3 * M * D * 2);
+    const size_t o_xe = carve(h->fuse_ln ? M * D * 2 : 16), o_xp = carve(h->fuse_ln ? M * D * 2 : 16),
+                 o_xs = carve(h->fuse_ln ? M * D * 2 : 16),
+                 o_stats = carve(h->fuse_ln ? M * (D / 128 > 8 ? D / 128 : 8) * 8 : 16);
     std::vector<size_t> o_skip(h->n_in);
     for (int i = 0; i < h->n_in; ++i) o_skip[i] = carve(M * D * 2);
     const size_t o_pf = carve(static_cast<size_t>(B) * h->n_patch * h->P * 4), o_z = carve(zel * 4),
@@ -251,6 +259,10 @@ int get_plan(usp_handle* h, int B, Plan** out) {
     p->xa16 = base + o_xa;
     p->xb16 = base + o_xb;
     p->qkv16 = base + o_qkv;
+    p->xe16 = base + o_xe;
+    p->xp16 = base + o_xp;
+    p->xs16 = base + o_xs;
+    p->stats = reinterpret_cast<float*>(base + o_stats);
     for (int i = 0; i < h->n_in; ++i) p->skip16.push_back(base + o_skip[i]);
     p->pf = reinterpret_cast<float*>(base + o_pf);
     p->z = reinterpret_cast<float*>(base + o_z);
@@ -270,6 +282,11 @@ int get_plan(usp_handle* h, int B, Plan** out) {
     ok &= make_map_2d(&p->m_m, p->m16, M, Hd, GEMM_BM, opd);
     ok &= make_map_2d(&p->m_xa, p->xa16, M, D, GEMM_BM, opd);
     ok &= make_map_2d(&p->m_xb, p->xb16, M, D, GEMM_BM, opd);
+    if (h->fuse_ln) {
+        ok &= make_map_2d(&p->m_xe, p->xe16, M, D, GEMM_BM, opd);
+        ok &= make_map_2d(&p->m_xp, p->xp16, M, D, GEMM_BM, opd);
+        ok &= make_map_2d(&p->m_xs, p->xs16, M, D, GEMM_BM, opd);
+    }
     p->m_skip.resize(h->n_in);
     for (int i = 0; i < h->n_in; ++i) ok &= make_map_2d(&p->m_skip[i], p->skip16[i], M, D, GEMM_BM, opd);
     const long long BH = static_cast<long long>(B) * h->cfg.num_heads;
@@ -320,9 +337,17 @@ void prof_mark(usp_handle* h, int cls, cudaStream_t s) {
             return fail(h, USP_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
     } while (0)
 
+struct LnUse {               // folded-LayerNorm arguments of one GEMM launch
+    const float* stats = nullptr;  // consumer: partial row statistics to normalise with
+    int np = 0;
+    const float* c = nullptr;
+    const float* d = nullptr;
+    float* stats_out = nullptr;    // producer: where to write the partial statistics of its output
+};
+
 int run_gemm(usp_handle* h, int epi, const CUtensorMap& a0, const CUtensorMap* a1, const Weight& w,
              const float* bias, const float* resid, float* out32, void* out16, int M, int N, int K, int K0,
-             cudaStream_t s) {
+             cudaStream_t s, const LnUse* ln = nullptr) {
     GemmMaps maps;
     maps.a0 = a0;
     maps.a1 = a1 ? *a1 : a0;
@@ -339,6 +364,11 @@ int run_gemm(usp_handle* h, int epi, const CUtensorMap& a0, const CUtensorMap* a
     g.bias = bias; g.resid = resid; g.out32 = out32; g.out16 = out16;
     g.L = h->L; g.H = h->cfg.num_heads;
     g.qkv_stride = static_cast<long long>(M) * h->D;
+    if (ln) {
+        g.ln_stats = ln->stats; g.ln_np = ln->np; g.ln_c = ln->c; g.ln_d = ln->d;
+        g.ln_inv_d = 1.0f / static_cast<float>(h->D);
+        g.stats_out = ln->stats_out;
+    }
     cudaError_t e = launch_gemm(epi, maps, g, h->num_sms, s);
     if (e != cudaSuccess) return fail(h, USP_ERR_CUDA, std::string("launch_gemm: ") + cudaGetErrorString(e));
     return USP_OK;
@@ -368,32 +398,53 @@ int enqueue_forward(usp_handle* h, Plan* p, const FwdIO& io, cudaStream_t s) {
     ea.freqs = h->freqs;
     ea.delta = io.edit_loc == USP_EDIT_HEAD ? io.delta : nullptr;
     ea.out32 = p->x32;
+    ea.opd = opd;
+    if (h->fuse_ln) { ea.out16 = p->xe16; ea.stats = p->stats; }
     ea.B = B; ea.C = h->cfg.in_chans; ea.S = h->cfg.img_size; ea.p = h->cfg.patch_size; ea.D = D; ea.L = L;
     ea.n_ctx = h->cfg.num_clip_token; ea.has_label = (h->cfg.num_classes > 0 && io.y != nullptr) ? 1 : 0;
     prof_mark(h, 0, s);
     KTRY(launch_embed(ea, s));
 
     const CUtensorMap* xprev = nullptr;  // 16-bit copy of the previous block's output
+    // fused-LayerNorm path: the un-normalised 16-bit stream feeding the next qkv GEMM and the number of
+    // (sum, sumsq) partials per row its producer wrote
+    const CUtensorMap* cur16 = &p->m_xe;
+    int cur_np = 8;
+    const int gemm_np = D / 128;
     for (int bi = 0; bi < h->n_blocks; ++bi) {
         const BlockW& bw = h->blocks[bi];
         const bool is_in = bi < h->n_in;
         const bool is_out = bi > h->n_in;
         const int oj = bi - h->n_in - 1;
+        const bool fuse = h->fuse_ln;
         int rc;
         if (is_out && bw.skw >= 0) {
             // skip_linear(cat[x, skip]) with a two-source K loop; skips are consumed LIFO (libs/uvit.py:340)
             const int si = h->n_in - 1 - oj;
+            LnUse ln;
+            ln.stats_out = p->stats;
             prof_mark(h, 7, s);
             rc = run_gemm(h, EPI_BIAS_F32, *xprev, &p->m_skip[si], h->w[bw.skw], h->w[bw.skb].d32, nullptr, p->x32,
-                          nullptr, M, D, 2 * D, D, s);
+                          fuse ? p->xs16 : nullptr, M, D, 2 * D, D, s, fuse ? &ln : nullptr);
             ++nk;
             if (rc) return rc;
+            cur16 = &p->m_xs;
+            cur_np = gemm_np;
         }
-        prof_mark(h, 1, s);
-        KTRY(launch_layernorm(p->x32, h->w[bw.n1w].d32, h->w[bw.n1b].d32, p->h16, M, D, opd, s));
-        prof_mark(h, 2, s);
-        rc = run_gemm(h, EPI_QKV, p->m_h, nullptr, h->w[bw.qkvw], bw.qkvb >= 0 ? h->w[bw.qkvb].d32 : nullptr,
-                      nullptr, nullptr, p->qkv16, M, 3 * D, D, D, s);
+        if (fuse) {
+            // norm1 folded into the qkv GEMM: A = un-normalised 16-bit x, epilogue applies rstd / mean / beta
+            LnUse ln;
+            ln.stats = p->stats; ln.np = cur_np; ln.c = bw.qkv_c; ln.d = bw.qkv_d;
+            prof_mark(h, 2, s);
+            rc = run_gemm(h, EPI_QKV, *cur16, nullptr, h->w[bw.qkvw], nullptr, nullptr, nullptr, p->qkv16, M, 3 * D, D,
+                          D, s, &ln);
+        } else {
+            prof_mark(h, 1, s);
+            KTRY(launch_layernorm(p->x32, h->w[bw.n1w].d32, h->w[bw.n1b].d32, p->h16, M, D, opd, s));
+            prof_mark(h, 2, s);
+            rc = run_gemm(h, EPI_QKV, p->m_h, nullptr, h->w[bw.qkvw], bw.qkvb >= 0 ? h->w[bw.qkvb].d32 : nullptr,
+                          nullptr, nullptr, p->qkv16, M, 3 * D, D, D, s);
+        }
         ++nk;
         if (rc) return rc;
         AttnArgs aa;
@@ -401,33 +452,52 @@ int enqueue_forward(usp_handle* h, Plan* p, const FwdIO& io, cudaStream_t s) {
         aa.B = B; aa.H = h->cfg.num_heads; aa.L = L; aa.D = D; aa.opd = opd; aa.out16 = p->a16; aa.num_sms = h->num_sms; aa.q16 = p->qkv16;
         prof_mark(h, 3, s);
         KTRY(launch_attention(p->m_q, p->m_k, p->m_v, aa, s));
-        prof_mark(h, 4, s);
-        rc = run_gemm(h, EPI_BIAS_RESID, p->m_a, nullptr, h->w[bw.projw], h->w[bw.projb].d32, p->x32, p->x32,
-                      nullptr, M, D, D, D, s);
+        {
+            LnUse ln;
+            ln.stats_out = p->stats;
+            prof_mark(h, 4, s);
+            rc = run_gemm(h, EPI_BIAS_RESID, p->m_a, nullptr, h->w[bw.projw], h->w[bw.projb].d32, p->x32, p->x32,
+                          fuse ? p->xp16 : nullptr, M, D, D, D, s, fuse ? &ln : nullptr);
+        }
         ++nk;
         if (rc) return rc;
-        prof_mark(h, 1, s);
-        KTRY(launch_layernorm(p->x32, h->w[bw.n2w].d32, h->w[bw.n2b].d32, p->h16, M, D, opd, s));
-        prof_mark(h, 5, s);
-        rc = run_gemm(h, EPI_BIAS_GELU, p->m_h, nullptr, h->w[bw.fc1w], h->w[bw.fc1b].d32, nullptr, nullptr,
-                      p->m16, M, Hd, D, D, s);
+        if (fuse) {
+            LnUse ln;
+            ln.stats = p->stats; ln.np = gemm_np; ln.c = bw.fc1_c; ln.d = bw.fc1_d;
+            prof_mark(h, 5, s);
+            rc = run_gemm(h, EPI_BIAS_GELU, p->m_xp, nullptr, h->w[bw.fc1w], nullptr, nullptr, nullptr, p->m16, M, Hd,
+                          D, D, s, &ln);
+        } else {
+            prof_mark(h, 1, s);
+            KTRY(launch_layernorm(p->x32, h->w[bw.n2w].d32, h->w[bw.n2b].d32, p->h16, M, D, opd, s));
+            prof_mark(h, 5, s);
+            rc = run_gemm(h, EPI_BIAS_GELU, p->m_h, nullptr, h->w[bw.fc1w], h->w[bw.fc1b].d32, nullptr, nullptr,
+                          p->m16, M, Hd, D, D, s);
+        }
         ++nk;
         if (rc) return rc;
-        // 16-bit copy of the block output: a long skip (in-blocks) or the x half of the next skip_linear
+        // 16-bit copy of the block output: a long skip (in-blocks), the x half of the next skip_linear, and in the
+        // fused path also the next block's qkv operand
         void* o16 = nullptr;
         const CUtensorMap* omap = nullptr;
-        if (h->cfg.skip && bi + 1 < h->n_blocks) {
+        if ((h->cfg.skip || fuse) && bi + 1 < h->n_blocks) {
             if (is_in) { o16 = p->skip16[bi]; omap = &p->m_skip[bi]; }
             else if (((bi - h->n_in) & 1) == 0) { o16 = p->xa16; omap = &p->m_xa; }
             else { o16 = p->xb16; omap = &p->m_xb; }
         }
-        prof_mark(h, 6, s);
-        rc = run_gemm(h, EPI_BIAS_RESID, p->m_m, nullptr, h->w[bw.fc2w], h->w[bw.fc2b].d32, p->x32, p->x32, o16, M,
-                      D, Hd, Hd, s);
+        {
+            LnUse ln;
+            ln.stats_out = p->stats;
+            prof_mark(h, 6, s);
+            rc = run_gemm(h, EPI_BIAS_RESID, p->m_m, nullptr, h->w[bw.fc2w], h->w[bw.fc2b].d32, p->x32, p->x32, o16, M,
+                          D, Hd, Hd, s, (fuse && o16) ? &ln : nullptr);
+        }
         ++nk;
         if (rc) return rc;
         // the mid block (and every out block) feeds the next skip_linear through its 16-bit copy
         xprev = is_in ? nullptr : omap;
+        cur16 = omap;
+        cur_np = gemm_np;
     }
 
     HeadArgs ha;
@@ -544,6 +614,7 @@ int usp_create(const usp_config* cfg, int device, usp_handle** out) {
     h->P = c.patch_size * c.patch_size * c.in_chans;
     h->n_in = c.depth / 2;
     h->n_blocks = 2 * h->n_in + 1;
+    h->fuse_ln = c.fuse_layernorm != 0 && h->D % 256 == 0 && h->Hd % 256 == 0;
     if (h->L > ATTN_MAX_L) return fail(nullptr, USP_ERR_UNSUPPORTED, "sequence length above 384 tokens is not built");
 
     const int64_t D = h->D;
@@ -605,6 +676,12 @@ void usp_destroy(usp_handle* h) {
         cudaFree(w.d32);
         cudaFree(w.d16);
     }
+    for (auto& b : h->blocks) {
+        cudaFree(b.qkv_c);
+        cudaFree(b.qkv_d);
+        cudaFree(b.fc1_c);
+        cudaFree(b.fc1_d);
+    }
     cudaFree(h->freqs);
     if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -639,9 +716,29 @@ int usp_finalize_weights(usp_handle* h, void* stream) {
     CUDA_TRY(h, cudaSetDevice(h->device));
     for (auto& w : h->w)
         if (!w.set) return fail(h, USP_ERR_STATE, "weight never set: " + w.name);
+    if (h->fuse_ln) {
+        // norm1 -> qkv and norm2 -> fc1: W' = W * gamma (packed 16-bit), c = rowsum(W'), d = W beta + bias
+        for (auto& b : h->blocks) {
+            const int D = h->D, Hd = h->Hd;
+            if (!b.qkv_c) {
+                CUDA_TRY(h, cudaMalloc(&b.qkv_c, 3 * D * 4));
+                CUDA_TRY(h, cudaMalloc(&b.qkv_d, 3 * D * 4));
+                CUDA_TRY(h, cudaMalloc(&b.fc1_c, Hd * 4));
+                CUDA_TRY(h, cudaMalloc(&b.fc1_d, Hd * 4));
+            }
+            CUDA_TRY(h, launch_fold_ln(h->w[b.qkvw].d32, h->w[b.n1w].d32, h->w[b.n1b].d32,
+                                       b.qkvb >= 0 ? h->w[b.qkvb].d32 : nullptr, h->w[b.qkvw].d16, b.qkv_c, b.qkv_d,
+                                       3 * D, D, h->cfg.operand_dtype, s));
+            CUDA_TRY(h, launch_fold_ln(h->w[b.fc1w].d32, h->w[b.n2w].d32, h->w[b.n2b].d32, h->w[b.fc1b].d32,
+                                       h->w[b.fc1w].d16, b.fc1_c, b.fc1_d, Hd, D, h->cfg.operand_dtype, s));
+        }
+    }
     for (auto& w : h->w) {
         if (!w.gemm) continue;
-        CUDA_TRY(h, launch_convert16(w.d32, w.d16, w.numel, h->cfg.operand_dtype, s));
+        bool folded = false;
+        if (h->fuse_ln)
+            for (auto& b : h->blocks) folded = folded || (&w == &h->w[b.qkvw]) || (&w == &h->w[b.fc1w]);
+        if (!folded) CUDA_TRY(h, launch_convert16(w.d32, w.d16, w.numel, h->cfg.operand_dtype, s));
         const int N = static_cast<int>(w.shape[0]), K = static_cast<int>(w.shape[1]);
         if (!make_map_2d(&w.map, w.d16, N, K, gemm_weight_box_rows(), h->cfg.operand_dtype))
             return fail(h, USP_ERR_CUDA, "cuTensorMapEncodeTiled failed for " + w.name);

@@ -467,23 +467,17 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                     uint32_t r[32];
                     tmem_ld32(t_row + O_COL + part * 32, r);
                     tmem_ld_wait();
-                    uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(a.out16) +
-                                                         (static_cast<long long>(bh / a.H) * L + l) * a.D +
-                                                         (bh % a.H) * HD + part * 32);
+                    uint16_t* op = reinterpret_cast<uint16_t*>(a.out16) +
+                                   (static_cast<long long>(bh / a.H) * L + l) * a.D + (bh % a.H) * HD + part * 32;
+                    uint32_t u[16];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        float v[8];
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[8 * j + e]) * inv;
-                        uint4 u;
-                        if (a.opd == OPD_FP16) {
-                            u.x = Op16<OPD_FP16>::pack(v[0], v[1]); u.y = Op16<OPD_FP16>::pack(v[2], v[3]);
-                            u.z = Op16<OPD_FP16>::pack(v[4], v[5]); u.w = Op16<OPD_FP16>::pack(v[6], v[7]);
-                        } else {
-                            u.x = Op16<OPD_BF16>::pack(v[0], v[1]); u.y = Op16<OPD_BF16>::pack(v[2], v[3]);
-                            u.z = Op16<OPD_BF16>::pack(v[4], v[5]); u.w = Op16<OPD_BF16>::pack(v[6], v[7]);
-                        }
-                        if (row_ok) op[j] = u;
+                    for (int j = 0; j < 16; ++j) {
+                        const float v0 = __uint_as_float(r[2 * j]) * inv, v1 = __uint_as_float(r[2 * j + 1]) * inv;
+                        u[j] = a.opd == OPD_FP16 ? Op16<OPD_FP16>::pack(v0, v1) : Op16<OPD_BF16>::pack(v0, v1);
+                    }
+                    if (row_ok) {
+                        st_global_v8_b32(op, u);
+                        st_global_v8_b32(op + 16, u + 8);
                     }
                 }
                 // the O read-out above must retire before the next tile's PV-MMA overwrites O: that MMA is only

@@ -60,6 +60,9 @@ __global__ void __launch_bounds__(256) embed_kernel(const EmbedArgs a) {
     }
     __syncthreads();
 
+    float st1[EMB_TOK], st2[EMB_TOK];   // this thread's partial row statistics (folded-LayerNorm path)
+#pragma unroll
+    for (int i = 0; i < EMB_TOK; ++i) st1[i] = st2[i] = 0.f;
     for (int d = threadIdx.x; d < D; d += blockDim.x) {
         const float* wrow = a.w + static_cast<long long>(d) * P;
         const float bias = a.bias[d];
@@ -74,7 +77,10 @@ __global__ void __launch_bounds__(256) embed_kernel(const EmbedArgs a) {
                 wr[4 * q] = w4.x; wr[4 * q + 1] = w4.y; wr[4 * q + 2] = w4.z; wr[4 * q + 3] = w4.w;
             }
         }
-        for (int l = l0; l < l1; ++l) {
+#pragma unroll
+        for (int i = 0; i < EMB_TOK; ++i) {
+            const int l = l0 + i;
+            if (l >= l1) break;
             float* out = a.out32 + (static_cast<long long>(b) * a.L + l) * D;
             const float pos = a.pos[static_cast<long long>(l) * D + d];
             float v;
@@ -92,13 +98,30 @@ __global__ void __launch_bounds__(256) embed_kernel(const EmbedArgs a) {
                 float acc = 0.f;
                 if (p16) {
 #pragma unroll
-                    for (int f = 0; f < 16; ++f) acc = fmaf(wr[f], feat[l - l0][f], acc);
+                    for (int f = 0; f < 16; ++f) acc = fmaf(wr[f], feat[i][f], acc);
                 } else {
-                    for (int f = 0; f < P; ++f) acc = fmaf(__ldg(wrow + f), feat[l - l0][f], acc);
+                    for (int f = 0; f < P; ++f) acc = fmaf(__ldg(wrow + f), feat[i][f], acc);
                 }
                 v = acc + bias;
             }
-            out[d] = v + pos;
+            v += pos;
+            out[d] = v;
+            if (a.out16 != nullptr)
+                reinterpret_cast<uint16_t*>(a.out16)[(static_cast<long long>(b) * a.L + l) * D + d] =
+                    a.opd == OPD_FP16 ? Op16<OPD_FP16>::one(v) : Op16<OPD_BF16>::one(v);
+            st1[i] += v;
+            st2[i] = fmaf(v, v, st2[i]);
+        }
+    }
+    if (a.stats != nullptr) {
+        // one (sum, sum of squares) slot per (row, warp): the consumer adds the 8 slots in fixed order
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+        for (int i = 0; i < EMB_TOK; ++i) {
+            const float s1 = warp_sum(st1[i]), s2 = warp_sum(st2[i]);
+            if (lane == 0 && l0 + i < a.L)
+                reinterpret_cast<float2*>(a.stats)[(static_cast<long long>(b) * a.L + l0 + i) * 8 + warp] =
+                    make_float2(s1, s2);
         }
     }
 }
@@ -273,6 +296,48 @@ __global__ void convert16_kernel(const float* __restrict__ in, uint16_t* __restr
         out[i] = opd == OPD_FP16 ? Op16<OPD_FP16>::one(in[i]) : Op16<OPD_BF16>::one(in[i]);
 }
 
+// one block per output row n of W[N,K]
+__global__ void __launch_bounds__(256) fold_ln_kernel(const float* __restrict__ W, const float* __restrict__ gamma,
+                                                      const float* __restrict__ beta, const float* __restrict__ bias,
+                                                      uint16_t* __restrict__ w16, float* __restrict__ c,
+                                                      float* __restrict__ d, int K, int opd) {
+    const int n = blockIdx.x;
+    float cs = 0.f, ds = 0.f;
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+        const float w = W[static_cast<long long>(n) * K + k];
+        const float wg = w * gamma[k];
+        float wr;
+        uint16_t h;
+        if (opd == OPD_FP16) {
+            h = Op16<OPD_FP16>::one(wg);
+            wr = __half2float(*reinterpret_cast<__half*>(&h));
+        } else {
+            h = Op16<OPD_BF16>::one(wg);
+            wr = __bfloat162float(*reinterpret_cast<__nv_bfloat16*>(&h));
+        }
+        w16[static_cast<long long>(n) * K + k] = h;
+        cs += wr;
+        ds = fmaf(beta[k], w, ds);
+    }
+    __shared__ float sc[8], sd[8];
+    cs = warp_sum(cs);
+    ds = warp_sum(ds);
+    if ((threadIdx.x & 31) == 0) {
+        sc[threadIdx.x >> 5] = cs;
+        sd[threadIdx.x >> 5] = ds;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float a = 0.f, b = 0.f;
+        for (int i = 0; i < 8; ++i) {
+            a += sc[i];
+            b += sd[i];
+        }
+        c[n] = a;
+        d[n] = b + (bias != nullptr ? bias[n] : 0.f);
+    }
+}
+
 __global__ void step_kernel(StepState* st, const float* __restrict__ grid, const unsigned char* __restrict__ mask,
                             int stage) {
     pdl_wait();
@@ -344,6 +409,12 @@ cudaError_t launch_convert16(const float* in, void* out16, long long n, int opd,
     if (blocks < 1) blocks = 1;
     return launch_pdl(convert16_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, s, in,
                       reinterpret_cast<uint16_t*>(out16), n, opd);
+}
+
+cudaError_t launch_fold_ln(const float* W, const float* gamma, const float* beta, const float* bias, void* w16,
+                           float* c, float* d, int N, int K, int opd, cudaStream_t s) {
+    fold_ln_kernel<<<N, 256, 0, s>>>(W, gamma, beta, bias, reinterpret_cast<uint16_t*>(w16), c, d, K, opd);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_step(StepState* st, const float* grid, const unsigned char* mask, int stage, cudaStream_t s) {

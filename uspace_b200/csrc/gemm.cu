@@ -159,7 +159,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
             mbar_wait(&tmem_full_bar[as], aphase);
             tc_fence_after();
 
-            const EpiRow row = epi_row(g, EPI, m);
+            EpiRow row = epi_row(g, EPI, m);
 #pragma unroll 1
             for (int c = 0; c < BN / 32; ++c) {
                 uint32_t r[32];
@@ -248,6 +248,9 @@ static bool force_1cta() {
 
 cudaError_t launch_gemm(int epi, const GemmMaps& maps, const GemmArgs& a, int num_sms, cudaStream_t s) {
     if (a.M <= 0 || a.N % 128 != 0 || a.K % BK != 0 || a.K0 % BK != 0 || a.K0 > a.K) return cudaErrorInvalidValue;
+    // the folded-LayerNorm epilogues are implemented by the pair kernel only
+    if ((a.ln_stats != nullptr || a.stats_out != nullptr) && (force_1cta() || !gemm2_supported(epi, maps, a)))
+        return cudaErrorNotSupported;
     if (!force_1cta() && gemm2_supported(epi, maps, a)) {
         static int diag = -1;
         if (diag < 0) {

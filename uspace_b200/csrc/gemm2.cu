@@ -231,7 +231,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
             const int m0 = (tile / n_tiles_n) * (2 * BM) + static_cast<int>(rank) * BM;
             const int n0 = (tile % n_tiles_n) * BN;   // the two column halves take interleaved chunks, so that at
                                                       // any moment the CTA touches 256 B contiguous per output row
-            const EpiRow row = epi_row(g, EPI, m0 + rloc);
+            EpiRow row = epi_row(g, EPI, m0 + rloc);
 
             mbar_wait_idle(&tmem_full_bar[as], aphase);
             tc_fence_after();
@@ -277,6 +277,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(&tmem_empty_bar[as], 0);
+            if (EPI == EPI_BIAS_RESID || EPI == EPI_BIAS_F32) epi_store_stats(g, row, (n0 / 128) + half);
         }
     }
 

@@ -34,6 +34,8 @@ struct EpiRow {          // per-row bookkeeping, computed once per tile
     int m;               // global row
     bool ok;             // m < M
     long long qkv_row;   // EPI_QKV: (b*H*L + l) * 64
+    float mean, rstd;    // folded LayerNorm (consumer GEMMs)
+    float s1, s2;        // partial row statistics being accumulated (producer GEMMs)
 };
 
 __device__ __forceinline__ EpiRow epi_row(const GemmArgs& g, int epi, int m) {
@@ -41,6 +43,22 @@ __device__ __forceinline__ EpiRow epi_row(const GemmArgs& g, int epi, int m) {
     r.m = m;
     r.ok = m < g.M;
     r.qkv_row = 0;
+    r.mean = 0.f;
+    r.rstd = 1.f;
+    r.s1 = r.s2 = 0.f;
+    if (g.ln_stats != nullptr && r.ok) {
+        // fixed-order sum of the producer's partials: deterministic (no atomics anywhere)
+        const float2* sp = reinterpret_cast<const float2*>(g.ln_stats) + static_cast<long long>(m) * g.ln_np;
+        float a = 0.f, b = 0.f;
+        for (int i = 0; i < g.ln_np; ++i) {
+            const float2 p = __ldg(sp + i);
+            a += p.x;
+            b += p.y;
+        }
+        r.mean = a * g.ln_inv_d;
+        const float var = fmaxf(b * g.ln_inv_d - r.mean * r.mean, 0.f);
+        r.rstd = rsqrtf(var + 1e-5f);
+    }
     if (epi == EPI_QKV) {
         const int b = m / g.L;
         const int l = m - b * g.L;
@@ -59,13 +77,24 @@ __device__ __forceinline__ void epi_load_resid(const GemmArgs& g, const EpiRow& 
 }
 
 template <int EPI>
-__device__ __forceinline__ void epi_chunk(const GemmArgs& g, const EpiRow& row, int n, const uint32_t* r,
+__device__ __forceinline__ void epi_chunk(const GemmArgs& g, EpiRow& row, int n, const uint32_t* r,
                                           const float4* resid) {
     if (!row.ok) return;
     float v[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-    if (g.bias != nullptr) {
+    if (g.ln_stats != nullptr) {
+        const float nm = -row.mean;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+            const float4 c4 = __ldg(reinterpret_cast<const float4*>(g.ln_c + n + j));
+            const float4 d4 = __ldg(reinterpret_cast<const float4*>(g.ln_d + n + j));
+            v[j] = fmaf(row.rstd, fmaf(nm, c4.x, v[j]), d4.x);
+            v[j + 1] = fmaf(row.rstd, fmaf(nm, c4.y, v[j + 1]), d4.y);
+            v[j + 2] = fmaf(row.rstd, fmaf(nm, c4.z, v[j + 2]), d4.z);
+            v[j + 3] = fmaf(row.rstd, fmaf(nm, c4.w, v[j + 3]), d4.w);
+        }
+    } else if (g.bias != nullptr) {
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
             const float4 b4 = __ldg(reinterpret_cast<const float4*>(g.bias + n + j));
@@ -80,6 +109,13 @@ __device__ __forceinline__ void epi_chunk(const GemmArgs& g, const EpiRow& row, 
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             v[4 * j] += resid[j].x; v[4 * j + 1] += resid[j].y; v[4 * j + 2] += resid[j].z; v[4 * j + 3] += resid[j].w;
+        }
+    }
+    if ((EPI == EPI_BIAS_RESID || EPI == EPI_BIAS_F32) && g.stats_out != nullptr) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            row.s1 += v[j];
+            row.s2 = fmaf(v[j], v[j], row.s2);
         }
     }
     if (EPI == EPI_BIAS_RESID || EPI == EPI_BIAS_F32) {
@@ -108,4 +144,13 @@ __device__ __forceinline__ void epi_chunk(const GemmArgs& g, const EpiRow& row, 
     }
 }
 
+}  // namespace usp
+
+namespace usp {
+// after a tile: publish this thread's (row, 128-column group) partial statistics
+__device__ __forceinline__ void epi_store_stats(const GemmArgs& g, const EpiRow& row, int group) {
+    if (g.stats_out != nullptr && row.ok)
+        reinterpret_cast<float2*>(g.stats_out)[static_cast<long long>(row.m) * (g.N / 128) + group] =
+            make_float2(row.s1, row.s2);
+}
 }  // namespace usp

@@ -29,6 +29,18 @@ struct GemmArgs {
     int L, H;            // EPI_QKV: tokens per sample, heads (head_dim = 64)
     long long qkv_stride;  // EPI_QKV: elements between the q, k and v planes
     int diag;              // diagnostics (env USP_GEMM_DIAG): 1 = skip TMA loads after the first ring fill (results invalid)
+    // ---- LayerNorm folded into the GEMMs (usp_config.fuse_layernorm) ----
+    // consumer side (qkv / fc1): A is the UN-normalised 16-bit stream x, W is pre-scaled by gamma, and
+    //   out[m,n] = rstd_m * (acc[m,n] - mean_m * ln_c[n]) + ln_d[n]
+    // with ln_c[n] = sum_k W'[n,k], ln_d[n] = sum_k beta_k W[n,k] + bias[n]   (libs/uvit.py:160-161 algebraically)
+    const float* ln_stats; // [M, ln_np, 2] per-row partial (sum, sum of squares) written by the producer, or nullptr
+    const float* ln_c;     // [N]
+    const float* ln_d;     // [N]
+    int ln_np;             // partials per row
+    float ln_inv_d;        // 1 / embed_dim
+    // producer side (skip / proj / fc2): partial row statistics of the fp32 values it writes, one slot per
+    // (row, 128-column group): [M, N/128, 2]
+    float* stats_out;
 };
 
 struct GemmMaps {
@@ -86,6 +98,9 @@ struct EmbedArgs {
     const float* freqs;    // [D/2]
     const float* delta;    // head edit table [nsteps+1, C*S*S] or nullptr
     float* out32;          // [B*L, D]
+    void* out16;           // optional un-normalised 16-bit copy [B*L, D] (folded-LayerNorm path)
+    float* stats;          // optional [B*L, 8, 2] partial row statistics (one slot per warp of the block)
+    int opd;
     int B, C, S, p, D, L, n_ctx, has_label;
 };
 cudaError_t launch_embed(const EmbedArgs& a, cudaStream_t s);
@@ -120,6 +135,10 @@ struct FinalArgs {
 cudaError_t launch_final(const FinalArgs& a, cudaStream_t s);
 
 cudaError_t launch_convert16(const float* in, void* out16, long long n, int opd, cudaStream_t s);
+// Fold a LayerNorm into the Linear that consumes it: w16[n,k] = round16(W[n,k] * gamma[k]),
+// c[n] = sum_k w16[n,k], d[n] = sum_k beta[k] * W[n,k] (+ bias[n])
+cudaError_t launch_fold_ln(const float* W, const float* gamma, const float* beta, const float* bias, void* w16,
+                           float* c, float* d, int N, int K, int opd, cudaStream_t s);
 // stage 0: start interval `next` (t = grid[next]) and advance; stage 1: second Heun stage (t = grid[cur+1])
 cudaError_t launch_step(StepState* st, const float* grid, const unsigned char* mask, int stage, cudaStream_t s);
 

@@ -14,7 +14,7 @@ def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
-def config_from_kwargs(kw: dict, operand_dtype: str = "fp16") -> _lib.UspConfig:
+def config_from_kwargs(kw: dict, operand_dtype: str = "fp16", fuse_layernorm: bool = False) -> _lib.UspConfig:
     """Map the reference ctor kwargs (libs/uvit.py:183-202, libs/uvit_t2i.py:193-211) to usp_config."""
     if kw.get("mlp_time_embed", False):
         raise NotImplementedError("mlp_time_embed=True is not used by any reference config and is not built")
@@ -36,17 +36,20 @@ def config_from_kwargs(kw: dict, operand_dtype: str = "fp16") -> _lib.UspConfig:
     c.conv = int(bool(kw.get("conv", True)))
     c.skip = int(bool(kw.get("skip", True)))
     c.operand_dtype = _lib.OPERAND[operand_dtype]
+    c.fuse_layernorm = int(bool(fuse_layernorm))
     return c
 
 
 class Engine:
-    def __init__(self, ctor_kwargs: dict, device: torch.device, operand_dtype: str = "fp16"):
+    def __init__(self, ctor_kwargs: dict, device: torch.device, operand_dtype: str = "fp16",
+                 fuse_layernorm: bool = False):
         if device.type != "cuda":
             raise RuntimeError("uspace_b200 runs on CUDA (sm_100a) only; there is no CPU path")
         self.lib = _lib.load()
         self.device = device
-        self.cfg = config_from_kwargs(ctor_kwargs, operand_dtype)
+        self.cfg = config_from_kwargs(ctor_kwargs, operand_dtype, fuse_layernorm)
         self.operand_dtype = operand_dtype
+        self.fuse_layernorm = bool(fuse_layernorm)
         self.handle = C.c_void_p()
         idx = device.index if device.index is not None else torch.cuda.current_device()
         _lib.check(self.lib.usp_create(C.byref(self.cfg), idx, C.byref(self.handle)), None, "usp_create")

@@ -75,6 +75,9 @@ class _UViTBase(nn.Module):
     """Parameter container + engine lifecycle shared by the uncond/class and t2i models."""
 
     operand_dtype = "fp16"  # tensor-core operand type ("fp16" or "bf16"); fp32 accumulate either way
+    # fold norm1 / norm2 into the qkv / fc1 GEMM epilogues (exact algebra, no LayerNorm kernels).  Parity-tested, but
+    # measured neutral on B200 (the GEMM epilogues are the scarcer resource), so the separate LayerNorm stays default.
+    fuse_layernorm = False
 
     def _build(self, img_size, patch_size, in_chans, embed_dim, depth, num_heads, mlp_ratio, qkv_bias,
                mlp_time_embed, conv, skip, extras):
@@ -128,10 +131,11 @@ class _UViTBase(nn.Module):
             raise RuntimeError(
                 "uspace_b200: the inference path needs the model on a CUDA (sm_100a) device; there is no CPU "
                 "fallback — move the module with .to('cuda') / accelerator.prepare first")
-        if self._engine is None or self._engine.device != dev or self._engine.operand_dtype != self.operand_dtype:
+        if (self._engine is None or self._engine.device != dev or self._engine.operand_dtype != self.operand_dtype
+                or self._engine.fuse_layernorm != bool(self.fuse_layernorm)):
             if self._engine is not None:
                 self._engine.close()
-            self._engine = Engine(self._ctor_kwargs, dev, self.operand_dtype)
+            self._engine = Engine(self._ctor_kwargs, dev, self.operand_dtype, self.fuse_layernorm)
             self._engine_versions = None
         ver = self._versions()
         if ver != self._engine_versions:  # load_state_dict / optimizer step / .to() happened
