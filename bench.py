@@ -295,7 +295,12 @@ def main():
                          "achieved": achieved, "peak": pk["sustained"], "unit": "TFLOP/s", "frac": achieved / pk["sustained"],
                          "peak_kind": f"bf16_tflops_sustained of {pk['src']} (kernel timed inside a long step); burst {pk['burst']}",
                          "launches": gemm_launches, "avg_launch_ms": gemm_ms / max(1, gemm_launches),
-                         "share_of_forward": gemm_ms / fwd_ms, "traffic": None},
+                         "share_of_forward": gemm_ms / fwd_ms,
+                         # DRAM read+write bytes per GEMM launch (mean over the 94 launches of one evaluation) from the
+                         # `ncu --set full` capture profiles/r01d_ncu_gemm.md (qkv 93.8, proj 119.1, fc1 128.6,
+                         # fc2 288.6 MB measured; skip_linear 140 MB estimated); algorithmic operand+result bytes: 193.5 MB
+                         "traffic": 155.7e6 if (args.workload == "c2" and Bl == 64) else None,
+                         "algorithmic_bytes": 193.5e6 if (args.workload == "c2" and Bl == 64) else None},
             "kernel_ms_per_forward": {k: round(v[0], 4) for k, v in prof.items()},
             "clocks": clocks, "finite": finite,
         }
