@@ -118,6 +118,42 @@ def cpu_port_forward_time(cfg, t2i, B, max_seconds=25.0, warmup=1, reps=3):
     return statistics.median(times), len(times)
 
 
+def torch_eager_on_gpu(wl, dev, nfe):
+    """Context only (not the product, not the reference arm): the reference's algorithm as plain torch-eager library
+    calls on the same B200 (fp32 as shipped - Attention.forward forces .float(), libs/uvit.py:93 - and bf16 autocast),
+    timed on a few velocity evaluations at the workload's batch, extrapolated like the CPU baseline."""
+    import torch
+
+    from oracle import uvit_oracle as O
+    from uspace_b200.uvit import UViT, UViTT2I
+    O.FAST = True
+    torch.manual_seed(0)
+    sd = {k: v.to(dev) for k, v in (UViTT2I if wl["t2i"] else UViT)(**wl["cfg"]).state_dict().items()}
+    B = wl["batch"]
+    x = torch.randn(B, 4, 32, 32, device=dev)
+    t = torch.full((B,), 0.5, device=dev)
+    ctx = torch.randn(B, 77, 768, device=dev) if wl["t2i"] else None
+    out = {}
+    with torch.no_grad():
+        for name, ac in (("fp32", False), ("bf16_autocast", True)):
+            try:
+                with torch.autocast("cuda", dtype=torch.bfloat16, enabled=ac):
+                    for _ in range(2):
+                        O.uvit_forward(sd, wl["cfg"], x, t, context=ctx)
+                    torch.cuda.synchronize()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    for _ in range(3):
+                        O.uvit_forward(sd, wl["cfg"], x, t, context=ctx)
+                    e1.record()
+                    torch.cuda.synchronize()
+                out[name] = {"images_per_s": B / (e0.elapsed_time(e1) / 3 * 1e-3 * nfe), "ms_per_forward": e0.elapsed_time(e1) / 3}
+            except Exception as ex:  # context only: never fail the benchmark because of it
+                out[name] = {"error": str(ex)[:120]}
+    out["note"] = "oracle restatement through torch library kernels on the GPU; extrapolated from 3 forwards; context only"
+    return out
+
+
 def run_reference(args, wl):
     """Reference arm: the reference algorithm on the host cores (oracle port), bounded sample per step."""
     rank = int(os.environ.get("RANK", "0"))
@@ -309,6 +345,8 @@ def main():
             res["cpu_baseline"] = {"value": 8 / (tf * nfe), "unit": "images/s", "cores": os.cpu_count(), "kind": "port",
                                    "sample": f"{n} velocity evaluations at batch 8 on the host cores (torch fp32 oracle), "
                                              f"images/s = 8/(t_fwd*{nfe}) extrapolated from per-forward time"}
+        if world == 1 and not args.no_cpu_baseline:
+            res["torch_eager_b200"] = torch_eager_on_gpu(wl, dev, nfe)
         print(json.dumps(res))
     if world > 1:
         dist.barrier()

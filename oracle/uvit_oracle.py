@@ -107,7 +107,7 @@ def unpatchify_index(C: int, S: int, p: int) -> Tensor:
 # ----------------------------------------------------------------------------------------------
 def timestep_embedding(t: Tensor, dim: int, max_period: float = 10000.0) -> Tensor:
     half = dim // 2
-    freqs = torch.exp(-math.log(max_period) * torch.arange(half, dtype=torch.float32) / half).to(t.dtype)
+    freqs = torch.exp(-math.log(max_period) * torch.arange(half, dtype=torch.float32) / half).to(device=t.device, dtype=t.dtype)
     args = t[:, None] * freqs[None]
     emb = torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
     if dim % 2:

@@ -134,3 +134,15 @@ def test_fast_library_mode_equals_explicit_formulas():
     finally:
         O.FAST = False
     assert rel(b, a) < 2e-6
+
+
+def test_config0_single_euler_step_small_deep16(golden_dir):
+    """BASELINE.json configs[0]: lfm_cm256_uvit_small_deep16, one Euler step, batch 2, CPU (plumbing check)."""
+    case = CASES["small16_uncond"]
+    sd = build_model(case, UViT, UViTT2I).state_dict()
+    x, _, _, _ = build_inputs(case)
+    h = 0.02
+    z1 = O.odeint_fixed(lambda t, z: O.uvit_forward(sd, case["cfg"], z, t.expand(z.shape[0])), x, 0.0, h, h, "euler")
+    v0 = O.uvit_forward(sd, case["cfg"], x, torch.zeros(2))
+    assert z1.shape == x.shape and torch.isfinite(z1).all()
+    assert rel(z1, x + np.float32(h) * v0) < 1e-6
