@@ -58,6 +58,14 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
           "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
         : "memory");
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // V rows as the B operand in MN-major form (see attention.cu): 64 head-dim elements contiguous per key row
@@ -71,14 +79,15 @@ __device__ __forceinline__ uint64_t umma_desc_v_mn(uint32_t saddr) {
     return d;
 }
 
-template <bool REGS>
+template <int MODE>   // 0: two-pass softmax (any L <= 352), 1: score-row share in registers (L <= 320),
+                      // 2: registers + software-pipelined tiles (L <= 288)
 __global__ void __launch_bounds__(THREADS, 1)
 attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                   const __grid_constant__ CUtensorMap tmV, const AttnArgs a) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
-    __shared__ __align__(8) uint64_t q_full[2], kv_full[2], bar_s, p_stage[6], bar_o, tail_done, tail_go;
+    __shared__ __align__(8) uint64_t q_full[2], kv_full[2], bar_s, s_free, p_stage[6], bar_o, tail_done, tail_go;
     __shared__ float t_q[HD], t_p[MAX_L2], t_red[2][4], t_o[3][HD];
     __shared__ uint32_t tmem_base_smem;
     __shared__ float s_max[2][QT], s_sum[2][QT];
@@ -97,7 +106,10 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     const int n_items = a.B * a.H;
     const int nch = (L + 31) / 32;          // 32-column score chunks
     const int n0 = (nch + 1) / 2;           // chunks handled by column-part 0
-    const int S_COL = 0, O_COL = L16, P1_COL = L16 + 64;
+    constexpr bool REGS = MODE >= 1;
+    constexpr bool PIPE = MODE == 2;
+    // PIPE keeps P in its own columns so that the next tile's S-MMA may overwrite S while P is still being consumed
+    const int S_COL = 0, PP_COL = L16, O_COL = PIPE ? L16 + 16 * nch : L16, P1_COL = L16 + 64;
 
     // smem: Q[2] | K[2] | V[2]
     uint8_t* sQ = smem;
@@ -110,6 +122,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
             mbar_init(&kv_full[i], 1);
         }
         mbar_init(&bar_s, 1);
+        mbar_init(&s_free, 256);
         for (int i = 0; i < 6; ++i) mbar_init(&p_stage[i], 256);
         mbar_init(&bar_o, 1);
         mbar_init(&tail_done, 3);
@@ -247,6 +260,94 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
             }
             __syncwarp();
         }
+        if (PIPE) {
+            // ---------- software-pipelined issue: S-MMA(g+1) goes out as soon as S(g) sits in registers ----------
+            const int n_tiles = ((n_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
+                                 static_cast<int>(gridDim.x)) * n_qt;   // tiles this CTA will process
+            const int nks = L16 / 16;
+            auto issue_s = [&](int gg) {   // S = Q K^T for tile gg (all lanes call; one elected lane issues)
+                const int nn_ = gg / n_qt;
+                mbar_wait(&q_full[gg & 1], (gg >> 1) & 1);
+                if (gg % n_qt == 0) mbar_wait(&kv_full[nn_ & 1], (nn_ >> 1) & 1);
+                tc_fence_after();
+                const uint64_t qdesc = umma_desc_sw128(smem_u32(sQ + (gg & 1) * QTILE_BYTES));
+                const uint32_t kbase = smem_u32(sK + (nn_ & 1) * kv_bytes);
+                if (elect_one()) {
+                    for (int c0 = 0; c0 < L16; c0 += 256) {
+                        const int nn = (L16 - c0) < 256 ? (L16 - c0) : 256;
+                        const uint32_t idesc = umma_idesc(fmt, QT, nn, 0, 0);
+                        const uint64_t kdesc = umma_desc_sw128(kbase + c0 * 128);
+#pragma unroll
+                        for (int k = 0; k < HD / 16; ++k)
+                            umma_f16(tmem_base + S_COL + c0, qdesc + (k * 2), kdesc + (k * 2), idesc, k != 0);
+                    }
+                    umma_commit(&bar_s);
+                }
+                __syncwarp();
+            };
+            auto load_q = [&](int gg) {    // Q tile of this CTA's tile gg into buffer gg & 1 (elected lane only)
+                const int bhq = static_cast<int>(blockIdx.x) + (gg / n_qt) * static_cast<int>(gridDim.x);
+                mbar_expect_tx(&q_full[gg & 1], QTILE_BYTES);
+                tma_load_3d(&tmQ, &q_full[gg & 1], sQ + (gg & 1) * QTILE_BYTES, 0, (gg % n_qt) * QT, bhq);
+            };
+            if (n_tiles > 0) {
+                if (n_tiles > 1 && elect_one()) load_q(1);   // Q(0) was loaded by the prologue above
+                __syncwarp();
+                issue_s(0);
+            }
+            for (int g = 0; g < n_tiles; ++g) {
+                const int n = g / n_qt, t = g % n_qt;
+                const int bh = static_cast<int>(blockIdx.x) + n * static_cast<int>(gridDim.x);
+                if (t == 0) {
+                    // the previous item's last PV has retired: its K/V buffer may be refilled
+                    if (g > 0) mbar_wait(&bar_o, (g - 1) & 1);
+                    if (elect_one()) {
+                        if (tail_simt) {
+                            if (n > 0) mbar_wait(&tail_done, (n - 1) & 1);
+                            mbar_arrive(&tail_go);
+                        }
+                        if (bh + static_cast<int>(gridDim.x) < n_items) {
+                            const int nb = (n & 1) ^ 1;
+                            const int bh2 = bh + gridDim.x;
+                            mbar_expect_tx(&kv_full[nb], 2 * kv_bytes);
+                            for (int c = 0; c < 2; ++c) {
+                                tma_load_3d(&tmK, &kv_full[nb], sK + nb * kv_bytes + c * hrows * 128, 0, c * hrows, bh2);
+                                tma_load_3d(&tmV, &kv_full[nb], sV + nb * kv_bytes + c * hrows * 128, 0, c * hrows, bh2);
+                            }
+                        }
+                    }
+                    __syncwarp();
+                }
+                // S(g) is in the softmax warps' registers: the S columns and Q buffer g & 1 are free again
+                mbar_wait(&s_free, g & 1);
+                if (g + 2 < n_tiles && elect_one()) load_q(g + 2);
+                __syncwarp();
+                if (g + 1 < n_tiles) issue_s(g + 1);
+                // ---- O(g) = P V, stage by stage as P chunks are published ----
+                const uint32_t vbase = smem_u32(sV + (n & 1) * kv_bytes);
+                for (int st = 0; st < n0; ++st) {
+                    mbar_wait(&p_stage[st], g & 1);
+                    tc_fence_after();
+                    if (elect_one()) {
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const int c = h == 0 ? st : n0 + st;
+                            if (c >= nch) continue;
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) {
+                                const int kk = 2 * c + e;
+                                if (kk >= nks) continue;
+                                const uint64_t vdesc = umma_desc_v_mn(vbase + kk * 16 * 128);
+                                umma_f16_ts(tmem_base + O_COL, tmem_base + PP_COL + 16 * c + 8 * e, vdesc, idesc_o,
+                                            !(st == 0 && h == 0 && e == 0));
+                            }
+                        }
+                        if (st == n0 - 1) umma_commit(&bar_o);
+                    }
+                    __syncwarp();
+                }
+            }
+        } else {
         int g = 0;  // global tile counter of this CTA
         int n = 0;  // item counter of this CTA
         for (int bh = blockIdx.x; bh < n_items; bh += gridDim.x, ++n) {
@@ -327,6 +428,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                 }
             }
         }
+        }   // !PIPE
     } else {
         // ===================== softmax / output warps (two threads per query row) =====================
         asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
@@ -337,6 +439,108 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         const float c2 = 0.125f * 1.44269504088896340736f;  // hd^-0.5 * log2(e)
         const int c_lo = part == 0 ? 0 : n0;
         const int c_hi = part == 0 ? n0 : nch;
+        if (PIPE) {
+            // ---------- pipelined order: S(g) -> registers, release S, max, [finish tile g-1: O read-out], exp, P ----
+            auto store_o = [&](int pbh, int pl, bool prow_ok, bool pwarp_ok, float pinv, int pg) {
+                mbar_wait(&bar_o, pg & 1);
+                tc_fence_after();
+                if (pwarp_ok) {
+                    uint16_t* op = reinterpret_cast<uint16_t*>(a.out16) +
+                                   (static_cast<long long>(pbh / a.H) * L + pl) * a.D + (pbh % a.H) * HD + part * 32;
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh) {   // 16 columns at a time: the score registers stay live
+                        uint32_t r[16];
+                        tmem_ld16(t_row + O_COL + part * 32 + hh * 16, r);
+                        tmem_ld_wait();
+                        uint32_t u[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float v0 = __uint_as_float(r[2 * j]) * pinv, v1 = __uint_as_float(r[2 * j + 1]) * pinv;
+                            u[j] = a.opd == OPD_FP16 ? Op16<OPD_FP16>::pack(v0, v1) : Op16<OPD_BF16>::pack(v0, v1);
+                        }
+                        if (prow_ok) st_global_v8_b32(op + hh * 16, u);
+                    }
+                }
+                tc_fence_before();
+            };
+            int g = 0;
+            int p_bh = 0, p_l = 0;
+            bool p_row_ok = false, p_warp_ok = false;
+            float p_inv = 0.f;
+            const int cnt = c_hi - c_lo;
+            for (int bh = blockIdx.x; bh < n_items; bh += gridDim.x) {
+                for (int t = 0; t < n_qt; ++t, ++g) {
+                    const int l = t * QT + row;
+                    const bool row_ok = l < L;
+                    const bool warp_ok = __any_sync(0xffffffffu, row_ok);
+                    uint32_t r[5][32];
+                    mbar_wait(&bar_s, g & 1);
+                    tc_fence_after();
+                    if (warp_ok) {
+#pragma unroll
+                        for (int k = 0; k < 5; ++k)
+                            if (k < cnt) tmem_ld32(t_row + S_COL + (c_lo + k) * 32, r[k]);
+                        tmem_ld_wait();
+                    }
+                    tc_fence_before();
+                    mbar_arrive(&s_free);            // the control warp may overwrite S with the next tile now
+                    float mx = -INFINITY;
+                    if (warp_ok) {
+#pragma unroll
+                        for (int k = 0; k < 5; ++k) {
+                            if (k < cnt) {
+                                const int c = c_lo + k;
+                                if (c * 32 + 32 <= L) {
+#pragma unroll
+                                    for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(r[k][j]));
+                                } else {
+#pragma unroll
+                                    for (int j = 0; j < 32; ++j)
+                                        if (c * 32 + j < L) mx = fmaxf(mx, __uint_as_float(r[k][j]));
+                                }
+                            }
+                        }
+                    }
+                    s_max[part][row] = mx;
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                    mx = fmaxf(s_max[0][row], s_max[1][row]);
+                    const float mxs = mx * c2;
+                    // the previous tile's PV has had the whole S load / max phase to finish
+                    if (g > 0) store_o(p_bh, p_l, p_row_ok, p_warp_ok, p_inv, g - 1);
+                    float sum = 0.f;
+#pragma unroll
+                    for (int k = 0; k < 5; ++k) {
+                        if (k < n0) {
+                            if (warp_ok && k < cnt) {
+                                const int c = c_lo + k;
+                                uint32_t w[16];
+                                const bool full = (c * 32 + 32 <= L);
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) {
+                                    float p0 = ex2_approx(fmaf(__uint_as_float(r[k][2 * j]), c2, -mxs));
+                                    float p1 = ex2_approx(fmaf(__uint_as_float(r[k][2 * j + 1]), c2, -mxs));
+                                    if (!full) {
+                                        if (c * 32 + 2 * j >= L) p0 = 0.f;
+                                        if (c * 32 + 2 * j + 1 >= L) p1 = 0.f;
+                                    }
+                                    sum += p0 + p1;
+                                    w[j] = a.opd == OPD_FP16 ? Op16<OPD_FP16>::pack(p0, p1) : Op16<OPD_BF16>::pack(p0, p1);
+                                }
+                                tmem_st16(t_row + PP_COL + 16 * c, w);
+                                tmem_st_wait();
+                            }
+                            tc_fence_before();
+                            mbar_arrive(&p_stage[k]);
+                        }
+                    }
+                    s_sum[part][row] = sum;
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                    p_inv = 1.0f / (s_sum[0][row] + s_sum[1][row]);
+                    p_bh = bh; p_l = l; p_row_ok = row_ok; p_warp_ok = warp_ok;
+                }
+            }
+            if (g > 0) store_o(p_bh, p_l, p_row_ok, p_warp_ok, p_inv, g - 1);
+        } else {
         int g = 0;
         for (int bh = blockIdx.x; bh < n_items; bh += gridDim.x) {
             for (int t = 0; t < n_qt; ++t, ++g) {
@@ -485,6 +689,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                 tc_fence_before();
             }
         }
+        }   // !PIPE
     }
 
     tc_fence_before();
@@ -500,10 +705,12 @@ int smem_bytes_for(int L) {
 }  // namespace
 
 cudaError_t attention2_configure() {
-    cudaError_t e = cudaFuncSetAttribute(attention2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(attention2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          smem_bytes_for(MAX_L2));
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(attention2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    e = cudaFuncSetAttribute(attention2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes_for(MAX_L2));
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(attention2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 smem_bytes_for(MAX_L2));
 }
 
@@ -526,9 +733,21 @@ cudaError_t launch_attention2(const CUtensorMap& q, const CUtensorMap& k, const 
     AttnArgs a2 = a;
     a2.diag = diag;
     const int nch = (a.L + 31) / 32;
-    if ((nch + 1) / 2 <= 5)   // each thread's share of a score row fits in registers (L <= 320)
-        return launch_pdl(attention2_kernel<true>, dim3(grid), dim3(THREADS), smem_bytes_for(a.L), s, q, k, v, a2);
-    return launch_pdl(attention2_kernel<false>, dim3(grid), dim3(THREADS), smem_bytes_for(a.L), s, q, k, v, a2);
+    const int L16 = (a.L + 15) & ~15;
+    static int max_mode = -1;   // USP_ATTN_MODE caps the variant (A/B comparison, debugging)
+    if (max_mode < 0) {
+        const char* e = getenv("USP_ATTN_MODE");
+        max_mode = e ? atoi(e) : 2;
+    }
+    int mode = 0;
+    if ((nch + 1) / 2 <= 5) mode = 1;                              // score-row share fits in registers (L <= 320)
+    if (mode == 1 && L16 + 16 * nch + 64 <= TMEM_COLS) mode = 2;   // room for a private P region (L <= 288)
+    if (mode > max_mode) mode = max_mode;
+    if (mode == 2)
+        return launch_pdl(attention2_kernel<2>, dim3(grid), dim3(THREADS), smem_bytes_for(a.L), s, q, k, v, a2);
+    if (mode == 1)
+        return launch_pdl(attention2_kernel<1>, dim3(grid), dim3(THREADS), smem_bytes_for(a.L), s, q, k, v, a2);
+    return launch_pdl(attention2_kernel<0>, dim3(grid), dim3(THREADS), smem_bytes_for(a.L), s, q, k, v, a2);
 }
 
 }  // namespace usp
