@@ -25,6 +25,7 @@ __device__ __forceinline__ float warp_sum(float v) {
 constexpr int EMB_TOK = 16;
 constexpr int EMB_MAXP = 64;   // C*p*p upper bound
 
+template <bool EXTRA>   // EXTRA: also emit the 16-bit copy and the partial row statistics (folded-LayerNorm path)
 __global__ void __launch_bounds__(256) embed_kernel(const EmbedArgs a) {
     pdl_wait();
     pdl_launch();
@@ -106,14 +107,16 @@ __global__ void __launch_bounds__(256) embed_kernel(const EmbedArgs a) {
             }
             v += pos;
             out[d] = v;
-            if (a.out16 != nullptr)
+            if (EXTRA && a.out16 != nullptr)
                 reinterpret_cast<uint16_t*>(a.out16)[(static_cast<long long>(b) * a.L + l) * D + d] =
                     a.opd == OPD_FP16 ? Op16<OPD_FP16>::one(v) : Op16<OPD_BF16>::one(v);
-            st1[i] += v;
-            st2[i] = fmaf(v, v, st2[i]);
+            if (EXTRA) {
+                st1[i] += v;
+                st2[i] = fmaf(v, v, st2[i]);
+            }
         }
     }
-    if (a.stats != nullptr) {
+    if (EXTRA && a.stats != nullptr) {
         // one (sum, sum of squares) slot per (row, warp): the consumer adds the 8 slots in fixed order
         const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
@@ -363,7 +366,9 @@ __global__ void step_kernel(StepState* st, const float* __restrict__ grid, const
 
 cudaError_t launch_embed(const EmbedArgs& a, cudaStream_t s) {
     if (a.C * a.p * a.p > 64) return cudaErrorInvalidValue;
-    return launch_pdl(embed_kernel, dim3((a.L + EMB_TOK - 1) / EMB_TOK, a.B), dim3(256), 0, s, a);
+    if (a.out16 != nullptr || a.stats != nullptr)
+        return launch_pdl(embed_kernel<true>, dim3((a.L + EMB_TOK - 1) / EMB_TOK, a.B), dim3(256), 0, s, a);
+    return launch_pdl(embed_kernel<false>, dim3((a.L + EMB_TOK - 1) / EMB_TOK, a.B), dim3(256), 0, s, a);
 }
 
 cudaError_t launch_layernorm(const float* x, const float* g, const float* b, void* out16, int M, int D, int opd,
