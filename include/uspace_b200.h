@@ -56,6 +56,14 @@ typedef struct usp_config {
     int32_t fuse_layernorm;  /* 1: fold norm1/norm2 into the qkv / fc1 GEMMs (no LayerNorm kernels) */
 } usp_config;
 
+/* Post-softmax attention column re-weighting ("p2p_rescale": tools/utils_t2i.py:196-224,265-296, called from
+ * libs/uvit_t2i.py:104): attn[:, :, :, j] *= colscale[b, j] after the softmax, without re-normalisation. */
+typedef struct usp_attn_edit {
+    const float* colscale;   /* [B, L] fp32, device or host; 1.0 leaves a key column untouched              */
+    uint64_t block_mask;     /* bit i set: apply in the i-th executed block (in, mid, out order); ~0 = "all" */
+    float t_edit;            /* sampling only: active while float(f"{t:.2f}") <= t_edit                      */
+} usp_attn_edit;
+
 enum { USP_METHOD_EULER = 0, USP_METHOD_HEUN = 1 };
 enum { USP_EDIT_NONE = 0, USP_EDIT_HEAD = 1, USP_EDIT_TAIL = 2 };
 
@@ -78,6 +86,10 @@ const char* usp_weight_name(const usp_handle* h, int i);
 int usp_forward(usp_handle* h, const float* x, const float* t, const float* context, const int64_t* y,
                 float* out, int B, void* stream);
 
+/* usp_forward with the attention edit applied unconditionally in the masked blocks (edit may be NULL). */
+int usp_forward_edit(usp_handle* h, const float* x, const float* t, const float* context, const int64_t* y,
+                     float* out, int B, const usp_attn_edit* edit, void* stream);
+
 /* Replaces odeint(func, z, [t0,t1], method, options=dict(step_size)) as called by CNF.decode (t0=0,t1=1) and
  * CNF.encode (t0=1,t1=0) (flow_matching.py:118-125,140-147): torchdiffeq fixed-grid semantics, one CUDA graph
  * per step replayed on `stream`.  z is updated in place.
@@ -87,6 +99,10 @@ int usp_forward(usp_handle* h, const float* x, const float* t, const float* cont
 int usp_sample(usp_handle* h, float* z, const float* context, const int64_t* y, int B, float t0, float t1,
                float step_size, int method, const float* delta_table, float write_scale, float t_edit,
                int edit_loc, void* stream);
+/* usp_sample plus the attention edit of dissect_lfm_t2i.py's "p2p" mode (attn may be NULL). */
+int usp_sample_edit(usp_handle* h, float* z, const float* context, const int64_t* y, int B, float t0, float t1,
+                    float step_size, int method, const float* delta_table, float write_scale, float t_edit,
+                    int edit_loc, const usp_attn_edit* attn, void* stream);
 /* Same with HOST buffers: copies z (and context / y / delta_table) host->device, samples, copies z back,
  * and synchronises. This is the end-to-end call bench.py times. */
 int usp_sample_host(usp_handle* h, float* z_host, const float* context_host, const int64_t* y_host, int B, float t0,

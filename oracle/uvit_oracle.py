@@ -163,10 +163,11 @@ def mlp(x: Tensor, sd: Dict[str, Tensor], pre: str) -> Tensor:
     return linear(h, sd[pre + ".mlp.fc2.weight"], sd[pre + ".mlp.fc2.bias"])
 
 
-def block(x: Tensor, sd: Dict[str, Tensor], pre: str, H: int, skip: Optional[Tensor] = None) -> Tensor:
+def block(x: Tensor, sd: Dict[str, Tensor], pre: str, H: int, skip: Optional[Tensor] = None,
+          vscale: Optional[Tensor] = None) -> Tensor:
     if pre + ".skip_linear.weight" in sd:
         x = linear(torch.cat([x, skip], dim=-1), sd[pre + ".skip_linear.weight"], sd[pre + ".skip_linear.bias"])
-    x = x + attention(layer_norm(x, sd[pre + ".norm1.weight"], sd[pre + ".norm1.bias"]), sd, pre, H)
+    x = x + attention(layer_norm(x, sd[pre + ".norm1.weight"], sd[pre + ".norm1.bias"]), sd, pre, H, vscale)
     x = x + mlp(layer_norm(x, sd[pre + ".norm2.weight"], sd[pre + ".norm2.bias"]), sd, pre)
     return x
 
@@ -184,8 +185,11 @@ def should_edit(t: float, t_edit) -> bool:
 
 def uvit_forward(sd: Dict[str, Tensor], cfg: dict, x: Tensor, t: Tensor, y: Optional[Tensor] = None,
                  context: Optional[Tensor] = None, head_delta: Optional[Tensor] = None,
-                 tail_delta: Optional[Tensor] = None) -> Tensor:
-    """UViT.forward on a flat state_dict.  head_delta / tail_delta are already scaled [C,S,S] edits or None."""
+                 tail_delta: Optional[Tensor] = None, attn_colscale: Optional[Tensor] = None,
+                 attn_blocks=None) -> Tensor:
+    """UViT.forward on a flat state_dict.  head_delta / tail_delta are already scaled [C,S,S] edits or None.
+    attn_colscale [B, L] re-weights post-softmax attention columns (p2p_rescale, tools/utils_t2i.py:196-224) in the
+    executed blocks listed in attn_blocks (None = all)."""
     d = model_dims(cfg)
     dt = x.dtype
     if any(v.dtype != dt for v in sd.values()):
@@ -207,12 +211,21 @@ def uvit_forward(sd: Dict[str, Tensor], cfg: dict, x: Tensor, t: Tensor, y: Opti
             h = torch.cat([sd["label_emb.weight"][y][:, None, :], h], dim=1)
     h = h + sd["pos_embed"]
     skips: List[Tensor] = []
+    bid = 0
+
+    def vs():
+        on = attn_colscale is not None and (attn_blocks is None or bid in attn_blocks)
+        return attn_colscale.to(dt) if on else None
+
     for i in range(d["n_in"]):
-        h = block(h, sd, f"in_blocks.{i}", d["H"])
+        h = block(h, sd, f"in_blocks.{i}", d["H"], None, vs())
         skips.append(h)
-    h = block(h, sd, "mid_block", d["H"])
+        bid += 1
+    h = block(h, sd, "mid_block", d["H"], None, vs())
+    bid += 1
     for i in range(d["n_in"]):
-        h = block(h, sd, f"out_blocks.{i}", d["H"], skips.pop())
+        h = block(h, sd, f"out_blocks.{i}", d["H"], skips.pop(), vs())
+        bid += 1
     h = layer_norm(h, sd["norm.weight"], sd["norm.bias"])
     h = h @ sd["decoder_pred.weight"].T + sd["decoder_pred.bias"]
     h = h[:, d["extras"]:, :]
@@ -261,7 +274,8 @@ def odeint_fixed(func: Callable[[Tensor, Tensor], Tensor], z: Tensor, t0: float,
 def sample(sd: Dict[str, Tensor], cfg: dict, z: Tensor, t0: float = 0.0, t1: float = 1.0, step_size: float = 0.02,
            method: str = "euler", y: Optional[Tensor] = None, context: Optional[Tensor] = None,
            delta_table: Optional[Tensor] = None, write_scale: float = 0.0, t_edit: float = 0.0,
-           edit_loc: Optional[str] = None) -> Tensor:
+           edit_loc: Optional[str] = None, attn_colscale: Optional[Tensor] = None, attn_blocks=None,
+           attn_t_edit: float = 0.0) -> Tensor:
     """CNF.decode / CNF.encode (flow_matching.py:102-151) with the write_attr edit hook; delta_table rows are
     indexed by grid point (== the delta_{t:.2f}.npy file the reference would load at that time)."""
     grid = fixed_grid(t0, t1, step_size, torch.float32)
@@ -272,6 +286,9 @@ def sample(sd: Dict[str, Tensor], cfg: dict, z: Tensor, t0: float = 0.0, t1: flo
         if edit_loc is not None and delta_table is not None and should_edit(float(t), t_edit):
             dlt = delta_table[lookup[float(t)]] * write_scale
             hd, td = (dlt, None) if edit_loc == "head" else (None, dlt)
-        return uvit_forward(sd, cfg, x, t.expand(x.shape[0]), y=y, context=context, head_delta=hd, tail_delta=td)
+        # attention edit: float(f"{t:.2f}") <= t_edit, "0.00" included (tools/utils_t2i.py:284)
+        cs = attn_colscale if (attn_colscale is not None and float(f"{float(t):.2f}") <= attn_t_edit) else None
+        return uvit_forward(sd, cfg, x, t.expand(x.shape[0]), y=y, context=context, head_delta=hd, tail_delta=td,
+                            attn_colscale=cs, attn_blocks=attn_blocks)
 
     return odeint_fixed(func, z, t0, t1, step_size, method)

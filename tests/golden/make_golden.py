@@ -65,6 +65,17 @@ def main():
                     v = ref(z, tt, ctx)[0] if t2i else ref(z, tt, y, edit_loc=None)[0]
                     z = z + (grid[i + 1] - grid[i]) * v
                 out["euler"] = z.numpy()
+            if case.get("p2p"):
+                # the reference's attention-editing branch (libs/uvit_t2i.py:91-107 + tools/utils_t2i.py:265-296)
+                pp = case["p2p"]
+                kw = dict(dissect_name="p2p", fm_direction="decode", t_edit=pp["t_edit"], block_id=pp["block_id"],
+                          token_kwargs=dict(token_dissect="p2p_rescale", p2p_multiplier=pp["multiplier"]),
+                          target_context_ids=[np.array(i) for i in pp["ids"]])
+                tt = torch.full((x.shape[0],), pp["t"])
+                out["p2p_forward"] = ref(x, tt, ctx, **kw)[0].numpy()
+                out["p2p_plain"] = ref(x, tt, ctx)[0].numpy()
+                kw_all = dict(kw, block_id="all")
+                out["p2p_all_blocks"] = ref(x, tt, ctx, **kw_all)[0].numpy()
             if case.get("edit"):
                 # the reference's own edit hook (libs/dissection.py:115-157) reading delta_{t:.2f}.npy from disk
                 e = case["edit"]

@@ -411,3 +411,61 @@ def test_two_gpu_sharded_sampling_matches_single_gpu():
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "MP_CHECK_OK" in r.stdout
+
+
+def _p2p_kwargs(case):
+    pp = case["p2p"]
+    return dict(dissect_name="p2p", fm_direction="decode", t_edit=pp["t_edit"], block_id=pp["block_id"],
+                token_kwargs=dict(token_dissect="p2p_rescale", p2p_multiplier=pp["multiplier"]),
+                target_context_ids=[np.array(i) for i in pp["ids"]])
+
+
+def test_p2p_attention_rescale_forward_matches_reference_golden(golden_dir):
+    """dissect_lfm_t2i.py "p2p" mode through the module call, against the reference's own editing branch."""
+    case = CASES["tiny_t2i"]
+    pp = case["p2p"]
+    g = golden(golden_dir, "tiny_t2i")
+    m = model("tiny_t2i")
+    x, _, _, ctx = build_inputs(case)
+    kw = _p2p_kwargs(case)
+    with torch.no_grad():
+        t_in = torch.full((x.shape[0],), pp["t"], device=dev())
+        out = m(x.to(dev()), t_in, context=ctx.to(dev()), **kw)[0]
+        out_all = m(x.to(dev()), t_in, context=ctx.to(dev()), **dict(kw, block_id="all"))[0]
+        t_late = torch.full((x.shape[0],), 0.9, device=dev())
+        late_edit = m(x.to(dev()), t_late, context=ctx.to(dev()), **kw)[0]
+        late_plain = m(x.to(dev()), t_late, context=ctx.to(dev()))[0]
+    assert rel(out, g["p2p_forward"]) < 1.5e-3
+    assert rel(out_all, g["p2p_all_blocks"]) < 1.5e-3
+    assert rel(out, g["p2p_plain"]) > 1e-3
+    assert torch.equal(late_edit, late_plain)   # t > t_edit: the hook is inactive (tools/utils_t2i.py:284)
+
+
+@pytest.mark.parametrize("method", ["euler", "heun"])
+def test_p2p_attention_rescale_sampling_against_oracle(method):
+    case = CASES["tiny_t2i"]
+    pp = case["p2p"]
+    m = model("tiny_t2i")
+    x, _, _, ctx = build_inputs(case)
+    sd = {k: v.cpu() for k, v in m.state_dict().items()}
+    # a strong edit (every context token, every block) so that the edited trajectory is far from the plain one
+    ids, mult = [list(range(77)), list(range(77))], [30.0, -20.0]
+    cs = torch.ones(case["B"], 334)
+    for i, tid in enumerate(ids):
+        cs[i, torch.tensor(tid) + 1] = mult[i]
+    h = 0.2
+    want = O.sample(sd, case["cfg"], x.double(), 0.0, 1.0, h, method, context=ctx.double(), attn_colscale=cs.double(),
+                    attn_blocks=None, attn_t_edit=pp["t_edit"])
+    kw = dict(dissect_name="p2p", t_edit=pp["t_edit"], block_id="all",
+              token_kwargs=dict(token_dissect="p2p_rescale", p2p_multiplier=mult),
+              target_context_ids=[np.array(i) for i in ids],
+              solver_kwargs=dict(solver="fixed", solver_fix=method, solver_fix_step=h))
+    got = CNFT2I(m).decode(x.to(dev()), context=ctx.to(dev()), **kw)
+    assert rel(got, want) < 1e-3
+    plain = O.sample(sd, case["cfg"], x.double(), 0.0, 1.0, h, method, context=ctx.double())
+    assert rel(want, plain) > 5e-2
+    assert rel(got.double().cpu() - plain, want - plain) < 2e-2   # the edit itself, not just the trajectory
+    # encode never edits the attention map (fm_direction == "encode", tools/utils_t2i.py:276-277)
+    enc = CNFT2I(m).encode(x.to(dev()), context=ctx.to(dev()), **kw)
+    enc_want = O.sample(sd, case["cfg"], x.double(), 1.0, 0.0, h, method, context=ctx.double())
+    assert rel(enc, enc_want) < 1e-3

@@ -13,7 +13,8 @@ from oracle import uvit_oracle as O
 from tests.golden.cases import CASES
 from uspace_b200 import _lib, parallel
 from uspace_b200.engine import config_from_kwargs, time_grid
-from uspace_b200.flow_matching import CNF, CNFT2I, build_delta_table, should_edit
+from uspace_b200.flow_matching import (CNF, CNFT2I, block_mask_from_ids, build_attn_edit, build_delta_table,
+                                       should_edit)
 from uspace_b200.uvit import UViT, UViTT2I, get_nnet
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -221,3 +222,23 @@ def test_sharded_sampling_gathers_in_rank_order_gloo(n_total):
     want = (parallel.global_noise(n_total, shape=(4, 8, 8)) * 2.0 + 1.0).numpy()
     for r in range(2):
         assert res[r].shape == want.shape and np.array_equal(res[r], want)
+
+
+def test_attention_edit_from_reference_kwargs():
+    kw = dict(dissect_name="p2p", fm_direction="decode", t_edit=0.4, block_id=[1, 3],
+              token_kwargs=dict(token_dissect="p2p_rescale", p2p_multiplier=[2.0, -1.5]),
+              target_context_ids=[np.array([3, 4]), np.array([])])
+    e = build_attn_edit(2, 334, **kw)
+    assert e["block_mask"] == 0b1010 and e["t_edit"] == 0.4
+    assert e["colscale"][0, 4] == 2.0 and e["colscale"][0, 5] == 2.0 and e["colscale"][0, 3] == 1.0  # +1: time token
+    assert (e["colscale"][1] == 1).all()                                  # empty id list: untouched
+    assert build_attn_edit(2, 334, **dict(kw, fm_direction="encode")) is None
+    assert build_attn_edit(2, 334, **dict(kw, dissect_name="write_attr")) is None
+    assert build_attn_edit(2, 334, **dict(kw, token_kwargs=dict(token_dissect="lp_add"))) is None
+    with pytest.raises(NotImplementedError):
+        build_attn_edit(2, 334, **dict(kw, token_kwargs=dict(token_dissect="p2p_replace")))
+    assert block_mask_from_ids("all") == (1 << 64) - 1 and block_mask_from_ids(None) == (1 << 64) - 1
+    assert block_mask_from_ids(5) == 32
+    e = build_attn_edit(3, 334, **dict(kw, token_kwargs=dict(token_dissect="p2p_rescale", p2p_multiplier=-3),
+                                       target_context_ids=[np.array([0])] * 3))
+    assert (e["colscale"][:, 1] == -3).all()

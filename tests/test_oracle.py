@@ -146,3 +146,29 @@ def test_config0_single_euler_step_small_deep16(golden_dir):
     v0 = O.uvit_forward(sd, case["cfg"], x, torch.zeros(2))
     assert z1.shape == x.shape and torch.isfinite(z1).all()
     assert rel(z1, x + np.float32(h) * v0) < 1e-6
+
+
+def _p2p_colscale(case, L):
+    pp = case["p2p"]
+    cs = torch.ones(case["B"], L)
+    for i, ids in enumerate(pp["ids"]):
+        cs[i, torch.tensor(ids) + 1] = pp["multiplier"][i]
+    return cs
+
+
+def test_oracle_p2p_attention_rescale_matches_reference(golden_dir):
+    """Post-softmax column re-weighting == the reference's editing_attention_map_vit / _p2p_rescale branch."""
+    case = CASES["tiny_t2i"]
+    pp = case["p2p"]
+    g = load(golden_dir, "tiny_t2i")
+    sd = build_model(case, UViT, UViTT2I).state_dict()
+    x, _, _, ctx = build_inputs(case)
+    t = torch.full((x.shape[0],), pp["t"])
+    cs = _p2p_colscale(case, 334)
+    got = O.uvit_forward(sd, case["cfg"], x, t, context=ctx, attn_colscale=cs, attn_blocks=pp["block_id"])
+    assert rel(got, g["p2p_forward"]) < 2e-6
+    got_all = O.uvit_forward(sd, case["cfg"], x, t, context=ctx, attn_colscale=cs, attn_blocks=None)
+    assert rel(got_all, g["p2p_all_blocks"]) < 2e-6
+    plain = O.uvit_forward(sd, case["cfg"], x, t, context=ctx)
+    assert rel(plain, g["p2p_plain"]) < 2e-6
+    assert rel(g["p2p_forward"], g["p2p_plain"]) > 1e-3   # the edit is visible

@@ -24,6 +24,10 @@ class UspConfig(C.Structure):
         "clip_dim", "num_clip_token", "qkv_bias", "conv", "skip", "operand_dtype", "fuse_layernorm")]
 
 
+class UspAttnEdit(C.Structure):
+    _fields_ = [("colscale", C.c_void_p), ("block_mask", C.c_uint64), ("t_edit", C.c_float)]
+
+
 _lib = None
 
 _vp, _i, _f, _i64 = C.c_void_p, C.c_int, C.c_float, C.c_int64
@@ -36,6 +40,8 @@ _SIGNATURES = {
     "usp_num_weights": (_i, [_vp]),
     "usp_weight_name": (C.c_char_p, [_vp, _i]),
     "usp_forward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
+    "usp_forward_edit": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, C.POINTER(UspAttnEdit), _vp]),
+    "usp_sample_edit": (_i, [_vp, _vp, _vp, _vp, _i, _f, _f, _f, _i, _vp, _f, _f, _i, C.POINTER(UspAttnEdit), _vp]),
     "usp_sample": (_i, [_vp, _vp, _vp, _vp, _i, _f, _f, _f, _i, _vp, _f, _f, _i, _vp]),
     "usp_sample_host": (_i, [_vp, _vp, _vp, _vp, _i, _f, _f, _f, _i, _vp, _f, _f, _i]),
     "usp_grid_size": (_i, [_f, _f, _f]),

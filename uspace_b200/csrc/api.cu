@@ -119,9 +119,11 @@ struct Plan {
     unsigned char* mask = nullptr;
     float* delta = nullptr;
     size_t delta_cap = 0;
+    float* colscale = nullptr;      // [B, L] attention column weights (p2p edit)
+    unsigned char* amask = nullptr; // per grid point: attention edit active
     CUtensorMap m_h, m_a, m_m, m_xa, m_xb, m_q, m_k, m_v, m_ctx, m_xe, m_xp, m_xs;
     std::vector<CUtensorMap> m_skip;
-    std::map<int, cudaGraphExec_t> graphs;
+    std::map<std::pair<int, uint64_t>, cudaGraphExec_t> graphs;   // (method / edit flags, attention block mask)
 };
 
 constexpr int MAX_GRID = 4096;
@@ -247,7 +249,8 @@ int get_plan(usp_handle* h, int B, Plan** out) {
                  o_ctx32 = carve(nctx ? static_cast<size_t>(B) * nctx * cdim * 4 : 16),
                  o_ctx16 = carve(nctx ? static_cast<size_t>(B) * nctx * cdim * 2 : 16);
     const size_t o_y = carve(static_cast<size_t>(B) * 8), o_st = carve(sizeof(StepState)),
-                 o_grid = carve(MAX_GRID * 4), o_mask = carve(MAX_GRID);
+                 o_grid = carve(MAX_GRID * 4), o_mask = carve(MAX_GRID), o_amask = carve(MAX_GRID),
+                 o_cs = carve(static_cast<size_t>(B) * L * 4);
     p->bytes = off;
     CUDA_TRY(h, cudaMalloc(&p->slab, off));
     CUDA_TRY(h, cudaMemset(p->slab, 0, off));
@@ -275,6 +278,8 @@ int get_plan(usp_handle* h, int B, Plan** out) {
     p->st = reinterpret_cast<StepState*>(base + o_st);
     p->grid = reinterpret_cast<float*>(base + o_grid);
     p->mask = reinterpret_cast<unsigned char*>(base + o_mask);
+    p->amask = reinterpret_cast<unsigned char*>(base + o_amask);
+    p->colscale = reinterpret_cast<float*>(base + o_cs);
 
     bool ok = true;
     ok &= make_map_2d(&p->m_h, p->h16, M, D, GEMM_BM, opd);
@@ -312,6 +317,8 @@ struct FwdIO {
     bool has_ctx;
     const float* delta;     // edit table or nullptr
     int edit_loc;
+    const float* colscale;  // attention column weights [B, L] or nullptr (p2p edit)
+    uint64_t block_mask;    // blocks the attention edit applies to
     // final stage
     const float* base;
     const float* aux;
@@ -450,6 +457,7 @@ int enqueue_forward(usp_handle* h, Plan* p, const FwdIO& io, cudaStream_t s) {
         AttnArgs aa;
         memset(&aa, 0, sizeof(aa));
         aa.B = B; aa.H = h->cfg.num_heads; aa.L = L; aa.D = D; aa.opd = opd; aa.out16 = p->a16; aa.num_sms = h->num_sms; aa.q16 = p->qkv16;
+        if (io.colscale != nullptr && ((io.block_mask >> bi) & 1ull)) { aa.vscale = io.colscale; aa.st = io.st; }
         prof_mark(h, 3, s);
         KTRY(launch_attention(p->m_q, p->m_k, p->m_v, aa, s));
         {
@@ -751,6 +759,11 @@ int usp_finalize_weights(usp_handle* h, void* stream) {
 
 int usp_forward(usp_handle* h, const float* x, const float* t, const float* context, const int64_t* y, float* out,
                 int B, void* stream) {
+    return usp_forward_edit(h, x, t, context, y, out, B, nullptr, stream);
+}
+
+int usp_forward_edit(usp_handle* h, const float* x, const float* t, const float* context, const int64_t* y,
+                     float* out, int B, const usp_attn_edit* edit, void* stream) {
     int rc = check_ready(h, B);
     if (rc) return rc;
     if (!x || !t || !out) return fail(h, USP_ERR_INVALID, "null tensor");
@@ -772,6 +785,11 @@ int usp_forward(usp_handle* h, const float* x, const float* t, const float* cont
     memset(&io, 0, sizeof(io));
     io.x = x; io.tvec = t; io.y = reinterpret_cast<const long long*>(y); io.has_ctx = context != nullptr;
     io.out = out; io.m1 = 1.f;
+    if (edit != nullptr && edit->colscale != nullptr) {
+        CUDA_TRY(h, cudaMemcpyAsync(p->colscale, edit->colscale, static_cast<size_t>(B) * h->L * 4, cudaMemcpyDefault, s));
+        io.colscale = p->colscale;
+        io.block_mask = edit->block_mask;
+    }
     rc = enqueue_forward(h, p, io, s);
     if (rc) return rc;
     CUDA_TRY(h, cudaEventRecord(h->ev1, s));
@@ -821,6 +839,13 @@ int usp_time_grid(float t0, float t1, float step_size, float* out, int cap) {
 int usp_sample(usp_handle* h, float* z, const float* context, const int64_t* y, int B, float t0, float t1,
                float step_size, int method, const float* delta_table, float write_scale, float t_edit, int edit_loc,
                void* stream) {
+    return usp_sample_edit(h, z, context, y, B, t0, t1, step_size, method, delta_table, write_scale, t_edit, edit_loc,
+                           nullptr, stream);
+}
+
+int usp_sample_edit(usp_handle* h, float* z, const float* context, const int64_t* y, int B, float t0, float t1,
+                    float step_size, int method, const float* delta_table, float write_scale, float t_edit,
+                    int edit_loc, const usp_attn_edit* attn, void* stream) {
     int rc = check_ready(h, B);
     if (rc) return rc;
     if (!z) return fail(h, USP_ERR_INVALID, "null latent");
@@ -867,6 +892,18 @@ int usp_sample(usp_handle* h, float* z, const float* context, const int64_t* y, 
     CUDA_TRY(h, cudaEventRecord(h->ev0, s));
     CUDA_TRY(h, cudaMemcpyAsync(p->grid, grid.data(), n * 4, cudaMemcpyHostToDevice, s));
     CUDA_TRY(h, cudaMemcpyAsync(p->mask, mask.data(), n, cudaMemcpyHostToDevice, s));
+    // attention edit: active while float(f"{t:.2f}") <= t_edit (tools/utils_t2i.py:284; "0.00" is NOT excluded here)
+    const bool use_attn = attn != nullptr && attn->colscale != nullptr && attn->block_mask != 0;
+    std::vector<unsigned char> amask(n, 0);
+    if (use_attn) {
+        for (int i = 0; i < n; ++i) {
+            char buf[64];
+            snprintf(buf, sizeof(buf), "%.2f", static_cast<double>(grid[i]));
+            amask[i] = atof(buf) <= static_cast<double>(attn->t_edit) ? 1 : 0;
+        }
+        CUDA_TRY(h, cudaMemcpyAsync(p->colscale, attn->colscale, static_cast<size_t>(B) * h->L * 4, cudaMemcpyDefault, s));
+    }
+    CUDA_TRY(h, cudaMemcpyAsync(p->amask, amask.data(), n, cudaMemcpyHostToDevice, s));
     StepState st0;
     memset(&st0, 0, sizeof(st0));
     st0.write_scale = write_scale;
@@ -878,19 +915,21 @@ int usp_sample(usp_handle* h, float* z, const float* context, const int64_t* y, 
         if (rc) return rc;
     }
 
-    const int key = method | (edit_loc << 2) | ((y ? 1 : 0) << 4);
+    const std::pair<int, uint64_t> key(method | (edit_loc << 2) | ((y ? 1 : 0) << 4) | ((use_attn ? 1 : 0) << 5),
+                                       use_attn ? attn->block_mask : 0);
     auto git = p->graphs.find(key);
     if (git == p->graphs.end()) {
         // capture one ODE step on the private stream; every pointer it touches is plan-owned
         cudaGraph_t graph = nullptr;
         CUDA_TRY(h, cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal));
         auto body = [&]() -> int {
-            cudaError_t e = launch_step(p->st, p->grid, p->mask, 0, h->cap_stream);
+            cudaError_t e = launch_step(p->st, p->grid, p->mask, p->amask, 0, h->cap_stream);
             if (e != cudaSuccess) return fail(h, USP_ERR_CUDA, std::string("launch_step: ") + cudaGetErrorString(e));
             FwdIO io;
             memset(&io, 0, sizeof(io));
             io.st = p->st; io.y = y ? p->y : nullptr; io.has_ctx = context != nullptr;
             io.delta = edit_loc != USP_EDIT_NONE ? p->delta : nullptr; io.edit_loc = edit_loc;
+            if (use_attn) { io.colscale = p->colscale; io.block_mask = attn->block_mask; }
             if (method == USP_METHOD_EULER) {
                 io.x = p->z; io.base = p->z; io.out = p->z; io.m1 = 1.f;
                 return enqueue_forward(h, p, io, h->cap_stream);
@@ -898,7 +937,7 @@ int usp_sample(usp_handle* h, float* z, const float* context, const int64_t* y, 
             io.x = p->z; io.base = p->z; io.vstore = p->k1; io.out = p->ztmp; io.m1 = 1.f;
             int r = enqueue_forward(h, p, io, h->cap_stream);
             if (r) return r;
-            e = launch_step(p->st, p->grid, p->mask, 1, h->cap_stream);
+            e = launch_step(p->st, p->grid, p->mask, p->amask, 1, h->cap_stream);
             if (e != cudaSuccess) return fail(h, USP_ERR_CUDA, std::string("launch_step: ") + cudaGetErrorString(e));
             io.x = p->ztmp; io.base = p->z; io.aux = p->k1; io.vstore = nullptr; io.out = p->z;
             io.m1 = 0.5f; io.m2 = 0.5f;

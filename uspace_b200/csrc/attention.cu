@@ -273,6 +273,8 @@ static bool force_v1() {
 cudaError_t launch_attention(const CUtensorMap& q, const CUtensorMap& k, const CUtensorMap& v, const AttnArgs& a,
                              cudaStream_t s) {
     if (a.L < 1 || a.L > ATTN_MAX_L || a.D != a.H * HD) return cudaErrorInvalidValue;
+    // the column re-weighting (p2p) hook lives in the persistent kernel only
+    if (a.vscale != nullptr && (force_v1() || !attention2_supported(a))) return cudaErrorNotSupported;
     if (!force_v1() && attention2_supported(a)) return launch_attention2(q, k, v, a, a.num_sms, s);
     dim3 grid((a.L + QT - 1) / QT, a.B * a.H);
     return launch_pdl(attention_kernel, grid, dim3(ATTN_THREADS), ATTN_SMEM, s, q, k, v, a);

@@ -148,6 +148,8 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
             const float c2 = 0.125f * 1.44269504088896340736f;
             int n = 0;
             for (int bh = blockIdx.x; bh < n_items; bh += gridDim.x, ++n) {
+                const float* cs = (a.vscale != nullptr && (a.st == nullptr || a.st->attn_on != 0))
+                                      ? a.vscale + static_cast<long long>(bh / a.H) * L : nullptr;   // p2p column weights
                 const uint8_t* kbuf = sK + (n & 1) * kv_bytes;
                 const uint8_t* vbuf = sV + (n & 1) * kv_bytes;
                 mbar_wait(&tail_go, n & 1);
@@ -201,6 +203,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                             const uint32_t w = a.opd == OPD_FP16 ? Op16<OPD_FP16>::pack(p, 0.f) : Op16<OPD_BF16>::pack(p, 0.f);
                             sum += p;
                             p = (a.opd == OPD_FP16 ? Op16<OPD_FP16>::unpack(w) : Op16<OPD_BF16>::unpack(w)).x;
+                            if (cs != nullptr) p *= __ldg(cs + j);
                             t_p[j] = p;
                         }
                     }
@@ -469,6 +472,8 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
             float p_inv = 0.f;
             const int cnt = c_hi - c_lo;
             for (int bh = blockIdx.x; bh < n_items; bh += gridDim.x) {
+                const float* cs = (a.vscale != nullptr && (a.st == nullptr || a.st->attn_on != 0))
+                                      ? a.vscale + static_cast<long long>(bh / a.H) * L : nullptr;   // p2p column weights
                 for (int t = 0; t < n_qt; ++t, ++g) {
                     const int l = t * QT + row;
                     const bool row_ok = l < L;
@@ -524,6 +529,10 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                                         if (c * 32 + 2 * j + 1 >= L) p1 = 0.f;
                                     }
                                     sum += p0 + p1;
+                                    if (cs != nullptr) {   // p2p column re-weighting, after the (unscaled) row sum
+                                        p0 *= __ldg(cs + c * 32 + 2 * j);
+                                        p1 *= (c * 32 + 2 * j + 1 < L) ? __ldg(cs + c * 32 + 2 * j + 1) : 0.f;
+                                    }
                                     w[j] = a.opd == OPD_FP16 ? Op16<OPD_FP16>::pack(p0, p1) : Op16<OPD_BF16>::pack(p0, p1);
                                 }
                                 tmem_st16(t_row + PP_COL + 16 * c, w);
@@ -543,6 +552,8 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         } else {
         int g = 0;
         for (int bh = blockIdx.x; bh < n_items; bh += gridDim.x) {
+            const float* cs = (a.vscale != nullptr && (a.st == nullptr || a.st->attn_on != 0))
+                                  ? a.vscale + static_cast<long long>(bh / a.H) * L : nullptr;   // p2p column weights
             for (int t = 0; t < n_qt; ++t, ++g) {
                 const int l = t * QT + row;
                 const bool row_ok = l < L;
@@ -601,6 +612,10 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                                         if (c * 32 + 2 * j + 1 >= L) p1 = 0.f;
                                     }
                                     sum += p0 + p1;
+                                    if (cs != nullptr) {
+                                        p0 *= __ldg(cs + c * 32 + 2 * j);
+                                        p1 *= (c * 32 + 2 * j + 1 < L) ? __ldg(cs + c * 32 + 2 * j + 1) : 0.f;
+                                    }
                                     w[j] = a.opd == OPD_FP16 ? Op16<OPD_FP16>::pack(p0, p1) : Op16<OPD_BF16>::pack(p0, p1);
                                 }
                                 const uint32_t pcol = c < n0 ? S_COL + 16 * c : P1_COL + 16 * (c - n0);
@@ -648,6 +663,11 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                         }
 #pragma unroll
                         for (int j = 0; j < 32; ++j) sum += p[j];
+                        if (cs != nullptr) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (c * 32 + j < L) p[j] *= __ldg(cs + c * 32 + j);
+                        }
                         uint32_t w[16];
 #pragma unroll
                         for (int j = 0; j < 16; ++j)

@@ -342,7 +342,7 @@ __global__ void __launch_bounds__(256) fold_ln_kernel(const float* __restrict__ 
 }
 
 __global__ void step_kernel(StepState* st, const float* __restrict__ grid, const unsigned char* __restrict__ mask,
-                            int stage) {
+                            const unsigned char* __restrict__ amask, int stage) {
     pdl_wait();
     pdl_launch();
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
@@ -354,11 +354,13 @@ __global__ void step_kernel(StepState* st, const float* __restrict__ grid, const
         st->dt = grid[i + 1] - grid[i];
         st->edit = mask[i] ? st->write_scale : 0.f;
         st->didx = i;
+        st->attn_on = amask[i];
     } else {
         const int i = st->cur;
         st->t = grid[i + 1];
         st->edit = mask[i + 1] ? st->write_scale : 0.f;
         st->didx = i + 1;
+        st->attn_on = amask[i + 1];
     }
 }
 
@@ -422,8 +424,9 @@ cudaError_t launch_fold_ln(const float* W, const float* gamma, const float* beta
     return cudaGetLastError();
 }
 
-cudaError_t launch_step(StepState* st, const float* grid, const unsigned char* mask, int stage, cudaStream_t s) {
-    return launch_pdl(step_kernel, dim3(1), dim3(32), 0, s, st, grid, mask, stage);
+cudaError_t launch_step(StepState* st, const float* grid, const unsigned char* mask, const unsigned char* amask,
+                        int stage, cudaStream_t s) {
+    return launch_pdl(step_kernel, dim3(1), dim3(32), 0, s, st, grid, mask, amask, stage);
 }
 
 }  // namespace usp

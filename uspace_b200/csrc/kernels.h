@@ -63,7 +63,9 @@ struct AttnArgs {
     int opd;
     int num_sms;       // persistent grid size
     void* out16;       // [B*L, D] 16-bit, heads merged "(H hd)"
-    const float* vscale;  // optional per-(sample,key) V-row scale [B, L] (p2p re-weighting), or nullptr
+    const float* vscale;  // optional post-softmax column re-weighting [B, L] (p2p_rescale, tools/utils_t2i.py:196-224):
+                          // O = sum_j (p_j * m_j) v_j / sum_j p_j  (no re-normalisation), or nullptr
+    const struct StepState* st;  // sampling: apply vscale only while st->attn_on != 0; nullptr: always apply
     int diag;             // diagnostics (env USP_ATTN_DIAG): 1 = no MUFU, 2 = no softmax arithmetic at all (results invalid)
     const void* q16;      // raw pointer to Q [B*H, L, 64] (the SIMT tail-row path reads its query rows directly)
 };
@@ -82,7 +84,7 @@ struct StepState {       // lives in device memory; advanced by step_kernel insi
     float edit;          // write_scale if the edit is active at `t`, else 0
     float write_scale;
     int didx;            // row of the edit table that belongs to `t`
-    int pad;
+    int attn_on;         // attention re-weighting active at `t` (float(f"{t:.2f}") <= t_edit)
 };
 
 struct EmbedArgs {
@@ -140,6 +142,7 @@ cudaError_t launch_convert16(const float* in, void* out16, long long n, int opd,
 cudaError_t launch_fold_ln(const float* W, const float* gamma, const float* beta, const float* bias, void* w16,
                            float* c, float* d, int N, int K, int opd, cudaStream_t s);
 // stage 0: start interval `next` (t = grid[next]) and advance; stage 1: second Heun stage (t = grid[cur+1])
-cudaError_t launch_step(StepState* st, const float* grid, const unsigned char* mask, int stage, cudaStream_t s);
+cudaError_t launch_step(StepState* st, const float* grid, const unsigned char* mask, const unsigned char* amask,
+                        int stage, cudaStream_t s);
 
 }  // namespace usp

@@ -90,7 +90,18 @@ class Engine:
         if x.dim() != 4 or x.shape[1:] != (self.C, self.S, self.S):
             raise ValueError(f"latent must be [B,{self.C},{self.S},{self.S}], got {tuple(x.shape)}")
 
-    def forward(self, x, t, y=None, context=None) -> torch.Tensor:
+    def _attn_edit(self, attn_edit, B):
+        """attn_edit = dict(colscale=[B, L] tensor, block_mask=int, t_edit=float) -> (ctypes struct, keep-alive)."""
+        if attn_edit is None:
+            return None, None
+        cs = attn_edit["colscale"].to(self.device, torch.float32).contiguous()
+        if cs.shape[0] != B:
+            raise ValueError(f"attention colscale must be [B={B}, L], got {tuple(cs.shape)}")
+        e = _lib.UspAttnEdit(C.c_void_p(cs.data_ptr()), int(attn_edit.get("block_mask", (1 << 64) - 1)) & ((1 << 64) - 1),
+                             float(attn_edit.get("t_edit", float("inf"))))
+        return e, cs
+
+    def forward(self, x, t, y=None, context=None, attn_edit=None) -> torch.Tensor:
         self._check_latent(x)
         B = x.shape[0]
         x = x.to(self.device, torch.float32).contiguous()
@@ -100,12 +111,14 @@ class Engine:
         if context is not None:
             context = context.to(self.device, torch.float32).contiguous()
         out = torch.empty_like(x)
-        _lib.check(self.lib.usp_forward(self.handle, _ptr(x), _ptr(t), _ptr(context), _ptr(y), _ptr(out), B,
-                                        self._stream()), self.handle, "usp_forward")
+        edit, _keep = self._attn_edit(attn_edit, B)
+        _lib.check(self.lib.usp_forward_edit(self.handle, _ptr(x), _ptr(t), _ptr(context), _ptr(y), _ptr(out), B,
+                                             C.byref(edit) if edit is not None else None, self._stream()),
+                   self.handle, "usp_forward")
         return out
 
     def sample(self, z, t0=0.0, t1=1.0, step_size=0.02, method="euler", y=None, context=None, delta_table=None,
-               write_scale=0.0, t_edit=0.0, edit_loc=None) -> torch.Tensor:
+               write_scale=0.0, t_edit=0.0, edit_loc=None, attn_edit=None) -> torch.Tensor:
         """Device-resident fixed-grid integration; returns a new tensor (z is not modified)."""
         self._check_latent(z)
         B = z.shape[0]
@@ -119,9 +132,11 @@ class Engine:
             n = self.lib.usp_grid_size(t0, t1, step_size)
             if delta_table.shape != (n, self.C, self.S, self.S):
                 raise ValueError(f"delta_table must be [{n},{self.C},{self.S},{self.S}]")
-        _lib.check(self.lib.usp_sample(self.handle, _ptr(zz), _ptr(context), _ptr(y), B, t0, t1, step_size,
-                                       _lib.METHOD[method], _ptr(delta_table), write_scale, t_edit,
-                                       _lib.EDIT_LOC[edit_loc], self._stream()), self.handle, "usp_sample")
+        edit, _keep = self._attn_edit(attn_edit, B)
+        _lib.check(self.lib.usp_sample_edit(self.handle, _ptr(zz), _ptr(context), _ptr(y), B, t0, t1, step_size,
+                                            _lib.METHOD[method], _ptr(delta_table), write_scale, t_edit,
+                                            _lib.EDIT_LOC[edit_loc], C.byref(edit) if edit is not None else None,
+                                            self._stream()), self.handle, "usp_sample")
         return zz
 
     def sample_host(self, z_host, t0=0.0, t1=1.0, step_size=0.02, method="euler", y=None, context=None,

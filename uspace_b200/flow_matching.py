@@ -77,6 +77,48 @@ def build_delta_table(grid, shape, **kwargs):
     return torch.from_numpy(table), loc
 
 
+_ATTN_EDIT_NAMES = ("p2p", "local_prompt", "sampled_image_editing")
+
+
+def block_mask_from_ids(block_id) -> int:
+    """should_edit_attention_by_blockids (tools/utils_t2i.py:227-240) as a bit mask over executed blocks."""
+    if block_id is None or (isinstance(block_id, str) and block_id == "all"):
+        return (1 << 64) - 1
+    if isinstance(block_id, int):
+        return 1 << block_id
+    if isinstance(block_id, (list, tuple)):
+        m = 0
+        for b in block_id:
+            m |= 1 << int(b)
+        return m
+    raise ValueError(f"unknown target_block_id {block_id}")
+
+
+def build_attn_edit(B: int, L: int, **kwargs):
+    """The attention edit the reference would apply for these kwargs (libs/uvit_t2i.py:91-107 ->
+    tools/utils_t2i.py:265-296,196-224), or None.  Only "p2p_rescale" changes the attention map ("lp_*" edits act on
+    the prompt / context, not on the map; "p2p_replace" raises in the reference too)."""
+    if kwargs.get("dissect_name") not in _ATTN_EDIT_NAMES:
+        return None
+    if kwargs.get("fm_direction") == "encode":
+        return None
+    tk = kwargs.get("token_kwargs") or {}
+    mode = tk.get("token_dissect")
+    if mode is None or str(mode).startswith("lp_"):
+        return None
+    if mode != "p2p_rescale":
+        raise NotImplementedError(f"token_dissect={mode!r}")
+    ids = kwargs["target_context_ids"]
+    mult = tk["p2p_multiplier"]
+    mults = [mult] * len(ids) if isinstance(mult, (int, float)) else list(mult)
+    cs = torch.ones(B, L, dtype=torch.float32)
+    for i, tid in enumerate(ids):
+        tid = np.asarray(tid, dtype=np.int64)
+        if tid.size > 0:
+            cs[i, torch.from_numpy(tid) + 1] = float(mults[i])   # + TIME_TOKEN_NUM: [time, ctx x 77, patches]
+    return dict(colscale=cs, block_mask=block_mask_from_ids(kwargs.get("block_id")), t_edit=float(kwargs["t_edit"]))
+
+
 class _CNFBase(nn.Module):
     def __init__(self, net):
         super().__init__()
@@ -134,8 +176,12 @@ class _CNFBase(nn.Module):
             table, loc = build_delta_table(time_grid(t0, t1, h), z.shape[1:], **kwargs)
         ws = float(kwargs.get("write_scale") or 0.0) if table is not None else 0.0
         # rows where should_edit() is false are zero, so the library's own mask can stay wide open
+        attn = None
+        if isinstance(self, CNFT2I):
+            attn = build_attn_edit(z.shape[0], engine.cfg.num_clip_token + 1 + (engine.S // engine.cfg.patch_size) ** 2,
+                                   **kwargs)
         return engine.sample(z, t0, t1, h, ode_kwargs["method"], delta_table=table, write_scale=ws,
-                             t_edit=float("inf"), edit_loc=loc, **self._cond_kw(cond))
+                             t_edit=float("inf"), edit_loc=loc, attn_edit=attn, **self._cond_kw(cond))
 
     def _decode(self, z: Tensor, cond, **kwargs) -> Tensor:
         """flow_matching.py:130-151."""

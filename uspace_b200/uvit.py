@@ -240,7 +240,14 @@ class UViTT2I(_UViTBase):
             tok = self.patch_embed.proj(x).flatten(2).transpose(1, 2)
             tok = torch.cat((self._time_token(timesteps), self.context_embed(context.to(x.device)), tok), dim=1)
             return self._trunk_autograd(tok), None
-        return self.engine().forward(x, timesteps, context=context), None
+        attn = None
+        if kwargs.get("dissect_name") in ("p2p", "local_prompt", "sampled_image_editing"):
+            # the reference's attention-editing branch (libs/uvit_t2i.py:91-107): active for t <= t_edit in decode
+            from .flow_matching import build_attn_edit
+            attn = build_attn_edit(x.shape[0], self.pos_embed.shape[1], **kwargs)
+            if attn is not None and not float(f"{timesteps[0].item():.2f}") <= attn["t_edit"]:
+                attn = None
+        return self.engine().forward(x, timesteps, context=context, attn_edit=attn), None
 
 
 def get_nnet(name, **kwargs):
