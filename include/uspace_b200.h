@@ -103,6 +103,23 @@ int usp_sample(usp_handle* h, float* z, const float* context, const int64_t* y, 
 int usp_sample_edit(usp_handle* h, float* z, const float* context, const int64_t* y, int B, float t0, float t1,
                     float step_size, int method, const float* delta_table, float write_scale, float t_edit,
                     int edit_loc, const usp_attn_edit* attn, void* stream);
+/* Adaptive Dormand-Prince 5(4): replaces odeint(func, z, [t0, t1], method="dopri5", rtol=, atol=)[-1] at
+ * flow_matching.py:79-84 (default sampling), :50-57 (solver="adaptive") and :172-179 (adaptive tail of "fixadp");
+ * flow_matching_t2i.py likewise. Step acceptance, the next step size and the dense-output evaluation at t1 run on
+ * the device; the host reads one small state record per attempted step, so this call SYNCHRONISES `stream`.
+ * The rms error norm spans the whole batch (torchdiffeq's default), i.e. results depend on how a batch is split.
+ * delta_digits: [n_rows, C, S, S] rows keyed by the "%.2f" digit of the evaluation time, row i <-> delta_{i/100:.2f}.npy
+ * (n_rows <= 128; NULL iff edit_loc == USP_EDIT_NONE). */
+typedef struct usp_adaptive_stats {
+    int32_t n_accept, n_reject, nfe;
+    float last_ratio;   /* error ratio of the last attempted step */
+    double last_dt;     /* size of the last accepted step */
+} usp_adaptive_stats;
+#define USP_METHOD_DOPRI5 2
+int usp_sample_adaptive(usp_handle* h, float* z, const float* context, const int64_t* y, int B, float t0, float t1,
+                        double rtol, double atol, const float* delta_digits, int n_rows, float write_scale,
+                        float t_edit, int edit_loc, const usp_attn_edit* attn, int max_steps,
+                        usp_adaptive_stats* stats, void* stream);
 /* Same with HOST buffers: copies z (and context / y / delta_table) host->device, samples, copies z back,
  * and synchronises. This is the end-to-end call bench.py times. */
 int usp_sample_host(usp_handle* h, float* z_host, const float* context_host, const int64_t* y_host, int B, float t0,

@@ -292,3 +292,132 @@ def sample(sd: Dict[str, Tensor], cfg: dict, z: Tensor, t0: float = 0.0, t1: flo
                             attn_colscale=cs, attn_blocks=attn_blocks)
 
     return odeint_fixed(func, z, t0, t1, step_size, method)
+
+
+# ----------------------------------------------------------------------------------------------
+# adaptive dopri5 (torchdiffeq RKAdaptiveStepsizeODESolver semantics, restated; PARITY UNPINNED: torchdiffeq is
+# an un-vendored, unpinned dependency (README.md:121) that is installed nowhere here.  The constants below are
+# checked mathematically in tests/test_oracle.py: Dormand-Prince A/B/C against scipy's RK45, order conditions of
+# the embedded pair, accuracy of the mid-point weights.)
+# Call sites: flow_matching.py:79-84 (default sampling), :50-57 ("adaptive"), :172-179 ("fixadp" tail).
+# ----------------------------------------------------------------------------------------------
+DP_ALPHA = [1 / 5, 3 / 10, 4 / 5, 8 / 9, 1.0, 1.0]
+DP_BETA = [
+    [1 / 5],
+    [3 / 40, 9 / 40],
+    [44 / 45, -56 / 15, 32 / 9],
+    [19372 / 6561, -25360 / 2187, 64448 / 6561, -212 / 729],
+    [9017 / 3168, -355 / 33, 46732 / 5247, 49 / 176, -5103 / 18656],
+    [35 / 384, 0.0, 500 / 1113, 125 / 192, -2187 / 6784, 11 / 84],
+]
+DP_C_SOL = [35 / 384, 0.0, 500 / 1113, 125 / 192, -2187 / 6784, 11 / 84, 0.0]
+# Shampine's 4th-order companion, the pair torchdiffeq's "dopri5" uses
+DP_C_ERROR = [35 / 384 - 1951 / 21600, 0.0, 500 / 1113 - 22642 / 50085, 125 / 192 - 451 / 720,
+              -2187 / 6784 - -12231 / 42400, 11 / 84 - 649 / 6300, -1.0 / 60.0]
+DP_C_MID = [6025192743 / 30085553152 / 2, 0.0, 51252292925 / 65400821598 / 2, -2691868925 / 45128329728 / 2,
+            187940372067 / 1594534317056 / 2, -1776094331 / 19743644256 / 2, 11237099 / 235043384 / 2]
+DP_SAFETY, DP_IFACTOR, DP_DFACTOR = 0.9, 10.0, 0.2
+
+
+def _rms(x: Tensor) -> float:
+    """torchdiffeq's default norm: sqrt(mean(x^2)) over the WHOLE state tensor (the batch shares one step size)."""
+    return float(x.double().pow(2).mean().sqrt())
+
+
+def dopri5_step(func, s0: float, y0: Tensor, f0: Tensor, dt: float):
+    """One Dormand-Prince step: returns (y1, f1, error estimate, stage derivatives k[0..6])."""
+    k = [f0]
+    yi = y0
+    for i in range(6):
+        si = s0 + dt if DP_ALPHA[i] == 1.0 else s0 + DP_ALPHA[i] * dt
+        yi = y0 + sum(k[j] * (DP_BETA[i][j] * dt) for j in range(i + 1))
+        k.append(func(si, yi))
+    err = sum(k[j] * (DP_C_ERROR[j] * dt) for j in range(7))
+    return yi, k[6], err, k          # FSAL: c_sol[:-1] == beta[-1], so y1 is the last stage's state
+
+
+def dopri5_initial_step(func, s0: float, y0: Tensor, f0: Tensor, rtol: float, atol: float) -> float:
+    """Hairer's starting step as torchdiffeq's _select_initial_step computes it (order argument = 4)."""
+    scale = atol + y0.abs() * rtol
+    d0, d1 = _rms(y0 / scale), _rms(f0 / scale)
+    h0 = 1e-6 if (d0 < 1e-5 or d1 < 1e-5) else 0.01 * d0 / d1
+    f1 = func(s0 + h0, y0 + h0 * f0)
+    d2 = _rms((f1 - f0) / scale) / h0
+    h1 = max(1e-6, h0 * 1e-3) if (d1 <= 1e-15 and d2 <= 1e-15) else (0.01 / max(d1, d2)) ** (1.0 / 5.0)
+    return min(100 * h0, h1)
+
+
+def dopri5_interp(y0, y1, k, dt, x: float) -> Tensor:
+    """4th-order dense output on the accepted step, x = (t - t0) / (t1 - t0)."""
+    y_mid = y0 + sum(k[j] * (DP_C_MID[j] * dt) for j in range(7))
+    f0, f1 = k[0], k[6]
+    a = 2 * dt * (f1 - f0) - 8 * (y1 + y0) + 16 * y_mid
+    b = dt * (5 * f0 - 3 * f1) + 18 * y0 + 14 * y1 - 32 * y_mid
+    c = dt * (f1 - 4 * f0) - 11 * y0 - 5 * y1 + 16 * y_mid
+    d = dt * f0
+    return y0 + x * d + x ** 2 * c + x ** 3 * b + x ** 4 * a
+
+
+def odeint_dopri5(func: Callable[[float, Tensor], Tensor], z: Tensor, t0: float, t1: float, rtol: float = 1e-5,
+                  atol: float = 1e-5, max_steps: int = 100000, stats: Optional[dict] = None) -> Tensor:
+    """odeint(func, z, [t0, t1], method="dopri5", rtol, atol)[-1].  Steps are never clipped to t1: the last accepted
+    step overshoots and the result is the dense-output polynomial evaluated at t1.  Decreasing time integrates
+    g(s, y) = -f(-s, y) over s = -t."""
+    sgn = 1.0 if t1 >= t0 else -1.0
+    g = (lambda s, y: func(s, y)) if sgn > 0 else (lambda s, y: -func(-s, y))
+    s0, s_end = sgn * t0, sgn * t1
+    y0 = z
+    f0 = g(s0, y0)
+    dt = dopri5_initial_step(g, s0, y0, f0, rtol, atol)
+    n_acc = n_rej = 0
+    nfe = 2
+    while True:
+        if n_acc + n_rej >= max_steps:
+            raise RuntimeError("max_num_steps exceeded")
+        y1, f1, err, k = dopri5_step(g, s0, y0, f0, dt)
+        nfe += 6
+        tol = atol + rtol * torch.maximum(y0.abs(), y1.abs())
+        ratio = _rms(err / tol)
+        accept = ratio <= 1.0
+        if ratio == 0.0:
+            factor = DP_IFACTOR
+        else:
+            factor = min(DP_IFACTOR, max(DP_SAFETY / ratio ** 0.2, 1.0 if ratio < 1.0 else DP_DFACTOR))
+        if accept:
+            n_acc += 1
+            if s0 + dt >= s_end:
+                if stats is not None:
+                    stats.update(n_accept=n_acc, n_reject=n_rej, nfe=nfe)
+                return dopri5_interp(y0, y1, k, dt, (s_end - s0) / dt)
+            s0, y0, f0 = s0 + dt, y1, f1
+        else:
+            n_rej += 1
+        dt = dt * factor
+
+
+def digit_index(t: float) -> int:
+    """Index of the delta_{t:.2f}.npy file / mask entry that belongs to time t."""
+    return int(round(float(f"{t:.2f}") * 100))
+
+
+def sample_adaptive(sd: Dict[str, Tensor], cfg: dict, z: Tensor, t0: float = 0.0, t1: float = 1.0, rtol: float = 1e-5,
+                    atol: float = 1e-5, y: Optional[Tensor] = None, context: Optional[Tensor] = None,
+                    delta_digits: Optional[Tensor] = None, write_scale: float = 0.0, t_edit: float = 0.0,
+                    edit_loc: Optional[str] = None, attn_colscale: Optional[Tensor] = None, attn_blocks=None,
+                    attn_t_edit: float = 0.0, stats: Optional[dict] = None) -> Tensor:
+    """CNF.decode with method="dopri5".  delta_digits[i] is the row delta_{i/100:.2f}.npy would supply; the model
+    sees the time rounded to fp32, like the reference's fp32 stage times."""
+    def func(t: float, x: Tensor) -> Tensor:
+        tf = float(torch.tensor(t, dtype=torch.float32))
+        hd = td = None
+        if edit_loc is not None and delta_digits is not None and should_edit(tf, t_edit):
+            i = digit_index(tf)
+            if 0 <= i < delta_digits.shape[0]:
+                dlt = delta_digits[i] * write_scale
+                hd, td = (dlt, None) if edit_loc == "head" else (None, dlt)
+        cs = attn_colscale if (attn_colscale is not None and float(f"{tf:.2f}") <= attn_t_edit) else None
+        tt = torch.full((x.shape[0],), tf, dtype=torch.float32)
+        return uvit_forward(sd, cfg, x, tt, y=y, context=context, head_delta=hd, tail_delta=td,
+                            attn_colscale=cs, attn_blocks=attn_blocks)
+
+    return odeint_dopri5(func, z, t0, t1, rtol, atol, stats=stats)

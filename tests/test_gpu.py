@@ -469,3 +469,100 @@ def test_p2p_attention_rescale_sampling_against_oracle(method):
     enc = CNFT2I(m).encode(x.to(dev()), context=ctx.to(dev()), **kw)
     enc_want = O.sample(sd, case["cfg"], x.double(), 1.0, 0.0, h, method, context=ctx.double())
     assert rel(enc, enc_want) < 1e-3
+
+
+# ---- adaptive dopri5 (csrc/ode.cu) -----------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["tiny_uncond", "tiny_class", "tiny_t2i"])
+def test_adaptive_dopri5_against_oracle(name):
+    case = CASES[name]
+    m = model(name)
+    x, _, y, ctx = build_inputs(case)
+    sd = {k: v.cpu().double() for k, v in m.state_dict().items()}
+    so, sg = {}, {}
+    want = O.sample_adaptive(sd, case["cfg"], x.double(), 0.0, 1.0, 1e-5, 1e-5, y=y,
+                             context=None if ctx is None else ctx.double(), stats=so)
+    got = m.engine().sample_adaptive(x.to(dev()), 0.0, 1.0, 1e-5, 1e-5, y=y, context=ctx, stats=sg)
+    assert rel(got, want) < 1e-3
+    assert sg["nfe"] == 2 + 6 * (sg["n_accept"] + sg["n_reject"])
+    # 16-bit operand noise in the velocity reads as extra local error: the device run may take more steps
+    assert so["n_accept"] <= sg["n_accept"] <= 4 * so["n_accept"] + 4
+
+
+def test_adaptive_reversed_time_and_mid_interval():
+    case = CASES["tiny_uncond"]
+    m = model("tiny_uncond")
+    x = build_inputs(case)[0]
+    sd = {k: v.cpu().double() for k, v in m.state_dict().items()}
+    for t0, t1 in ((1.0, 0.0), (0.4, 1.0)):
+        want = O.sample_adaptive(sd, case["cfg"], x.double(), t0, t1, 1e-5, 1e-5)
+        got = m.engine().sample_adaptive(x.to(dev()), t0, t1, 1e-5, 1e-5)
+        assert rel(got, want) < 1e-3
+    # round trip through the two directions
+    z = m.engine().sample_adaptive(x.to(dev()), 1.0, 0.0, 1e-5, 1e-5)
+    back = m.engine().sample_adaptive(z, 0.0, 1.0, 1e-5, 1e-5)
+    assert rel(back, x) < 1e-3
+
+
+def test_adaptive_is_deterministic_and_tighter_tolerance_takes_more_steps():
+    m = model("tiny_uncond")
+    x = build_inputs(CASES["tiny_uncond"])[0].to(dev())
+    a, b, sa, sb = None, None, {}, {}
+    a = m.engine().sample_adaptive(x, 0.0, 1.0, 1e-5, 1e-5, stats=sa)
+    b = m.engine().sample_adaptive(x, 0.0, 1.0, 1e-5, 1e-5, stats=sb)
+    assert torch.equal(a, b) and sa == sb
+    st = {}
+    c = m.engine().sample_adaptive(x, 0.0, 1.0, 1e-3, 1e-3, stats=st)
+    assert st["n_accept"] <= sa["n_accept"] and rel(c, a) < 1e-2
+    with pytest.raises(RuntimeError, match="max_steps"):
+        m.engine().sample_adaptive(x, 0.0, 1.0, 1e-5, 1e-5, max_steps=1)
+    with pytest.raises(RuntimeError, match="t0 != t1"):
+        m.engine().sample_adaptive(x, 0.5, 0.5)
+
+
+def test_cnf_default_adaptive_and_fixadp_against_oracle(tmp_path):
+    """flow_matching.py:79-84 (non-dissection default = dopri5) and :153-180 (decode_fixadp with the tail edit)."""
+    case = CASES["tiny_uncond"]
+    m = model("tiny_uncond")
+    x = build_inputs(case)[0]
+    sd = {k: v.cpu().double() for k, v in m.state_dict().items()}
+    cnf = CNF(m)
+    got = cnf.decode(x.to(dev()), y=None, solver_kwargs=dict(solver="adaptive"))
+    want = O.sample_adaptive(sd, case["cfg"], x.double(), 0.0, 1.0, 1e-5, 1e-5)
+    assert rel(got, want) < 1e-3 and cnf.last_solver_stats["n_accept"] >= 2
+    # fixadp: Euler on [0, t_edit] with the edit at every grid point, dopri5 on [t_edit, 1] where the hook still
+    # fires for evaluations that print as "0.40"
+    # (a large edit: the discontinuity it puts between f(0.40) and the later stages forces rejected steps)
+    x = x[:1]
+    h, t_mid, scale = 0.1, 0.4, 40.0
+    rng = torch.Generator().manual_seed(5)
+    grid_table = torch.zeros(5, 4, 32, 32)
+    digits = torch.zeros(101, 4, 32, 32)
+    for i in range(1, 5):
+        d = 0.3 * torch.randn(2, 4, 32, 32, generator=rng)
+        np.save(tmp_path / f"delta_{i * h:.2f}.npy", d.numpy())
+        grid_table[i] = d[1]
+        digits[10 * i] = d[1]
+    kw = dict(dissect_task="uspace_uvit", dissect_name="write_attr", write_path_root=str(tmp_path), ith_attr=1,
+              t_edit=t_mid, write_scale=scale, edit_loc="tail",
+              solver_kwargs=dict(solver="fixadp", solver_fix="euler", solver_fix_step=h, solver_adaptive="dopri5"))
+    got = cnf.decode(x.to(dev()), y=None, **kw)
+    mid = O.sample(sd, case["cfg"], x.double(), 0.0, t_mid, h, "euler", delta_table=grid_table.double(),
+                   write_scale=scale, t_edit=t_mid, edit_loc="tail")
+    want = O.sample_adaptive(sd, case["cfg"], mid, t_mid, 1.0, 1e-5, 1e-5, delta_digits=digits.double(),
+                             write_scale=scale, t_edit=t_mid, edit_loc="tail")
+    assert rel(got, want) < 1e-3
+    assert cnf.last_solver_stats["n_reject"] >= 3
+    plain = O.sample_adaptive(sd, case["cfg"], mid, t_mid, 1.0, 1e-5, 1e-5)
+    assert rel(want, plain) > 1e-2            # the "0.40" evaluations of the adaptive phase were edited
+    assert rel(got.double().cpu() - plain, want - plain) < 3e-2
+
+
+def test_adaptive_agrees_with_fine_fixed_grid_on_north_star_model():
+    """Size-independent property on U-ViT-L: dopri5(1e-5) and Heun(h = 0.01) integrate the same field."""
+    m = model("large_uncond")
+    g = torch.Generator().manual_seed(1230)
+    x = torch.randn(8, 4, 32, 32, generator=g).to(dev())
+    st = {}
+    ada = m.engine().sample_adaptive(x, 0.0, 1.0, 1e-5, 1e-5, stats=st)
+    fine = m.engine().sample(x, 0.0, 1.0, 0.01, "heun")
+    assert rel(ada, fine) < 1e-3 and st["n_accept"] >= 2

@@ -13,7 +13,8 @@ from oracle import uvit_oracle as O
 from tests.golden.cases import CASES
 from uspace_b200 import _lib, parallel
 from uspace_b200.engine import config_from_kwargs, time_grid
-from uspace_b200.flow_matching import (CNF, CNFT2I, block_mask_from_ids, build_attn_edit, build_delta_table,
+from uspace_b200.flow_matching import (CNF, CNFT2I, block_mask_from_ids, build_attn_edit, build_delta_digits,
+                                        build_delta_table,
                                        should_edit)
 from uspace_b200.uvit import UViT, UViTT2I, get_nnet
 
@@ -137,13 +138,37 @@ def test_cnf_rejects_unbuilt_solvers():
     z, ctx = torch.zeros(1, 4, 32, 32), torch.zeros(1, 77, 768)
     for solver in ("adaptive", "fixadp"):
         with pytest.raises(NotImplementedError):
-            cnf.decode(z, ctx, dissect_name="p2p", solver_kwargs=dict(solver=solver))
-    with pytest.raises(NotImplementedError):  # non-dissection mode == dopri5 in the reference
-        cnf.get_ode_kwargs(solver_kwargs=dict(solver="fixed"))
+            cnf.decode(z, ctx, dissect_name="p2p", t_edit=0.4,
+                       solver_kwargs=dict(solver=solver, solver_fix="euler", solver_fix_step=0.1, solver_adaptive="bosh3"))
+    with pytest.raises(NotImplementedError):
+        cnf.decode(z, ctx, dissect_name="p2p", solver_kwargs=dict(solver="other"))
+    with pytest.raises(KeyError):   # the reference indexes kwargs["solver_kwargs"] unconditionally (flow_matching.py:138)
+        cnf.decode(z, ctx)
     with pytest.raises(NotImplementedError):
         cnf.get_ode_kwargs(dissect_name="x", solver_kwargs=dict(solver="fixed", solver_fix="rk4", solver_fix_step=.1))
-    ok = cnf.get_ode_kwargs(dissect_name="x", solver_kwargs=dict(solver="fixed", solver_fix="euler", solver_fix_step=0.02))
-    assert ok == dict(method="euler", options=dict(step_size=0.02))
+    # flow_matching.py:38-85
+    assert cnf.get_ode_kwargs(solver_kwargs=dict(solver="fixed")) == dict(method="dopri5", rtol=1e-5, atol=1e-5)
+    sk = dict(solver="fixed", solver_fix="euler", solver_fix_step=0.02, solver_adaptive="dopri5")
+    fixed = dict(method="euler", rtol=1e-5, atol=1e-5, options=dict(step_size=0.02))
+    adaptive = dict(method="dopri5", rtol=1e-5, atol=1e-5)
+    assert cnf.get_ode_kwargs(dissect_name="x", solver_kwargs=sk) == fixed
+    assert cnf.get_ode_kwargs(dissect_name="x", solver_kwargs=dict(sk, solver="adaptive")) == adaptive
+    assert cnf.get_ode_kwargs(dissect_name="x", solver_kwargs=dict(sk, solver="fixadp")) == (fixed, adaptive)
+
+
+def test_delta_digits_table(tmp_path):
+    rng = np.random.default_rng(1)
+    files = {d: rng.standard_normal((3, 4, 32, 32)).astype(np.float32) for d in ("0.00", "0.07", "0.40", "0.41")}
+    for d, a in files.items():
+        np.save(tmp_path / f"delta_{d}.npy", a)
+    kw = dict(dissect_task="uspace_uvit", dissect_name="write_attr", write_path_root=str(tmp_path), t_edit=0.4,
+              edit_loc="head", ith_attr=1)
+    tab, loc = build_delta_digits((4, 32, 32), **kw)
+    assert loc == "head" and tab.shape == (101, 4, 32, 32)
+    assert np.array_equal(tab[7].numpy(), files["0.07"][1]) and np.array_equal(tab[40].numpy(), files["0.40"][1])
+    # "0.00" never edits, 0.41 > t_edit, missing files stay zero
+    assert not tab[0].any() and not tab[41].any() and not tab[8].any()
+    assert build_delta_digits((4, 32, 32), dissect_name=None) == (None, None)
 
 
 def test_delta_table_from_reference_file_layout(tmp_path):

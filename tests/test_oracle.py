@@ -172,3 +172,72 @@ def test_oracle_p2p_attention_rescale_matches_reference(golden_dir):
     plain = O.uvit_forward(sd, case["cfg"], x, t, context=ctx)
     assert rel(plain, g["p2p_plain"]) < 2e-6
     assert rel(g["p2p_forward"], g["p2p_plain"]) > 1e-3   # the edit is visible
+
+
+# ---- adaptive dopri5 (torchdiffeq is absent: the restated constants are pinned mathematically) ----------------
+def test_dopri5_tableau_against_scipy_and_order_conditions():
+    from scipy.integrate._ivp.rk import RK45
+    assert np.allclose(RK45.C[1:], O.DP_ALPHA[:5], rtol=0, atol=1e-15)
+    assert np.allclose(RK45.B, O.DP_C_SOL[:6], rtol=0, atol=1e-15)
+    for i in range(5):
+        assert np.allclose(RK45.A[i + 1][:i + 1], O.DP_BETA[i], rtol=0, atol=1e-15)
+    assert O.DP_BETA[5] == O.DP_C_SOL[:6]          # FSAL: the last stage state is the 5th-order solution
+    # the embedded companion b^ = c_sol - c_error is a 4th-order method: all 8 rooted-tree conditions up to order 4
+    c = np.array([0.0] + O.DP_ALPHA)
+    A = np.zeros((7, 7))
+    for i, row in enumerate(O.DP_BETA):
+        A[i + 1, :len(row)] = row
+    for b, order in ((np.array(O.DP_C_SOL), 5), (np.array(O.DP_C_SOL) - np.array(O.DP_C_ERROR), 4)):
+        assert abs(b.sum() - 1) < 1e-14
+        assert abs(b @ c - 1 / 2) < 1e-14
+        assert abs(b @ c ** 2 - 1 / 3) < 1e-14 and abs(b @ A @ c - 1 / 6) < 1e-14
+        assert abs(b @ c ** 3 - 1 / 4) < 1e-14 and abs((b * c) @ A @ c - 1 / 8) < 1e-14
+        assert abs(b @ A @ c ** 2 - 1 / 12) < 1e-14 and abs(b @ A @ A @ c - 1 / 24) < 1e-14
+        if order == 5:
+            assert abs(b @ c ** 4 - 1 / 5) < 1e-14
+    # the companion really is only 4th order (so the difference is an error estimate, not zero)
+    assert abs((np.array(O.DP_C_SOL) - np.array(O.DP_C_ERROR)) @ c ** 4 - 1 / 5) > 1e-4
+    assert abs(sum(O.DP_C_ERROR)) < 1e-15
+
+
+def test_dopri5_dense_output_and_step():
+    f = lambda t, y: y * np.cos(t)                       # y = y0 exp(sin t)
+    y0 = torch.tensor([1.0, -2.0], dtype=torch.float64)
+    errs = []
+    for dt in (0.2, 0.1):
+        y1, f1, err, k = O.dopri5_step(f, 0.0, y0, f(0.0, y0), dt)
+        assert torch.allclose(f1, f(dt, y1))
+        errs.append(float((y1 - y0 * np.exp(np.sin(dt))).abs().max()))
+        for x in (0.0, 0.25, 0.5, 1.0):
+            mid = O.dopri5_interp(y0, y1, k, dt, x)
+            assert float((mid - y0 * np.exp(np.sin(x * dt))).abs().max()) < 2e-6 * (dt / 0.2) ** 5 + 1e-15
+    assert errs[0] / errs[1] > 40                        # local error ~ dt^6
+
+
+def test_dopri5_against_closed_form_and_scipy():
+    from scipy.integrate import solve_ivp
+    f = lambda t, y: -2.0 * y + torch.sin(5.0 * torch.as_tensor(t)) * torch.ones_like(y)
+    y0 = torch.tensor([1.0, 0.5, -3.0], dtype=torch.float64)
+    ref = solve_ivp(lambda t, y: -2.0 * y + np.sin(5.0 * t), (0.0, 1.0), y0.numpy(), rtol=1e-13, atol=1e-13).y[:, -1]
+    for tol, bound in ((1e-5, 1e-4), (1e-8, 1e-7)):    # global error ~ a few local tolerances
+        st = {}
+        y = O.odeint_dopri5(f, y0, 0.0, 1.0, tol, tol, stats=st)
+        assert np.abs(y.numpy() - ref).max() < bound
+        sp = solve_ivp(lambda t, y: -2.0 * y + np.sin(5.0 * t), (0.0, 1.0), y0.numpy(), rtol=tol, atol=tol, method="RK45")
+        # same family of controller (Hairer start, 0.9 safety, [0.2, 10] clamp): step counts agree within a few
+        assert abs((st["n_accept"] + st["n_reject"]) - (sp.nfev - 2) // 6) <= 3
+        assert st["nfe"] == 2 + 6 * (st["n_accept"] + st["n_reject"])
+    # reversed time returns to the start
+    back = O.odeint_dopri5(f, torch.as_tensor(ref), 1.0, 0.0, 1e-9, 1e-9)
+    assert (back - y0).abs().max() < 1e-6
+
+
+def test_oracle_adaptive_sampling_agrees_with_a_fine_fixed_grid():
+    case = CASES["tiny_uncond"]
+    sd = {k: v.double() for k, v in build_model(case, UViT, UViTT2I).state_dict().items()}
+    x = build_inputs(case)[0][:1].double()
+    st = {}
+    ada = O.sample_adaptive(sd, case["cfg"], x, 0.0, 1.0, 1e-5, 1e-5, stats=st)
+    fine = O.sample(sd, case["cfg"], x, 0.0, 1.0, 0.01, "heun")
+    assert rel(ada, fine) < 5e-5 and st["n_accept"] >= 2
+    assert O.digit_index(0.125) == 12 and O.digit_index(0.4049999) == 40 and O.digit_index(0.405001) == 41

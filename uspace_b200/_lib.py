@@ -28,6 +28,11 @@ class UspAttnEdit(C.Structure):
     _fields_ = [("colscale", C.c_void_p), ("block_mask", C.c_uint64), ("t_edit", C.c_float)]
 
 
+class UspAdaptiveStats(C.Structure):
+    _fields_ = [("n_accept", C.c_int32), ("n_reject", C.c_int32), ("nfe", C.c_int32), ("last_ratio", C.c_float),
+                ("last_dt", C.c_double)]
+
+
 _lib = None
 
 _vp, _i, _f, _i64 = C.c_void_p, C.c_int, C.c_float, C.c_int64
@@ -43,6 +48,8 @@ _SIGNATURES = {
     "usp_forward_edit": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, C.POINTER(UspAttnEdit), _vp]),
     "usp_sample_edit": (_i, [_vp, _vp, _vp, _vp, _i, _f, _f, _f, _i, _vp, _f, _f, _i, C.POINTER(UspAttnEdit), _vp]),
     "usp_sample": (_i, [_vp, _vp, _vp, _vp, _i, _f, _f, _f, _i, _vp, _f, _f, _i, _vp]),
+    "usp_sample_adaptive": (_i, [_vp, _vp, _vp, _vp, _i, _f, _f, C.c_double, C.c_double, _vp, _i, _f, _f, _i,
+                                 C.POINTER(UspAttnEdit), _i, C.POINTER(UspAdaptiveStats), _vp]),
     "usp_sample_host": (_i, [_vp, _vp, _vp, _vp, _i, _f, _f, _f, _i, _vp, _f, _f, _i]),
     "usp_grid_size": (_i, [_f, _f, _f]),
     "usp_time_grid": (_i, [_f, _f, _f, C.POINTER(_f), _i]),

@@ -3,6 +3,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <math.h>
+#include <cmath>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -121,12 +122,24 @@ struct Plan {
     size_t delta_cap = 0;
     float* colscale = nullptr;      // [B, L] attention column weights (p2p edit)
     unsigned char* amask = nullptr; // per grid point: attention edit active
+    float* rk_k = nullptr;          // [RK_STAGES][B,C,S,S] stage derivatives of the adaptive solver
+    RkState* rs = nullptr;
+    double* rk_partials = nullptr;  // [2][RK_MAX_PARTIALS]
     CUtensorMap m_h, m_a, m_m, m_xa, m_xb, m_q, m_k, m_v, m_ctx, m_xe, m_xp, m_xs;
     std::vector<CUtensorMap> m_skip;
     std::map<std::pair<int, uint64_t>, cudaGraphExec_t> graphs;   // (method / edit flags, attention block mask)
 };
 
 constexpr int MAX_GRID = 4096;
+
+// The reference keys its hooks on the string f"{t:.2f}" and compares float(digit) <= t_edit with a python float.
+// t_edit crosses this ABI as fp32 (0.7f < 0.70), so the digit is rounded to fp32 as well before comparing.
+bool digit_leq(double t, float t_edit, bool* is_zero) {
+    char buf[64];
+    snprintf(buf, sizeof(buf), "%.2f", t);
+    if (is_zero) *is_zero = strcmp(buf, "0.00") == 0;
+    return static_cast<float>(atof(buf)) <= t_edit;
+}
 
 }  // namespace
 
@@ -146,6 +159,7 @@ struct usp_handle {
     std::map<int, std::unique_ptr<Plan>> plans;
     cudaStream_t cap_stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    RkState* rs_host = nullptr;   // pinned mirror of the adaptive solver's device state
     bool ev_valid = false;
     int kernels_per_forward = 0;
     std::string err;
@@ -250,7 +264,8 @@ int get_plan(usp_handle* h, int B, Plan** out) {
                  o_ctx16 = carve(nctx ? static_cast<size_t>(B) * nctx * cdim * 2 : 16);
     const size_t o_y = carve(static_cast<size_t>(B) * 8), o_st = carve(sizeof(StepState)),
                  o_grid = carve(MAX_GRID * 4), o_mask = carve(MAX_GRID), o_amask = carve(MAX_GRID),
-                 o_cs = carve(static_cast<size_t>(B) * L * 4);
+                 o_cs = carve(static_cast<size_t>(B) * L * 4), o_rkk = carve(RK_STAGES * zel * 4),
+                 o_rs = carve(sizeof(RkState)), o_rkp = carve(2 * RK_MAX_PARTIALS * 8);
     p->bytes = off;
     CUDA_TRY(h, cudaMalloc(&p->slab, off));
     CUDA_TRY(h, cudaMemset(p->slab, 0, off));
@@ -280,6 +295,9 @@ int get_plan(usp_handle* h, int B, Plan** out) {
     p->mask = reinterpret_cast<unsigned char*>(base + o_mask);
     p->amask = reinterpret_cast<unsigned char*>(base + o_amask);
     p->colscale = reinterpret_cast<float*>(base + o_cs);
+    p->rk_k = reinterpret_cast<float*>(base + o_rkk);
+    p->rs = reinterpret_cast<RkState*>(base + o_rs);
+    p->rk_partials = reinterpret_cast<double*>(base + o_rkp);
 
     bool ok = true;
     ok &= make_map_2d(&p->m_h, p->h16, M, D, GEMM_BM, opd);
@@ -691,6 +709,7 @@ void usp_destroy(usp_handle* h) {
         cudaFree(b.fc1_d);
     }
     cudaFree(h->freqs);
+    if (h->rs_host) cudaFreeHost(h->rs_host);
     if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -873,9 +892,9 @@ int usp_sample_edit(usp_handle* h, float* z, const float* context, const int64_t
     std::vector<unsigned char> mask(n, 0);
     if (edit_loc != USP_EDIT_NONE) {
         for (int i = 0; i < n; ++i) {
-            char buf[64];
-            snprintf(buf, sizeof(buf), "%.2f", static_cast<double>(grid[i]));
-            mask[i] = (strcmp(buf, "0.00") != 0 && atof(buf) <= static_cast<double>(t_edit)) ? 1 : 0;
+            bool zero = false;
+            const bool le = digit_leq(static_cast<double>(grid[i]), t_edit, &zero);
+            mask[i] = (!zero && le) ? 1 : 0;
         }
         const size_t dbytes = static_cast<size_t>(n) * C * S * S * 4;
         if (p->delta_cap < dbytes) {
@@ -896,11 +915,7 @@ int usp_sample_edit(usp_handle* h, float* z, const float* context, const int64_t
     const bool use_attn = attn != nullptr && attn->colscale != nullptr && attn->block_mask != 0;
     std::vector<unsigned char> amask(n, 0);
     if (use_attn) {
-        for (int i = 0; i < n; ++i) {
-            char buf[64];
-            snprintf(buf, sizeof(buf), "%.2f", static_cast<double>(grid[i]));
-            amask[i] = atof(buf) <= static_cast<double>(attn->t_edit) ? 1 : 0;
-        }
+        for (int i = 0; i < n; ++i) amask[i] = digit_leq(static_cast<double>(grid[i]), attn->t_edit, nullptr) ? 1 : 0;
         CUDA_TRY(h, cudaMemcpyAsync(p->colscale, attn->colscale, static_cast<size_t>(B) * h->L * 4, cudaMemcpyDefault, s));
     }
     CUDA_TRY(h, cudaMemcpyAsync(p->amask, amask.data(), n, cudaMemcpyHostToDevice, s));
@@ -960,6 +975,163 @@ int usp_sample_edit(usp_handle* h, float* z, const float* context, const int64_t
     for (int i = 0; i + 1 < n; ++i) CUDA_TRY(h, cudaGraphLaunch(git->second, s));
     CUDA_TRY(h, cudaMemcpyAsync(z, p->z, zbytes, cudaMemcpyDefault, s));
     CUDA_TRY(h, cudaEventRecord(h->ev1, s));
+    h->ev_valid = true;
+    return USP_OK;
+}
+
+int usp_sample_adaptive(usp_handle* h, float* z, const float* context, const int64_t* y, int B, float t0, float t1,
+                        double rtol, double atol, const float* delta_digits, int n_rows, float write_scale,
+                        float t_edit, int edit_loc, const usp_attn_edit* attn, int max_steps,
+                        usp_adaptive_stats* stats, void* stream) {
+    int rc = check_ready(h, B);
+    if (rc) return rc;
+    if (!z) return fail(h, USP_ERR_INVALID, "null latent");
+    if ((h->cfg.num_clip_token > 0) != (context != nullptr))
+        return fail(h, USP_ERR_INVALID, "context must be given exactly for the t2i model");
+    if ((y != nullptr) != (h->cfg.num_classes > 0))
+        return fail(h, USP_ERR_INVALID, "y must be given exactly for the class-conditional model (num_classes > 0)");
+    if (edit_loc != USP_EDIT_NONE && edit_loc != USP_EDIT_HEAD && edit_loc != USP_EDIT_TAIL)
+        return fail(h, USP_ERR_INVALID, "edit_loc must be none, head or tail (\"mid\" is broken in the reference)");
+    if ((edit_loc != USP_EDIT_NONE) != (delta_digits != nullptr))
+        return fail(h, USP_ERR_INVALID, "delta_digits must be given exactly when edit_loc is head or tail");
+    if (delta_digits && (n_rows < 1 || n_rows > RK_DIGITS)) return fail(h, USP_ERR_INVALID, "n_rows must be in [1, 128]");
+    if (!(rtol > 0.0) || !(atol >= 0.0) || !(t0 != t1) || !std::isfinite(t0) || !std::isfinite(t1))
+        return fail(h, USP_ERR_INVALID, "need rtol > 0, atol >= 0 and t0 != t1");
+    if (max_steps <= 0) max_steps = 1 << 20;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    Plan* p = nullptr;
+    rc = get_plan(h, B, &p);
+    if (rc) return rc;
+    if (!h->rs_host) CUDA_TRY(h, cudaMallocHost(&h->rs_host, sizeof(RkState)));
+
+    const int C = h->cfg.in_chans, S = h->cfg.img_size;
+    const long long zel = static_cast<long long>(B) * C * S * S;
+    const size_t zbytes = static_cast<size_t>(zel) * 4;
+    const bool use_attn = attn != nullptr && attn->colscale != nullptr && attn->block_mask != 0;
+    // hook masks keyed by the digit i <-> "%.2f" of i / 100 (libs/dissection.py:21-26: "0.00" never edits;
+    // tools/utils_t2i.py:284: "0.00" included)
+    std::vector<unsigned char> emask(RK_DIGITS, 0), amask(RK_DIGITS, 0);
+    for (int i = 0; i < RK_DIGITS; ++i) {
+        bool zero = false;
+        if (edit_loc != USP_EDIT_NONE) emask[i] = (digit_leq(i / 100.0, t_edit, &zero) && !zero && i < n_rows) ? 1 : 0;
+        if (use_attn) amask[i] = digit_leq(i / 100.0, attn->t_edit, nullptr) ? 1 : 0;
+    }
+    if (edit_loc != USP_EDIT_NONE) {
+        const size_t dbytes = static_cast<size_t>(n_rows) * C * S * S * 4;
+        if (p->delta_cap < dbytes) {
+            for (auto& g : p->graphs) cudaGraphExecDestroy(g.second);
+            p->graphs.clear();
+            if (p->delta) CUDA_TRY(h, cudaFree(p->delta));
+            p->delta = nullptr;
+            CUDA_TRY(h, cudaMalloc(&p->delta, dbytes));
+            p->delta_cap = dbytes;
+        }
+        CUDA_TRY(h, cudaMemcpyAsync(p->delta, delta_digits, dbytes, cudaMemcpyDefault, s));
+    }
+    CUDA_TRY(h, cudaEventRecord(h->ev0, s));
+    CUDA_TRY(h, cudaMemcpyAsync(p->mask, emask.data(), RK_DIGITS, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(h, cudaMemcpyAsync(p->amask, amask.data(), RK_DIGITS, cudaMemcpyHostToDevice, s));
+    if (use_attn)
+        CUDA_TRY(h, cudaMemcpyAsync(p->colscale, attn->colscale, static_cast<size_t>(B) * h->L * 4, cudaMemcpyDefault, s));
+    const float sign = t1 >= t0 ? 1.f : -1.f;
+    RkState rs0;
+    memset(&rs0, 0, sizeof(rs0));
+    rs0.s0 = static_cast<double>(sign) * static_cast<double>(t0);
+    rs0.s_end = static_cast<double>(sign) * static_cast<double>(t1);
+    rs0.rtol = rtol; rs0.atol = atol; rs0.sign = sign; rs0.write_scale = write_scale; rs0.n_rows = delta_digits ? n_rows : 0;
+    // pageable source: the copy is staged before the call returns, so the stack object may go out of scope
+    CUDA_TRY(h, cudaMemcpyAsync(p->rs, &rs0, sizeof(rs0), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(h, cudaMemcpyAsync(p->z, z, zbytes, cudaMemcpyDefault, s));
+    if (y) CUDA_TRY(h, cudaMemcpyAsync(p->y, y, static_cast<size_t>(B) * 8, cudaMemcpyDefault, s));
+    if (context) {
+        rc = embed_context(h, p, context, s);
+        if (rc) return rc;
+    }
+
+    RkArgs ra;
+    memset(&ra, 0, sizeof(ra));
+    ra.rs = p->rs; ra.st = p->st; ra.y0 = p->z; ra.k = p->rk_k; ra.ytmp = p->ztmp; ra.out = p->z;
+    ra.partials = p->rk_partials; ra.emask = p->mask; ra.amask = p->amask; ra.n = zel;
+    auto velocity = [&](const float* x, int stage, cudaStream_t cs) -> int {
+        FwdIO io;
+        memset(&io, 0, sizeof(io));
+        io.x = x; io.st = p->st; io.y = y ? p->y : nullptr; io.has_ctx = context != nullptr;
+        io.delta = edit_loc != USP_EDIT_NONE ? p->delta : nullptr; io.edit_loc = edit_loc;
+        if (use_attn) { io.colscale = p->colscale; io.block_mask = attn->block_mask; }
+        io.out = p->rk_k + static_cast<long long>(stage) * zel; io.m1 = sign;   // base == nullptr: k = sign * v
+        return enqueue_forward(h, p, io, cs);
+    };
+#define RK_TRY(expr)                                                                                   \
+    do {                                                                                               \
+        cudaError_t _e = (expr);                                                                       \
+        if (_e != cudaSuccess) return fail(h, USP_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+    } while (0)
+    // starting step (two evaluations): k0 = f(s0, y0);  h0 from |y0|, |k0|;  k1 = f(s0 + h0, y0 + h0 k0);  dt
+    RK_TRY(launch_rk_stage(ra, 0, s));
+    rc = velocity(p->z, 0, s);
+    if (rc) return rc;
+    RK_TRY(launch_rk_control(ra, 0, s));
+    RK_TRY(launch_rk_stage(ra, -1, s));
+    rc = velocity(p->ztmp, 1, s);
+    if (rc) return rc;
+    RK_TRY(launch_rk_control(ra, 1, s));
+
+    const std::pair<int, uint64_t> key(USP_METHOD_DOPRI5 | (edit_loc << 2) | ((y ? 1 : 0) << 4) | ((use_attn ? 1 : 0) << 5) |
+                                           ((sign < 0.f ? 1 : 0) << 6),
+                                       use_attn ? attn->block_mask : 0);
+    auto git = p->graphs.find(key);
+    if (git == p->graphs.end()) {
+        // one attempted step: six stage evaluations, error norm, controller, commit
+        cudaGraph_t graph = nullptr;
+        CUDA_TRY(h, cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal));
+        auto body = [&]() -> int {
+            for (int st = 1; st <= 6; ++st) {
+                RK_TRY(launch_rk_stage(ra, st, h->cap_stream));
+                const int r = velocity(p->ztmp, st, h->cap_stream);
+                if (r) return r;
+            }
+            RK_TRY(launch_rk_control(ra, 2, h->cap_stream));
+            RK_TRY(launch_rk_commit(ra, h->cap_stream));
+            return USP_OK;
+        };
+        const int brc = body();
+        cudaError_t ce = cudaStreamEndCapture(h->cap_stream, &graph);
+        if (brc) {
+            if (graph) cudaGraphDestroy(graph);
+            return brc;
+        }
+        if (ce != cudaSuccess) return fail(h, USP_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce));
+        cudaGraphExec_t exec = nullptr;
+        ce = cudaGraphInstantiate(&exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ce != cudaSuccess) return fail(h, USP_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ce));
+        p->graphs[key] = exec;
+        git = p->graphs.find(key);
+    }
+#undef RK_TRY
+    double last_dt = 0.0;
+    for (int attempt = 0;; ++attempt) {
+        if (attempt >= max_steps) return fail(h, USP_ERR_STATE, "adaptive solver: max_steps attempted steps without reaching t1");
+        CUDA_TRY(h, cudaGraphLaunch(git->second, s));
+        CUDA_TRY(h, cudaMemcpyAsync(h->rs_host, p->rs, sizeof(RkState), cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(h, cudaStreamSynchronize(s));
+        const RkState& r = *h->rs_host;
+        if (r.accept) last_dt = r.dt_prev;
+        if (r.done) break;
+        if (!std::isfinite(r.dt) || !(r.s0 + r.dt > r.s0))
+            return fail(h, USP_ERR_STATE, "adaptive solver: step size underflow or non-finite error estimate");
+    }
+    if (stats) {
+        stats->n_accept = h->rs_host->n_accept;
+        stats->n_reject = h->rs_host->n_reject;
+        stats->nfe = h->rs_host->nfe;
+        stats->last_ratio = h->rs_host->ratio;
+        stats->last_dt = last_dt;
+    }
+    CUDA_TRY(h, cudaMemcpyAsync(z, p->z, zbytes, cudaMemcpyDefault, s));
+    CUDA_TRY(h, cudaEventRecord(h->ev1, s));
+    CUDA_TRY(h, cudaStreamSynchronize(s));
     h->ev_valid = true;
     return USP_OK;
 }

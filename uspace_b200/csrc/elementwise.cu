@@ -283,6 +283,10 @@ __global__ void __launch_bounds__(256) final_kernel(const FinalArgs a) {
         a.out[i] = v;
         return;
     }
+    if (a.base == nullptr) {   // general Runge-Kutta stage: keep the (direction-signed) derivative only
+        a.out[i] = a.m1 * v;
+        return;
+    }
     if (a.vstore != nullptr) a.vstore[i] = v;
     const float dt = a.st->dt;
     float inc = a.m1 * v;

@@ -145,4 +145,48 @@ cudaError_t launch_fold_ln(const float* W, const float* gamma, const float* beta
 cudaError_t launch_step(StepState* st, const float* grid, const unsigned char* mask, const unsigned char* amask,
                         int stage, cudaStream_t s);
 
+// ---- adaptive Dormand-Prince 5(4) (csrc/ode.cu) -------------------------------------------------
+// torchdiffeq's RKAdaptiveStepsizeODESolver restated with the controller on the device: time-like quantities are
+// fp64, the state and the stage times handed to the velocity field fp32 (its mixed-precision convention).
+constexpr int RK_STAGES = 7;          // k[0..6]; k[6] of an accepted step is k[0] of the next (FSAL)
+constexpr int RK_MAX_PARTIALS = 4096;
+constexpr int RK_DIGITS = 128;        // rows of the "%.2f"-indexed edit masks (0.00 .. 1.27)
+struct RkState {
+    double s0;          // solver time at the start of the current step (ascending; model time = sign * s)
+    double dt;          // step the next attempt will try
+    double s_end;
+    double s0_prev;     // the step the last attempt covered (read by rk_commit)
+    double dt_prev;
+    double rtol, atol;
+    float sign;
+    float write_scale;
+    float h0;           // starting-step candidate (between the two initial evaluations)
+    float d0, d1;
+    float ratio;        // error ratio of the last attempt
+    int accept;         // decision of the last attempt
+    int done;           // the last accepted step reached s_end: the result has been written
+    int n_accept, n_reject, nfe;
+    int n_rows;         // rows of the edit table
+};
+struct RkArgs {
+    RkState* rs;
+    StepState* st;
+    float* y0;                 // [n] state at the start of the step (advanced by rk_commit)
+    float* k;                  // [RK_STAGES][n]
+    float* ytmp;               // [n] stage state (y1 after the last stage)
+    float* out;                // [n] result
+    double* partials;          // [2][RK_MAX_PARTIALS]
+    const unsigned char* emask;   // [RK_DIGITS] write-edit active for digit i
+    const unsigned char* amask;   // [RK_DIGITS] attention edit active for digit i
+    long long n;
+};
+// stage 1..6: ytmp = y0 + dt * sum_j beta[stage][j] k_j and the stage time; stage 0: time of the very first
+// evaluation; stage -1: the probe point of the starting-step search (ytmp = y0 + h0 * k0)
+cudaError_t launch_rk_stage(const RkArgs& a, int stage, cudaStream_t s);
+// what: 0 = norms of y0/scale and k0/scale -> h0;  1 = norm of (k1 - k0)/scale -> first dt;
+//       2 = error ratio of the attempted step -> accept / reject, next dt, counters
+cudaError_t launch_rk_control(const RkArgs& a, int what, cudaStream_t s);
+// accepted: (y0, k0) <- (y1, k6), or the dense-output polynomial at s_end into `out` when the step reached it
+cudaError_t launch_rk_commit(const RkArgs& a, cudaStream_t s);
+
 }  // namespace usp

@@ -139,6 +139,36 @@ class Engine:
                                             self._stream()), self.handle, "usp_sample")
         return zz
 
+    def sample_adaptive(self, z, t0=0.0, t1=1.0, rtol=1e-5, atol=1e-5, y=None, context=None, delta_digits=None,
+                        write_scale=0.0, t_edit=0.0, edit_loc=None, attn_edit=None, max_steps=0, stats=None):
+        """Adaptive dopri5 (torchdiffeq semantics) from t0 to t1; returns a new tensor.  ``delta_digits`` rows are
+        keyed by the "%.2f" digit of the evaluation time.  ``stats`` (dict) receives n_accept / n_reject / nfe.
+        Synchronises the current stream (the host reads the step controller's verdict once per attempted step)."""
+        self._check_latent(z)
+        B = z.shape[0]
+        zz = z.to(self.device, torch.float32).contiguous().clone()
+        if y is not None:
+            y = y.to(self.device, torch.int64).contiguous()
+        if context is not None:
+            context = context.to(self.device, torch.float32).contiguous()
+        n_rows = 0
+        if delta_digits is not None:
+            delta_digits = delta_digits.to(self.device, torch.float32).contiguous()
+            n_rows = delta_digits.shape[0]
+            if delta_digits.shape[1:] != (self.C, self.S, self.S) or not 1 <= n_rows <= 128:
+                raise ValueError(f"delta_digits must be [<=128,{self.C},{self.S},{self.S}]")
+        edit, _keep = self._attn_edit(attn_edit, B)
+        st = _lib.UspAdaptiveStats()
+        _lib.check(self.lib.usp_sample_adaptive(self.handle, _ptr(zz), _ptr(context), _ptr(y), B, t0, t1, rtol, atol,
+                                                _ptr(delta_digits), n_rows, write_scale, t_edit,
+                                                _lib.EDIT_LOC[edit_loc], C.byref(edit) if edit is not None else None,
+                                                int(max_steps), C.byref(st), self._stream()),
+                   self.handle, "usp_sample_adaptive")
+        if stats is not None:
+            stats.update(n_accept=st.n_accept, n_reject=st.n_reject, nfe=st.nfe, last_ratio=st.last_ratio,
+                         last_dt=st.last_dt)
+        return zz
+
     def sample_host(self, z_host, t0=0.0, t1=1.0, step_size=0.02, method="euler", y=None, context=None,
                     delta_table=None, write_scale=0.0, t_edit=0.0, edit_loc=None) -> torch.Tensor:
         """End-to-end call on HOST tensors (ideally pinned): H2D, sample, D2H, synchronise. In place on z_host."""

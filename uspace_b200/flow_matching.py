@@ -4,11 +4,12 @@
 ``torchdiffeq.odeint`` call (flow_matching.py:118-125,140-147) is replaced by the library's fixed-grid
 Euler / Heun loop: one CUDA-graph-captured step replayed on the current stream, no host sync per NFE.
 
-Built: ``solver="fixed"`` with ``solver_fix`` in {"euler", "heun"}; the "write_attr" / "write_pca" edit hook at
-``edit_loc`` head / tail (libs/dissection.py:115-186) through a pre-loaded delta table.
-Not built (NotImplementedError): adaptive dopri5 (``solver="adaptive"``, the non-dissection default, and the
-adaptive tail of ``"fixadp"``), the activation-dump "read" mode, ``edit_loc="mid"`` (broken in the reference
-for U-ViT).
+Built: ``solver="fixed"`` with ``solver_fix`` in {"euler", "heun"}; ``solver="adaptive"`` / the non-dissection
+default / the adaptive tail of ``"fixadp"`` with dopri5 (step control and dense output on the device, torchdiffeq
+semantics restated in csrc/ode.cu); the "write_attr" / "write_pca" edit hook at ``edit_loc`` head / tail
+(libs/dissection.py:115-186) through a pre-loaded delta table; the "p2p_rescale" attention edit.
+Not built (NotImplementedError): other torchdiffeq methods (midpoint, rk4, bosh3, adaptive_heun), the
+activation-dump "read" mode, ``edit_loc="mid"`` (broken in the reference for U-ViT).
 """
 from __future__ import annotations
 
@@ -22,6 +23,9 @@ from torch import Tensor
 from .engine import time_grid
 
 _FIXED_METHODS = ("euler", "heun")
+_ADAPTIVE_METHODS = ("dopri5",)
+_RTOL = 1e-5   # flow_matching.py:11-12
+_ATOL = 1e-5
 
 
 def should_edit(timestep_digit: str, t_edit) -> bool:
@@ -74,6 +78,34 @@ def build_delta_table(grid, shape, **kwargs):
         else:
             table[i] = _read_delta(os.path.join(root, f"pca{kwargs.get('pca_n')}_{digit}.npy"),
                                    kwargs.get("ith_component"))
+    return torch.from_numpy(table), loc
+
+
+def build_delta_digits(shape, n_rows: int = 101, **kwargs):
+    """The same edit for a solver whose evaluation times are not known in advance: row i holds what the hook would
+    load for timestep_digit f"{i/100:.2f}" (libs/dissection.py:139-183).  Files that do not exist give a zero row (the
+    reference raises FileNotFoundError if the solver ever evaluates there).  Returns (table, edit_loc) or (None, None)."""
+    name = kwargs.get("dissect_name")
+    if kwargs.get("dissect_task") != "uspace_uvit" or name in (None, "none"):
+        return None, None
+    if name == "read":
+        raise NotImplementedError("dissect_name='read' (per-NFE activation dump) is not built")
+    if name not in ("write_attr", "write_pca"):
+        raise ValueError(f"dissect_name should be read or write, here is {name}")
+    loc = kwargs.get("edit_loc")
+    if loc == "mid":
+        raise NotImplementedError("edit_loc='mid' is broken in the reference for U-ViT and is not built")
+    if loc not in ("head", "tail"):
+        return None, None
+    root = kwargs["write_path_root"]
+    table = np.zeros((n_rows,) + tuple(shape), dtype=np.float32)
+    for i in range(n_rows):
+        digit = f"{i / 100:.2f}"
+        if not should_edit(digit, kwargs.get("t_edit")):
+            continue
+        path = os.path.join(root, f"delta_{digit}.npy" if name == "write_attr" else f"pca{kwargs.get('pca_n')}_{digit}.npy")
+        if os.path.exists(path):
+            table[i] = _read_delta(path, kwargs.get("ith_attr") if name == "write_attr" else kwargs.get("ith_component"))
     return torch.from_numpy(table), loc
 
 
@@ -141,21 +173,29 @@ class _CNFBase(nn.Module):
         return "dissect_name" in kwargs and kwargs["dissect_name"] is not None
 
     def get_ode_kwargs(self, **kwargs):
-        """flow_matching.py:38-85, restricted to what is built (fixed grid)."""
+        """flow_matching.py:38-85: the odeint keyword set (a (fixed, adaptive) pair for "fixadp")."""
         if not self.is_dissection_mode(kwargs):
-            raise NotImplementedError(
-                "adaptive dopri5 (the reference's non-dissection default) is not built; pass dissect_name and "
-                "solver_kwargs=dict(solver='fixed', solver_fix='euler'|'heun', solver_fix_step=h)")
+            return dict(method="dopri5", rtol=_RTOL, atol=_ATOL)
         sk = kwargs["solver_kwargs"]
-        if sk["solver"] != "fixed":
-            raise NotImplementedError(f"solver={sk['solver']!r}: only the fixed-grid solver is built")
-        return self._fixed_kwargs(sk)
+        if sk["solver"] == "fixed":
+            return self._fixed_kwargs(sk)
+        if sk["solver"] == "adaptive":
+            return self._adaptive_kwargs(sk)
+        if sk["solver"] == "fixadp":
+            return self._fixed_kwargs(sk), self._adaptive_kwargs(sk)
+        raise NotImplementedError(f"solver={sk['solver']}")
+
+    @staticmethod
+    def _adaptive_kwargs(sk):
+        if sk["solver_adaptive"] not in _ADAPTIVE_METHODS:
+            raise NotImplementedError(f"solver_adaptive={sk['solver_adaptive']!r}: built methods are {_ADAPTIVE_METHODS}")
+        return dict(method=sk["solver_adaptive"], rtol=_RTOL, atol=_ATOL)
 
     @staticmethod
     def _fixed_kwargs(sk):
         if sk["solver_fix"] not in _FIXED_METHODS:
             raise NotImplementedError(f"solver_fix={sk['solver_fix']!r}: built methods are {_FIXED_METHODS}")
-        return dict(method=sk["solver_fix"], options=dict(step_size=float(sk["solver_fix_step"])))
+        return dict(method=sk["solver_fix"], rtol=_RTOL, atol=_ATOL, options=dict(step_size=float(sk["solver_fix_step"])))
 
     def training_losses(self, x, cond, sigma_min, **kwargs):
         """flow_matching.py:88-100 (runs the differentiable PyTorch graph of the mirror module)."""
@@ -168,28 +208,44 @@ class _CNFBase(nn.Module):
 
     @torch.no_grad()
     def _integrate(self, z: Tensor, cond, t0: float, t1: float, ode_kwargs: dict, **kwargs) -> Tensor:
+        """odeint(func, z, [t0, t1], **ode_kwargs)[-1] on the library: fixed grid if ode_kwargs carries a step_size,
+        adaptive dopri5 otherwise."""
         net = self.net.module if hasattr(self.net, "module") else self.net  # DDP / accelerate wrapper
         engine = net.engine()
-        h = ode_kwargs["options"]["step_size"]
-        table, loc = None, None
-        if self.is_dissection_mode(kwargs):
-            table, loc = build_delta_table(time_grid(t0, t1, h), z.shape[1:], **kwargs)
-        ws = float(kwargs.get("write_scale") or 0.0) if table is not None else 0.0
-        # rows where should_edit() is false are zero, so the library's own mask can stay wide open
         attn = None
         if isinstance(self, CNFT2I):
             attn = build_attn_edit(z.shape[0], engine.cfg.num_clip_token + 1 + (engine.S // engine.cfg.patch_size) ** 2,
                                    **kwargs)
-        return engine.sample(z, t0, t1, h, ode_kwargs["method"], delta_table=table, write_scale=ws,
-                             t_edit=float("inf"), edit_loc=loc, attn_edit=attn, **self._cond_kw(cond))
+        dissect = self.is_dissection_mode(kwargs)
+        if "options" in ode_kwargs:
+            h = ode_kwargs["options"]["step_size"]
+            table, loc = build_delta_table(time_grid(t0, t1, h), z.shape[1:], **kwargs) if dissect else (None, None)
+            ws = float(kwargs.get("write_scale") or 0.0) if table is not None else 0.0
+            # rows where should_edit() is false are zero, so the library's own mask can stay wide open
+            return engine.sample(z, t0, t1, h, ode_kwargs["method"], delta_table=table, write_scale=ws,
+                                 t_edit=float("inf"), edit_loc=loc, attn_edit=attn, **self._cond_kw(cond))
+        if ode_kwargs["method"] not in _ADAPTIVE_METHODS:
+            raise NotImplementedError(f"method={ode_kwargs['method']!r}")
+        table, loc = build_delta_digits(z.shape[1:], **kwargs) if dissect else (None, None)
+        ws = float(kwargs.get("write_scale") or 0.0) if table is not None else 0.0
+        self.last_solver_stats = {}
+        return engine.sample_adaptive(z, t0, t1, ode_kwargs["rtol"], ode_kwargs["atol"], delta_digits=table,
+                                      write_scale=ws, t_edit=float("inf"), edit_loc=loc, attn_edit=attn,
+                                      stats=self.last_solver_stats, **self._cond_kw(cond))
 
     def _decode(self, z: Tensor, cond, **kwargs) -> Tensor:
-        """flow_matching.py:130-151."""
+        """flow_matching.py:130-180 (decode + decode_fixadp)."""
         solver = kwargs["solver_kwargs"]["solver"]
-        if solver == "fixed":
+        if solver in ("fixed", "adaptive"):
             return self._integrate(z, cond, 0.0, 1.0, self.get_ode_kwargs(**kwargs), **kwargs)
-        if solver in ("adaptive", "fixadp"):
-            raise NotImplementedError(f"solver={solver!r} needs adaptive dopri5, which is not built")
+        if solver == "fixadp":
+            t_mid = kwargs["t_edit"]
+            assert t_mid >= 0 and t_mid <= 1, f"t_mid={t_mid}"
+            fixed_kw, adaptive_kw = self.get_ode_kwargs(**kwargs)
+            mid = self._integrate(z, cond, 0.0, float(t_mid), fixed_kw, **kwargs) if t_mid > 0 else z
+            if t_mid >= 1:
+                return mid
+            return self._integrate(mid, cond, float(t_mid), 1.0, adaptive_kw, **kwargs)
         raise NotImplementedError(f"unknown solver {kwargs['solver_kwargs']}")
 
 
