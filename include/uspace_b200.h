@@ -103,6 +103,21 @@ int usp_sample(usp_handle* h, float* z, const float* context, const int64_t* y, 
 int usp_sample_edit(usp_handle* h, float* z, const float* context, const int64_t* y, int B, float t0, float t1,
                     float step_size, int method, const float* delta_table, float write_scale, float t_edit,
                     int edit_loc, const usp_attn_edit* attn, void* stream);
+/* Semantic-direction sweep: the loop `for write_scale in write_scales: sample_fn(input_z, write_scale=...)` of
+ * sample_for_hspace_vis (tools/utils_vis.py:189-201) as ONE batch of B * n_scales samples - copy s of latent b is
+ * integrated with write_scale = write_scales[s] (host array) and lands in out[b][s] ("(b s)" order of the
+ * reference's image grid). Samples are independent, so every row is bit-identical to a separate usp_sample call.
+ * z: [B, C, S, S] (not modified), out: [B, n_scales, C, S, S]; context / y are per input latent ([B, ...]). */
+int usp_sample_sweep(usp_handle* h, const float* z, float* out, const float* context, const int64_t* y, int B,
+                     const float* write_scales, int n_scales, float t0, float t1, float step_size, int method,
+                     const float* delta_table, float t_edit, int edit_loc, void* stream);
+/* The "read" mode of the hook (libs/dissection.py:126-136): integrate like usp_sample and keep, for every velocity
+ * evaluation, the activation at edit_loc - USP_EDIT_HEAD: the latent handed to the network; USP_EDIT_TAIL: the
+ * predicted velocity. trace: [grid points, B, C, S, S] (device or host), row i <-> the evaluation at grid[i], i.e.
+ * the array the reference saves as f"{batch_id}_{grid[i]:.2f}.npy"; rows never evaluated (the last grid point under
+ * Euler) are zero. A later evaluation at the same grid point overwrites an earlier one, like the reference's files. */
+int usp_sample_read(usp_handle* h, float* z, const float* context, const int64_t* y, int B, float t0, float t1,
+                    float step_size, int method, int edit_loc, float* trace, void* stream);
 /* Adaptive Dormand-Prince 5(4): replaces odeint(func, z, [t0, t1], method="dopri5", rtol=, atol=)[-1] at
  * flow_matching.py:79-84 (default sampling), :50-57 (solver="adaptive") and :172-179 (adaptive tail of "fixadp");
  * flow_matching_t2i.py likewise. Step acceptance, the next step size and the dense-output evaluation at t1 run on

@@ -566,3 +566,87 @@ def test_adaptive_agrees_with_fine_fixed_grid_on_north_star_model():
     ada = m.engine().sample_adaptive(x, 0.0, 1.0, 1e-5, 1e-5, stats=st)
     fine = m.engine().sample(x, 0.0, 1.0, 0.01, "heun")
     assert rel(ada, fine) < 1e-3 and st["n_accept"] >= 2
+
+
+# ---- scale sweep in one batch, "read" mode ------------------------------------------------------------------
+@pytest.mark.parametrize("name,method,loc", [("tiny_uncond", "euler", "tail"), ("tiny_class", "heun", "head"),
+                                             ("tiny_t2i", "euler", "tail")])
+def test_scale_sweep_rows_equal_separate_runs_bit_exact(name, method, loc):
+    case = CASES[name]
+    m = model(name)
+    x, _, y, ctx = build_inputs(case)
+    eng = m.engine()
+    h = 0.2
+    g = torch.Generator().manual_seed(21)
+    table = 0.2 * torch.randn(6, 4, 32, 32, generator=g)
+    scales = [-2.1, 0.0, 0.5, 2.0]
+    out = eng.sample_sweep(x.to(dev()), scales, 0.0, 1.0, h, method, y=y, context=ctx, delta_table=table, t_edit=0.4,
+                           edit_loc=loc)
+    assert out.shape == (case["B"], len(scales), 4, 32, 32)
+    for s, scale in enumerate(scales):
+        one = eng.sample(x.to(dev()), 0.0, 1.0, h, method, y=y, context=ctx, delta_table=table, write_scale=scale,
+                         t_edit=0.4, edit_loc=loc)
+        assert torch.equal(out[:, s], one), (name, scale)
+    assert not torch.equal(out[:, 0], out[:, 1])
+
+
+def test_sweep_driver_mirror_against_oracle(tmp_path):
+    """tools/utils_vis.py:189-201 through uspace_b200.sweep.sample_write_scales: "(b s)" order, oracle per scale."""
+    from uspace_b200.sweep import sample_write_scales
+    case = CASES["tiny_uncond"]
+    m = model("tiny_uncond")
+    x = build_inputs(case)[0]
+    sd = {k: v.cpu() for k, v in m.state_dict().items()}
+    h = 0.1
+    rng = torch.Generator().manual_seed(3)
+    table = torch.zeros(11, 4, 32, 32)
+    for i in range(1, 5):
+        d = 0.1 * torch.randn(3, 4, 32, 32, generator=rng)
+        np.save(tmp_path / f"delta_{i * h:.2f}.npy", d.numpy())
+        table[i] = (d[0] + d[2]) / 2
+    scales = [-2.0, 0.0, 1.0]
+    kw = dict(dissect_task="uspace_uvit", dissect_name="write_attr", write_path_root=str(tmp_path), ith_attr="0_2",
+              t_edit=0.4, edit_loc="tail", solver_kwargs=dict(solver="fixed", solver_fix="euler", solver_fix_step=h))
+    got = sample_write_scales(CNF(m), x.to(dev()), scales, None, **kw)
+    assert got.shape == (case["B"] * 3, 4, 32, 32)
+    got = got.reshape(case["B"], 3, 4, 32, 32)
+    for s, scale in enumerate(scales):
+        want = O.sample(sd, case["cfg"], x.double(), 0.0, 1.0, h, "euler", delta_table=table.double(),
+                        write_scale=scale, t_edit=0.4, edit_loc="tail")
+        assert rel(got[:, s], want) < 1e-3
+    # an adaptive solver falls back to the reference's loop (its step size depends on the batch)
+    kw["solver_kwargs"] = dict(solver="adaptive", solver_adaptive="dopri5")
+    loop = sample_write_scales(CNF(m), x.to(dev()), scales[:2], None, **kw)
+    assert loop.shape == (case["B"] * 2, 4, 32, 32) and torch.isfinite(loop).all()
+
+
+def test_read_mode_trace_and_files(tmp_path):
+    """dissect_name="read" (libs/dissection.py:126-136): the activation at edit_loc of every evaluation."""
+    case = CASES["tiny_uncond"]
+    m = model("tiny_uncond")
+    x = build_inputs(case)[0]
+    sd = {k: v.cpu() for k, v in m.state_dict().items()}
+    eng = m.engine()
+    h = 0.25
+    z_h, states = eng.sample_read(x.to(dev()), 1.0, 0.0, h, "euler", edit_loc="head")
+    z_t, vels = eng.sample_read(x.to(dev()), 1.0, 0.0, h, "euler", edit_loc="tail")
+    plain = eng.sample(x.to(dev()), 1.0, 0.0, h, "euler")
+    assert torch.equal(z_h, plain) and torch.equal(z_t, plain)     # reading does not disturb the trajectory
+    assert states.shape == (5, 3, 4, 32, 32)
+    assert torch.equal(states[0].cpu(), x) and not states[4].any() and not vels[4].any()
+    grid = O.fixed_grid(1.0, 0.0, h)
+    for i in range(4):
+        v = O.uvit_forward(sd, case["cfg"], states[i].cpu().double(), grid[i].expand(3))
+        assert rel(vels[i], v) < 1.5e-3
+        nxt = states[i + 1] if i < 3 else plain
+        assert (states[i] + (grid[i + 1] - grid[i]).item() * vels[i] - nxt).abs().max() < 1e-5
+    # through the CNF mirror: the files the reference would have written during encode (dissect_lfm.py:216-228)
+    kw = dict(dissect_task="uspace_uvit", dissect_name="read", read_path_root=str(tmp_path / "dump"), batch_id=7,
+              edit_loc="tail", solver_kwargs=dict(solver="fixed", solver_fix="euler", solver_fix_step=h))
+    enc = CNF(m).encode(x.to(dev()), y=None, **kw)
+    assert torch.equal(enc, plain)
+    assert sorted(os.listdir(tmp_path / "dump")) == ["7_0.25.npy", "7_0.50.npy", "7_0.75.npy", "7_1.00.npy"]
+    assert np.array_equal(np.load(tmp_path / "dump" / "7_0.75.npy"), vels[1].cpu().numpy())
+    # Heun also evaluates at the last grid point
+    _, tr = eng.sample_read(x.to(dev()), 0.0, 1.0, 0.5, "heun", edit_loc="head")
+    assert tr.shape[0] == 3 and tr[2].any()

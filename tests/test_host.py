@@ -190,8 +190,9 @@ def test_delta_table_from_reference_file_layout(tmp_path):
     tab, _ = build_delta_table(grid, (4, 32, 32), ith_attr="1_4", **kw)  # multi-attribute mean (dissection.py:63-68)
     assert np.allclose(tab[1].numpy(), (files["0.10"][1] + files["0.10"][4]) / 2)
     assert build_delta_table(grid, (4, 32, 32), dissect_name=None) == (None, None)
-    with pytest.raises(NotImplementedError):
-        build_delta_table(grid, (4, 32, 32), dissect_task="uspace_uvit", dissect_name="read")
+    assert build_delta_table(grid, (4, 32, 32), dissect_task="uspace_uvit", dissect_name="read") == (None, None)
+    with pytest.raises(NotImplementedError):   # "read" under an adaptive solver
+        build_delta_digits((4, 32, 32), dissect_task="uspace_uvit", dissect_name="read")
     with pytest.raises(NotImplementedError):
         build_delta_table(grid, (4, 32, 32), **dict(kw, edit_loc="mid"))
 

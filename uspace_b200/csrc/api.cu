@@ -120,8 +120,11 @@ struct Plan {
     unsigned char* mask = nullptr;
     float* delta = nullptr;
     size_t delta_cap = 0;
+    float* trace = nullptr;         // [n_grid, B, C, S, S] activation dump of the "read" mode (grown on demand)
+    size_t trace_cap = 0;
     float* colscale = nullptr;      // [B, L] attention column weights (p2p edit)
     unsigned char* amask = nullptr; // per grid point: attention edit active
+    float* sscale = nullptr;        // [B] per-sample write_scale (usp_sample_sweep)
     float* rk_k = nullptr;          // [RK_STAGES][B,C,S,S] stage derivatives of the adaptive solver
     RkState* rs = nullptr;
     double* rk_partials = nullptr;  // [2][RK_MAX_PARTIALS]
@@ -231,6 +234,7 @@ int get_plan(usp_handle* h, int B, Plan** out) {
             for (auto& g : kv.second->graphs) cudaGraphExecDestroy(g.second);
             cudaFree(kv.second->slab);
             cudaFree(kv.second->delta);
+            cudaFree(kv.second->trace);
         }
         h->plans.clear();
     }
@@ -265,7 +269,8 @@ int get_plan(usp_handle* h, int B, Plan** out) {
     const size_t o_y = carve(static_cast<size_t>(B) * 8), o_st = carve(sizeof(StepState)),
                  o_grid = carve(MAX_GRID * 4), o_mask = carve(MAX_GRID), o_amask = carve(MAX_GRID),
                  o_cs = carve(static_cast<size_t>(B) * L * 4), o_rkk = carve(RK_STAGES * zel * 4),
-                 o_rs = carve(sizeof(RkState)), o_rkp = carve(2 * RK_MAX_PARTIALS * 8);
+                 o_rs = carve(sizeof(RkState)), o_rkp = carve(2 * RK_MAX_PARTIALS * 8),
+                 o_ss = carve(static_cast<size_t>(B) * 4);
     p->bytes = off;
     CUDA_TRY(h, cudaMalloc(&p->slab, off));
     CUDA_TRY(h, cudaMemset(p->slab, 0, off));
@@ -295,6 +300,7 @@ int get_plan(usp_handle* h, int B, Plan** out) {
     p->mask = reinterpret_cast<unsigned char*>(base + o_mask);
     p->amask = reinterpret_cast<unsigned char*>(base + o_amask);
     p->colscale = reinterpret_cast<float*>(base + o_cs);
+    p->sscale = reinterpret_cast<float*>(base + o_ss);
     p->rk_k = reinterpret_cast<float*>(base + o_rkk);
     p->rs = reinterpret_cast<RkState*>(base + o_rs);
     p->rk_partials = reinterpret_cast<double*>(base + o_rkp);
@@ -335,6 +341,8 @@ struct FwdIO {
     bool has_ctx;
     const float* delta;     // edit table or nullptr
     int edit_loc;
+    const float* sscale;    // per-sample write_scale [B] (scale sweep) or nullptr
+    float* trace;           // "read" dump [n_grid, B, C, S, S] at edit_loc or nullptr
     const float* colscale;  // attention column weights [B, L] or nullptr (p2p edit)
     uint64_t block_mask;    // blocks the attention edit applies to
     // final stage
@@ -422,6 +430,8 @@ int enqueue_forward(usp_handle* h, Plan* p, const FwdIO& io, cudaStream_t s) {
     ea.label = h->i_label >= 0 ? h->w[h->i_label].d32 : nullptr;
     ea.freqs = h->freqs;
     ea.delta = io.edit_loc == USP_EDIT_HEAD ? io.delta : nullptr;
+    ea.sscale = io.sscale;
+    ea.trace = io.edit_loc == USP_EDIT_HEAD ? io.trace : nullptr;
     ea.out32 = p->x32;
     ea.opd = opd;
     if (h->fuse_ln) { ea.out16 = p->xe16; ea.stats = p->stats; }
@@ -539,6 +549,8 @@ int enqueue_forward(usp_handle* h, Plan* p, const FwdIO& io, cudaStream_t s) {
     fa.cw = h->i_fw >= 0 ? h->w[h->i_fw].d32 : nullptr;
     fa.cb = h->i_fb >= 0 ? h->w[h->i_fb].d32 : nullptr;
     fa.delta = io.edit_loc == USP_EDIT_TAIL ? io.delta : nullptr;
+    fa.sscale = io.sscale;
+    fa.trace = io.edit_loc == USP_EDIT_TAIL ? io.trace : nullptr;
     fa.st = io.st; fa.base = io.base; fa.aux = io.aux; fa.vstore = io.vstore; fa.out = io.out;
     fa.m1 = io.m1; fa.m2 = io.m2;
     fa.B = B; fa.C = h->cfg.in_chans; fa.S = h->cfg.img_size; fa.p = h->cfg.patch_size;
@@ -697,6 +709,7 @@ void usp_destroy(usp_handle* h) {
         for (auto& g : kv.second->graphs) cudaGraphExecDestroy(g.second);
         cudaFree(kv.second->slab);
         cudaFree(kv.second->delta);
+        cudaFree(kv.second->trace);
     }
     for (auto& w : h->w) {
         cudaFree(w.d32);
@@ -862,12 +875,20 @@ int usp_sample(usp_handle* h, float* z, const float* context, const int64_t* y, 
                            nullptr, stream);
 }
 
-int usp_sample_edit(usp_handle* h, float* z, const float* context, const int64_t* y, int B, float t0, float t1,
-                    float step_size, int method, const float* delta_table, float write_scale, float t_edit,
-                    int edit_loc, const usp_attn_edit* attn, void* stream) {
+namespace {
+// One fixed-grid integration of `rep` copies of each of the B0 inputs (B = B0 * rep samples, copy r of input b at
+// row b * rep + r).  rep == 1: the plain sampler, in place on z_out == z_in.  rep > 1 (scale sweep): copy r uses
+// write_scale scales_host[r], z_out is [B0, rep, C, S, S].
+int sample_impl(usp_handle* h, const float* z_in, float* z, const float* context, const int64_t* y, int B0, int rep,
+                const float* scales_host, float t0, float t1, float step_size, int method, const float* delta_table,
+                float write_scale, float t_edit, int edit_loc, const usp_attn_edit* attn, float* trace_out,
+                void* stream) {
+    if (rep < 1 || B0 < 1 || static_cast<long long>(B0) * rep > (1 << 20)) return fail(h, USP_ERR_INVALID, "bad batch / repeat count");
+    const int B = B0 * rep;
     int rc = check_ready(h, B);
     if (rc) return rc;
-    if (!z) return fail(h, USP_ERR_INVALID, "null latent");
+    if (!z || !z_in) return fail(h, USP_ERR_INVALID, "null latent");
+    if (rep > 1 && attn != nullptr) return fail(h, USP_ERR_INVALID, "the scale sweep does not take an attention edit");
     if ((h->cfg.num_clip_token > 0) != (context != nullptr))
         return fail(h, USP_ERR_INVALID, "context must be given exactly for the t2i model");
     if ((y != nullptr) != (h->cfg.num_classes > 0))
@@ -875,8 +896,10 @@ int usp_sample_edit(usp_handle* h, float* z, const float* context, const int64_t
     if (method != USP_METHOD_EULER && method != USP_METHOD_HEUN) return fail(h, USP_ERR_INVALID, "unknown method");
     if (edit_loc != USP_EDIT_NONE && edit_loc != USP_EDIT_HEAD && edit_loc != USP_EDIT_TAIL)
         return fail(h, USP_ERR_INVALID, "edit_loc must be none, head or tail (\"mid\" is broken in the reference)");
-    if ((edit_loc != USP_EDIT_NONE) != (delta_table != nullptr))
+    if (trace_out == nullptr && (edit_loc != USP_EDIT_NONE) != (delta_table != nullptr))
         return fail(h, USP_ERR_INVALID, "delta_table must be given exactly when edit_loc is head or tail");
+    if (trace_out != nullptr && (edit_loc == USP_EDIT_NONE || delta_table != nullptr || rep != 1))
+        return fail(h, USP_ERR_INVALID, "the read mode takes edit_loc head or tail and no delta_table");
     std::vector<float> grid;
     const int n = build_grid(t0, t1, step_size, &grid);
     if (n < 2) return fail(h, USP_ERR_INVALID, "bad time grid (t0 == t1, step_size <= 0 or more than 4096 points)");
@@ -890,7 +913,19 @@ int usp_sample_edit(usp_handle* h, float* z, const float* context, const int64_t
     const size_t zbytes = static_cast<size_t>(B) * C * S * S * 4;
     // should_edit (libs/dissection.py:21-26): timestep_digit = f"{t:.2f}"; "0.00" never edits; float(digit) <= t_edit
     std::vector<unsigned char> mask(n, 0);
-    if (edit_loc != USP_EDIT_NONE) {
+    if (trace_out != nullptr) {
+        const size_t tbytes = static_cast<size_t>(n) * zbytes;
+        if (p->trace_cap < tbytes) {
+            for (auto& g : p->graphs) cudaGraphExecDestroy(g.second);
+            p->graphs.clear();
+            if (p->trace) CUDA_TRY(h, cudaFree(p->trace));
+            p->trace = nullptr;
+            p->trace_cap = 0;
+            CUDA_TRY(h, cudaMalloc(&p->trace, tbytes));
+            p->trace_cap = tbytes;
+        }
+        CUDA_TRY(h, cudaMemsetAsync(p->trace, 0, tbytes, s));
+    } else if (edit_loc != USP_EDIT_NONE) {
         for (int i = 0; i < n; ++i) {
             bool zero = false;
             const bool le = digit_leq(static_cast<double>(grid[i]), t_edit, &zero);
@@ -923,14 +958,36 @@ int usp_sample_edit(usp_handle* h, float* z, const float* context, const int64_t
     memset(&st0, 0, sizeof(st0));
     st0.write_scale = write_scale;
     CUDA_TRY(h, cudaMemcpyAsync(p->st, &st0, sizeof(st0), cudaMemcpyHostToDevice, s));
-    CUDA_TRY(h, cudaMemcpyAsync(p->z, z, zbytes, cudaMemcpyDefault, s));
-    if (y) CUDA_TRY(h, cudaMemcpyAsync(p->y, y, static_cast<size_t>(B) * 8, cudaMemcpyDefault, s));
+    const bool sweep = rep > 1;
+    if (!sweep) {
+        CUDA_TRY(h, cudaMemcpyAsync(p->z, z_in, zbytes, cudaMemcpyDefault, s));
+        if (y) CUDA_TRY(h, cudaMemcpyAsync(p->y, y, static_cast<size_t>(B) * 8, cudaMemcpyDefault, s));
+    } else {
+        // replicate every input `rep` times ("(b s)" order, tools/utils_vis.py:199-201) with strided copies
+        const size_t zrow = static_cast<size_t>(C) * S * S * 4;
+        std::vector<float> ss(B);
+        for (int i = 0; i < B; ++i) ss[i] = scales_host[i % rep];
+        CUDA_TRY(h, cudaMemcpyAsync(p->sscale, ss.data(), static_cast<size_t>(B) * 4, cudaMemcpyHostToDevice, s));
+        for (int r = 0; r < rep; ++r) {
+            CUDA_TRY(h, cudaMemcpy2DAsync(reinterpret_cast<char*>(p->z) + r * zrow, rep * zrow, z_in, zrow, zrow, B0,
+                                          cudaMemcpyDefault, s));
+            if (y) CUDA_TRY(h, cudaMemcpy2DAsync(reinterpret_cast<char*>(p->y) + r * 8, rep * 8, y, 8, 8, B0, cudaMemcpyDefault, s));
+        }
+        if (context) {
+            const size_t crow = static_cast<size_t>(h->cfg.num_clip_token) * h->cfg.clip_dim * 4;
+            for (int r = 0; r < rep; ++r)
+                CUDA_TRY(h, cudaMemcpy2DAsync(reinterpret_cast<char*>(p->ctx32) + r * crow, rep * crow, context, crow, crow,
+                                              B0, cudaMemcpyDefault, s));
+            context = p->ctx32;
+        }
+    }
     if (context) {
         rc = embed_context(h, p, context, s);
         if (rc) return rc;
     }
 
-    const std::pair<int, uint64_t> key(method | (edit_loc << 2) | ((y ? 1 : 0) << 4) | ((use_attn ? 1 : 0) << 5),
+    const std::pair<int, uint64_t> key(method | (edit_loc << 2) | ((y ? 1 : 0) << 4) | ((use_attn ? 1 : 0) << 5) |
+                                           ((sweep ? 1 : 0) << 7) | ((trace_out ? 1 : 0) << 8),
                                        use_attn ? attn->block_mask : 0);
     auto git = p->graphs.find(key);
     if (git == p->graphs.end()) {
@@ -943,7 +1000,9 @@ int usp_sample_edit(usp_handle* h, float* z, const float* context, const int64_t
             FwdIO io;
             memset(&io, 0, sizeof(io));
             io.st = p->st; io.y = y ? p->y : nullptr; io.has_ctx = context != nullptr;
-            io.delta = edit_loc != USP_EDIT_NONE ? p->delta : nullptr; io.edit_loc = edit_loc;
+            io.delta = (edit_loc != USP_EDIT_NONE && !trace_out) ? p->delta : nullptr; io.edit_loc = edit_loc;
+            io.trace = trace_out ? p->trace : nullptr;
+            io.sscale = sweep ? p->sscale : nullptr;
             if (use_attn) { io.colscale = p->colscale; io.block_mask = attn->block_mask; }
             if (method == USP_METHOD_EULER) {
                 io.x = p->z; io.base = p->z; io.out = p->z; io.m1 = 1.f;
@@ -974,9 +1033,39 @@ int usp_sample_edit(usp_handle* h, float* z, const float* context, const int64_t
     }
     for (int i = 0; i + 1 < n; ++i) CUDA_TRY(h, cudaGraphLaunch(git->second, s));
     CUDA_TRY(h, cudaMemcpyAsync(z, p->z, zbytes, cudaMemcpyDefault, s));
+    if (trace_out) CUDA_TRY(h, cudaMemcpyAsync(trace_out, p->trace, static_cast<size_t>(n) * zbytes, cudaMemcpyDefault, s));
     CUDA_TRY(h, cudaEventRecord(h->ev1, s));
     h->ev_valid = true;
     return USP_OK;
+}
+}  // namespace
+
+int usp_sample_edit(usp_handle* h, float* z, const float* context, const int64_t* y, int B, float t0, float t1,
+                    float step_size, int method, const float* delta_table, float write_scale, float t_edit,
+                    int edit_loc, const usp_attn_edit* attn, void* stream) {
+    return sample_impl(h, z, z, context, y, B, 1, nullptr, t0, t1, step_size, method, delta_table, write_scale, t_edit,
+                       edit_loc, attn, nullptr, stream);
+}
+
+int usp_sample_read(usp_handle* h, float* z, const float* context, const int64_t* y, int B, float t0, float t1,
+                    float step_size, int method, int edit_loc, float* trace, void* stream) {
+    if (!h) return USP_ERR_INVALID;
+    if (!trace) return fail(h, USP_ERR_INVALID, "null trace buffer");
+    return sample_impl(h, z, z, context, y, B, 1, nullptr, t0, t1, step_size, method, nullptr, 0.f, 0.f, edit_loc, nullptr,
+                       trace, stream);
+}
+
+int usp_sample_sweep(usp_handle* h, const float* z, float* out, const float* context, const int64_t* y, int B,
+                     const float* write_scales, int n_scales, float t0, float t1, float step_size, int method,
+                     const float* delta_table, float t_edit, int edit_loc, void* stream) {
+    if (!h) return USP_ERR_INVALID;
+    if (!write_scales || n_scales < 1) return fail(h, USP_ERR_INVALID, "write_scales must hold at least one value");
+    if (edit_loc == USP_EDIT_NONE) return fail(h, USP_ERR_INVALID, "a scale sweep needs edit_loc head or tail");
+    if (n_scales == 1)   // same code path as rep > 1 needs the per-sample vector; keep it uniform
+        return sample_impl(h, z, out, context, y, B, 1, nullptr, t0, t1, step_size, method, delta_table, write_scales[0],
+                           t_edit, edit_loc, nullptr, nullptr, stream);
+    return sample_impl(h, z, out, context, y, B, n_scales, write_scales, t0, t1, step_size, method, delta_table, 1.0f,
+                       t_edit, edit_loc, nullptr, nullptr, stream);
 }
 
 int usp_sample_adaptive(usp_handle* h, float* z, const float* context, const int64_t* y, int B, float t0, float t1,

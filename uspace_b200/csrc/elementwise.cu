@@ -53,9 +53,12 @@ __global__ void __launch_bounds__(256) embed_kernel(const EmbedArgs a) {
             const int idx = (c * S + ph * p + p1) * S + pw * p + p2;
             float v = a.x[static_cast<long long>(b) * C * S * S + idx];
             if (a.delta != nullptr && a.st != nullptr) {
-                const float sc = a.st->edit;
+                float sc = a.st->edit;
+                if (sc != 0.f && a.sscale != nullptr) sc = a.sscale[b];
                 if (sc != 0.f) v += a.delta[static_cast<long long>(a.st->didx) * C * S * S + idx] * sc;
             }
+            if (a.trace != nullptr && a.st != nullptr)   // dissect_name="read" (libs/dissection.py:126-136)
+                a.trace[(static_cast<long long>(a.st->didx) * a.B + b) * C * S * S + idx] = v;
             feat[tk][f] = v;
         }
     }
@@ -276,9 +279,11 @@ __global__ void __launch_bounds__(256) final_kernel(const FinalArgs a) {
     }
     const int chw = static_cast<int>(i % (static_cast<long long>(C) * S * S));
     if (a.delta != nullptr && a.st != nullptr) {
-        const float sc = a.st->edit;
+        float sc = a.st->edit;
+        if (sc != 0.f && a.sscale != nullptr) sc = a.sscale[b];
         if (sc != 0.f) v += a.delta[static_cast<long long>(a.st->didx) * C * S * S + chw] * sc;
     }
+    if (a.trace != nullptr && a.st != nullptr) a.trace[static_cast<long long>(a.st->didx) * n + i] = v;
     if (a.st == nullptr) {
         a.out[i] = v;
         return;

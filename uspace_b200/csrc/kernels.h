@@ -99,6 +99,8 @@ struct EmbedArgs {
     const float* label;    // label_emb.weight [num_classes, D] or nullptr
     const float* freqs;    // [D/2]
     const float* delta;    // head edit table [nsteps+1, C*S*S] or nullptr
+    const float* sscale;   // optional per-sample write_scale [B] (scale sweep); nullptr: st->edit for every sample
+    float* trace;          // optional "read" dump at edit_loc head: trace[st->didx][B,C,S,S] = the latent as the net sees it
     float* out32;          // [B*L, D]
     void* out16;           // optional un-normalised 16-bit copy [B*L, D] (folded-LayerNorm path)
     float* stats;          // optional [B*L, 8, 2] partial row statistics (one slot per warp of the block)
@@ -126,6 +128,8 @@ struct FinalArgs {
     const float* cw;       // final_layer.weight [C,C,3,3] or nullptr (conv=False)
     const float* cb;       // [C]
     const float* delta;    // tail edit table [nsteps+1, C*S*S] or nullptr
+    const float* sscale;   // optional per-sample write_scale [B] (scale sweep)
+    float* trace;          // optional "read" dump at edit_loc tail: trace[st->didx][B,C,S,S] = the velocity
     const StepState* st;   // nullptr for a plain forward
     const float* base;     // ODE: state the update starts from
     const float* aux;      // Heun stage 2: k1

@@ -169,6 +169,47 @@ class Engine:
                          last_dt=st.last_dt)
         return zz
 
+    def sample_sweep(self, z, write_scales, t0=0.0, t1=1.0, step_size=0.02, method="euler", y=None, context=None,
+                     delta_table=None, t_edit=0.0, edit_loc="tail") -> torch.Tensor:
+        """All ``write_scales`` of the semantic-direction sweep in one batch: returns [B, len(write_scales), C, S, S]."""
+        self._check_latent(z)
+        B = z.shape[0]
+        zz = z.to(self.device, torch.float32).contiguous()
+        if y is not None:
+            y = y.to(self.device, torch.int64).contiguous()
+        if context is not None:
+            context = context.to(self.device, torch.float32).contiguous()
+        n = self.lib.usp_grid_size(t0, t1, step_size)
+        if delta_table is None or delta_table.shape != (n, self.C, self.S, self.S):
+            raise ValueError(f"delta_table must be [{n},{self.C},{self.S},{self.S}]")
+        delta_table = delta_table.to(self.device, torch.float32).contiguous()
+        scales = (C.c_float * len(write_scales))(*[float(s) for s in write_scales])
+        out = torch.empty((B, len(write_scales), self.C, self.S, self.S), device=self.device, dtype=torch.float32)
+        _lib.check(self.lib.usp_sample_sweep(self.handle, _ptr(zz), _ptr(out), _ptr(context), _ptr(y), B, scales,
+                                             len(write_scales), t0, t1, step_size, _lib.METHOD[method],
+                                             _ptr(delta_table), t_edit, _lib.EDIT_LOC[edit_loc], self._stream()),
+                   self.handle, "usp_sample_sweep")
+        return out
+
+    def sample_read(self, z, t0=0.0, t1=1.0, step_size=0.02, method="euler", y=None, context=None, edit_loc="tail"):
+        """Integrate and also return the activation at ``edit_loc`` of every velocity evaluation:
+        (z_end, trace [grid points, B, C, S, S]); trace[i] belongs to the evaluation at grid[i]."""
+        self._check_latent(z)
+        B = z.shape[0]
+        zz = z.to(self.device, torch.float32).contiguous().clone()
+        if y is not None:
+            y = y.to(self.device, torch.int64).contiguous()
+        if context is not None:
+            context = context.to(self.device, torch.float32).contiguous()
+        n = self.lib.usp_grid_size(t0, t1, step_size)
+        if n < 2:
+            raise ValueError(f"bad time grid: t0={t0} t1={t1} step_size={step_size}")
+        trace = torch.empty((n, B, self.C, self.S, self.S), device=self.device, dtype=torch.float32)
+        _lib.check(self.lib.usp_sample_read(self.handle, _ptr(zz), _ptr(context), _ptr(y), B, t0, t1, step_size,
+                                            _lib.METHOD[method], _lib.EDIT_LOC[edit_loc], _ptr(trace), self._stream()),
+                   self.handle, "usp_sample_read")
+        return zz, trace
+
     def sample_host(self, z_host, t0=0.0, t1=1.0, step_size=0.02, method="euler", y=None, context=None,
                     delta_table=None, write_scale=0.0, t_edit=0.0, edit_loc=None) -> torch.Tensor:
         """End-to-end call on HOST tensors (ideally pinned): H2D, sample, D2H, synchronise. In place on z_host."""

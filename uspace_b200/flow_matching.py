@@ -7,9 +7,10 @@ Euler / Heun loop: one CUDA-graph-captured step replayed on the current stream, 
 Built: ``solver="fixed"`` with ``solver_fix`` in {"euler", "heun"}; ``solver="adaptive"`` / the non-dissection
 default / the adaptive tail of ``"fixadp"`` with dopri5 (step control and dense output on the device, torchdiffeq
 semantics restated in csrc/ode.cu); the "write_attr" / "write_pca" edit hook at ``edit_loc`` head / tail
-(libs/dissection.py:115-186) through a pre-loaded delta table; the "p2p_rescale" attention edit.
-Not built (NotImplementedError): other torchdiffeq methods (midpoint, rk4, bosh3, adaptive_heun), the
-activation-dump "read" mode, ``edit_loc="mid"`` (broken in the reference for U-ViT).
+(libs/dissection.py:115-186) through a pre-loaded delta table, and its "read" mode (the activation at ``edit_loc``
+of every evaluation, saved as ``{batch_id}_{t:.2f}.npy``) on the fixed grid; the "p2p_rescale" attention edit.
+Not built (NotImplementedError): other torchdiffeq methods (midpoint, rk4, bosh3, adaptive_heun), "read" under an
+adaptive solver, ``edit_loc="mid"`` (broken in the reference for U-ViT).
 """
 from __future__ import annotations
 
@@ -56,10 +57,8 @@ def build_delta_table(grid, shape, **kwargs):
     Returns (table [len(grid), C, S, S] float32 with zero rows where no edit applies, edit_loc) or (None, None).
     """
     name = kwargs.get("dissect_name")
-    if kwargs.get("dissect_task") != "uspace_uvit" or name in (None, "none"):
+    if kwargs.get("dissect_task") != "uspace_uvit" or name in (None, "none", "read"):
         return None, None
-    if name == "read":
-        raise NotImplementedError("dissect_name='read' (per-NFE activation dump) is not built")
     if name not in ("write_attr", "write_pca"):
         raise ValueError(f"dissect_name should be read or write, here is {name}")
     loc = kwargs.get("edit_loc")
@@ -89,7 +88,7 @@ def build_delta_digits(shape, n_rows: int = 101, **kwargs):
     if kwargs.get("dissect_task") != "uspace_uvit" or name in (None, "none"):
         return None, None
     if name == "read":
-        raise NotImplementedError("dissect_name='read' (per-NFE activation dump) is not built")
+        raise NotImplementedError("dissect_name='read' under an adaptive solver is not built")
     if name not in ("write_attr", "write_pca"):
         raise ValueError(f"dissect_name should be read or write, here is {name}")
     loc = kwargs.get("edit_loc")
@@ -217,6 +216,9 @@ class _CNFBase(nn.Module):
             attn = build_attn_edit(z.shape[0], engine.cfg.num_clip_token + 1 + (engine.S // engine.cfg.patch_size) ** 2,
                                    **kwargs)
         dissect = self.is_dissection_mode(kwargs)
+        reading = dissect and kwargs.get("dissect_task") == "uspace_uvit" and kwargs.get("dissect_name") == "read"
+        if reading:
+            return self._integrate_read(engine, z, cond, t0, t1, ode_kwargs, **kwargs)
         if "options" in ode_kwargs:
             h = ode_kwargs["options"]["step_size"]
             table, loc = build_delta_table(time_grid(t0, t1, h), z.shape[1:], **kwargs) if dissect else (None, None)
@@ -232,6 +234,27 @@ class _CNFBase(nn.Module):
         return engine.sample_adaptive(z, t0, t1, ode_kwargs["rtol"], ode_kwargs["atol"], delta_digits=table,
                                       write_scale=ws, t_edit=float("inf"), edit_loc=loc, attn_edit=attn,
                                       stats=self.last_solver_stats, **self._cond_kw(cond))
+
+    def _integrate_read(self, engine, z, cond, t0, t1, ode_kwargs, **kwargs) -> Tensor:
+        """dissect_name="read" (libs/dissection.py:126-136): np.save(f"{read_path_root}/{batch_id}_{t:.2f}", x) for the
+        activation x at edit_loc of every evaluation - gathered on the device, written after the last step."""
+        if "options" not in ode_kwargs:
+            raise NotImplementedError("dissect_name='read' under an adaptive solver is not built")
+        loc = kwargs.get("edit_loc")
+        if loc == "mid":
+            raise NotImplementedError("edit_loc='mid' is broken in the reference for U-ViT and is not built")
+        h, method = ode_kwargs["options"]["step_size"], ode_kwargs["method"]
+        if loc not in ("head", "tail"):     # the hook is never reached: a plain integration
+            return engine.sample(z, t0, t1, h, method, **self._cond_kw(cond))
+        out, trace = engine.sample_read(z, t0, t1, h, method, edit_loc=loc, **self._cond_kw(cond))
+        root = kwargs.get("read_path_root")
+        os.makedirs(root, exist_ok=True)
+        grid = time_grid(t0, t1, h)
+        n_eval = len(grid) if method == "heun" else len(grid) - 1   # Euler never evaluates at the last grid point
+        host = trace[:n_eval].cpu().numpy()
+        for i in range(n_eval):
+            np.save(os.path.join(root, f"{kwargs['batch_id']}_{grid[i]:.2f}"), host[i])
+        return out
 
     def _decode(self, z: Tensor, cond, **kwargs) -> Tensor:
         """flow_matching.py:130-180 (decode + decode_fixadp)."""
