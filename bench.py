@@ -39,6 +39,11 @@ WORKLOADS = {
                cfg=CFG_L_T2I, t2i=True, batch=32, method="heun", step=0.02),
     "c5": dict(name="dissect sweep: U-ViT-L, 50-step Euler, tail write_attr edit, batch=64 per GPU (configs[4])",
                cfg=CFG_L, t2i=False, batch=64, method="euler", step=0.02, edit=True),
+    # the whole sweep of configs/lfm_cm256_uvit_large.py:84 as one batch: 64 latents x 9 write_scales per GPU
+    "c5sweep": dict(name="dissect sweep: U-ViT-L, 50-step Euler, tail write_attr edit, 64 latents x 9 write_scales per GPU "
+                         "in one batch (configs[4], tools/utils_vis.py:189-201)",
+                    cfg=CFG_L, t2i=False, batch=64, method="euler", step=0.02, edit=True,
+                    scales=[-2.1, -1.5, -1.0, -0.5, 0.0, 0.5, 1.0, 1.5, 2.0]),
 }
 METRIC = "images/sec at 50 ODE steps, U-ViT-L 256"
 
@@ -240,7 +245,14 @@ def main():
     z_dev = z_loc.to(dev)
     ctx_dev = None if ctx_loc is None else ctx_loc.to(dev)
 
+    scales = wl.get("scales")
+    n_rep = len(scales) if scales else 1
+
     def step_device():
+        if scales:
+            out = eng.sample_sweep(z_dev, scales, 0.0, 1.0, wl["step"], wl["method"], delta_table=ekw["delta_table"],
+                                   t_edit=ekw["t_edit"], edit_loc=ekw["edit_loc"]).flatten(0, 1)
+            return parallel.gather_latents(out, Bg * n_rep) if world > 1 else out
         out = eng.sample(z_dev, 0.0, 1.0, wl["step"], wl["method"], context=ctx_dev, **ekw)
         return parallel.gather_latents(out, Bg) if world > 1 else out
 
@@ -276,7 +288,17 @@ def main():
     if delta is not None:
         ekw_h["delta_table"] = delta.clone().pin_memory()
 
+    if scales:
+        zh = torch.empty((Bl * n_rep, 4, 32, 32)).pin_memory()
+
     def step_host():
+        if scales:   # no host-buffer variant of the sweep in the ABI: the copies are done here, inside the timed region
+            o = eng.sample_sweep(zh_src.to(dev, non_blocking=True), scales, 0.0, 1.0, wl["step"], wl["method"],
+                                 delta_table=ekw_h["delta_table"].to(dev, non_blocking=True), t_edit=ekw["t_edit"],
+                                 edit_loc=ekw["edit_loc"])
+            zh.copy_(o.flatten(0, 1), non_blocking=True)
+            torch.cuda.synchronize()
+            return
         zh.copy_(zh_src)
         eng.sample_host(zh, 0.0, 1.0, wl["step"], wl["method"], context=ctx_h, **ekw_h)
 
@@ -290,8 +312,8 @@ def main():
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_s = e2e_s.item()
-    same = bool(torch.equal(zh.to(dev), out[rank * Bl:(rank + 1) * Bl] if world > 1 else out))
-    h2d = zh.numel() * 4 + (ctx_h.numel() * 4 if ctx_h is not None else 0) + (delta.numel() * 4 if delta is not None else 0)
+    same = bool(torch.equal(zh.to(dev), out[rank * Bl * n_rep:(rank + 1) * Bl * n_rep] if world > 1 else out))
+    h2d = zh_src.numel() * 4 + (ctx_h.numel() * 4 if ctx_h is not None else 0) + (delta.numel() * 4 if delta is not None else 0)
     d2h = zh.numel() * 4
 
     # ---- per-kernel-class device time of one velocity evaluation (events between launches) ----
@@ -312,7 +334,7 @@ def main():
         achieved = gemm_flops_img * Bl / (gemm_ms * 1e-3) / 1e12
         flops_img = eng.flops_per_forward()
         sec = ms_total * 1e-3
-        value = Bg * args.steps / sec
+        value = Bg * n_rep * args.steps / sec
         res = {
             "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -321,10 +343,10 @@ def main():
                        "parallelism": f"dp{world}", "weights": "random-init (reference ctor, seed 0)",
                        "accumulate": "fp32 (TMEM), fp32 residual stream / LayerNorm / softmax",
                        "l2": "activations per velocity evaluation (~1.9 GB at batch 64) exceed the 126 MB L2; no flush needed"},
-            "achieved_tflops_per_gpu": flops_img * Bl * nfe * args.steps / sec / 1e12,
-            "tensor_peak_frac_burst": flops_img * Bl * nfe * args.steps / sec / 1e12 / pk["burst"],
-            "tensor_peak_frac_sustained": flops_img * Bl * nfe * args.steps / sec / 1e12 / pk["sustained"],
-            "e2e": {"value": Bg * args.steps / e2e_s, "unit": "images/s", "h2d_bytes_per_step": h2d,
+            "achieved_tflops_per_gpu": flops_img * Bl * n_rep * nfe * args.steps / sec / 1e12,
+            "tensor_peak_frac_burst": flops_img * Bl * n_rep * nfe * args.steps / sec / 1e12 / pk["burst"],
+            "tensor_peak_frac_sustained": flops_img * Bl * n_rep * nfe * args.steps / sec / 1e12 / pk["sustained"],
+            "e2e": {"value": Bg * n_rep * args.steps / e2e_s, "unit": "images/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "matches_device_path": same},
             "gpu_launches": args.steps * (n_grid - 1) * nfe_per_step * (eng.kernels_per_forward() + 1),
             "roofline": {"bound": "tensor", "kernel": "usp::gemm2_kernel<EPI,LONGK> (2-CTA tcgen05 GEMM: all five U-ViT linears of one velocity evaluation)",

@@ -73,6 +73,9 @@ def model(name, opd="fp16"):
 @pytest.mark.parametrize("epi,M,N,K,K0", [
     ("bias_f32", 128, 256, 64, 64), ("bias_f32", 300, 384, 128, 128), ("bias_f32", 514, 1024, 2048, 1024),
     ("qkv", 514, 3072, 1024, 1024), ("qkv", 771, 768, 256, 256), ("bias_gelu", 514, 4096, 1024, 1024),
+    # full-size problems (>= 148 tiles): the wide ones on CTA pairs, N = 1024 on clusters of 4 with multicast A loads
+    ("qkv", 16448, 3072, 1024, 1024), ("bias_gelu", 10688, 4096, 1024, 1024), ("bias_resid", 16448, 1024, 4096, 4096),
+    ("bias_f32", 10688, 1024, 2048, 1024),
     ("bias_resid", 514, 1024, 4096, 4096), ("bias_resid", 16448, 1024, 1024, 1024),
     ("bias_f32", 16448, 1024, 2048, 1024), ("qkv", 10688, 3072, 1024, 1024)])
 def test_gemm_epilogues(lib, opd, epi, M, N, K, K0):

@@ -560,15 +560,6 @@ int enqueue_forward(usp_handle* h, Plan* p, const FwdIO& io, cudaStream_t s) {
     return USP_OK;
 }
 
-bool is_device_ptr(const void* p) {
-    cudaPointerAttributes at;
-    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
-        cudaGetLastError();
-        return false;
-    }
-    return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
-}
-
 int check_ready(usp_handle* h, int B) {
     if (!h) return USP_ERR_INVALID;
     if (!h->finalized) return fail(h, USP_ERR_STATE, "weights not finalised: call usp_finalize_weights first");

@@ -79,7 +79,7 @@ __device__ __forceinline__ uint64_t umma_desc_v_mn(uint32_t saddr) {
     return d;
 }
 
-template <int MODE>   // 0: two-pass softmax (any L <= 352), 1: score-row share in registers (L <= 320),
+template <int MODE, bool EDIT>   // EDIT: p2p column re-weighting compiled in.  MODE 0: two-pass softmax (any L <= 352), 1: score-row share in registers (L <= 320),
                       // 2: registers + software-pipelined tiles (L <= 288)
 __global__ void __launch_bounds__(THREADS, 1)
 attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -148,7 +148,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
             const float c2 = 0.125f * 1.44269504088896340736f;
             int n = 0;
             for (int bh = blockIdx.x; bh < n_items; bh += gridDim.x, ++n) {
-                const float* cs = (a.vscale != nullptr && (a.st == nullptr || a.st->attn_on != 0))
+                const float* cs = (EDIT && a.vscale != nullptr && (a.st == nullptr || a.st->attn_on != 0))
                                       ? a.vscale + static_cast<long long>(bh / a.H) * L : nullptr;   // p2p column weights
                 const uint8_t* kbuf = sK + (n & 1) * kv_bytes;
                 const uint8_t* vbuf = sV + (n & 1) * kv_bytes;
@@ -203,7 +203,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                             const uint32_t w = a.opd == OPD_FP16 ? Op16<OPD_FP16>::pack(p, 0.f) : Op16<OPD_BF16>::pack(p, 0.f);
                             sum += p;
                             p = (a.opd == OPD_FP16 ? Op16<OPD_FP16>::unpack(w) : Op16<OPD_BF16>::unpack(w)).x;
-                            if (cs != nullptr) p *= __ldg(cs + j);
+                            if (EDIT && cs != nullptr) p *= __ldg(cs + j);
                             t_p[j] = p;
                         }
                     }
@@ -472,7 +472,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
             float p_inv = 0.f;
             const int cnt = c_hi - c_lo;
             for (int bh = blockIdx.x; bh < n_items; bh += gridDim.x) {
-                const float* cs = (a.vscale != nullptr && (a.st == nullptr || a.st->attn_on != 0))
+                const float* cs = (EDIT && a.vscale != nullptr && (a.st == nullptr || a.st->attn_on != 0))
                                       ? a.vscale + static_cast<long long>(bh / a.H) * L : nullptr;   // p2p column weights
                 for (int t = 0; t < n_qt; ++t, ++g) {
                     const int l = t * QT + row;
@@ -529,7 +529,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                                         if (c * 32 + 2 * j + 1 >= L) p1 = 0.f;
                                     }
                                     sum += p0 + p1;
-                                    if (cs != nullptr) {   // p2p column re-weighting, after the (unscaled) row sum
+                                    if (EDIT && cs != nullptr) {   // p2p column re-weighting, after the (unscaled) row sum
                                         p0 *= __ldg(cs + c * 32 + 2 * j);
                                         p1 *= (c * 32 + 2 * j + 1 < L) ? __ldg(cs + c * 32 + 2 * j + 1) : 0.f;
                                     }
@@ -552,7 +552,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         } else {
         int g = 0;
         for (int bh = blockIdx.x; bh < n_items; bh += gridDim.x) {
-            const float* cs = (a.vscale != nullptr && (a.st == nullptr || a.st->attn_on != 0))
+            const float* cs = (EDIT && a.vscale != nullptr && (a.st == nullptr || a.st->attn_on != 0))
                                   ? a.vscale + static_cast<long long>(bh / a.H) * L : nullptr;   // p2p column weights
             for (int t = 0; t < n_qt; ++t, ++g) {
                 const int l = t * QT + row;
@@ -612,7 +612,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                                         if (c * 32 + 2 * j + 1 >= L) p1 = 0.f;
                                     }
                                     sum += p0 + p1;
-                                    if (cs != nullptr) {
+                                    if (EDIT && cs != nullptr) {
                                         p0 *= __ldg(cs + c * 32 + 2 * j);
                                         p1 *= (c * 32 + 2 * j + 1 < L) ? __ldg(cs + c * 32 + 2 * j + 1) : 0.f;
                                     }
@@ -663,7 +663,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                         }
 #pragma unroll
                         for (int j = 0; j < 32; ++j) sum += p[j];
-                        if (cs != nullptr) {
+                        if (EDIT && cs != nullptr) {
 #pragma unroll
                             for (int j = 0; j < 32; ++j)
                                 if (c * 32 + j < L) p[j] *= __ldg(cs + c * 32 + j);
@@ -725,13 +725,16 @@ int smem_bytes_for(int L) {
 }  // namespace
 
 cudaError_t attention2_configure() {
-    cudaError_t e = cudaFuncSetAttribute(attention2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         smem_bytes_for(MAX_L2));
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(attention2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes_for(MAX_L2));
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(attention2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                smem_bytes_for(MAX_L2));
+    const int bytes = smem_bytes_for(MAX_L2);
+    cudaError_t e;
+#define USP_ATTN_CFG(M, E)                                                                                     \
+    if ((e = cudaFuncSetAttribute(attention2_kernel<M, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != \
+        cudaSuccess)                                                                                           \
+        return e;
+    USP_ATTN_CFG(0, false) USP_ATTN_CFG(1, false) USP_ATTN_CFG(2, false)
+    USP_ATTN_CFG(0, true) USP_ATTN_CFG(1, true) USP_ATTN_CFG(2, true)
+#undef USP_ATTN_CFG
+    return cudaSuccess;
 }
 
 bool attention2_supported(const AttnArgs& a) {
@@ -763,11 +766,16 @@ cudaError_t launch_attention2(const CUtensorMap& q, const CUtensorMap& k, const 
     if ((nch + 1) / 2 <= 5) mode = 1;                              // score-row share fits in registers (L <= 320)
     if (mode == 1 && L16 + 16 * nch + 64 <= TMEM_COLS) mode = 2;   // room for a private P region (L <= 288)
     if (mode > max_mode) mode = max_mode;
-    if (mode == 2)
-        return launch_pdl(attention2_kernel<2>, dim3(grid), dim3(THREADS), smem_bytes_for(a.L), s, q, k, v, a2);
-    if (mode == 1)
-        return launch_pdl(attention2_kernel<1>, dim3(grid), dim3(THREADS), smem_bytes_for(a.L), s, q, k, v, a2);
-    return launch_pdl(attention2_kernel<0>, dim3(grid), dim3(THREADS), smem_bytes_for(a.L), s, q, k, v, a2);
+    // the p2p column re-weighting lives in its own instantiations: in the plain ones the hook costs registers in the
+    // softmax loop (ptxas spilled 448 B in MODE 2 and the kernel ran 3x slower)
+    const bool edit = a.vscale != nullptr;
+#define USP_ATTN_LAUNCH(M, E) \
+    return launch_pdl(attention2_kernel<M, E>, dim3(grid), dim3(THREADS), smem_bytes_for(a.L), s, q, k, v, a2)
+    if (mode == 2) { if (edit) USP_ATTN_LAUNCH(2, true); USP_ATTN_LAUNCH(2, false); }
+    if (mode == 1) { if (edit) USP_ATTN_LAUNCH(1, true); USP_ATTN_LAUNCH(1, false); }
+    if (edit) USP_ATTN_LAUNCH(0, true);
+    USP_ATTN_LAUNCH(0, false);
+#undef USP_ATTN_LAUNCH
 }
 
 }  // namespace usp

@@ -150,6 +150,19 @@ __device__ __forceinline__ void tma_load_2d_cg2(const CUtensorMap* m, uint32_t b
         : "memory");
 }
 
+// 2-CTA + multicast: the box lands at the same offset in every CTA of cta_mask; each destination's completion is
+// signalled on the barrier at the same offset in the LEADER of that destination's pair (bar_local is this CTA's
+// shared::cta address of the barrier with the peer bit cleared - CUTLASS's Sm100MmaPeerBitMask convention).
+__device__ __forceinline__ void tma_load_2d_cg2_mc(const CUtensorMap* m, uint32_t bar_local, void* dst, int c0, int c1,
+                                                   uint16_t cta_mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
+        "[%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_local & 0xFEFFFFFFu), "r"(c0), "r"(c1),
+          "h"(cta_mask)
+        : "memory");
+}
+
 // ----------------------------------------------------------------------------------------------
 // tcgen05 / TMEM
 // ----------------------------------------------------------------------------------------------

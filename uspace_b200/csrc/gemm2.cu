@@ -14,6 +14,9 @@
 //               direct-load epilogue spent 60 % of its samples in long-scoreboard stalls on the residual and ran
 //               `proj` at 28 % tensor activity).  A chunk is released back to the loader as soon as its rows are in
 //               registers; results leave through full 128-byte per-row global stores.
+// 16-bit results (qkv, fc1) leave through per-row 32-byte global stores.  Staging them in shared memory for TMA
+// stores was built and measured (round 1): no gain - the cost of the stores is their share of the SM <-> L2 traffic
+// (see DESIGN.md section 4), not LSU issue, and the staging buffers cost a ring stage.
 #include "common.cuh"
 #include "gemm_epilogue.cuh"
 #include "kernels.h"
@@ -45,28 +48,14 @@ struct Cfg2 {
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024;
 };
 
-__device__ __forceinline__ uint32_t mapa_rank(uint32_t saddr, uint32_t rank) {
-    uint32_t r;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
-    return r;
-}
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* src, int c0, int c1) {
-    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
-                 ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(src)), "r"(c0), "r"(c1)
-                 : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void bulk_wait_read() {
-    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
-}
-template <int N>
-__device__ __forceinline__ void bulk_wait() {
-    asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
-}
 
-template <int EPI, bool LONGK>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
+// NP = CTA pairs per cluster.  NP == 2 (cluster of 4): the two pairs compute horizontally adjacent tiles (same 256
+// rows of A, different 256 columns of W) and every A box is fetched ONCE and multicast to the two CTAs that need it
+// (pair p issues the A load of k-blocks with kb % 2 == p).  The GEMMs run at the chip's L2 -> SM delivery cap
+// (~6300 B/clk: 1 MB of operands per 256x256x1024 tile is 12 TB/s at 1530 TFLOP/s), so operand bytes per flop,
+// not tensor-pipe rate, set their speed; sharing A removes a quarter of them.
+template <int EPI, bool LONGK, int NP>
+__global__ void __cluster_dims__(2 * NP, 1, 1) __launch_bounds__(THREADS, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
              const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmR,
              const __grid_constant__ CUtensorMap tmO, const GemmArgs g) {
@@ -89,12 +78,15 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const uint32_t rank = cluster_ctarank();
+    const uint32_t crank = cluster_ctarank();     // 0 .. 2*NP-1
+    const uint32_t rank = crank & 1;              // position inside the pair
+    const int pair = static_cast<int>(crank >> 1);
     const bool leader = rank == 0;
-    const int cluster_id = blockIdx.x >> 1;
-    const int n_clusters = gridDim.x >> 1;
+    const int cluster_id = blockIdx.x / (2 * NP);
+    const int n_clusters = gridDim.x / (2 * NP);
 
-    const int n_tiles_n = g.N / BN;
+    // work items: NP horizontally adjacent tiles per cluster step; this pair takes column tile (item % nn) * NP + pair
+    const int n_tiles_n = g.N / BN / NP;
     const int n_tiles_m = (g.M + 2 * BM - 1) / (2 * BM);
     const int n_tiles = n_tiles_m * n_tiles_n;
     const int nkb = g.K / BK;
@@ -107,7 +99,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
         if (STAGED) tma_prefetch_desc(&tmR);
         for (int i = 0; i < STAGES; ++i) {
             mbar_init(&full_bar[i], 1);
-            mbar_init(&empty_bar[i], 1);
+            mbar_init(&empty_bar[i], NP);     // one commit per pair that reads (or shares the A box of) this slot
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tmem_full_bar[i], 1);
@@ -135,21 +127,32 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
             uint32_t phase = 0;
             for (int tile = cluster_id; tile < n_tiles; tile += n_clusters) {
                 const int m0 = (tile / n_tiles_n) * (2 * BM) + static_cast<int>(rank) * BM;
-                const int n0 = (tile % n_tiles_n) * BN + static_cast<int>(rank) * (BN / 2);
+                const int n0 = ((tile % n_tiles_n) * NP + pair) * BN + static_cast<int>(rank) * (BN / 2);
                 for (int kb = 0; kb < nkb; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sa = smem + stage * STAGE_BYTES;
                     uint8_t* sb = sa + A_BYTES;
-                    const uint32_t lead_full = mapa_rank(smem_u32(&full_bar[stage]), 0);
+                    // the pair leader's barrier: this CTA's own address with the peer bit cleared
+                    const uint32_t lead_full = smem_u32(&full_bar[stage]) & 0xFEFFFFFFu;
                     if (g.diag == 1 && (tile != cluster_id || kb >= STAGES)) {
                         // diagnostic: no operand traffic at all, the MMAs re-read whatever the ring holds
                         if (leader && elect_one()) mbar_arrive(&full_bar[stage]);
                     } else if (elect_one()) {
                         if (leader) mbar_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);
-                        if (kb < nkb0)
-                            tma_load_2d_cg2(&tmA0, lead_full, sa, kb * BK, m0);
-                        else
-                            tma_load_2d_cg2(&tmA1, lead_full, sa, (kb - nkb0) * BK, m0);
+                        if (NP == 1) {
+                            if (kb < nkb0)
+                                tma_load_2d_cg2(&tmA0, lead_full, sa, kb * BK, m0);
+                            else
+                                tma_load_2d_cg2(&tmA1, lead_full, sa, (kb - nkb0) * BK, m0);
+                        } else if ((kb & 1) == pair) {
+                            // this CTA's 128 rows of A are also the rows of the CTA at the same position in the
+                            // other pair: one L2 read, two destinations
+                            const uint16_t mask = static_cast<uint16_t>(0x5u << rank);
+                            if (kb < nkb0)
+                                tma_load_2d_cg2_mc(&tmA0, lead_full, sa, kb * BK, m0, mask);
+                            else
+                                tma_load_2d_cg2_mc(&tmA1, lead_full, sa, (kb - nkb0) * BK, m0, mask);
+                        }
                         tma_load_2d_cg2(&tmB, lead_full, sb, kb * BK, n0);
                     }
                     __syncwarp();
@@ -181,8 +184,11 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
 #pragma unroll
                         for (int k = 0; k < BK / 16; ++k)
                             umma_f16_cg2(d_tmem, adesc + (k * 2), bdesc + (k * 2), idesc, (kb | k) != 0);
-                        umma_commit_cg2(&empty_bar[stage], 0b11);   // frees the slot in both CTAs
-                        if (kb == nkb - 1) umma_commit_cg2(&tmem_full_bar[as], 0b11);  // accumulators ready (both CTAs)
+                        // frees the slot in every CTA of the cluster (NP == 2: the other pair's producers multicast
+                        // A boxes into this pair's slots, so they count this pair's commit too)
+                        umma_commit_cg2(&empty_bar[stage], static_cast<uint16_t>((1u << (2 * NP)) - 1));
+                        if (kb == nkb - 1)   // accumulators ready (both CTAs of this pair)
+                            umma_commit_cg2(&tmem_full_bar[as], static_cast<uint16_t>(0x3u << (2 * pair)));
                     }
                     __syncwarp();
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -196,7 +202,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
             int i = 0;  // chunk counter per half (both halves advance together)
             for (int tile = cluster_id; tile < n_tiles; tile += n_clusters) {
                 const int m0 = (tile / n_tiles_n) * (2 * BM) + static_cast<int>(rank) * BM;
-                const int n0 = (tile % n_tiles_n) * BN;
+                const int n0 = ((tile % n_tiles_n) * NP + pair) * BN;
                 for (int c = 0; c < 4; ++c, ++i) {
                     const int b = i % NBUF;
                     const uint32_t ph = (i / NBUF) & 1;
@@ -229,7 +235,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
             const int as = t & 1;
             const uint32_t aphase = (t >> 1) & 1;
             const int m0 = (tile / n_tiles_n) * (2 * BM) + static_cast<int>(rank) * BM;
-            const int n0 = (tile % n_tiles_n) * BN;   // the two column halves take interleaved chunks, so that at
+            const int n0 = ((tile % n_tiles_n) * NP + pair) * BN;   // the two column halves take interleaved chunks, so that at
                                                       // any moment the CTA touches 256 B contiguous per output row
             EpiRow row = epi_row(g, EPI, m0 + rloc);
 
@@ -276,7 +282,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
             // release this accumulator stage to the leader's MMA warp
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(&tmem_empty_bar[as], 0);
+            if (lane == 0) mbar_arrive_cluster(&tmem_empty_bar[as], crank & ~1u);
             if (EPI == EPI_BIAS_RESID || EPI == EPI_BIAS_F32) epi_store_stats(g, row, (n0 / 128) + half);
         }
     }
@@ -287,13 +293,54 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
     if (warp == 1) tmem_dealloc_cg2<TMEM_COLS>(tmem_base);
 }
 
+// resident clusters of 4 CTAs (a GPC with an odd number of TPCs leaves one idle: 33 on B200, i.e. 132 of 148 SMs)
+template <int EPI, bool LONGK>
+int max_clusters4() {
+    static int cached = -1;
+    if (cached >= 0) return cached;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(4 * 64);
+    cfg.blockDim = dim3(THREADS);
+    cfg.dynamicSmemBytes = Cfg2<EPI, LONGK>::SMEM_BYTES;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 4; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, gemm2_kernel<EPI, LONGK, 2>, &cfg) != cudaSuccess) n = 0;
+    cached = n;
+    return n;
+}
+
+// USP_GEMM_CL4: 0 = never, 1 = whenever the shape allows, 2 (default) = only N <= 1024 (proj / fc2 / skip_linear: their
+// 260 tiles fill 3.94 of 4 waves on 33 clusters of 4 instead of 3.51 of 4 on 74 pairs; on the wide GEMMs the 16 idle
+// SMs cost more than the shared A saves)
+inline int gemm_cluster4_mode() {
+    static int mode = -1;
+    if (mode < 0) {
+        const char* e = getenv("USP_GEMM_CL4");
+        mode = e ? atoi(e) : 2;
+    }
+    return mode;
+}
+
 template <int EPI, bool LONGK>
 cudaError_t launch2k(const GemmMaps& maps, const GemmArgs& a, int num_sms, cudaStream_t s) {
     const int n_tiles = ((a.M + 2 * BM - 1) / (2 * BM)) * (a.N / BN);
+    GemmArgs a2 = a;
+    const int cl4 = gemm_cluster4_mode();
+    if (cl4 && (cl4 == 1 || a.N <= 1024) && (a.N / BN) % 2 == 0 && n_tiles >= num_sms) {
+        int c4 = max_clusters4<EPI, LONGK>();
+        if (c4 > 0) {
+            if (n_tiles / 2 < c4) c4 = n_tiles / 2;
+            return launch_pdl(gemm2_kernel<EPI, LONGK, 2>, dim3(4 * c4), dim3(THREADS), Cfg2<EPI, LONGK>::SMEM_BYTES, s,
+                              maps.a0, maps.a1, maps.b, maps.r32, maps.o32, a2);
+        }
+    }
     int clusters = num_sms / 2;
     if (n_tiles < clusters) clusters = n_tiles;
-    return launch_pdl(gemm2_kernel<EPI, LONGK>, dim3(2 * clusters), dim3(THREADS), Cfg2<EPI, LONGK>::SMEM_BYTES, s,
-                      maps.a0, maps.a1, maps.b, maps.r32, maps.o32, a);
+    return launch_pdl(gemm2_kernel<EPI, LONGK, 1>, dim3(2 * clusters), dim3(THREADS), Cfg2<EPI, LONGK>::SMEM_BYTES, s,
+                      maps.a0, maps.a1, maps.b, maps.r32, maps.o32, a2);
 }
 
 template <int EPI>
@@ -304,10 +351,16 @@ cudaError_t launch2(const GemmMaps& maps, const GemmArgs& a, int num_sms, cudaSt
 
 template <int EPI>
 cudaError_t configure2() {
-    cudaError_t e = cudaFuncSetAttribute(gemm2_kernel<EPI, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(gemm2_kernel<EPI, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg2<EPI, false>::SMEM_BYTES);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(gemm2_kernel<EPI, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 Cfg2<EPI, false>::SMEM_BYTES);
     if (e != cudaSuccess || EPI != EPI_BIAS_RESID) return e;
-    return cudaFuncSetAttribute(gemm2_kernel<EPI, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    e = cudaFuncSetAttribute(gemm2_kernel<EPI, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             Cfg2<EPI, true>::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(gemm2_kernel<EPI, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 Cfg2<EPI, true>::SMEM_BYTES);
 }
 

@@ -76,11 +76,10 @@ __device__ __forceinline__ void epi_load_resid(const GemmArgs& g, const EpiRow& 
     }
 }
 
+// the arithmetic of one 32-column chunk: accumulator -> value to store
 template <int EPI>
-__device__ __forceinline__ void epi_chunk(const GemmArgs& g, EpiRow& row, int n, const uint32_t* r,
-                                          const float4* resid) {
-    if (!row.ok) return;
-    float v[32];
+__device__ __forceinline__ void epi_math(const GemmArgs& g, EpiRow& row, int n, const uint32_t* r,
+                                         const float4* resid, float* v) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
     if (g.ln_stats != nullptr) {
@@ -101,7 +100,7 @@ __device__ __forceinline__ void epi_chunk(const GemmArgs& g, EpiRow& row, int n,
             v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
         }
     }
-    if (EPI == EPI_BIAS_GELU) {
+    if (EPI == EPI_BIAS_GELU && !(g.diag & 8)) {   // diag 8: skip the GELU arithmetic (diagnostic)
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = gelu_erf_fast(v[j]);
     }
@@ -118,6 +117,14 @@ __device__ __forceinline__ void epi_chunk(const GemmArgs& g, EpiRow& row, int n,
             row.s2 = fmaf(v[j], v[j], row.s2);
         }
     }
+}
+
+template <int EPI>
+__device__ __forceinline__ void epi_chunk(const GemmArgs& g, EpiRow& row, int n, const uint32_t* r,
+                                          const float4* resid) {
+    if (!row.ok) return;
+    float v[32];
+    epi_math<EPI>(g, row, n, r, resid, v);
     if (EPI == EPI_BIAS_RESID || EPI == EPI_BIAS_F32) {
         if (g.out32 != nullptr && !(g.diag & 4)) {   // diag 4: skip the fp32 store (diagnostic)
             float* op = g.out32 + static_cast<long long>(row.m) * g.N + n;
@@ -135,7 +142,7 @@ __device__ __forceinline__ void epi_chunk(const GemmArgs& g, EpiRow& row, int n,
     } else if (g.out16 != nullptr) {
         o16 = reinterpret_cast<uint16_t*>(g.out16) + static_cast<long long>(row.m) * g.N + n;
     }
-    if (o16 != nullptr) {
+    if (o16 != nullptr && !(g.diag & 16)) {        // diag 16: skip the 16-bit store (diagnostic)
         uint32_t u[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) u[j] = pack16(g.opd, v[2 * j], v[2 * j + 1]);
