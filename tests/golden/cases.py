@@ -44,3 +44,16 @@ def build_inputs(case):
 def build_model(case, cls_uncond, cls_t2i):
     torch.manual_seed(case["seed"])
     return (cls_t2i if case["t2i"] else cls_uncond)(**case["cfg"]).eval()
+
+
+def attr_delta_inputs():
+    """Synthetic "read"-mode dump for the attribute-direction golden: features [B, T, C, W, H], encoded latents
+    [B, C, W, H], FFHQ-style binary attributes [B, 11], the evaluation-time strings and the number of batches."""
+    import numpy as np
+    rng = np.random.default_rng(2024)
+    B, times, batch_num = 12, ["0.25", "0.50", "1.00"], 3
+    feats = rng.standard_normal((B, len(times), 4, 8, 8)).astype(np.float32)
+    latent = rng.standard_normal((B, 4, 8, 8)).astype(np.float32)
+    attr = (rng.random((B, 11)) < 0.5).astype(np.int64)
+    attr[0], attr[1] = 1, 0          # every attribute has at least one positive and one negative sample
+    return feats, latent, attr, times, batch_num

@@ -653,3 +653,44 @@ def test_read_mode_trace_and_files(tmp_path):
     # Heun also evaluates at the last grid point
     _, tr = eng.sample_read(x.to(dev()), 0.0, 1.0, 0.5, "heun", edit_loc="head")
     assert tr.shape[0] == 3 and tr[2].any()
+
+
+def test_read_delta_write_closed_loop(tmp_path):
+    """The reference's three-stage workflow on this library: (1) "read" the tail activation while encoding labelled
+    latents (dissect_lfm.py:216-228), (2) delta_t = mean(attr = 1) - mean(attr = 0) (tools/utils_attr.py:160-206),
+    (3) decode with "write_attr" reading those files (libs/dissection.py:138-157) - checked against the oracle."""
+    from uspace_b200 import attr_delta
+    case = CASES["tiny_uncond"]
+    m = model("tiny_uncond")
+    sd = {k: v.cpu() for k, v in m.state_dict().items()}
+    cnf = CNF(m)
+    root = str(tmp_path / "feat")
+    h = 0.25
+    sk = dict(solver="fixed", solver_fix="euler", solver_fix_step=h)
+    g = torch.Generator().manual_seed(77)
+    attrs = (torch.rand(6, 11, generator=g) < 0.5).long()
+    attrs[0], attrs[1] = 1, 0
+    lat = []
+    for b in range(2):                                   # two batches of three "real" latents
+        x = torch.randn(3, 4, 32, 32, generator=g)
+        z = cnf.encode(x.to(dev()), y=None, dissect_task="uspace_uvit", dissect_name="read", read_path_root=root,
+                       batch_id=b, edit_loc="tail", solver_kwargs=sk)
+        lat.append(z.cpu())
+    attr_delta.save_latents(root, torch.cat(lat).numpy(), attrs.numpy())
+    times = attr_delta.extract_deltas_by_attr(root, batch_num=2)
+    assert times == ["0.25", "0.50", "0.75", "1.00"]
+    delta = np.load(os.path.join(root, "delta_0.25.npy"))
+    assert delta.shape == (11, 4, 32, 32) and np.abs(delta).max() > 0
+    # decode fresh noise with attribute 3 pushed: grid 0, .25, .5, .75 -> edits at .25 and .5 (t_edit = 0.5)
+    x = torch.randn(2, 4, 32, 32, generator=g)
+    kw = dict(dissect_task="uspace_uvit", dissect_name="write_attr", write_path_root=root, ith_attr=3, t_edit=0.5,
+              write_scale=4.0, edit_loc="tail", solver_kwargs=sk)
+    got = cnf.decode(x.to(dev()), y=None, **kw)
+    table = torch.zeros(5, 4, 32, 32)
+    table[1] = torch.from_numpy(np.load(os.path.join(root, "delta_0.25.npy"))[3])
+    table[2] = torch.from_numpy(np.load(os.path.join(root, "delta_0.50.npy"))[3])
+    want = O.sample(sd, case["cfg"], x.double(), 0.0, 1.0, h, "euler", delta_table=table.double(), write_scale=4.0,
+                    t_edit=0.5, edit_loc="tail")
+    assert rel(got, want) < 1e-3
+    plain = O.sample(sd, case["cfg"], x.double(), 0.0, 1.0, h, "euler")
+    assert rel(want, plain) > 1e-3

@@ -293,3 +293,29 @@ def test_hot_kernels_do_not_spill(tmp_path):
             if "attention2_kernelILi" in name and "ELb1E" in name:
                 continue
             assert int(spill) == 0 and int(stack) == 0, (src, name, stack, spill)
+
+
+# ---- attribute directions: the offline step between "read" and "write_attr" ----------------------------------
+def test_attr_delta_matches_reference_golden(golden_dir, tmp_path):
+    """uspace_b200.attr_delta on the reference's file formats == tools/utils_attr.py (golden made by the reference)."""
+    from tests.golden.cases import attr_delta_inputs
+    from uspace_b200 import attr_delta
+    g = np.load(os.path.join(golden_dir, "attr_delta.npz"))
+    feats, latent, attr, times, batch_num = attr_delta_inputs()
+    root = str(tmp_path / "dump")
+    assert attr_delta.save_latents(root, latent, attr).endswith("latents.npy.npz")
+    per = feats.shape[0] // batch_num
+    for ti, ts in enumerate(times):
+        for b in range(batch_num):
+            np.save(os.path.join(root, f"{b}_{ts}"), feats[b * per:(b + 1) * per, ti])
+    np.save(os.path.join(root, "pca4_0.25"), np.zeros(3))      # ignored, like latent* and delta* (utils_attr.py:94-101)
+    assert attr_delta.extract_deltas_by_attr(root, batch_num) == times
+    assert attr_delta.extract_deltas_by_attr(root, batch_num, cal_latentz_delta_only=True) == []
+    for ts in times:
+        got = np.load(os.path.join(root, f"delta_{ts}.npy"))
+        assert got.shape == (11, 4, 8, 8) and np.array_equal(got, g[f"delta_{ts}"])
+    assert np.array_equal(np.load(os.path.join(root, "delta_latentz.npy")), g["delta_latentz"])
+    # a second pass ignores the delta files it wrote itself
+    assert attr_delta.extract_deltas_by_attr(root, batch_num) == times
+    with pytest.raises(ValueError):
+        attr_delta.cal_delta_direction(0, np.zeros((4, 7)), np.zeros((4, 2)))
