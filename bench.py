@@ -349,15 +349,17 @@ def main():
             "e2e": {"value": Bg * n_rep * args.steps / e2e_s, "unit": "images/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "matches_device_path": same},
             "gpu_launches": args.steps * (n_grid - 1) * nfe_per_step * (eng.kernels_per_forward() + 1),
-            "roofline": {"bound": "tensor", "kernel": "usp::gemm2_kernel<EPI,LONGK> (2-CTA tcgen05 GEMM: all five U-ViT linears of one velocity evaluation)",
+            "roofline": {"bound": "tensor", "kernel": "usp::gemm2_kernel<EPI,LONGK,NP> (2-CTA tcgen05 GEMM: all five U-ViT linears of one velocity evaluation)",
+                         "note": "the kernel itself is limited by SM<->L2 delivery at its 256x256 pair tile (~1530 TFLOP/s without "
+                                 "epilogue traffic, the same ceiling cuBLAS shows); see profiles/r01f_gemm_traffic_experiments.md",
                          "achieved": achieved, "peak": pk["sustained"], "unit": "TFLOP/s", "frac": achieved / pk["sustained"],
                          "peak_kind": f"bf16_tflops_sustained of {pk['src']} (kernel timed inside a long step); burst {pk['burst']}",
                          "launches": gemm_launches, "avg_launch_ms": gemm_ms / max(1, gemm_launches),
                          "share_of_forward": gemm_ms / fwd_ms,
                          # DRAM read+write bytes per GEMM launch (mean over the 94 launches of one evaluation) from the
-                         # `ncu --set full` capture profiles/r01d_ncu_gemm.md (qkv 93.8, proj 119.1, fc1 128.6,
-                         # fc2 288.6 MB measured; skip_linear 140 MB estimated); algorithmic operand+result bytes: 193.5 MB
-                         "traffic": 155.7e6 if (args.workload == "c2" and Bl == 64) else None,
+                         # `ncu --set full` capture profiles/r01f_ncu_gemm.md (qkv 94.6, proj 121.6, fc1 128.6,
+                         # fc2 278.4 MB measured; skip_linear 140 MB estimated); algorithmic operand+result bytes: 193.5 MB
+                         "traffic": 154.1e6 if (args.workload == "c2" and Bl == 64) else None,
                          "algorithmic_bytes": 193.5e6 if (args.workload == "c2" and Bl == 64) else None},
             "kernel_ms_per_forward": {k: round(v[0], 4) for k, v in prof.items()},
             "clocks": clocks, "finite": finite,

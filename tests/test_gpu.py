@@ -402,6 +402,24 @@ def test_error_paths():
         eng.sample(z, 0.0, 1.0, 0.5, edit_loc="tail")
     with pytest.raises(KeyError):
         eng.load_state_dict({})
+    lib, h = eng.lib, eng.handle
+    st = _lib.UspAdaptiveStats()
+    # C ABI, invalid arguments: status < 0 and a message, nothing launched
+    assert lib.usp_sample_adaptive(h, P(z), None, None, 1, 0.0, 1.0, 0.0, 1e-5, None, 0, 0.0, 0.0, 0, None, 0,
+                                   C.byref(st), stream()) < 0
+    assert b"rtol" in lib.usp_last_error(h)
+    assert lib.usp_sample_adaptive(h, P(z), None, None, 1, 0.0, 1.0, 1e-5, 1e-5, P(z), 200, 1.0, 0.4, 2, None, 0,
+                                   C.byref(st), stream()) < 0
+    assert b"n_rows" in lib.usp_last_error(h)
+    sc = (C.c_float * 2)(1.0, 2.0)
+    assert lib.usp_sample_sweep(h, P(z), P(z), None, None, 1, sc, 2, 0.0, 1.0, 0.5, 0, None, 0.4, 0, stream()) < 0
+    assert b"edit_loc" in lib.usp_last_error(h)
+    assert lib.usp_sample_sweep(h, P(z), P(z), None, None, 1, None, 0, 0.0, 1.0, 0.5, 0, P(z), 0.4, 2, stream()) < 0
+    assert lib.usp_sample_read(h, P(z), None, None, 1, 0.0, 1.0, 0.5, 0, 2, None, stream()) < 0
+    assert lib.usp_sample_read(h, P(z), None, None, 1, 0.0, 1.0, 0.5, 0, 0, P(z), stream()) < 0
+    assert b"read mode" in lib.usp_last_error(h)
+    assert lib.usp_sample_edit(h, P(z), None, None, 1, 0.0, 1.0, 0.5, 7, None, 0.0, 0.0, 0, None, stream()) < 0
+    assert b"unknown method" in lib.usp_last_error(h)
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
