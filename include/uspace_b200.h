@@ -64,7 +64,10 @@ typedef struct usp_attn_edit {
     float t_edit;            /* sampling only: active while float(f"{t:.2f}") <= t_edit                      */
 } usp_attn_edit;
 
-enum { USP_METHOD_EULER = 0, USP_METHOD_HEUN = 1 };
+/* torchdiffeq fixed-grid methods: "euler", "heun2"-style Heun (2 NFE), "midpoint" (2 NFE), "rk4" = the 3/8 rule of
+ * rk4_alt_step_func (4 NFE). The write edit is keyed by grid point, so under midpoint / rk4 it is applied only at
+ * stages that sit on a grid point (the reference would look for a delta file of the in-between time). */
+enum { USP_METHOD_EULER = 0, USP_METHOD_HEUN = 1, USP_METHOD_MIDPOINT = 2, USP_METHOD_RK4 = 3 };
 enum { USP_EDIT_NONE = 0, USP_EDIT_HEAD = 1, USP_EDIT_TAIL = 2 };
 
 /* Replaces UViT.__init__ (libs/uvit.py:182-291): allocates parameter storage on `device`. */
@@ -130,7 +133,7 @@ typedef struct usp_adaptive_stats {
     float last_ratio;   /* error ratio of the last attempted step */
     double last_dt;     /* size of the last accepted step */
 } usp_adaptive_stats;
-#define USP_METHOD_DOPRI5 2
+#define USP_METHOD_DOPRI5 4
 int usp_sample_adaptive(usp_handle* h, float* z, const float* context, const int64_t* y, int B, float t0, float t1,
                         double rtol, double atol, const float* delta_digits, int n_rows, float write_scale,
                         float t_edit, int edit_loc, const usp_attn_edit* attn, int max_steps,

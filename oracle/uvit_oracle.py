@@ -266,6 +266,17 @@ def odeint_fixed(func: Callable[[Tensor, Tensor], Tensor], z: Tensor, t0: float,
             k1 = func(ta, y)
             k2 = func(tb, y + dt * k1)
             y = y + dt * 0.5 * (k1 + k2)
+        elif method == "midpoint":      # torchdiffeq Midpoint._step_func
+            half = 0.5 * (tb - ta)
+            y = y + dt * func(ta + half, y + func(ta, y) * half.to(z.dtype))
+        elif method == "rk4":           # torchdiffeq rk4_alt_step_func (3/8 rule), fp32 stage times
+            h32 = tb - ta
+            third, two_thirds = torch.tensor(1.0 / 3.0, dtype=ta.dtype), torch.tensor(2.0 / 3.0, dtype=ta.dtype)
+            k1 = func(ta, y)
+            k2 = func(ta + h32 * third, y + dt * k1 / 3.0)
+            k3 = func(ta + h32 * two_thirds, y + dt * (k2 - k1 / 3.0))
+            k4 = func(tb, y + dt * (k1 - k2 + k3))
+            y = y + (k1 + 3.0 * (k2 + k3) + k4) * dt * 0.125
         else:
             raise NotImplementedError(method)
     return y
@@ -283,7 +294,9 @@ def sample(sd: Dict[str, Tensor], cfg: dict, z: Tensor, t0: float = 0.0, t1: flo
 
     def func(t: Tensor, x: Tensor) -> Tensor:
         hd = td = None
-        if edit_loc is not None and delta_table is not None and should_edit(float(t), t_edit):
+        # stages between grid points (midpoint, rk4) have no row in a grid-keyed table: no edit there
+        if (edit_loc is not None and delta_table is not None and float(t) in lookup
+                and should_edit(float(t), t_edit)):
             dlt = delta_table[lookup[float(t)]] * write_scale
             hd, td = (dlt, None) if edit_loc == "head" else (None, dlt)
         # attention edit: float(f"{t:.2f}") <= t_edit, "0.00" included (tools/utils_t2i.py:284)

@@ -712,3 +712,54 @@ def test_read_delta_write_closed_loop(tmp_path):
     assert rel(got, want) < 1e-3
     plain = O.sample(sd, case["cfg"], x.double(), 0.0, 1.0, h, "euler")
     assert rel(want, plain) > 1e-3
+
+
+# ---- torchdiffeq's other fixed-grid methods ----------------------------------------------------------------
+@pytest.mark.parametrize("name,method,h", [("tiny_uncond", "midpoint", 0.25), ("tiny_uncond", "rk4", 0.25),
+                                           ("tiny_class", "rk4", 0.5), ("tiny_t2i", "midpoint", 0.2)])
+def test_midpoint_and_rk4_against_oracle(name, method, h):
+    case = CASES[name]
+    m = model(name)
+    x, _, y, ctx = build_inputs(case)
+    sd = {k: v.cpu() for k, v in m.state_dict().items()}
+    want = O.sample(sd, case["cfg"], x.double(), 0.0, 1.0, h, method, y=y, context=None if ctx is None else ctx.double())
+    got = m.engine().sample(x.to(dev()), 0.0, 1.0, h, method, y=y, context=ctx)
+    assert rel(got, want) < 1e-3
+    euler = O.sample(sd, case["cfg"], x.double(), 0.0, 1.0, h, "euler", y=y, context=None if ctx is None else ctx.double())
+    assert rel(got.double().cpu() - euler, want - euler) < 5e-2     # the higher-order correction itself
+    # reversed time through the CNF mirror
+    kw = dict(dissect_name="none", solver_kwargs=dict(solver="fixed", solver_fix=method, solver_fix_step=h))
+    if ctx is None:
+        enc = CNF(m).encode(x.to(dev()), y=y, **kw)
+    else:
+        enc = CNFT2I(m).encode(x.to(dev()), context=ctx.to(dev()), **kw)
+    enc_want = O.sample(sd, case["cfg"], x.double(), 1.0, 0.0, h, method, y=y,
+                        context=None if ctx is None else ctx.double())
+    assert rel(enc, enc_want) < 1e-3
+
+
+def test_rk4_with_grid_point_edit_and_attention_rule():
+    """Edits under rk4: the write edit fires at the stages that sit on grid points (k1 at t_i, k4 at t_{i+1}); the
+    attention edit follows its "%.2f" rule at every stage, in-between ones included."""
+    case = CASES["tiny_t2i"]
+    m = model("tiny_t2i")
+    x, _, _, ctx = build_inputs(case)
+    sd = {k: v.cpu() for k, v in m.state_dict().items()}
+    g = torch.Generator().manual_seed(4)
+    table = 0.3 * torch.randn(3, 4, 32, 32, generator=g)      # grid 0, 0.5, 1.0
+    cs = torch.ones(case["B"], 334)
+    cs[:, 1:78] = 25.0
+    got = m.engine().sample(x.to(dev()), 0.0, 1.0, 0.5, "rk4", context=ctx, delta_table=table, write_scale=2.0,
+                            t_edit=0.5, edit_loc="tail",
+                            attn_edit=dict(colscale=cs, block_mask=(1 << 64) - 1, t_edit=0.2))
+    want = O.sample(sd, case["cfg"], x.double(), 0.0, 1.0, 0.5, "rk4", context=ctx.double(),
+                    delta_table=table.double(), write_scale=2.0, t_edit=0.5, edit_loc="tail",
+                    attn_colscale=cs.double(), attn_blocks=None, attn_t_edit=0.2)
+    assert rel(got, want) < 1e-3
+    # attention edit active at t = 0 and t = 1/6 ("0.17" <= 0.2) only: dropping the in-between rule must be visible
+    no_mid = O.sample(sd, case["cfg"], x.double(), 0.0, 1.0, 0.5, "rk4", context=ctx.double(),
+                      delta_table=table.double(), write_scale=2.0, t_edit=0.5, edit_loc="tail",
+                      attn_colscale=cs.double(), attn_blocks=None, attn_t_edit=0.1)
+    assert rel(want, no_mid) > 5e-3
+    with pytest.raises(RuntimeError, match="read mode"):
+        m.engine().sample_read(x.to(dev()), 0.0, 1.0, 0.5, "rk4", context=ctx, edit_loc="tail")

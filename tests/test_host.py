@@ -145,7 +145,7 @@ def test_cnf_rejects_unbuilt_solvers():
     with pytest.raises(KeyError):   # the reference indexes kwargs["solver_kwargs"] unconditionally (flow_matching.py:138)
         cnf.decode(z, ctx)
     with pytest.raises(NotImplementedError):
-        cnf.get_ode_kwargs(dissect_name="x", solver_kwargs=dict(solver="fixed", solver_fix="rk4", solver_fix_step=.1))
+        cnf.get_ode_kwargs(dissect_name="x", solver_kwargs=dict(solver="fixed", solver_fix="dopri8", solver_fix_step=.1))
     # flow_matching.py:38-85
     assert cnf.get_ode_kwargs(solver_kwargs=dict(solver="fixed")) == dict(method="dopri5", rtol=1e-5, atol=1e-5)
     sk = dict(solver="fixed", solver_fix="euler", solver_fix_step=0.02, solver_adaptive="dopri5")

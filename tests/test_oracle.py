@@ -241,3 +241,26 @@ def test_oracle_adaptive_sampling_agrees_with_a_fine_fixed_grid():
     fine = O.sample(sd, case["cfg"], x, 0.0, 1.0, 0.01, "heun")
     assert rel(ada, fine) < 5e-5 and st["n_accept"] >= 2
     assert O.digit_index(0.125) == 12 and O.digit_index(0.4049999) == 40 and O.digit_index(0.405001) == 41
+
+
+def test_fixed_midpoint_and_rk4_orders_of_accuracy():
+    """torchdiffeq "midpoint" (2nd order) and "rk4" (3/8 rule, 4th order) as restated in odeint_fixed."""
+    f = lambda t, y: y * torch.cos(t.double())
+    y0 = torch.tensor([1.0, -0.5], dtype=torch.float64)
+    exact = y0 * np.exp(np.sin(1.0))
+    errs = {}
+    for method in ("euler", "heun", "midpoint", "rk4"):
+        errs[method] = [float((O.odeint_fixed(f, y0, 0.0, 1.0, h, method) - exact).abs().max()) for h in (0.1, 0.05)]
+    assert 1.7 < errs["euler"][0] / errs["euler"][1] < 2.3
+    assert 3.4 < errs["heun"][0] / errs["heun"][1] < 4.6
+    assert 3.4 < errs["midpoint"][0] / errs["midpoint"][1] < 4.6
+    assert 12.0 < errs["rk4"][0] / errs["rk4"][1] < 20.0      # fp32 grid times put a floor under the finest error
+    assert errs["rk4"][0] < 1e-5 < errs["midpoint"][0]
+    # one rk4 step against the textbook 3/8-rule combination
+    h = 0.5
+    k1 = f(torch.tensor(0.0), y0)
+    k2 = f(torch.tensor(h / 3), y0 + h * k1 / 3)
+    k3 = f(torch.tensor(2 * h / 3), y0 + h * (k2 - k1 / 3))
+    k4 = f(torch.tensor(h), y0 + h * (k1 - k2 + k3))
+    one = O.odeint_fixed(f, y0, 0.0, h, h, "rk4")
+    assert (one - (y0 + h * (k1 + 3 * k2 + 3 * k3 + k4) / 8)).abs().max() < 1e-7

@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libuspace_b200.so")
 
 USP_OK = 0
-METHOD = {"euler": 0, "heun": 1}
+METHOD = {"euler": 0, "heun": 1, "midpoint": 2, "rk4": 3}
 EDIT_LOC = {None: 0, "none": 0, "head": 1, "tail": 2}
 OPERAND = {"bf16": 0, "fp16": 1}
 EPI = {"qkv": 0, "bias_gelu": 1, "bias_resid": 2, "bias_f32": 3}

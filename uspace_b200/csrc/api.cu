@@ -348,9 +348,11 @@ struct FwdIO {
     // final stage
     const float* base;
     const float* aux;
-    float* vstore;
+    float* vstore;          // running combination 1 (vs_a * v + vs_b * old)
+    float* acc2;            // running combination 2 (a2_a * v + a2_b * old)
     float* out;
     float m1, m2;
+    float vs_a, vs_b, a2_a, a2_b;
 };
 
 void prof_mark(usp_handle* h, int cls, cudaStream_t s) {
@@ -551,8 +553,9 @@ int enqueue_forward(usp_handle* h, Plan* p, const FwdIO& io, cudaStream_t s) {
     fa.delta = io.edit_loc == USP_EDIT_TAIL ? io.delta : nullptr;
     fa.sscale = io.sscale;
     fa.trace = io.edit_loc == USP_EDIT_TAIL ? io.trace : nullptr;
-    fa.st = io.st; fa.base = io.base; fa.aux = io.aux; fa.vstore = io.vstore; fa.out = io.out;
+    fa.st = io.st; fa.base = io.base; fa.aux = io.aux; fa.vstore = io.vstore; fa.acc2 = io.acc2; fa.out = io.out;
     fa.m1 = io.m1; fa.m2 = io.m2;
+    fa.vs_a = io.vs_a; fa.vs_b = io.vs_b; fa.a2_a = io.a2_a; fa.a2_b = io.a2_b;
     fa.B = B; fa.C = h->cfg.in_chans; fa.S = h->cfg.img_size; fa.p = h->cfg.patch_size;
     KTRY(launch_final(fa, s));
     prof_mark(h, -1, s);
@@ -884,13 +887,15 @@ int sample_impl(usp_handle* h, const float* z_in, float* z, const float* context
         return fail(h, USP_ERR_INVALID, "context must be given exactly for the t2i model");
     if ((y != nullptr) != (h->cfg.num_classes > 0))
         return fail(h, USP_ERR_INVALID, "y must be given exactly for the class-conditional model (num_classes > 0)");
-    if (method != USP_METHOD_EULER && method != USP_METHOD_HEUN) return fail(h, USP_ERR_INVALID, "unknown method");
+    if (method < USP_METHOD_EULER || method > USP_METHOD_RK4) return fail(h, USP_ERR_INVALID, "unknown method");
     if (edit_loc != USP_EDIT_NONE && edit_loc != USP_EDIT_HEAD && edit_loc != USP_EDIT_TAIL)
         return fail(h, USP_ERR_INVALID, "edit_loc must be none, head or tail (\"mid\" is broken in the reference)");
     if (trace_out == nullptr && (edit_loc != USP_EDIT_NONE) != (delta_table != nullptr))
         return fail(h, USP_ERR_INVALID, "delta_table must be given exactly when edit_loc is head or tail");
     if (trace_out != nullptr && (edit_loc == USP_EDIT_NONE || delta_table != nullptr || rep != 1))
         return fail(h, USP_ERR_INVALID, "the read mode takes edit_loc head or tail and no delta_table");
+    if (trace_out != nullptr && method > USP_METHOD_HEUN)
+        return fail(h, USP_ERR_INVALID, "the read mode is keyed by grid point: euler or heun only");
     std::vector<float> grid;
     const int n = build_grid(t0, t1, step_size, &grid);
     if (n < 2) return fail(h, USP_ERR_INVALID, "bad time grid (t0 == t1, step_size <= 0 or more than 4096 points)");
@@ -948,6 +953,7 @@ int sample_impl(usp_handle* h, const float* z_in, float* z, const float* context
     StepState st0;
     memset(&st0, 0, sizeof(st0));
     st0.write_scale = write_scale;
+    st0.attn_t_edit = use_attn ? attn->t_edit : -1.f;
     CUDA_TRY(h, cudaMemcpyAsync(p->st, &st0, sizeof(st0), cudaMemcpyHostToDevice, s));
     const bool sweep = rep > 1;
     if (!sweep) {
@@ -977,8 +983,8 @@ int sample_impl(usp_handle* h, const float* z_in, float* z, const float* context
         if (rc) return rc;
     }
 
-    const std::pair<int, uint64_t> key(method | (edit_loc << 2) | ((y ? 1 : 0) << 4) | ((use_attn ? 1 : 0) << 5) |
-                                           ((sweep ? 1 : 0) << 7) | ((trace_out ? 1 : 0) << 8),
+    const std::pair<int, uint64_t> key(method | (edit_loc << 3) | ((y ? 1 : 0) << 5) | ((use_attn ? 1 : 0) << 6) |
+                                           ((sweep ? 1 : 0) << 8) | ((trace_out ? 1 : 0) << 9),
                                        use_attn ? attn->block_mask : 0);
     auto git = p->graphs.find(key);
     if (git == p->graphs.end()) {
@@ -995,17 +1001,54 @@ int sample_impl(usp_handle* h, const float* z_in, float* z, const float* context
             io.trace = trace_out ? p->trace : nullptr;
             io.sscale = sweep ? p->sscale : nullptr;
             if (use_attn) { io.colscale = p->colscale; io.block_mask = attn->block_mask; }
+            // every stage: out = base + dt * (m1 * v + m2 * aux), with v the velocity at the stage's (t, x)
+            auto stage_time = [&](int kind, float frac) -> int {
+                cudaError_t e2 = launch_step(p->st, p->grid, p->mask, p->amask, kind, h->cap_stream, frac);
+                if (e2 != cudaSuccess) return fail(h, USP_ERR_CUDA, std::string("launch_step: ") + cudaGetErrorString(e2));
+                return USP_OK;
+            };
+            int r;
             if (method == USP_METHOD_EULER) {
                 io.x = p->z; io.base = p->z; io.out = p->z; io.m1 = 1.f;
                 return enqueue_forward(h, p, io, h->cap_stream);
             }
-            io.x = p->z; io.base = p->z; io.vstore = p->k1; io.out = p->ztmp; io.m1 = 1.f;
-            int r = enqueue_forward(h, p, io, h->cap_stream);
-            if (r) return r;
-            e = launch_step(p->st, p->grid, p->mask, p->amask, 1, h->cap_stream);
-            if (e != cudaSuccess) return fail(h, USP_ERR_CUDA, std::string("launch_step: ") + cudaGetErrorString(e));
-            io.x = p->ztmp; io.base = p->z; io.aux = p->k1; io.vstore = nullptr; io.out = p->z;
-            io.m1 = 0.5f; io.m2 = 0.5f;
+            if (method == USP_METHOD_HEUN) {
+                io.x = p->z; io.base = p->z; io.vstore = p->k1; io.vs_a = 1.f; io.out = p->ztmp; io.m1 = 1.f;
+                if ((r = enqueue_forward(h, p, io, h->cap_stream))) return r;
+                if ((r = stage_time(1, 0.f))) return r;
+                io.x = p->ztmp; io.base = p->z; io.aux = p->k1; io.vstore = nullptr; io.out = p->z;
+                io.m1 = 0.5f; io.m2 = 0.5f;
+                return enqueue_forward(h, p, io, h->cap_stream);
+            }
+            if (method == USP_METHOD_MIDPOINT) {
+                // y_mid = y0 + dt/2 f(t0, y0);  y1 = y0 + dt f(t0 + dt/2, y_mid)
+                io.x = p->z; io.base = p->z; io.out = p->ztmp; io.m1 = 0.5f;
+                if ((r = enqueue_forward(h, p, io, h->cap_stream))) return r;
+                if ((r = stage_time(2, 0.5f))) return r;
+                io.x = p->ztmp; io.base = p->z; io.out = p->z; io.m1 = 1.f;
+                return enqueue_forward(h, p, io, h->cap_stream);
+            }
+            // rk4 = torchdiffeq's rk4_alt_step_func (3/8 rule).  R1 (k1 buffer) carries the stage combination,
+            // R2 (first slot of the adaptive solver's k array) the weighted sum for the final update.
+            float* R1 = p->k1;
+            float* R2 = p->rk_k;
+            const float third = 1.0f / 3.0f;
+            // k1: y2 = y0 + dt/3 k1;  R1 = k1;  R2 = k1
+            io.x = p->z; io.base = p->z; io.out = p->ztmp; io.m1 = third;
+            io.vstore = R1; io.vs_a = 1.f; io.vs_b = 0.f; io.acc2 = R2; io.a2_a = 1.f; io.a2_b = 0.f;
+            if ((r = enqueue_forward(h, p, io, h->cap_stream))) return r;
+            if ((r = stage_time(2, third))) return r;
+            // k2: y3 = y0 + dt (k2 - k1/3);  R1 = k1 - k2;  R2 += 3 k2
+            io.x = p->ztmp; io.aux = R1; io.m1 = 1.f; io.m2 = -third;
+            io.vs_a = -1.f; io.vs_b = 1.f; io.a2_a = 3.f; io.a2_b = 1.f;
+            if ((r = enqueue_forward(h, p, io, h->cap_stream))) return r;
+            if ((r = stage_time(2, 2.0f / 3.0f))) return r;
+            // k3: y4 = y0 + dt (k1 - k2 + k3);  R2 += 3 k3
+            io.m1 = 1.f; io.m2 = 1.f; io.vstore = nullptr;
+            if ((r = enqueue_forward(h, p, io, h->cap_stream))) return r;
+            if ((r = stage_time(1, 0.f))) return r;
+            // k4: y1 = y0 + dt/8 (k1 + 3 k2 + 3 k3 + k4)
+            io.aux = R2; io.acc2 = nullptr; io.out = p->z; io.m1 = 0.125f; io.m2 = 0.125f;
             return enqueue_forward(h, p, io, h->cap_stream);
         };
         const int brc = body();
@@ -1157,8 +1200,8 @@ int usp_sample_adaptive(usp_handle* h, float* z, const float* context, const int
     if (rc) return rc;
     RK_TRY(launch_rk_control(ra, 1, s));
 
-    const std::pair<int, uint64_t> key(USP_METHOD_DOPRI5 | (edit_loc << 2) | ((y ? 1 : 0) << 4) | ((use_attn ? 1 : 0) << 5) |
-                                           ((sign < 0.f ? 1 : 0) << 6),
+    const std::pair<int, uint64_t> key(USP_METHOD_DOPRI5 | (edit_loc << 3) | ((y ? 1 : 0) << 5) | ((use_attn ? 1 : 0) << 6) |
+                                           ((sign < 0.f ? 1 : 0) << 7),
                                        use_attn ? attn->block_mask : 0);
     auto git = p->graphs.find(key);
     if (git == p->graphs.end()) {

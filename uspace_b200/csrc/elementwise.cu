@@ -292,10 +292,11 @@ __global__ void __launch_bounds__(256) final_kernel(const FinalArgs a) {
         a.out[i] = a.m1 * v;
         return;
     }
-    if (a.vstore != nullptr) a.vstore[i] = v;
     const float dt = a.st->dt;
     float inc = a.m1 * v;
     if (a.aux != nullptr) inc += a.m2 * a.aux[i];
+    if (a.vstore != nullptr) a.vstore[i] = a.vs_b != 0.f ? fmaf(a.vs_b, a.vstore[i], a.vs_a * v) : a.vs_a * v;
+    if (a.acc2 != nullptr) a.acc2[i] = a.a2_b != 0.f ? fmaf(a.a2_b, a.acc2[i], a.a2_a * v) : a.a2_a * v;
     a.out[i] = a.base[i] + dt * inc;
 }
 
@@ -351,7 +352,7 @@ __global__ void __launch_bounds__(256) fold_ln_kernel(const float* __restrict__ 
 }
 
 __global__ void step_kernel(StepState* st, const float* __restrict__ grid, const unsigned char* __restrict__ mask,
-                            const unsigned char* __restrict__ amask, int stage) {
+                            const unsigned char* __restrict__ amask, int stage, float frac) {
     pdl_wait();
     pdl_launch();
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
@@ -364,12 +365,21 @@ __global__ void step_kernel(StepState* st, const float* __restrict__ grid, const
         st->edit = mask[i] ? st->write_scale : 0.f;
         st->didx = i;
         st->attn_on = amask[i];
-    } else {
+    } else if (stage == 1) {
         const int i = st->cur;
         st->t = grid[i + 1];
         st->edit = mask[i + 1] ? st->write_scale : 0.f;
         st->didx = i + 1;
         st->attn_on = amask[i + 1];
+    } else {
+        const int i = st->cur;
+        const float t = __fadd_rn(grid[i], __fmul_rn(st->dt, frac));   // t0 + dt * frac in the grid's precision
+        st->t = t;
+        st->edit = 0.f;
+        st->didx = i;
+        // float(f"{t:.2f}") <= t_edit with both sides in fp32 (see digit_leq in api.cu)
+        const float digit = static_cast<float>(rint(static_cast<double>(t) * 100.0) / 100.0);
+        st->attn_on = (st->attn_t_edit >= 0.f && digit <= st->attn_t_edit) ? 1 : 0;
     }
 }
 
@@ -434,8 +444,8 @@ cudaError_t launch_fold_ln(const float* W, const float* gamma, const float* beta
 }
 
 cudaError_t launch_step(StepState* st, const float* grid, const unsigned char* mask, const unsigned char* amask,
-                        int stage, cudaStream_t s) {
-    return launch_pdl(step_kernel, dim3(1), dim3(32), 0, s, st, grid, mask, amask, stage);
+                        int stage, cudaStream_t s, float frac) {
+    return launch_pdl(step_kernel, dim3(1), dim3(32), 0, s, st, grid, mask, amask, stage, frac);
 }
 
 }  // namespace usp

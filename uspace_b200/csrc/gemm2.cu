@@ -57,8 +57,7 @@ struct Cfg2 {
 template <int EPI, bool LONGK, int NP>
 __global__ void __cluster_dims__(2 * NP, 1, 1) __launch_bounds__(THREADS, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
-             const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmR,
-             const __grid_constant__ CUtensorMap tmO, const GemmArgs g) {
+             const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmR, const GemmArgs g) {
     using Cfg = Cfg2<EPI, LONGK>;
     constexpr int STAGES = Cfg::STAGES;
     constexpr bool STAGED = Cfg::STAGED;
@@ -334,13 +333,13 @@ cudaError_t launch2k(const GemmMaps& maps, const GemmArgs& a, int num_sms, cudaS
         if (c4 > 0) {
             if (n_tiles / 2 < c4) c4 = n_tiles / 2;
             return launch_pdl(gemm2_kernel<EPI, LONGK, 2>, dim3(4 * c4), dim3(THREADS), Cfg2<EPI, LONGK>::SMEM_BYTES, s,
-                              maps.a0, maps.a1, maps.b, maps.r32, maps.o32, a2);
+                              maps.a0, maps.a1, maps.b, maps.r32, a2);
         }
     }
     int clusters = num_sms / 2;
     if (n_tiles < clusters) clusters = n_tiles;
     return launch_pdl(gemm2_kernel<EPI, LONGK, 1>, dim3(2 * clusters), dim3(THREADS), Cfg2<EPI, LONGK>::SMEM_BYTES, s,
-                      maps.a0, maps.a1, maps.b, maps.r32, maps.o32, a2);
+                      maps.a0, maps.a1, maps.b, maps.r32, a2);
 }
 
 template <int EPI>

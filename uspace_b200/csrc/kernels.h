@@ -28,7 +28,8 @@ struct GemmArgs {
     void* out16;         // [M,N] 16-bit (or QKV base) or nullptr
     int L, H;            // EPI_QKV: tokens per sample, heads (head_dim = 64)
     long long qkv_stride;  // EPI_QKV: elements between the q, k and v planes
-    int diag;              // diagnostics (env USP_GEMM_DIAG): 1 = skip TMA loads after the first ring fill (results invalid)
+    int diag;              // diagnostics (env USP_GEMM_DIAG, results invalid): 1 = no operand TMA loads after the first
+                           // ring fill, 2 = no residual loads, 4 / 16 = no fp32 / 16-bit result stores, 8 = no GELU
     // ---- LayerNorm folded into the GEMMs (usp_config.fuse_layernorm) ----
     // consumer side (qkv / fc1): A is the UN-normalised 16-bit stream x, W is pre-scaled by gamma, and
     //   out[m,n] = rstd_m * (acc[m,n] - mean_m * ln_c[n]) + ln_d[n]
@@ -85,6 +86,7 @@ struct StepState {       // lives in device memory; advanced by step_kernel insi
     float write_scale;
     int didx;            // row of the edit table that belongs to `t`
     int attn_on;         // attention re-weighting active at `t` (float(f"{t:.2f}") <= t_edit)
+    float attn_t_edit;   // t_edit of the attention edit, for stages between grid points (negative: no attention edit)
 };
 
 struct EmbedArgs {
@@ -132,10 +134,12 @@ struct FinalArgs {
     float* trace;          // optional "read" dump at edit_loc tail: trace[st->didx][B,C,S,S] = the velocity
     const StepState* st;   // nullptr for a plain forward
     const float* base;     // ODE: state the update starts from
-    const float* aux;      // Heun stage 2: k1
-    float* vstore;         // Heun stage 1: where to keep k1 (or nullptr)
-    float* out;            // forward: v;  ODE: base + dt*(m1*v + m2*aux)
+    const float* aux;      // a stored derivative combination (Heun stage 2: k1), or nullptr
+    float* vstore;         // running combination 1: vstore = vs_a * v + vs_b * vstore (Heun stage 1: k1), or nullptr
+    float* acc2;           // running combination 2: acc2 = a2_a * v + a2_b * acc2 (rk4: k1 + 3 k2 + 3 k3), or nullptr
+    float* out;            // forward: v;  ODE: base + dt*(m1*v + m2*aux), aux read BEFORE the combinations are updated
     float m1, m2;
+    float vs_a, vs_b, a2_a, a2_b;
     int B, C, S, p;
 };
 cudaError_t launch_final(const FinalArgs& a, cudaStream_t s);
@@ -145,9 +149,11 @@ cudaError_t launch_convert16(const float* in, void* out16, long long n, int opd,
 // c[n] = sum_k w16[n,k], d[n] = sum_k beta[k] * W[n,k] (+ bias[n])
 cudaError_t launch_fold_ln(const float* W, const float* gamma, const float* beta, const float* bias, void* w16,
                            float* c, float* d, int N, int K, int opd, cudaStream_t s);
-// stage 0: start interval `next` (t = grid[next]) and advance; stage 1: second Heun stage (t = grid[cur+1])
+// stage 0: start interval `next` (t = grid[next]) and advance; stage 1: a stage at the interval's end (t = grid[cur+1]);
+// stage 2: a stage inside the interval, t = grid[cur] + frac * dt - no grid row, so no write edit; the attention edit
+// follows its "%.2f" rule against st->attn_t_edit
 cudaError_t launch_step(StepState* st, const float* grid, const unsigned char* mask, const unsigned char* amask,
-                        int stage, cudaStream_t s);
+                        int stage, cudaStream_t s, float frac = 0.f);
 
 // ---- adaptive Dormand-Prince 5(4) (csrc/ode.cu) -------------------------------------------------
 // torchdiffeq's RKAdaptiveStepsizeODESolver restated with the controller on the device: time-like quantities are

@@ -4,12 +4,12 @@
 ``torchdiffeq.odeint`` call (flow_matching.py:118-125,140-147) is replaced by the library's fixed-grid
 Euler / Heun loop: one CUDA-graph-captured step replayed on the current stream, no host sync per NFE.
 
-Built: ``solver="fixed"`` with ``solver_fix`` in {"euler", "heun"}; ``solver="adaptive"`` / the non-dissection
+Built: ``solver="fixed"`` with ``solver_fix`` in {"euler", "heun", "midpoint", "rk4"}; ``solver="adaptive"`` / the non-dissection
 default / the adaptive tail of ``"fixadp"`` with dopri5 (step control and dense output on the device, torchdiffeq
 semantics restated in csrc/ode.cu); the "write_attr" / "write_pca" edit hook at ``edit_loc`` head / tail
 (libs/dissection.py:115-186) through a pre-loaded delta table, and its "read" mode (the activation at ``edit_loc``
 of every evaluation, saved as ``{batch_id}_{t:.2f}.npy``) on the fixed grid; the "p2p_rescale" attention edit.
-Not built (NotImplementedError): other torchdiffeq methods (midpoint, rk4, bosh3, adaptive_heun), "read" under an
+Not built (NotImplementedError): other torchdiffeq methods (bosh3, adaptive_heun, ...), "read" under an
 adaptive solver, ``edit_loc="mid"`` (broken in the reference for U-ViT).
 """
 from __future__ import annotations
@@ -23,7 +23,7 @@ from torch import Tensor
 
 from .engine import time_grid
 
-_FIXED_METHODS = ("euler", "heun")
+_FIXED_METHODS = ("euler", "heun", "midpoint", "rk4")
 _ADAPTIVE_METHODS = ("dopri5",)
 _RTOL = 1e-5   # flow_matching.py:11-12
 _ATOL = 1e-5
