@@ -133,9 +133,10 @@ typedef struct usp_adaptive_stats {
     float last_ratio;   /* error ratio of the last attempted step */
     double last_dt;     /* size of the last accepted step */
 } usp_adaptive_stats;
-#define USP_METHOD_DOPRI5 4
+/* method: torchdiffeq's "dopri5" (5(4), 6 evaluations per step), "bosh3" (3(2), 3) or "adaptive_heun" (2(1), 1). */
+enum { USP_METHOD_DOPRI5 = 4, USP_METHOD_BOSH3 = 5, USP_METHOD_ADAPTIVE_HEUN = 6 };
 int usp_sample_adaptive(usp_handle* h, float* z, const float* context, const int64_t* y, int B, float t0, float t1,
-                        double rtol, double atol, const float* delta_digits, int n_rows, float write_scale,
+                        int method, double rtol, double atol, const float* delta_digits, int n_rows, float write_scale,
                         float t_edit, int edit_loc, const usp_attn_edit* attn, int max_steps,
                         usp_adaptive_stats* stats, void* stream);
 /* Same with HOST buffers: copies z (and context / y / delta_table) host->device, samples, copies z back,

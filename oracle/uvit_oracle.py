@@ -337,33 +337,53 @@ def _rms(x: Tensor) -> float:
     return float(x.double().pow(2).mean().sqrt())
 
 
-def dopri5_step(func, s0: float, y0: Tensor, f0: Tensor, dt: float):
-    """One Dormand-Prince step: returns (y1, f1, error estimate, stage derivatives k[0..6])."""
+# torchdiffeq's other adaptive tableaus: Bogacki-Shampine 3(2) ("bosh3") and Heun 2(1) ("adaptive_heun")
+ADAPTIVE_TABLEAUS = {
+    "dopri5": dict(order=5, alpha=DP_ALPHA, beta=DP_BETA, c_sol=DP_C_SOL, c_error=DP_C_ERROR, c_mid=DP_C_MID),
+    "bosh3": dict(order=3, alpha=[1 / 2, 3 / 4, 1.0], beta=[[1 / 2], [0.0, 3 / 4], [2 / 9, 1 / 3, 4 / 9]],
+                  c_sol=[2 / 9, 1 / 3, 4 / 9, 0.0], c_error=[2 / 9 - 7 / 24, 1 / 3 - 1 / 4, 4 / 9 - 1 / 3, -1 / 8],
+                  c_mid=[0.0, 0.5, 0.0, 0.0]),
+    "adaptive_heun": dict(order=2, alpha=[1.0], beta=[[1.0]], c_sol=[0.5, 0.5], c_error=[0.5, -0.5], c_mid=[0.5, 0.0]),
+}
+
+
+def rk_adaptive_step(func, s0: float, y0: Tensor, f0: Tensor, dt: float, tab: dict):
+    """One step of an embedded pair: returns (y1, f1, error estimate, stage derivatives).  As in torchdiffeq's
+    _runge_kutta_step, f1 is ALWAYS the last stage's derivative - exact FSAL only when c_sol[:-1] == beta[-1]."""
+    n = len(tab["alpha"])
     k = [f0]
     yi = y0
-    for i in range(6):
-        si = s0 + dt if DP_ALPHA[i] == 1.0 else s0 + DP_ALPHA[i] * dt
-        yi = y0 + sum(k[j] * (DP_BETA[i][j] * dt) for j in range(i + 1))
+    for i in range(n):
+        si = s0 + dt if tab["alpha"][i] == 1.0 else s0 + tab["alpha"][i] * dt
+        yi = y0 + sum(k[j] * (tab["beta"][i][j] * dt) for j in range(i + 1))
         k.append(func(si, yi))
-    err = sum(k[j] * (DP_C_ERROR[j] * dt) for j in range(7))
-    return yi, k[6], err, k          # FSAL: c_sol[:-1] == beta[-1], so y1 is the last stage's state
+    if not (tab["c_sol"][-1] == 0 and list(tab["c_sol"][:-1]) == list(tab["beta"][-1])):
+        yi = y0 + sum(k[j] * (tab["c_sol"][j] * dt) for j in range(n + 1))
+    err = sum(k[j] * (tab["c_error"][j] * dt) for j in range(n + 1))
+    return yi, k[n], err, k
 
 
-def dopri5_initial_step(func, s0: float, y0: Tensor, f0: Tensor, rtol: float, atol: float) -> float:
-    """Hairer's starting step as torchdiffeq's _select_initial_step computes it (order argument = 4)."""
+def dopri5_step(func, s0: float, y0: Tensor, f0: Tensor, dt: float):
+    """One Dormand-Prince step: returns (y1, f1, error estimate, stage derivatives k[0..6])."""
+    return rk_adaptive_step(func, s0, y0, f0, dt, ADAPTIVE_TABLEAUS["dopri5"])
+
+
+def dopri5_initial_step(func, s0: float, y0: Tensor, f0: Tensor, rtol: float, atol: float, order: int = 5) -> float:
+    """Hairer's starting step as torchdiffeq's _select_initial_step computes it (its order argument = order - 1)."""
     scale = atol + y0.abs() * rtol
     d0, d1 = _rms(y0 / scale), _rms(f0 / scale)
     h0 = 1e-6 if (d0 < 1e-5 or d1 < 1e-5) else 0.01 * d0 / d1
     f1 = func(s0 + h0, y0 + h0 * f0)
     d2 = _rms((f1 - f0) / scale) / h0
-    h1 = max(1e-6, h0 * 1e-3) if (d1 <= 1e-15 and d2 <= 1e-15) else (0.01 / max(d1, d2)) ** (1.0 / 5.0)
+    h1 = max(1e-6, h0 * 1e-3) if (d1 <= 1e-15 and d2 <= 1e-15) else (0.01 / max(d1, d2)) ** (1.0 / order)
     return min(100 * h0, h1)
 
 
-def dopri5_interp(y0, y1, k, dt, x: float) -> Tensor:
+def dopri5_interp(y0, y1, k, dt, x: float, c_mid=None) -> Tensor:
     """4th-order dense output on the accepted step, x = (t - t0) / (t1 - t0)."""
-    y_mid = y0 + sum(k[j] * (DP_C_MID[j] * dt) for j in range(7))
-    f0, f1 = k[0], k[6]
+    c_mid = DP_C_MID if c_mid is None else c_mid
+    y_mid = y0 + sum(k[j] * (c_mid[j] * dt) for j in range(len(c_mid)))
+    f0, f1 = k[0], k[-1]
     a = 2 * dt * (f1 - f0) - 8 * (y1 + y0) + 16 * y_mid
     b = dt * (5 * f0 - 3 * f1) + 18 * y0 + 14 * y1 - 32 * y_mid
     c = dt * (f1 - 4 * f0) - 11 * y0 - 5 * y1 + 16 * y_mid
@@ -372,36 +392,39 @@ def dopri5_interp(y0, y1, k, dt, x: float) -> Tensor:
 
 
 def odeint_dopri5(func: Callable[[float, Tensor], Tensor], z: Tensor, t0: float, t1: float, rtol: float = 1e-5,
-                  atol: float = 1e-5, max_steps: int = 100000, stats: Optional[dict] = None) -> Tensor:
-    """odeint(func, z, [t0, t1], method="dopri5", rtol, atol)[-1].  Steps are never clipped to t1: the last accepted
+                  atol: float = 1e-5, max_steps: int = 100000, stats: Optional[dict] = None,
+                  method: str = "dopri5") -> Tensor:
+    """odeint(func, z, [t0, t1], method=method, rtol, atol)[-1] for "dopri5" / "bosh3" / "adaptive_heun".  Steps are never clipped to t1: the last accepted
     step overshoots and the result is the dense-output polynomial evaluated at t1.  Decreasing time integrates
     g(s, y) = -f(-s, y) over s = -t."""
     sgn = 1.0 if t1 >= t0 else -1.0
     g = (lambda s, y: func(s, y)) if sgn > 0 else (lambda s, y: -func(-s, y))
     s0, s_end = sgn * t0, sgn * t1
+    tab = ADAPTIVE_TABLEAUS[method]
+    order, n_stage = tab["order"], len(tab["alpha"])
     y0 = z
     f0 = g(s0, y0)
-    dt = dopri5_initial_step(g, s0, y0, f0, rtol, atol)
+    dt = dopri5_initial_step(g, s0, y0, f0, rtol, atol, order)
     n_acc = n_rej = 0
     nfe = 2
     while True:
         if n_acc + n_rej >= max_steps:
             raise RuntimeError("max_num_steps exceeded")
-        y1, f1, err, k = dopri5_step(g, s0, y0, f0, dt)
-        nfe += 6
+        y1, f1, err, k = rk_adaptive_step(g, s0, y0, f0, dt, tab)
+        nfe += n_stage
         tol = atol + rtol * torch.maximum(y0.abs(), y1.abs())
         ratio = _rms(err / tol)
         accept = ratio <= 1.0
         if ratio == 0.0:
             factor = DP_IFACTOR
         else:
-            factor = min(DP_IFACTOR, max(DP_SAFETY / ratio ** 0.2, 1.0 if ratio < 1.0 else DP_DFACTOR))
+            factor = min(DP_IFACTOR, max(DP_SAFETY / ratio ** (1.0 / order), 1.0 if ratio < 1.0 else DP_DFACTOR))
         if accept:
             n_acc += 1
             if s0 + dt >= s_end:
                 if stats is not None:
                     stats.update(n_accept=n_acc, n_reject=n_rej, nfe=nfe)
-                return dopri5_interp(y0, y1, k, dt, (s_end - s0) / dt)
+                return dopri5_interp(y0, y1, k, dt, (s_end - s0) / dt, tab["c_mid"])
             s0, y0, f0 = s0 + dt, y1, f1
         else:
             n_rej += 1
@@ -417,8 +440,8 @@ def sample_adaptive(sd: Dict[str, Tensor], cfg: dict, z: Tensor, t0: float = 0.0
                     atol: float = 1e-5, y: Optional[Tensor] = None, context: Optional[Tensor] = None,
                     delta_digits: Optional[Tensor] = None, write_scale: float = 0.0, t_edit: float = 0.0,
                     edit_loc: Optional[str] = None, attn_colscale: Optional[Tensor] = None, attn_blocks=None,
-                    attn_t_edit: float = 0.0, stats: Optional[dict] = None) -> Tensor:
-    """CNF.decode with method="dopri5".  delta_digits[i] is the row delta_{i/100:.2f}.npy would supply; the model
+                    attn_t_edit: float = 0.0, stats: Optional[dict] = None, method: str = "dopri5") -> Tensor:
+    """CNF.decode with an adaptive method.  delta_digits[i] is the row delta_{i/100:.2f}.npy would supply; the model
     sees the time rounded to fp32, like the reference's fp32 stage times."""
     def func(t: float, x: Tensor) -> Tensor:
         tf = float(torch.tensor(t, dtype=torch.float32))
@@ -433,4 +456,4 @@ def sample_adaptive(sd: Dict[str, Tensor], cfg: dict, z: Tensor, t0: float = 0.0
         return uvit_forward(sd, cfg, x, tt, y=y, context=context, head_delta=hd, tail_delta=td,
                             attn_colscale=cs, attn_blocks=attn_blocks)
 
-    return odeint_dopri5(func, z, t0, t1, rtol, atol, stats=stats)
+    return odeint_dopri5(func, z, t0, t1, rtol, atol, stats=stats, method=method)

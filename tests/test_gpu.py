@@ -405,12 +405,15 @@ def test_error_paths():
     lib, h = eng.lib, eng.handle
     st = _lib.UspAdaptiveStats()
     # C ABI, invalid arguments: status < 0 and a message, nothing launched
-    assert lib.usp_sample_adaptive(h, P(z), None, None, 1, 0.0, 1.0, 0.0, 1e-5, None, 0, 0.0, 0.0, 0, None, 0,
+    assert lib.usp_sample_adaptive(h, P(z), None, None, 1, 0.0, 1.0, 4, 0.0, 1e-5, None, 0, 0.0, 0.0, 0, None, 0,
                                    C.byref(st), stream()) < 0
     assert b"rtol" in lib.usp_last_error(h)
-    assert lib.usp_sample_adaptive(h, P(z), None, None, 1, 0.0, 1.0, 1e-5, 1e-5, P(z), 200, 1.0, 0.4, 2, None, 0,
+    assert lib.usp_sample_adaptive(h, P(z), None, None, 1, 0.0, 1.0, 4, 1e-5, 1e-5, P(z), 200, 1.0, 0.4, 2, None, 0,
                                    C.byref(st), stream()) < 0
     assert b"n_rows" in lib.usp_last_error(h)
+    assert lib.usp_sample_adaptive(h, P(z), None, None, 1, 0.0, 1.0, 1, 1e-5, 1e-5, None, 0, 0.0, 0.0, 0, None, 0,
+                                   C.byref(st), stream()) < 0
+    assert b"adaptive method" in lib.usp_last_error(h)
     sc = (C.c_float * 2)(1.0, 2.0)
     assert lib.usp_sample_sweep(h, P(z), P(z), None, None, 1, sc, 2, 0.0, 1.0, 0.5, 0, None, 0.4, 0, stream()) < 0
     assert b"edit_loc" in lib.usp_last_error(h)
@@ -763,3 +766,42 @@ def test_rk4_with_grid_point_edit_and_attention_rule():
     assert rel(want, no_mid) > 5e-3
     with pytest.raises(RuntimeError, match="read mode"):
         m.engine().sample_read(x.to(dev()), 0.0, 1.0, 0.5, "rk4", context=ctx, edit_loc="tail")
+
+
+def test_scale_sweep_full_size_model_bit_exact():
+    """U-ViT-L, 8 latents x 9 write_scales (configs/lfm_cm256_uvit_large.py:84) in one batch of 72: every row equals
+    the separate batch-8 run bit for bit - across batch sizes AND across GEMM variants (the batch of 72 runs proj / fc2 /
+    skip_linear on clusters of 4 with multicast loads, the batch of 8 on CTA pairs)."""
+    m = model("large_uncond")
+    eng = m.engine()
+    g = torch.Generator().manual_seed(1230)
+    x = torch.randn(8, 4, 32, 32, generator=g).to(dev())
+    table = 0.1 * torch.randn(5, 4, 32, 32, generator=torch.Generator().manual_seed(1232))
+    scales = [-2.1, -1.5, -1.0, -0.5, 0.0, 0.5, 1.0, 1.5, 2.0]
+    out = eng.sample_sweep(x, scales, 0.0, 1.0, 0.25, "euler", delta_table=table, t_edit=0.5, edit_loc="tail")
+    assert out.shape == (8, 9, 4, 32, 32) and torch.isfinite(out).all()
+    for s in (0, 4, 8):
+        one = eng.sample(x, 0.0, 1.0, 0.25, "euler", delta_table=table, write_scale=scales[s], t_edit=0.5,
+                         edit_loc="tail")
+        assert torch.equal(out[:, s], one)
+    assert torch.equal(out[:, 4], eng.sample(x, 0.0, 1.0, 0.25, "euler"))     # scale 0 == no edit
+
+
+@pytest.mark.parametrize("method", ["bosh3", "adaptive_heun"])
+def test_other_adaptive_methods_against_oracle(method):
+    case = CASES["tiny_uncond"]
+    m = model("tiny_uncond")
+    x = build_inputs(case)[0][:1]
+    sd = {k: v.cpu().double() for k, v in m.state_dict().items()}
+    tol = 1e-5      # the two runs may accept / reject differently; both stay within a few tol of the true solution
+    so, sg = {}, {}
+    want = O.sample_adaptive(sd, case["cfg"], x.double(), 0.0, 1.0, tol, tol, stats=so, method=method)
+    got = m.engine().sample_adaptive(x.to(dev()), 0.0, 1.0, tol, tol, stats=sg, method=method)
+    assert rel(got, want) < 1e-3
+    n_stage = {"bosh3": 3, "adaptive_heun": 1}[method]
+    assert sg["nfe"] == 2 + n_stage * (sg["n_accept"] + sg["n_reject"])
+    assert so["n_accept"] <= sg["n_accept"] <= 4 * so["n_accept"] + 4
+    # through the CNF mirror, reversed direction
+    kw = dict(dissect_name="none", solver_kwargs=dict(solver="adaptive", solver_adaptive=method))
+    dec = CNF(m).decode(x.to(dev()), y=None, **kw)
+    assert rel(dec, want) < 1e-3

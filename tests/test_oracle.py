@@ -264,3 +264,40 @@ def test_fixed_midpoint_and_rk4_orders_of_accuracy():
     k4 = f(torch.tensor(h), y0 + h * (k1 - k2 + k3))
     one = O.odeint_fixed(f, y0, 0.0, h, h, "rk4")
     assert (one - (y0 + h * (k1 + 3 * k2 + 3 * k3 + k4) / 8)).abs().max() < 1e-7
+
+
+def test_bosh3_and_adaptive_heun_tableaus_and_accuracy():
+    """Order conditions of the restated Bogacki-Shampine 3(2) and Heun 2(1) pairs, and end-to-end accuracy."""
+    for name, orders in (("bosh3", (3, 2)), ("adaptive_heun", (2, 1))):
+        tab = O.ADAPTIVE_TABLEAUS[name]
+        n = len(tab["alpha"]) + 1
+        c = np.array([0.0] + list(tab["alpha"]))
+        A = np.zeros((n, n))
+        for i, row in enumerate(tab["beta"]):
+            A[i + 1, :len(row)] = row
+        assert np.allclose(A.sum(1), c)                       # row-sum condition
+        for b, order in ((np.array(tab["c_sol"]), orders[0]), (np.array(tab["c_sol"]) - np.array(tab["c_error"]), orders[1])):
+            assert abs(b.sum() - 1) < 1e-14
+            if order >= 2:
+                assert abs(b @ c - 1 / 2) < 1e-14
+            if order >= 3:
+                assert abs(b @ c ** 2 - 1 / 3) < 1e-14 and abs(b @ A @ c - 1 / 6) < 1e-14
+        assert abs(sum(tab["c_error"])) < 1e-15
+        # the mid-point weights reproduce y(t0 + dt/2) to second order at least
+        assert abs(sum(tab["c_mid"]) - 0.5) < 1e-15
+    from scipy.integrate._ivp.rk import RK23
+    assert np.allclose(RK23.C[1:], O.ADAPTIVE_TABLEAUS["bosh3"]["alpha"][:2])
+    assert np.allclose(RK23.B, O.ADAPTIVE_TABLEAUS["bosh3"]["c_sol"][:3])
+    assert np.allclose(RK23.E, -np.array(O.ADAPTIVE_TABLEAUS["bosh3"]["c_error"]))     # scipy: E = b^ - b
+    f = lambda t, y: -2.0 * y + torch.sin(5.0 * torch.as_tensor(t)) * torch.ones_like(y)
+    y0 = torch.tensor([1.0, 0.5, -3.0], dtype=torch.float64)
+    from scipy.integrate import solve_ivp
+    ref = solve_ivp(lambda t, y: -2.0 * y + np.sin(5.0 * t), (0.0, 1.0), y0.numpy(), rtol=1e-13, atol=1e-13).y[:, -1]
+    steps = {}
+    for method in ("dopri5", "bosh3", "adaptive_heun"):
+        st = {}
+        y = O.odeint_dopri5(f, y0, 0.0, 1.0, 1e-6, 1e-6, stats=st, method=method)
+        assert np.abs(y.numpy() - ref).max() < 2e-4, method      # global error: a few hundred local tolerances
+        steps[method] = st["n_accept"] + st["n_reject"]
+        assert st["nfe"] == 2 + len(O.ADAPTIVE_TABLEAUS[method]["alpha"]) * steps[method]
+    assert steps["dopri5"] < steps["bosh3"] < steps["adaptive_heun"]     # lower order, more steps

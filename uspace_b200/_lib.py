@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libuspace_b200.so")
 
 USP_OK = 0
 METHOD = {"euler": 0, "heun": 1, "midpoint": 2, "rk4": 3}
+ADAPTIVE_METHOD = {"dopri5": 4, "bosh3": 5, "adaptive_heun": 6}
 EDIT_LOC = {None: 0, "none": 0, "head": 1, "tail": 2}
 OPERAND = {"bf16": 0, "fp16": 1}
 EPI = {"qkv": 0, "bias_gelu": 1, "bias_resid": 2, "bias_f32": 3}
@@ -48,7 +49,7 @@ _SIGNATURES = {
     "usp_forward_edit": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, C.POINTER(UspAttnEdit), _vp]),
     "usp_sample_edit": (_i, [_vp, _vp, _vp, _vp, _i, _f, _f, _f, _i, _vp, _f, _f, _i, C.POINTER(UspAttnEdit), _vp]),
     "usp_sample": (_i, [_vp, _vp, _vp, _vp, _i, _f, _f, _f, _i, _vp, _f, _f, _i, _vp]),
-    "usp_sample_adaptive": (_i, [_vp, _vp, _vp, _vp, _i, _f, _f, C.c_double, C.c_double, _vp, _i, _f, _f, _i,
+    "usp_sample_adaptive": (_i, [_vp, _vp, _vp, _vp, _i, _f, _f, _i, C.c_double, C.c_double, _vp, _i, _f, _f, _i,
                                  C.POINTER(UspAttnEdit), _i, C.POINTER(UspAdaptiveStats), _vp]),
     "usp_sample_sweep": (_i, [_vp, _vp, _vp, _vp, _vp, _i, C.POINTER(_f), _i, _f, _f, _f, _i, _vp, _f, _i, _vp]),
     "usp_sample_read": (_i, [_vp, _vp, _vp, _vp, _i, _f, _f, _f, _i, _i, _vp, _vp]),

@@ -1103,7 +1103,7 @@ int usp_sample_sweep(usp_handle* h, const float* z, float* out, const float* con
 }
 
 int usp_sample_adaptive(usp_handle* h, float* z, const float* context, const int64_t* y, int B, float t0, float t1,
-                        double rtol, double atol, const float* delta_digits, int n_rows, float write_scale,
+                        int method, double rtol, double atol, const float* delta_digits, int n_rows, float write_scale,
                         float t_edit, int edit_loc, const usp_attn_edit* attn, int max_steps,
                         usp_adaptive_stats* stats, void* stream) {
     int rc = check_ready(h, B);
@@ -1118,6 +1118,10 @@ int usp_sample_adaptive(usp_handle* h, float* z, const float* context, const int
     if ((edit_loc != USP_EDIT_NONE) != (delta_digits != nullptr))
         return fail(h, USP_ERR_INVALID, "delta_digits must be given exactly when edit_loc is head or tail");
     if (delta_digits && (n_rows < 1 || n_rows > RK_DIGITS)) return fail(h, USP_ERR_INVALID, "n_rows must be in [1, 128]");
+    if (method < USP_METHOD_DOPRI5 || method > USP_METHOD_ADAPTIVE_HEUN)
+        return fail(h, USP_ERR_INVALID, "unknown adaptive method (dopri5, bosh3, adaptive_heun)");
+    const int rkm = method - USP_METHOD_DOPRI5;
+    const int n_stage = rk_stages(rkm);
     if (!(rtol > 0.0) || !(atol >= 0.0) || !(t0 != t1) || !std::isfinite(t0) || !std::isfinite(t1))
         return fail(h, USP_ERR_INVALID, "need rtol > 0, atol >= 0 and t0 != t1");
     if (max_steps <= 0) max_steps = 1 << 20;
@@ -1175,7 +1179,7 @@ int usp_sample_adaptive(usp_handle* h, float* z, const float* context, const int
     RkArgs ra;
     memset(&ra, 0, sizeof(ra));
     ra.rs = p->rs; ra.st = p->st; ra.y0 = p->z; ra.k = p->rk_k; ra.ytmp = p->ztmp; ra.out = p->z;
-    ra.partials = p->rk_partials; ra.emask = p->mask; ra.amask = p->amask; ra.n = zel;
+    ra.partials = p->rk_partials; ra.emask = p->mask; ra.amask = p->amask; ra.n = zel; ra.method = rkm;
     auto velocity = [&](const float* x, int stage, cudaStream_t cs) -> int {
         FwdIO io;
         memset(&io, 0, sizeof(io));
@@ -1200,20 +1204,21 @@ int usp_sample_adaptive(usp_handle* h, float* z, const float* context, const int
     if (rc) return rc;
     RK_TRY(launch_rk_control(ra, 1, s));
 
-    const std::pair<int, uint64_t> key(USP_METHOD_DOPRI5 | (edit_loc << 3) | ((y ? 1 : 0) << 5) | ((use_attn ? 1 : 0) << 6) |
+    const std::pair<int, uint64_t> key(method | (edit_loc << 3) | ((y ? 1 : 0) << 5) | ((use_attn ? 1 : 0) << 6) |
                                            ((sign < 0.f ? 1 : 0) << 7),
                                        use_attn ? attn->block_mask : 0);
     auto git = p->graphs.find(key);
     if (git == p->graphs.end()) {
-        // one attempted step: six stage evaluations, error norm, controller, commit
+        // one attempted step: the stage evaluations, error norm, controller, commit
         cudaGraph_t graph = nullptr;
         CUDA_TRY(h, cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal));
         auto body = [&]() -> int {
-            for (int st = 1; st <= 6; ++st) {
+            for (int st = 1; st <= n_stage; ++st) {
                 RK_TRY(launch_rk_stage(ra, st, h->cap_stream));
                 const int r = velocity(p->ztmp, st, h->cap_stream);
                 if (r) return r;
             }
+            if (!rk_fsal(rkm)) RK_TRY(launch_rk_stage(ra, RK_SOLUTION, h->cap_stream));
             RK_TRY(launch_rk_control(ra, 2, h->cap_stream));
             RK_TRY(launch_rk_commit(ra, h->cap_stream));
             return USP_OK;

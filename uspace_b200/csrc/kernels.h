@@ -158,7 +158,11 @@ cudaError_t launch_step(StepState* st, const float* grid, const unsigned char* m
 // ---- adaptive Dormand-Prince 5(4) (csrc/ode.cu) -------------------------------------------------
 // torchdiffeq's RKAdaptiveStepsizeODESolver restated with the controller on the device: time-like quantities are
 // fp64, the state and the stage times handed to the velocity field fp32 (its mixed-precision convention).
-constexpr int RK_STAGES = 7;          // k[0..6]; k[6] of an accepted step is k[0] of the next (FSAL)
+constexpr int RK_STAGES = 7;          // k[0..6]; the last k of an accepted step is k[0] of the next
+constexpr int RK_SOLUTION = 100;      // pseudo-stage of launch_rk_stage: ytmp = y0 + dt * sum c_sol[j] k[j] (non-FSAL methods)
+enum RkMethod : int { RK_DOPRI5 = 0, RK_BOSH3 = 1, RK_ADAPTIVE_HEUN = 2 };
+int rk_stages(int method);            // velocity evaluations per attempted step: 6 / 3 / 1
+bool rk_fsal(int method);             // the last stage's state is the step's solution
 constexpr int RK_MAX_PARTIALS = 4096;
 constexpr int RK_DIGITS = 128;        // rows of the "%.2f"-indexed edit masks (0.00 .. 1.27)
 struct RkState {
@@ -189,6 +193,7 @@ struct RkArgs {
     const unsigned char* emask;   // [RK_DIGITS] write-edit active for digit i
     const unsigned char* amask;   // [RK_DIGITS] attention edit active for digit i
     long long n;
+    int method;                // RkMethod
 };
 // stage 1..6: ytmp = y0 + dt * sum_j beta[stage][j] k_j and the stage time; stage 0: time of the very first
 // evaluation; stage -1: the probe point of the starting-step search (ytmp = y0 + h0 * k0)

@@ -15,25 +15,53 @@
 namespace usp {
 namespace {
 
-__constant__ float c_beta[6][6] = {
-    {1.f / 5, 0, 0, 0, 0, 0},
-    {3.f / 40, 9.f / 40, 0, 0, 0, 0},
-    {44.f / 45, -56.f / 15, 32.f / 9, 0, 0, 0},
-    {19372.f / 6561, -25360.f / 2187, 64448.f / 6561, -212.f / 729, 0, 0},
-    {9017.f / 3168, -355.f / 33, 46732.f / 5247, 49.f / 176, -5103.f / 18656, 0},
-    {35.f / 384, 0.f, 500.f / 1113, 125.f / 192, -2187.f / 6784, 11.f / 84},
+// Butcher tableaus of torchdiffeq's adaptive explicit methods (k[0] = f(t0, y0); stage i evaluates at
+// t0 + alpha[i-1] dt, y0 + dt sum_j beta[i-1][j] k[j]).  fsal: the last stage's state IS the solution (c_sol[:-1] ==
+// beta[-1]); otherwise y1 = y0 + dt sum c_sol[j] k[j] is formed separately - and, as in torchdiffeq, the derivative
+// carried into the next step is still the last stage's (for adaptive_heun that is f(t1, y0 + dt k0), not f(t1, y1)).
+struct Tableau {
+    int stages;    // evaluations per attempted step
+    int order;     // step-size exponent 1 / order; the starting step uses the same exponent
+    int fsal;
+    float alpha[6];
+    float beta[6][6];
+    float c_sol[7];
+    float c_err[7];
+    float c_mid[7];   // y(t0 + dt/2) ~ y0 + dt sum c_mid[j] k[j], for the 4th-order Hermite-type dense output
 };
-__constant__ float c_alpha[6] = {1.f / 5, 3.f / 10, 4.f / 5, 8.f / 9, 1.f, 1.f};
-// Shampine's companion weights (c_sol - c_hat), the pair torchdiffeq calls "dopri5"
-__constant__ float c_err[7] = {
-    static_cast<float>(35.0 / 384 - 1951.0 / 21600), 0.f, static_cast<float>(500.0 / 1113 - 22642.0 / 50085),
-    static_cast<float>(125.0 / 192 - 451.0 / 720),   static_cast<float>(-2187.0 / 6784 + 12231.0 / 42400),
-    static_cast<float>(11.0 / 84 - 649.0 / 6300),    static_cast<float>(-1.0 / 60)};
-__constant__ float c_mid[7] = {
-    static_cast<float>(6025192743.0 / 30085553152.0 / 2),   0.f,
-    static_cast<float>(51252292925.0 / 65400821598.0 / 2),  static_cast<float>(-2691868925.0 / 45128329728.0 / 2),
-    static_cast<float>(187940372067.0 / 1594534317056.0 / 2), static_cast<float>(-1776094331.0 / 19743644256.0 / 2),
-    static_cast<float>(11237099.0 / 235043384.0 / 2)};
+#define D_(x) static_cast<float>(x)
+__constant__ Tableau c_tab[3] = {
+    // dopri5: Dormand-Prince 5(4) with Shampine's companion weights
+    {6, 5, 1,
+     {1.f / 5, 3.f / 10, 4.f / 5, 8.f / 9, 1.f, 1.f},
+     {{1.f / 5, 0, 0, 0, 0, 0},
+      {3.f / 40, 9.f / 40, 0, 0, 0, 0},
+      {44.f / 45, -56.f / 15, 32.f / 9, 0, 0, 0},
+      {19372.f / 6561, -25360.f / 2187, 64448.f / 6561, -212.f / 729, 0, 0},
+      {9017.f / 3168, -355.f / 33, 46732.f / 5247, 49.f / 176, -5103.f / 18656, 0},
+      {35.f / 384, 0.f, 500.f / 1113, 125.f / 192, -2187.f / 6784, 11.f / 84}},
+     {35.f / 384, 0.f, 500.f / 1113, 125.f / 192, -2187.f / 6784, 11.f / 84, 0.f},
+     {D_(35.0 / 384 - 1951.0 / 21600), 0.f, D_(500.0 / 1113 - 22642.0 / 50085), D_(125.0 / 192 - 451.0 / 720),
+      D_(-2187.0 / 6784 + 12231.0 / 42400), D_(11.0 / 84 - 649.0 / 6300), D_(-1.0 / 60)},
+     {D_(6025192743.0 / 30085553152.0 / 2), 0.f, D_(51252292925.0 / 65400821598.0 / 2),
+      D_(-2691868925.0 / 45128329728.0 / 2), D_(187940372067.0 / 1594534317056.0 / 2),
+      D_(-1776094331.0 / 19743644256.0 / 2), D_(11237099.0 / 235043384.0 / 2)}},
+    // bosh3: Bogacki-Shampine 3(2)
+    {3, 3, 1,
+     {1.f / 2, 3.f / 4, 1.f, 0, 0, 0},
+     {{1.f / 2, 0, 0, 0, 0, 0}, {0.f, 3.f / 4, 0, 0, 0, 0}, {2.f / 9, 1.f / 3, 4.f / 9, 0, 0, 0}, {0}, {0}, {0}},
+     {2.f / 9, 1.f / 3, 4.f / 9, 0.f, 0, 0, 0},
+     {D_(2.0 / 9 - 7.0 / 24), D_(1.0 / 3 - 1.0 / 4), D_(4.0 / 9 - 1.0 / 3), D_(-1.0 / 8), 0, 0, 0},
+     {0.f, 0.5f, 0.f, 0.f, 0, 0, 0}},
+    // adaptive_heun: Heun 2(1)
+    {1, 2, 0,
+     {1.f, 0, 0, 0, 0, 0},
+     {{1.f, 0, 0, 0, 0, 0}, {0}, {0}, {0}, {0}, {0}},
+     {0.5f, 0.5f, 0, 0, 0, 0, 0},
+     {0.5f, -0.5f, 0, 0, 0, 0, 0},
+     {0.5f, 0.f, 0, 0, 0, 0, 0}},
+};
+#undef D_
 
 constexpr int RK_THREADS = 256;
 
@@ -62,11 +90,16 @@ __global__ void __launch_bounds__(RK_THREADS) rk_stage_kernel(RkArgs a, int stag
     const RkState* rs = a.rs;
     const float s0f = static_cast<float>(rs->s0);
     float dtf, s_stage;
-    if (stage > 0) {
+    const Tableau& T = c_tab[a.method];
+    const bool solution = stage == RK_SOLUTION;    // y1 of a non-FSAL method: a combination only, no evaluation
+    if (solution) {
+        dtf = static_cast<float>(rs->dt);
+        s_stage = 0.f;
+    } else if (stage > 0) {
         dtf = static_cast<float>(rs->dt);
         // t1 = (t0 + dt) rounded once; inner stages t0 + alpha * dt in the state's precision
-        s_stage = c_alpha[stage - 1] == 1.f ? static_cast<float>(rs->s0 + rs->dt)
-                                            : __fadd_rn(s0f, __fmul_rn(c_alpha[stage - 1], dtf));
+        s_stage = T.alpha[stage - 1] == 1.f ? static_cast<float>(rs->s0 + rs->dt)
+                                            : __fadd_rn(s0f, __fmul_rn(T.alpha[stage - 1], dtf));
     } else if (stage == 0) {
         dtf = 0.f;
         s_stage = s0f;
@@ -74,17 +107,21 @@ __global__ void __launch_bounds__(RK_THREADS) rk_stage_kernel(RkArgs a, int stag
         dtf = rs->h0;
         s_stage = static_cast<float>(rs->s0 + static_cast<double>(rs->h0));
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) set_stage_time(a, s_stage);
+    if (blockIdx.x == 0 && threadIdx.x == 0 && !solution) set_stage_time(a, s_stage);
     if (stage == 0) return;
-    float w[6];
-    const int nk = stage > 0 ? stage : 1;
+    float w[RK_STAGES];
+    const int nk = solution ? T.stages + 1 : (stage > 0 ? stage : 1);
 #pragma unroll
-    for (int j = 0; j < 6; ++j) w[j] = stage > 0 ? __fmul_rn(c_beta[stage - 1][j], dtf) : dtf;
+    for (int j = 0; j < RK_STAGES; ++j) {
+        if (solution) w[j] = __fmul_rn(T.c_sol[j], dtf);
+        else if (stage > 0) w[j] = j < 6 ? __fmul_rn(T.beta[stage - 1][j], dtf) : 0.f;
+        else w[j] = dtf;
+    }
     const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
     for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < a.n; i += stride) {
         float acc = 0.f;
 #pragma unroll
-        for (int j = 0; j < 6; ++j)
+        for (int j = 0; j < RK_STAGES; ++j)
             if (j < nk) acc = fmaf(a.k[j * a.n + i], w[j], acc);
         a.ytmp[i] = a.y0[i] + acc;
     }
@@ -107,6 +144,7 @@ __global__ void __launch_bounds__(RK_THREADS) rk_norm_kernel(RkArgs a, int what)
     const RkState* rs = a.rs;
     const float rtol = static_cast<float>(rs->rtol), atol = static_cast<float>(rs->atol);
     const float dtf = static_cast<float>(rs->dt);
+    const Tableau& T = c_tab[a.method];
     double p0 = 0.0, p1 = 0.0;
     const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
     for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < a.n; i += stride) {
@@ -123,7 +161,8 @@ __global__ void __launch_bounds__(RK_THREADS) rk_norm_kernel(RkArgs a, int what)
         } else {
             float e = 0.f;
 #pragma unroll
-            for (int j = 0; j < RK_STAGES; ++j) e = fmaf(a.k[j * a.n + i], __fmul_rn(c_err[j], dtf), e);
+            for (int j = 0; j < RK_STAGES; ++j)
+                if (j <= T.stages) e = fmaf(a.k[j * a.n + i], __fmul_rn(T.c_err[j], dtf), e);
             const float tol = atol + rtol * fmaxf(fabsf(y0), fabsf(a.ytmp[i]));
             const float u = e / tol;
             p0 += static_cast<double>(u) * u;
@@ -147,6 +186,7 @@ __global__ void __launch_bounds__(RK_THREADS) rk_control_kernel(RkArgs a, int wh
     p1 = block_sum(p1);
     if (threadIdx.x != 0) return;
     RkState* rs = a.rs;
+    const Tableau& T = c_tab[a.method];
     const double inv_n = 1.0 / static_cast<double>(a.n);
     if (what == 0) {
         const float d0 = static_cast<float>(sqrt(p0 * inv_n)), d1 = static_cast<float>(sqrt(p1 * inv_n));
@@ -159,7 +199,7 @@ __global__ void __launch_bounds__(RK_THREADS) rk_control_kernel(RkArgs a, int wh
         const float d2 = fabsf(static_cast<float>(sqrt(p0 * inv_n)) / h0);
         float h1;
         if (d1 <= 1e-15f && d2 <= 1e-15f) h1 = fmaxf(1e-6f, h0 * 1e-3f);
-        else h1 = powf(0.01f / fmaxf(d1, d2), 1.f / 5.f);
+        else h1 = powf(0.01f / fmaxf(d1, d2), 1.f / static_cast<float>(T.order));
         rs->dt = static_cast<double>(fminf(100.f * h0, fabsf(h1)));
         rs->nfe = 2;
     } else {
@@ -170,13 +210,13 @@ __global__ void __launch_bounds__(RK_THREADS) rk_control_kernel(RkArgs a, int wh
         if (ratio == 0.f) factor = 10.0;
         else {
             const double dfac = ratio < 1.f ? 1.0 : 0.2;
-            factor = fmin(10.0, fmax(0.9 / pow(static_cast<double>(ratio), 0.2), dfac));
+            factor = fmin(10.0, fmax(0.9 / pow(static_cast<double>(ratio), 1.0 / T.order), dfac));
         }
         rs->ratio = ratio;
         rs->accept = accept ? 1 : 0;
         rs->s0_prev = s0;
         rs->dt_prev = dt;
-        rs->nfe += 6;
+        rs->nfe += T.stages;
         if (accept) {
             rs->n_accept += 1;
             if (s0 + dt >= rs->s_end) rs->done = 1;
@@ -191,22 +231,25 @@ __global__ void __launch_bounds__(RK_THREADS) rk_control_kernel(RkArgs a, int wh
 __global__ void __launch_bounds__(RK_THREADS) rk_commit_kernel(RkArgs a) {
     const RkState* rs = a.rs;
     if (!rs->accept) return;
+    const Tableau& T = c_tab[a.method];
+    const long long last = static_cast<long long>(T.stages) * a.n;
     const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
     const long long i0 = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (!rs->done) {
         for (long long i = i0; i < a.n; i += stride) {
             a.y0[i] = a.ytmp[i];
-            a.k[i] = a.k[6 * a.n + i];
+            a.k[i] = a.k[last + i];
         }
         return;
     }
     const float dtf = static_cast<float>(rs->dt_prev);
     const float x = static_cast<float>((rs->s_end - rs->s0_prev) / rs->dt_prev);
     for (long long i = i0; i < a.n; i += stride) {
-        const float y0 = a.y0[i], y1 = a.ytmp[i], f0 = a.k[i], f1 = a.k[6 * a.n + i];
+        const float y0 = a.y0[i], y1 = a.ytmp[i], f0 = a.k[i], f1 = a.k[last + i];
         float m = 0.f;
 #pragma unroll
-        for (int j = 0; j < RK_STAGES; ++j) m = fmaf(a.k[j * a.n + i], __fmul_rn(c_mid[j], dtf), m);
+        for (int j = 0; j < RK_STAGES; ++j)
+            if (j <= T.stages) m = fmaf(a.k[j * a.n + i], __fmul_rn(T.c_mid[j], dtf), m);
         const float ym = y0 + m;
         const float ca = 2.f * dtf * (f1 - f0) - 8.f * (y1 + y0) + 16.f * ym;
         const float cb = dtf * (5.f * f0 - 3.f * f1) + 18.f * y0 + 14.f * y1 - 32.f * ym;
@@ -225,8 +268,15 @@ __global__ void __launch_bounds__(RK_THREADS) rk_commit_kernel(RkArgs a) {
 
 }  // namespace
 
+int rk_stages(int method) {
+    static const int n[3] = {6, 3, 1};
+    return method >= 0 && method < 3 ? n[method] : 0;
+}
+bool rk_fsal(int method) { return method != 2; }
+
 cudaError_t launch_rk_stage(const RkArgs& a, int stage, cudaStream_t s) {
-    if (stage < -1 || stage > 6) return cudaErrorInvalidValue;
+    if (a.method < 0 || a.method > 2) return cudaErrorInvalidValue;
+    if (stage != RK_SOLUTION && (stage < -1 || stage > rk_stages(a.method))) return cudaErrorInvalidValue;
     rk_stage_kernel<<<stage == 0 ? 1 : rk_blocks(a.n), RK_THREADS, 0, s>>>(a, stage);
     return cudaGetLastError();
 }

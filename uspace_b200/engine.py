@@ -140,8 +140,9 @@ class Engine:
         return zz
 
     def sample_adaptive(self, z, t0=0.0, t1=1.0, rtol=1e-5, atol=1e-5, y=None, context=None, delta_digits=None,
-                        write_scale=0.0, t_edit=0.0, edit_loc=None, attn_edit=None, max_steps=0, stats=None):
-        """Adaptive dopri5 (torchdiffeq semantics) from t0 to t1; returns a new tensor.  ``delta_digits`` rows are
+                        write_scale=0.0, t_edit=0.0, edit_loc=None, attn_edit=None, max_steps=0, stats=None,
+                        method="dopri5"):
+        """Adaptive dopri5 / bosh3 / adaptive_heun (torchdiffeq semantics) from t0 to t1; returns a new tensor.  ``delta_digits`` rows are
         keyed by the "%.2f" digit of the evaluation time.  ``stats`` (dict) receives n_accept / n_reject / nfe.
         Synchronises the current stream (the host reads the step controller's verdict once per attempted step)."""
         self._check_latent(z)
@@ -159,7 +160,8 @@ class Engine:
                 raise ValueError(f"delta_digits must be [<=128,{self.C},{self.S},{self.S}]")
         edit, _keep = self._attn_edit(attn_edit, B)
         st = _lib.UspAdaptiveStats()
-        _lib.check(self.lib.usp_sample_adaptive(self.handle, _ptr(zz), _ptr(context), _ptr(y), B, t0, t1, rtol, atol,
+        _lib.check(self.lib.usp_sample_adaptive(self.handle, _ptr(zz), _ptr(context), _ptr(y), B, t0, t1,
+                                                _lib.ADAPTIVE_METHOD[method], rtol, atol,
                                                 _ptr(delta_digits), n_rows, write_scale, t_edit,
                                                 _lib.EDIT_LOC[edit_loc], C.byref(edit) if edit is not None else None,
                                                 int(max_steps), C.byref(st), self._stream()),

@@ -5,11 +5,11 @@
 Euler / Heun loop: one CUDA-graph-captured step replayed on the current stream, no host sync per NFE.
 
 Built: ``solver="fixed"`` with ``solver_fix`` in {"euler", "heun", "midpoint", "rk4"}; ``solver="adaptive"`` / the non-dissection
-default / the adaptive tail of ``"fixadp"`` with dopri5 (step control and dense output on the device, torchdiffeq
+default / the adaptive tail of ``"fixadp"`` with dopri5, bosh3 or adaptive_heun (step control and dense output on the device, torchdiffeq
 semantics restated in csrc/ode.cu); the "write_attr" / "write_pca" edit hook at ``edit_loc`` head / tail
 (libs/dissection.py:115-186) through a pre-loaded delta table, and its "read" mode (the activation at ``edit_loc``
 of every evaluation, saved as ``{batch_id}_{t:.2f}.npy``) on the fixed grid; the "p2p_rescale" attention edit.
-Not built (NotImplementedError): other torchdiffeq methods (bosh3, adaptive_heun, ...), "read" under an
+Not built (NotImplementedError): other torchdiffeq methods (dopri8, fehlberg2, implicit_adams, ...), "read" under an
 adaptive solver, ``edit_loc="mid"`` (broken in the reference for U-ViT).
 """
 from __future__ import annotations
@@ -24,7 +24,7 @@ from torch import Tensor
 from .engine import time_grid
 
 _FIXED_METHODS = ("euler", "heun", "midpoint", "rk4")
-_ADAPTIVE_METHODS = ("dopri5",)
+_ADAPTIVE_METHODS = ("dopri5", "bosh3", "adaptive_heun")
 _RTOL = 1e-5   # flow_matching.py:11-12
 _ATOL = 1e-5
 
@@ -233,7 +233,8 @@ class _CNFBase(nn.Module):
         self.last_solver_stats = {}
         return engine.sample_adaptive(z, t0, t1, ode_kwargs["rtol"], ode_kwargs["atol"], delta_digits=table,
                                       write_scale=ws, t_edit=float("inf"), edit_loc=loc, attn_edit=attn,
-                                      stats=self.last_solver_stats, **self._cond_kw(cond))
+                                      stats=self.last_solver_stats, method=ode_kwargs["method"],
+                                      **self._cond_kw(cond))
 
     def _integrate_read(self, engine, z, cond, t0, t1, ode_kwargs, **kwargs) -> Tensor:
         """dissect_name="read" (libs/dissection.py:126-136): np.save(f"{read_path_root}/{batch_id}_{t:.2f}", x) for the
