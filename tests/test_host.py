@@ -139,7 +139,7 @@ def test_cnf_rejects_unbuilt_solvers():
     for solver in ("adaptive", "fixadp"):
         with pytest.raises(NotImplementedError):
             cnf.decode(z, ctx, dissect_name="p2p", t_edit=0.4,
-                       solver_kwargs=dict(solver=solver, solver_fix="euler", solver_fix_step=0.1, solver_adaptive="bosh3"))
+                       solver_kwargs=dict(solver=solver, solver_fix="euler", solver_fix_step=0.1, solver_adaptive="dopri8"))
     with pytest.raises(NotImplementedError):
         cnf.decode(z, ctx, dissect_name="p2p", solver_kwargs=dict(solver="other"))
     with pytest.raises(KeyError):   # the reference indexes kwargs["solver_kwargs"] unconditionally (flow_matching.py:138)
