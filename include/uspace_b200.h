@@ -139,6 +139,22 @@ int usp_sample_adaptive(usp_handle* h, float* z, const float* context, const int
                         int method, double rtol, double atol, const float* delta_digits, int n_rows, float write_scale,
                         float t_edit, int edit_loc, const usp_attn_edit* attn, int max_steps,
                         usp_adaptive_stats* stats, void* stream);
+/* ---- latent -> image decoder -------------------------------------------------------------------------------------
+ * Replaces FrozenAutoencoderKL.decode (libs/autoencoder.py:446-450: z / scale_factor -> post_quant_conv -> Decoder),
+ * the call dissect_lfm.py:86-98 / train_lfm.py make on every batch of sampled latents. Only the configuration of
+ * libs/autoencoder.py::get_model is built (ch 128, ch_mult 1-2-4-4, 2 res blocks, z_channels 4). Weight names are the
+ * reference state_dict keys "decoder.*" and "post_quant_conv.*" (fp32, host or device).
+ *   z [B, 4, S, S] (S in {16, 32, 48, 64}; 32 for the 256^2 models)  ->  out [B, 3, 8S, 8S], device pointers. */
+typedef struct usp_vae usp_vae;
+int usp_vae_create(int device, float scale_factor, usp_vae** out);
+void usp_vae_destroy(usp_vae* h);
+const char* usp_vae_last_error(const usp_vae* h);   /* h may be NULL: message of the last failed usp_vae_create */
+int usp_vae_num_weights(const usp_vae* h);
+const char* usp_vae_weight_name(const usp_vae* h, int i);
+int usp_vae_set_weight(usp_vae* h, const char* name, const void* data, const int64_t* shape, int ndim);
+int usp_vae_finalize(usp_vae* h, void* stream);      /* packs the convolution weights; synchronises */
+int usp_vae_decode(usp_vae* h, const float* z, float* out, int B, int S, void* stream);
+
 /* Same with HOST buffers: copies z (and context / y / delta_table) host->device, samples, copies z back,
  * and synchronises. This is the end-to-end call bench.py times. */
 int usp_sample_host(usp_handle* h, float* z_host, const float* context_host, const int64_t* y_host, int B, float t0,

@@ -57,3 +57,29 @@ def attr_delta_inputs():
     attr = (rng.random((B, 11)) < 0.5).astype(np.int64)
     attr[0], attr[1] = 1, 0          # every attribute has at least one positive and one negative sample
     return feats, latent, attr, times, batch_num
+
+
+# ---- latent -> image decoder (libs/autoencoder.py) ----------------------------------------------------------
+VAE_CASES = dict(seed=11, vae_small=dict(B=2, S=16, in_seed=21), vae_full=dict(B=1, S=32, in_seed=22))
+
+
+def vae_model():
+    """The mirror modules under the golden seed (== the reference's Decoder + post_quant_conv under that seed)."""
+    from uspace_b200.autoencoder import DDCONFIG, Decoder
+    torch.manual_seed(VAE_CASES["seed"])
+    dec = Decoder(**DDCONFIG)
+    pq = torch.nn.Conv2d(4, 4, 1)
+    return dec, pq
+
+
+def vae_state_dict():
+    dec, pq = vae_model()
+    sd = {f"decoder.{k}": v for k, v in dec.state_dict().items()}
+    sd.update({f"post_quant_conv.{k}": v for k, v in pq.state_dict().items()})
+    return sd
+
+
+def vae_latents(name):
+    c = VAE_CASES[name]
+    g = torch.Generator().manual_seed(c["in_seed"])
+    return 0.18215 * 4.0 * torch.randn(c["B"], 4, c["S"], c["S"], generator=g)    # scaled like encoded latents

@@ -805,3 +805,48 @@ def test_other_adaptive_methods_against_oracle(method):
     kw = dict(dissect_name="none", solver_kwargs=dict(solver="adaptive", solver_adaptive=method))
     dec = CNF(m).decode(x.to(dev()), y=None, **kw)
     assert rel(dec, want) < 1e-3
+
+
+# ---- latent -> image decoder (csrc/vae.cu) -----------------------------------------------------------------------
+VAE_TOL = 5e-3   # fp16 GEMM operands through 37 convolutions + GroupNorms; fp32 accumulate / residual / statistics
+
+_vae = {}
+
+
+def vae_model_gpu():
+    if "m" not in _vae:
+        from tests.golden.cases import vae_state_dict
+        from uspace_b200.autoencoder import get_model
+        m = get_model()
+        m.load_state_dict(vae_state_dict())
+        _vae["m"] = m.to(dev())
+    return _vae["m"]
+
+
+@pytest.mark.parametrize("name", ["vae_small", "vae_full"])
+def test_vae_decode_matches_reference_golden(golden_dir, name):
+    from tests.golden.cases import vae_latents
+    m = vae_model_gpu()
+    z = vae_latents(name)
+    got = m.decode(z.to(dev()))
+    want = golden(golden_dir, name)["decode"]
+    assert tuple(got.shape) == want.shape
+    assert rel(got, want) < VAE_TOL
+    assert torch.equal(m(z.to(dev()), "decode"), got)         # forward(inputs, fn) dispatch, deterministic
+
+
+def test_vae_decode_batch_independence_and_chunking():
+    """Chunks of 8 inside the library, GroupNorm statistics per sample: every image equals its own batch-1 decode."""
+    m = vae_model_gpu()
+    g = torch.Generator().manual_seed(5)
+    z = (0.7 * torch.randn(11, 4, 16, 16, generator=g)).to(dev())
+    out = m.decode(z)
+    assert out.shape == (11, 3, 128, 128) and torch.isfinite(out).all()
+    for i in (0, 7, 8, 10):
+        assert torch.equal(out[i:i + 1], m.decode(z[i:i + 1]))
+    from oracle import vae_oracle as V
+    from tests.golden.cases import vae_state_dict
+    want = V.decode({k: v.double() for k, v in vae_state_dict().items()}, z[9:11].cpu().double())
+    assert rel(out[9:11], want) < VAE_TOL
+    with pytest.raises(ValueError):
+        m.decode(torch.zeros(1, 4, 10, 10, device=dev()))

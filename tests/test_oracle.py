@@ -301,3 +301,37 @@ def test_bosh3_and_adaptive_heun_tableaus_and_accuracy():
         steps[method] = st["n_accept"] + st["n_reject"]
         assert st["nfe"] == 2 + len(O.ADAPTIVE_TABLEAUS[method]["alpha"]) * steps[method]
     assert steps["dopri5"] < steps["bosh3"] < steps["adaptive_heun"]     # lower order, more steps
+
+
+# ---- latent -> image decoder ------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["vae_small", "vae_full"])
+def test_vae_oracle_matches_reference_golden(golden_dir, name):
+    from oracle import vae_oracle as V
+    from tests.golden.cases import vae_latents, vae_state_dict
+    sd = vae_state_dict()
+    got = V.decode(sd, vae_latents(name))
+    want = load(golden_dir, name)["decode"]
+    assert got.shape == want.shape and rel(got, want) < 5e-6
+
+
+def test_vae_mirror_state_dict_layout_and_flops():
+    from oracle import vae_oracle as V
+    from uspace_b200.autoencoder import FrozenAutoencoderKL, get_model
+    m = get_model()
+    sd = m.state_dict()
+    assert len(sd) == 140 and sum(v.numel() for v in sd.values()) == 49490179 + 20   # Decoder + post_quant_conv
+    assert sd["decoder.up.1.block.0.nin_shortcut.weight"].shape == (256, 512, 1, 1)
+    assert sd["decoder.up.3.upsample.conv.weight"].shape == (512, 512, 3, 3)
+    assert "decoder.up.0.upsample.conv.weight" not in sd and sd["post_quant_conv.weight"].shape == (4, 4, 1, 1)
+    # a full reference checkpoint (encoder half included) loads; unknown keys do not
+    full = dict(sd, **{"encoder.conv_in.weight": torch.zeros(1), "quant_conv.weight": torch.zeros(1)})
+    m.load_state_dict(full)
+    with pytest.raises(RuntimeError):
+        m.load_state_dict(dict(sd, bogus=torch.zeros(1)))
+    with pytest.raises(RuntimeError, match="no CPU"):
+        m.decode(torch.zeros(1, 4, 32, 32))
+    with pytest.raises(NotImplementedError):
+        m.encode(torch.zeros(1, 3, 256, 256))
+    with pytest.raises(NotImplementedError):
+        FrozenAutoencoderKL(dict(V.DDCONFIG, ch=64))
+    assert V.flops_per_image(32) / 1e9 == pytest.approx(622.19, rel=1e-3)      # 0.62 TFLOP per 256^2 image

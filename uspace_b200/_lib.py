@@ -61,6 +61,14 @@ _SIGNATURES = {
     "usp_flops_per_forward": (C.c_double, [_vp]),
     "usp_last_forward_ms": (_i, [_vp, C.POINTER(_f)]),
     "usp_profile_forward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, C.POINTER(_f), C.POINTER(_i), _vp]),
+    "usp_vae_create": (_i, [_i, _f, C.POINTER(_vp)]),
+    "usp_vae_destroy": (None, [_vp]),
+    "usp_vae_last_error": (C.c_char_p, [_vp]),
+    "usp_vae_num_weights": (_i, [_vp]),
+    "usp_vae_weight_name": (C.c_char_p, [_vp, _i]),
+    "usp_vae_set_weight": (_i, [_vp, C.c_char_p, _vp, C.POINTER(_i64), _i]),
+    "usp_vae_finalize": (_i, [_vp, _vp]),
+    "usp_vae_decode": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
     "usp_op_convert16": (_i, [_vp, _vp, _i64, _i, _vp]),
     "usp_op_gemm": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "usp_op_attention": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
@@ -91,7 +99,7 @@ def load():
     return lib
 
 
-def check(rc: int, handle=None, what: str = "uspace_b200"):
+def check(rc: int, handle=None, what: str = "uspace_b200", vae: bool = False):
     if rc != USP_OK:
-        msg = load().usp_last_error(handle)
+        msg = load().usp_vae_last_error(handle) if (vae or what.startswith("usp_vae")) else load().usp_last_error(handle)
         raise RuntimeError(f"{what} failed (status {rc}): {msg.decode() if msg else '?'}")

@@ -1338,6 +1338,37 @@ int usp_op_convert16(const float* in, void* out16, int64_t n, int operand_dtype,
     return e == cudaSuccess ? USP_OK : op_fail("convert16", e);
 }
 
+}  // extern "C"
+
+namespace usp {
+// C[M,N] = A[M,K] W[N,K]^T + epilogue on raw device pointers (tensor maps are encoded per call): the GEMM entry of the
+// latent decoder (csrc/vae.cu).  Returns a message on failure.
+const char* gemm_raw(int epilogue, const void* a16, const void* w16, const float* bias, const float* resid,
+                     float* out32, void* out16, int M, int N, int K, int operand_dtype, int num_sms, cudaStream_t s) {
+    if (!get_encode_fn()) return "cuTensorMapEncodeTiled entry point not found";
+    if (gemm_configure() != cudaSuccess) return "gemm_configure failed";
+    GemmMaps maps;
+    bool ok = make_map_2d(&maps.a0, a16, M, K, GEMM_BM, operand_dtype);
+    maps.a1 = maps.a0;
+    ok &= make_map_2d(&maps.b, w16, N, K, gemm_weight_box_rows(), operand_dtype);
+    if (out32 != nullptr) {
+        maps.has_f32 = make_map_f32(&maps.o32, out32, M, N);
+        if (resid != nullptr) maps.has_f32 = maps.has_f32 && make_map_f32(&maps.r32, resid, M, N);
+        else maps.r32 = maps.o32;
+    }
+    if (!ok) return "cuTensorMapEncodeTiled failed";
+    GemmArgs g;
+    memset(&g, 0, sizeof(g));
+    g.M = M; g.N = N; g.K = K; g.K0 = K; g.opd = operand_dtype;
+    g.bias = bias; g.resid = resid; g.out32 = out32; g.out16 = out16;
+    g.L = 1; g.H = 1;
+    cudaError_t e = launch_gemm(epilogue, maps, g, num_sms, s);
+    return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+}
+}  // namespace usp
+
+extern "C" {
+
 int usp_op_gemm(int epilogue, const void* a16, const void* a16_second, const void* w16, const float* bias,
                 const float* resid, float* out32, void* out16, int M, int N, int K, int K0, int L, int H,
                 int operand_dtype, void* stream) {

@@ -155,6 +155,10 @@ cudaError_t launch_fold_ln(const float* W, const float* gamma, const float* beta
 cudaError_t launch_step(StepState* st, const float* grid, const unsigned char* mask, const unsigned char* amask,
                         int stage, cudaStream_t s, float frac = 0.f);
 
+// GEMM on raw device pointers (api.cu): nullptr on success, else a message
+const char* gemm_raw(int epilogue, const void* a16, const void* w16, const float* bias, const float* resid,
+                     float* out32, void* out16, int M, int N, int K, int operand_dtype, int num_sms, cudaStream_t s);
+
 // ---- adaptive Dormand-Prince 5(4) (csrc/ode.cu) -------------------------------------------------
 // torchdiffeq's RKAdaptiveStepsizeODESolver restated with the controller on the device: time-like quantities are
 // fp64, the state and the stage times handed to the velocity field fp32 (its mixed-precision convention).

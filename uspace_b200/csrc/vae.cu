@@ -1,0 +1,581 @@
+// Latent -> image decoder (FrozenAutoencoderKL.decode, libs/autoencoder.py:446-450 -> Decoder.forward :376-409):
+// the step right after the sampling path (dissect_lfm.py:86-98).  SURVEY.md section 8f "next-4".
+//
+// Layout: activations are NHWC, fp32 "residual" copies [B*H*W, C] plus fp16 GEMM operands.  Every convolution is a
+// GEMM on the tcgen05 kernels of the U-ViT path (csrc/gemm2.cu / gemm.cu through gemm_raw):
+//   3x3 conv  = im2col (fp16, K ordered (ky, kx, c), optional nearest x2 upsample folded into the gather) x W[Cout, 9C]
+//   1x1 conv  = the fp16 activation itself x W[Cout, Cin]
+// with bias (+ residual for the second conv of a ResnetBlock and for the attention's proj_out) in the GEMM epilogue,
+// which writes the NHWC fp32 result directly (row m = pixel, column n = output channel).  GroupNorm(32, eps 1e-6) +
+// swish produce the next fp16 operand (two-stage deterministic statistics, no atomics).  The single 1024-token
+// attention block is three GEMMs per image (q k^T, softmax rows, P v) - 1 GFLOP of 620.
+// Everything here is either a GEMM (tensor pipe) or a streaming pass (HBM); the im2col matrix is the price of reusing
+// the GEMM kernel unchanged (302 MB per image for the largest layer, written and read once).
+#include <cuda_fp16.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/uspace_b200.h"
+#include "common.cuh"
+#include "kernels.h"
+
+namespace usp {
+cudaError_t gemm_configure();
+namespace {
+
+constexpr int VT = 256;   // threads per block of the streaming kernels
+
+// ---- weights ------------------------------------------------------------------------------------------------
+// conv weight [Co, Ci, kh, kw] fp32 -> fp16 [Np, Kp] with k = (ky*kw + kx)*Ci + ci, zero padded
+__global__ void pack_conv_kernel(const float* __restrict__ w, __half* __restrict__ out, int Co, int Ci, int ks, int Np,
+                                 int Kp) {
+    const long long n = static_cast<long long>(Np) * Kp;
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const int co = static_cast<int>(i / Kp), k = static_cast<int>(i % Kp);
+        float v = 0.f;
+        if (co < Co && k < ks * ks * Ci) {
+            const int tap = k / Ci, ci = k % Ci;
+            v = w[((static_cast<long long>(co) * Ci + ci) * ks + tap / ks) * ks + tap % ks];
+        }
+        out[i] = __float2half_rn(v);
+    }
+}
+
+// ---- input: z NCHW / scale_factor -> post_quant_conv (1x1, 4 -> 4) -> fp16 NHWC ----------------------------------
+__global__ void vae_in_kernel(const float* __restrict__ z, const float* __restrict__ w, const float* __restrict__ b,
+                              __half* __restrict__ out, int B, int S, float inv_scale) {
+    const long long n = static_cast<long long>(B) * S * S;
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int bi = static_cast<int>(i / (S * S)), p = static_cast<int>(i % (S * S));
+    float v[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) v[c] = z[(static_cast<long long>(bi) * 4 + c) * S * S + p] * inv_scale;
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+        float acc = b[o];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc = fmaf(w[o * 4 + c], v[c], acc);
+        out[i * 4 + o] = __float2half_rn(acc);
+    }
+}
+
+// ---- im2col -------------------------------------------------------------------------------------------------------
+// in16 [B, Hin, Win, C] -> A [B*H*W, Kp] (H = Hin*up), A[m][(ky*3+kx)*C + c] = in(y+ky-1, x+kx-1) of the (nearest-
+// upsampled) image, zero outside.  VEC = channels per thread (8: one 16-byte vector; 4 for conv_in's C = 4).
+template <int VEC>
+__global__ void im2col_kernel(const __half* __restrict__ in, __half* __restrict__ A, int B, int Hin, int Win, int C,
+                              int up, int Kp) {
+    const int H = Hin * up, W = Win * up;
+    const int cv = C / VEC;                                  // vectors per tap
+    const int kv = Kp / VEC;                                 // vectors per row of A (padding columns included)
+    const long long n = static_cast<long long>(B) * H * W * kv;
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const long long m = i / kv;
+        const int j = static_cast<int>(i % kv);
+        const int tap = j / cv, c0 = (j % cv) * VEC;
+        const int x = static_cast<int>(m % W), y = static_cast<int>((m / W) % H), b = static_cast<int>(m / (static_cast<long long>(W) * H));
+        const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
+        if (VEC == 8) {
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (tap < 9 && yy >= 0 && yy < H && xx >= 0 && xx < W)
+                v = *reinterpret_cast<const uint4*>(in + ((static_cast<long long>(b) * Hin + yy / up) * Win + xx / up) * C + c0);
+            *reinterpret_cast<uint4*>(A + m * Kp + static_cast<long long>(j) * 8) = v;
+        } else {
+            uint2 v = make_uint2(0, 0);
+            if (tap < 9 && yy >= 0 && yy < H && xx >= 0 && xx < W)
+                v = *reinterpret_cast<const uint2*>(in + ((static_cast<long long>(b) * Hin + yy / up) * Win + xx / up) * C + c0);
+            *reinterpret_cast<uint2*>(A + m * Kp + static_cast<long long>(j) * 4) = v;
+        }
+    }
+}
+
+// ---- GroupNorm(32 groups, eps 1e-6, affine) [+ swish] -> fp16 -------------------------------------------------------
+// pass 1: per (sample, pixel chunk, group) partial sum / sum of squares; a thread always sees the same 4 channels
+__global__ void __launch_bounds__(VT) gn_partial_kernel(const float* __restrict__ x, double2* __restrict__ part, int HW,
+                                                        int C, int chunks) {
+    const int b = blockIdx.y, chunk = blockIdx.x;
+    const int qpp = C / 4;                       // float4 per pixel
+    const int ppi = VT / qpp;                    // pixels per block iteration (C <= 1024)
+    const int q = threadIdx.x % qpp, sub = threadIdx.x / qpp;
+    const int per = (HW + chunks - 1) / chunks;
+    const int p0 = chunk * per, p1 = min(HW, p0 + per);
+    float s = 0.f, ss = 0.f;
+    if (sub < ppi) {
+        for (int p = p0 + sub; p < p1; p += ppi) {
+            const float4 v = *reinterpret_cast<const float4*>(x + (static_cast<long long>(b) * HW + p) * C + q * 4);
+            s += (v.x + v.y) + (v.z + v.w);
+            ss += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+        }
+    }
+    __shared__ float sh_s[VT], sh_q[VT];
+    sh_s[threadIdx.x] = s;
+    sh_q[threadIdx.x] = ss;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        // group g owns quads [g*cpg/4, (g+1)*cpg/4) of every pixel slot; fixed summation order
+        const int qpg = qpp / 32;
+        double a = 0.0, c = 0.0;
+        for (int sb = 0; sb < ppi; ++sb)
+            for (int k = 0; k < qpg; ++k) {
+                const int t = sb * qpp + threadIdx.x * qpg + k;
+                a += sh_s[t];
+                c += sh_q[t];
+            }
+        part[(static_cast<long long>(b) * chunks + chunk) * 32 + threadIdx.x] = make_double2(a, c);
+    }
+}
+// pass 2: (mean, rstd) per (sample, group)
+__global__ void gn_final_kernel(const double2* __restrict__ part, float2* __restrict__ stats, int chunks, double inv_n) {
+    const int b = blockIdx.x, g = threadIdx.x;
+    double a = 0.0, c = 0.0;
+    for (int k = 0; k < chunks; ++k) {
+        const double2 p = part[(static_cast<long long>(b) * chunks + k) * 32 + g];
+        a += p.x;
+        c += p.y;
+    }
+    const double mean = a * inv_n;
+    const double var = fmax(c * inv_n - mean * mean, 0.0);
+    stats[b * 32 + g] = make_float2(static_cast<float>(mean), static_cast<float>(rsqrt(var + 1e-6)));
+}
+// pass 3: normalise, affine, optional swish x*sigmoid(x) (libs/autoencoder.py:26-28), fp16
+__global__ void gn_apply_kernel(const float* __restrict__ x, const float2* __restrict__ stats,
+                                const float* __restrict__ gamma, const float* __restrict__ beta, __half* __restrict__ out,
+                                long long n4, int HW, int C, int swish) {
+    const int qpp = C / 4, cpg = C / 32;
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        const int q = static_cast<int>(i % qpp);
+        const int b = static_cast<int>(i / (static_cast<long long>(qpp) * HW));
+        const float2 st = stats[b * 32 + (q * 4) / cpg];
+        const float4 v = reinterpret_cast<const float4*>(x)[i];
+        const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + q);
+        const float4 be = __ldg(reinterpret_cast<const float4*>(beta) + q);
+        float y[4] = {(v.x - st.x) * st.y * g.x + be.x, (v.y - st.x) * st.y * g.y + be.y,
+                      (v.z - st.x) * st.y * g.z + be.z, (v.w - st.x) * st.y * g.w + be.w};
+        if (swish) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) y[k] = y[k] / (1.f + __expf(-y[k]));
+        }
+        __half2 h0 = __floats2half2_rn(y[0], y[1]), h1 = __floats2half2_rn(y[2], y[3]);
+        uint2 u;
+        u.x = *reinterpret_cast<uint32_t*>(&h0);
+        u.y = *reinterpret_cast<uint32_t*>(&h1);
+        reinterpret_cast<uint2*>(out)[i] = u;
+    }
+}
+
+// ---- attention helpers ------------------------------------------------------------------------------------------------
+// softmax over the keys of one query row (libs/autoencoder.py:183-184): one warp per row
+__global__ void __launch_bounds__(VT) softmax_rows_kernel(const float* __restrict__ s, __half* __restrict__ p, int rows,
+                                                           int cols, float scale) {
+    const int row = blockIdx.x * (VT / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float* r = s + static_cast<long long>(row) * cols;
+    float mx = -INFINITY;
+    for (int j = lane; j < cols; j += 32) mx = fmaxf(mx, r[j]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.f;
+    for (int j = lane; j < cols; j += 32) sum += __expf((r[j] - mx) * scale);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float inv = 1.f / sum;
+    for (int j = lane; j < cols; j += 32)
+        p[static_cast<long long>(row) * cols + j] = __float2half_rn(__expf((r[j] - mx) * scale) * inv);
+}
+// out[c][r] = in[r][c]
+__global__ void transpose16_kernel(const __half* __restrict__ in, __half* __restrict__ out, int rows, int cols) {
+    __shared__ __half tile[32][33];
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y)
+        if (r0 + i < rows && c0 + threadIdx.x < cols) tile[i][threadIdx.x] = in[static_cast<long long>(r0 + i) * cols + c0 + threadIdx.x];
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y)
+        if (c0 + i < cols && r0 + threadIdx.x < rows) out[static_cast<long long>(c0 + i) * rows + r0 + threadIdx.x] = tile[threadIdx.x][i];
+}
+
+// ---- output: fp32 NHWC [M, Np] (first 3 channels) -> NCHW image ---------------------------------------------------
+__global__ void vae_out_kernel(const float* __restrict__ o, float* __restrict__ img, int B, int HW, int Np) {
+    const long long n = static_cast<long long>(B) * 3 * HW;
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int p = static_cast<int>(i % HW), c = static_cast<int>((i / HW) % 3), b = static_cast<int>(i / (3LL * HW));
+    img[i] = o[(static_cast<long long>(b) * HW + p) * Np + c];
+}
+
+inline int grid_for(long long n) {
+    long long b = (n + VT - 1) / VT;
+    if (b > 148LL * 32) b = 148LL * 32;
+    return static_cast<int>(b < 1 ? 1 : b);
+}
+
+struct VWeight {
+    std::string name;
+    std::vector<int64_t> shape;
+    long long numel = 0;
+    float* d32 = nullptr;
+    __half* d16 = nullptr;      // packed GEMM operand (conv weights)
+    float* bias_pad = nullptr;  // bias zero-padded to the GEMM's N (conv biases whose Cout is not a multiple of 128)
+    int Np = 0, Kp = 0;
+    bool set = false;
+};
+
+}  // namespace
+}  // namespace usp
+
+using namespace usp;
+
+struct usp_vae {
+    int device = 0, num_sms = 148;
+    float scale = 0.18215f;
+    std::vector<VWeight> w;
+    std::map<std::string, int> idx;
+    bool finalized = false;
+    std::string err;
+    // workspace for (chunk batch, latent side)
+    int ws_B = 0, ws_S = 0;
+    void* slab = nullptr;
+    float *f0 = nullptr, *f1 = nullptr, *f2 = nullptr, *f3 = nullptr;   // fp32 NHWC activations
+    __half *a16 = nullptr, *col = nullptr, *q16 = nullptr, *k16 = nullptr, *v16 = nullptr, *p16 = nullptr, *vt16 = nullptr;
+    float* s32 = nullptr;
+    double2* gn_part = nullptr;
+    float2* gn_stats = nullptr;
+};
+
+namespace {
+
+std::string g_vae_error;
+
+int vfail(usp_vae* h, int code, const std::string& msg) {
+    if (h) h->err = msg;
+    else g_vae_error = msg;
+    return code;
+}
+#define VTRY(h, expr)                                                                              \
+    do {                                                                                           \
+        cudaError_t _e = (expr);                                                                   \
+        if (_e != cudaSuccess) return vfail(h, USP_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+    } while (0)
+
+int add(usp_vae* h, const std::string& name, std::vector<int64_t> shape) {
+    VWeight w;
+    w.name = name;
+    w.shape = shape;
+    w.numel = 1;
+    for (auto s : shape) w.numel *= s;
+    h->w.push_back(w);
+    h->idx[name] = static_cast<int>(h->w.size()) - 1;
+    return static_cast<int>(h->w.size()) - 1;
+}
+void add_conv(usp_vae* h, const std::string& p, int ci, int co, int ks) {
+    add(h, p + ".weight", {co, ci, ks, ks});
+    add(h, p + ".bias", {co});
+}
+void add_norm(usp_vae* h, const std::string& p, int c) {
+    add(h, p + ".weight", {c});
+    add(h, p + ".bias", {c});
+}
+void add_res(usp_vae* h, const std::string& p, int ci, int co) {
+    add_norm(h, p + ".norm1", ci);
+    add_conv(h, p + ".conv1", ci, co, 3);
+    add_norm(h, p + ".norm2", co);
+    add_conv(h, p + ".conv2", co, co, 3);
+    if (ci != co) add_conv(h, p + ".nin_shortcut", ci, co, 1);
+}
+
+constexpr int CH = 128;
+constexpr int MULT[4] = {1, 2, 4, 4};
+constexpr int NRES = 2;
+
+const VWeight& W(const usp_vae* h, const std::string& n) { return h->w[h->idx.at(n)]; }
+
+// one convolution as im2col + GEMM.  in16: fp16 NHWC [B, Hin, Win, Ci]; result fp32 NHWC [B*H*W, Np] (+ optional fp16)
+int conv(usp_vae* h, const std::string& p, const __half* in16, int B, int Hin, int Win, int up, const float* resid,
+         float* out32, __half* out16, int epi, cudaStream_t s) {
+    const VWeight& w = W(h, p + ".weight");
+    const VWeight& b = W(h, p + ".bias");
+    const int Ci = static_cast<int>(w.shape[1]), ks = static_cast<int>(w.shape[2]);
+    const long long M = static_cast<long long>(B) * Hin * up * Win * up;
+    const __half* A = in16;
+    if (ks == 3) {
+        if (Ci % 8 == 0)
+            im2col_kernel<8><<<grid_for(M * (w.Kp / 8)), VT, 0, s>>>(in16, h->col, B, Hin, Win, Ci, up, w.Kp);
+        else
+            im2col_kernel<4><<<grid_for(M * (w.Kp / 4)), VT, 0, s>>>(in16, h->col, B, Hin, Win, Ci, up, w.Kp);
+        VTRY(h, cudaGetLastError());
+        A = h->col;
+    }
+    const char* e = gemm_raw(epi, A, w.d16, b.bias_pad, resid, out32, out16, static_cast<int>(M), w.Np, w.Kp, OPD_FP16,
+                             h->num_sms, s);
+    if (e) return vfail(h, USP_ERR_CUDA, "conv " + p + ": " + e);
+    return USP_OK;
+}
+
+// GroupNorm (+ swish) of fp32 NHWC x [B, HW, C] -> fp16
+int group_norm(usp_vae* h, const std::string& p, const float* x, int B, int HW, int C, bool swish, __half* out,
+               cudaStream_t s) {
+    int chunks = HW / 64;
+    if (chunks < 1) chunks = 1;
+    if (chunks > 64) chunks = 64;
+    gn_partial_kernel<<<dim3(chunks, B), VT, 0, s>>>(x, h->gn_part, HW, C, chunks);
+    gn_final_kernel<<<B, 32, 0, s>>>(h->gn_part, h->gn_stats, chunks, 1.0 / (static_cast<double>(HW) * (C / 32)));
+    const long long n4 = static_cast<long long>(B) * HW * C / 4;
+    gn_apply_kernel<<<grid_for(n4), VT, 0, s>>>(x, h->gn_stats, W(h, p + ".weight").d32, W(h, p + ".bias").d32, out, n4, HW, C,
+                                                swish ? 1 : 0);
+    VTRY(h, cudaGetLastError());
+    return USP_OK;
+}
+
+// ResnetBlock.forward (libs/autoencoder.py:114-134, temb is None): x [B, H*W, Ci] fp32 in `x`, result in `y`
+int res_block(usp_vae* h, const std::string& p, const float* x, float* t, float* r, float* y, int B, int H, int Ci, int Co,
+              cudaStream_t s) {
+    int rc;
+    if ((rc = group_norm(h, p + ".norm1", x, B, H * H, Ci, true, h->a16, s))) return rc;
+    if ((rc = conv(h, p + ".conv1", h->a16, B, H, H, 1, nullptr, t, nullptr, EPI_BIAS_F32, s))) return rc;
+    const float* resid = x;
+    if (Ci != Co) {
+        cudaError_t e = launch_convert16(x, h->a16, static_cast<long long>(B) * H * H * Ci, OPD_FP16, s);
+        if (e != cudaSuccess) return vfail(h, USP_ERR_CUDA, std::string("convert16: ") + cudaGetErrorString(e));
+        if ((rc = conv(h, p + ".nin_shortcut", h->a16, B, H, H, 1, nullptr, r, nullptr, EPI_BIAS_F32, s))) return rc;
+        resid = r;
+    }
+    if ((rc = group_norm(h, p + ".norm2", t, B, H * H, Co, true, h->a16, s))) return rc;
+    return conv(h, p + ".conv2", h->a16, B, H, H, 1, resid, y, nullptr, EPI_BIAS_RESID, s);
+}
+
+// AttnBlock.forward (libs/autoencoder.py:171-195): single head over H*W tokens of width C
+int attn_block(usp_vae* h, const std::string& p, const float* x, float* y, int B, int H, int C, cudaStream_t s) {
+    const int T = H * H;
+    int rc;
+    if ((rc = group_norm(h, p + ".norm", x, B, T, C, false, h->a16, s))) return rc;
+    if ((rc = conv(h, p + ".q", h->a16, B, H, H, 1, nullptr, nullptr, h->q16, EPI_BIAS_F32, s))) return rc;
+    if ((rc = conv(h, p + ".k", h->a16, B, H, H, 1, nullptr, nullptr, h->k16, EPI_BIAS_F32, s))) return rc;
+    if ((rc = conv(h, p + ".v", h->a16, B, H, H, 1, nullptr, nullptr, h->v16, EPI_BIAS_F32, s))) return rc;
+    const float scale = 1.0f / sqrtf(static_cast<float>(C));
+    for (int b = 0; b < B; ++b) {
+        const __half* qb = h->q16 + static_cast<long long>(b) * T * C;
+        const __half* kb = h->k16 + static_cast<long long>(b) * T * C;
+        const __half* vb = h->v16 + static_cast<long long>(b) * T * C;
+        const char* e = gemm_raw(EPI_BIAS_F32, qb, kb, nullptr, nullptr, h->s32, nullptr, T, T, C, OPD_FP16, h->num_sms, s);
+        if (e) return vfail(h, USP_ERR_CUDA, std::string("attention q k^T: ") + e);
+        softmax_rows_kernel<<<(T + VT / 32 - 1) / (VT / 32), VT, 0, s>>>(h->s32, h->p16, T, T, scale);
+        transpose16_kernel<<<dim3((C + 31) / 32, (T + 31) / 32), dim3(32, 8), 0, s>>>(vb, h->vt16, T, C);
+        VTRY(h, cudaGetLastError());
+        // h_[i, c] = sum_j P[i, j] v[j, c]: A = P [T, T], W = v^T [C, T]; the fp16 result is the operand of proj_out
+        e = gemm_raw(EPI_BIAS_F32, h->p16, h->vt16, nullptr, nullptr, nullptr, h->a16 + static_cast<long long>(b) * T * C, T, C, T,
+                     OPD_FP16, h->num_sms, s);
+        if (e) return vfail(h, USP_ERR_CUDA, std::string("attention P v: ") + e);
+    }
+    return conv(h, p + ".proj_out", h->a16, B, H, H, 1, x, y, nullptr, EPI_BIAS_RESID, s);
+}
+
+int ensure_workspace(usp_vae* h, int B, int S) {
+    if (h->slab && h->ws_B >= B && h->ws_S == S) return USP_OK;
+    if (h->slab) cudaFree(h->slab);
+    h->slab = nullptr;
+    const long long px = static_cast<long long>(S) * 8 * S * 8;                 // output pixels per image
+    const long long act = static_cast<long long>(B) * px * 256;                 // largest activation: 256 channels at full size
+    const long long colb = static_cast<long long>(B) * px * 2304;               // largest im2col: 9 * 256 at full size
+    const long long T = static_cast<long long>(S) * S, C = 512;
+    size_t off = 0;
+    auto carve = [&](size_t bytes) { size_t o = off; off = (off + bytes + 1023) / 1024 * 1024; return o; };
+    const size_t o_f0 = carve(act * 4), o_f1 = carve(act * 4), o_f2 = carve(act * 4), o_f3 = carve(act * 4);
+    const size_t o_a = carve(act * 2), o_col = carve(colb * 2);
+    const size_t o_q = carve(B * T * C * 2), o_k = carve(B * T * C * 2), o_v = carve(B * T * C * 2);
+    const size_t o_p = carve(T * T * 2), o_vt = carve(T * C * 2), o_s = carve(T * T * 4);
+    const size_t o_gp = carve(static_cast<size_t>(B) * 64 * 32 * sizeof(double2)), o_gs = carve(static_cast<size_t>(B) * 32 * sizeof(float2));
+    VTRY(h, cudaMalloc(&h->slab, off));
+    char* base = static_cast<char*>(h->slab);
+    h->f0 = reinterpret_cast<float*>(base + o_f0); h->f1 = reinterpret_cast<float*>(base + o_f1);
+    h->f2 = reinterpret_cast<float*>(base + o_f2); h->f3 = reinterpret_cast<float*>(base + o_f3);
+    h->a16 = reinterpret_cast<__half*>(base + o_a); h->col = reinterpret_cast<__half*>(base + o_col);
+    h->q16 = reinterpret_cast<__half*>(base + o_q); h->k16 = reinterpret_cast<__half*>(base + o_k);
+    h->v16 = reinterpret_cast<__half*>(base + o_v); h->p16 = reinterpret_cast<__half*>(base + o_p);
+    h->vt16 = reinterpret_cast<__half*>(base + o_vt); h->s32 = reinterpret_cast<float*>(base + o_s);
+    h->gn_part = reinterpret_cast<double2*>(base + o_gp); h->gn_stats = reinterpret_cast<float2*>(base + o_gs);
+    h->ws_B = B; h->ws_S = S;
+    return USP_OK;
+}
+
+// Decoder.forward for a chunk of B latents
+int decode_chunk(usp_vae* h, const float* z, float* img, int B, int S, cudaStream_t s) {
+    int rc;
+    const std::string d = "decoder.";
+    const long long n_in = static_cast<long long>(B) * S * S;
+    // z / scale -> post_quant_conv -> fp16 NHWC [B, S, S, 4]
+    vae_in_kernel<<<static_cast<unsigned>((n_in + VT - 1) / VT), VT, 0, s>>>(z, W(h, "post_quant_conv.weight").d32,
+                                                                               W(h, "post_quant_conv.bias").d32, h->a16, B, S,
+                                                                               1.0f / h->scale);
+    VTRY(h, cudaGetLastError());
+    float *x = h->f0, *y = h->f1, *t = h->f2, *r = h->f3;
+    int C = CH * MULT[3], H = S;
+    if ((rc = conv(h, d + "conv_in", h->a16, B, H, H, 1, nullptr, x, nullptr, EPI_BIAS_F32, s))) return rc;
+    if ((rc = res_block(h, d + "mid.block_1", x, t, r, y, B, H, C, C, s))) return rc;
+    std::swap(x, y);
+    if ((rc = attn_block(h, d + "mid.attn_1", x, y, B, H, C, s))) return rc;
+    std::swap(x, y);
+    if ((rc = res_block(h, d + "mid.block_2", x, t, r, y, B, H, C, C, s))) return rc;
+    std::swap(x, y);
+    for (int lvl = 3; lvl >= 0; --lvl) {
+        const int Co = CH * MULT[lvl];
+        for (int blk = 0; blk <= NRES; ++blk) {
+            const std::string p = d + "up." + std::to_string(lvl) + ".block." + std::to_string(blk);
+            if ((rc = res_block(h, p, x, t, r, y, B, H, C, Co, s))) return rc;
+            std::swap(x, y);
+            C = Co;
+        }
+        if (lvl != 0) {
+            // Upsample: nearest x2 folded into the im2col gather, then the 3x3 conv (libs/autoencoder.py:46-50)
+            cudaError_t e = launch_convert16(x, h->a16, static_cast<long long>(B) * H * H * C, OPD_FP16, s);
+            if (e != cudaSuccess) return vfail(h, USP_ERR_CUDA, std::string("convert16: ") + cudaGetErrorString(e));
+            if ((rc = conv(h, d + "up." + std::to_string(lvl) + ".upsample.conv", h->a16, B, H, H, 2, nullptr, y, nullptr,
+                           EPI_BIAS_F32, s)))
+                return rc;
+            std::swap(x, y);
+            H *= 2;
+        }
+    }
+    if ((rc = group_norm(h, d + "norm_out", x, B, H * H, C, true, h->a16, s))) return rc;
+    if ((rc = conv(h, d + "conv_out", h->a16, B, H, H, 1, nullptr, y, nullptr, EPI_BIAS_F32, s))) return rc;
+    const long long n_out = static_cast<long long>(B) * 3 * H * H;
+    vae_out_kernel<<<static_cast<unsigned>((n_out + VT - 1) / VT), VT, 0, s>>>(y, img, B, H * H, W(h, d + "conv_out.weight").Np);
+    VTRY(h, cudaGetLastError());
+    return USP_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int usp_vae_create(int device, float scale_factor, usp_vae** out) {
+    if (!out) return USP_ERR_INVALID;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return vfail(nullptr, USP_ERR_CUDA, "no CUDA device: the decoder has no CPU fallback");
+    }
+    cudaDeviceProp prop;
+    if (device < 0 || device >= ndev || cudaGetDeviceProperties(&prop, device) != cudaSuccess)
+        return vfail(nullptr, USP_ERR_INVALID, "bad device index");
+    if (prop.major != 10) return vfail(nullptr, USP_ERR_UNSUPPORTED, "built for sm_100a (B200) only");
+    if (!(scale_factor > 0.f)) return vfail(nullptr, USP_ERR_INVALID, "scale_factor must be positive");
+    std::unique_ptr<usp_vae> h(new usp_vae());
+    h->device = device;
+    h->num_sms = prop.multiProcessorCount;
+    h->scale = scale_factor;
+    // the reference's state_dict order (libs/autoencoder.py:303-373, 416-418)
+    const std::string d = "decoder.";
+    int C = CH * MULT[3];
+    add_conv(h.get(), d + "conv_in", 4, C, 3);
+    add_res(h.get(), d + "mid.block_1", C, C);
+    add_norm(h.get(), d + "mid.attn_1.norm", C);
+    for (const char* n : {"q", "k", "v", "proj_out"}) add_conv(h.get(), d + "mid.attn_1." + n, C, C, 1);
+    add_res(h.get(), d + "mid.block_2", C, C);
+    // creation runs from the deepest level up, names are indexed by level
+    int cin[4][3], cout[4];
+    int c = C;
+    for (int lvl = 3; lvl >= 0; --lvl) {
+        cout[lvl] = CH * MULT[lvl];
+        for (int blk = 0; blk <= NRES; ++blk) { cin[lvl][blk] = c; c = cout[lvl]; }
+    }
+    for (int lvl = 0; lvl < 4; ++lvl) {
+        for (int blk = 0; blk <= NRES; ++blk)
+            add_res(h.get(), d + "up." + std::to_string(lvl) + ".block." + std::to_string(blk), cin[lvl][blk], cout[lvl]);
+        if (lvl != 0) add_conv(h.get(), d + "up." + std::to_string(lvl) + ".upsample.conv", cout[lvl], cout[lvl], 3);
+    }
+    add_norm(h.get(), d + "norm_out", CH);
+    add_conv(h.get(), d + "conv_out", CH, 3, 3);
+    add_conv(h.get(), "post_quant_conv", 4, 4, 1);
+    *out = h.release();
+    return USP_OK;
+}
+
+void usp_vae_destroy(usp_vae* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    for (auto& w : h->w) {
+        cudaFree(w.d32);
+        cudaFree(w.d16);
+        cudaFree(w.bias_pad);
+    }
+    cudaFree(h->slab);
+    delete h;
+}
+
+const char* usp_vae_last_error(const usp_vae* h) { return h ? h->err.c_str() : g_vae_error.c_str(); }
+int usp_vae_num_weights(const usp_vae* h) { return h ? static_cast<int>(h->w.size()) : 0; }
+const char* usp_vae_weight_name(const usp_vae* h, int i) {
+    return (h && i >= 0 && i < static_cast<int>(h->w.size())) ? h->w[i].name.c_str() : nullptr;
+}
+
+int usp_vae_set_weight(usp_vae* h, const char* name, const void* data, const int64_t* shape, int ndim) {
+    if (!h || !name || !data || !shape) return USP_ERR_INVALID;
+    auto it = h->idx.find(name);
+    if (it == h->idx.end()) return vfail(h, USP_ERR_INVALID, std::string("unknown weight ") + name);
+    VWeight& w = h->w[it->second];
+    if (ndim != static_cast<int>(w.shape.size())) return vfail(h, USP_ERR_INVALID, std::string("rank mismatch for ") + name);
+    for (int i = 0; i < ndim; ++i)
+        if (shape[i] != w.shape[i]) return vfail(h, USP_ERR_INVALID, std::string("shape mismatch for ") + name);
+    VTRY(h, cudaSetDevice(h->device));
+    if (!w.d32) VTRY(h, cudaMalloc(&w.d32, w.numel * 4));
+    VTRY(h, cudaMemcpy(w.d32, data, w.numel * 4, cudaMemcpyDefault));
+    w.set = true;
+    h->finalized = false;
+    return USP_OK;
+}
+
+int usp_vae_finalize(usp_vae* h, void* stream) {
+    if (!h) return USP_ERR_INVALID;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    VTRY(h, cudaSetDevice(h->device));
+    for (auto& w : h->w)
+        if (!w.set) return vfail(h, USP_ERR_STATE, "weight not set: " + w.name);
+    for (size_t i = 0; i < h->w.size(); ++i) {
+        VWeight& w = h->w[i];
+        if (w.shape.size() != 4 || w.name == "post_quant_conv.weight") continue;
+        const int Co = static_cast<int>(w.shape[0]), Ci = static_cast<int>(w.shape[1]), ks = static_cast<int>(w.shape[2]);
+        w.Np = (Co + 127) / 128 * 128;
+        w.Kp = (ks * ks * Ci + 63) / 64 * 64;
+        if (!w.d16) VTRY(h, cudaMalloc(&w.d16, static_cast<size_t>(w.Np) * w.Kp * 2));
+        pack_conv_kernel<<<grid_for(static_cast<long long>(w.Np) * w.Kp), VT, 0, s>>>(w.d32, w.d16, Co, Ci, ks, w.Np, w.Kp);
+        VTRY(h, cudaGetLastError());
+        VWeight& b = h->w[i + 1];     // the bias follows its weight
+        if (!b.bias_pad) VTRY(h, cudaMalloc(&b.bias_pad, w.Np * 4));
+        VTRY(h, cudaMemsetAsync(b.bias_pad, 0, w.Np * 4, s));
+        VTRY(h, cudaMemcpyAsync(b.bias_pad, b.d32, Co * 4, cudaMemcpyDeviceToDevice, s));
+    }
+    VTRY(h, cudaStreamSynchronize(s));
+    h->finalized = true;
+    return USP_OK;
+}
+
+int usp_vae_decode(usp_vae* h, const float* z, float* out, int B, int S, void* stream) {
+    if (!h) return USP_ERR_INVALID;
+    if (!h->finalized) return vfail(h, USP_ERR_STATE, "weights not finalised");
+    if (!z || !out || B < 1) return vfail(h, USP_ERR_INVALID, "null buffer or empty batch");
+    if (S < 16 || S > 64 || S % 16 != 0)
+        return vfail(h, USP_ERR_INVALID, "latent side must be 16, 32, 48 or 64 (the attention GEMMs need S*S % 128 == 0)");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    VTRY(h, cudaSetDevice(h->device));
+    // chunks bound the im2col workspace (604 KB per output pixel row of the widest layer: 2.4 GB for 8 images at S = 32)
+    const int chunk = S <= 32 ? 8 : 2;
+    int rc = ensure_workspace(h, B < chunk ? B : chunk, S);
+    if (rc) return rc;
+    for (int b0 = 0; b0 < B; b0 += chunk) {
+        const int nb = B - b0 < chunk ? B - b0 : chunk;
+        rc = decode_chunk(h, z + static_cast<long long>(b0) * 4 * S * S, out + static_cast<long long>(b0) * 3 * 64 * S * S, nb, S, s);
+        if (rc) return rc;
+    }
+    return USP_OK;
+}
+
+}  // extern "C"
