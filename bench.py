@@ -48,6 +48,32 @@ WORKLOADS = {
 METRIC = "images/sec at 50 ODE steps, U-ViT-L 256"
 
 
+def decoder_line(latents, dev):
+    """Context, not the headline: the latent -> image decoder (csrc/vae.cu) on the latents the timed run produced."""
+    import torch
+
+    from oracle.vae_oracle import flops_per_image
+    from uspace_b200.autoencoder import get_model
+    try:
+        torch.manual_seed(0)
+        vae = get_model().to(dev)
+        z = latents.contiguous()
+        vae.decode(z)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(2):
+            img = vae.decode(z)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 2
+        return {"images_per_s": z.shape[0] / ms * 1e3, "batch": z.shape[0], "ms": ms,
+                "achieved_tflops": flops_per_image(32) * z.shape[0] / ms / 1e9, "finite": bool(torch.isfinite(img).all().item()),
+                "note": "FrozenAutoencoderKL.decode, random-init weights; follows sampling in the reference's pipeline"}
+    except Exception as e:   # context only: never fail the headline line
+        return {"error": str(e)[:200]}
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -371,6 +397,7 @@ def main():
                                              f"images/s = 8/(t_fwd*{nfe}) extrapolated from per-forward time"}
         if world == 1 and not args.no_cpu_baseline:
             res["torch_eager_b200"] = torch_eager_on_gpu(wl, dev, nfe)
+            res["decoder"] = decoder_line(out[:Bl] if not scales else out[:Bl], dev)
         print(json.dumps(res))
     if world > 1:
         dist.barrier()

@@ -43,6 +43,38 @@ EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const int*, const int*, cuuint32_t, cuuint32_t, const cuuint32_t*,
+                                   CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeIm2colFn get_im2col_fn() {
+    static EncodeIm2colFn fn = nullptr;
+    if (fn) return fn;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+        return nullptr;
+    fn = reinterpret_cast<EncodeIm2colFn>(p);
+    return fn;
+}
+// fp16 NHWC activation [n, h, w, c] as the A operand of a 3x3 / stride 1 / pad 1 convolution: 128 output pixels x 64
+// channels per load (the same 128-row x 128-byte swizzled box the plain GEMM stages), padding zero-filled by the TMA
+bool make_map_im2col(CUtensorMap* m, const void* ptr, long long n, long long h, long long w, long long c) {
+    EncodeIm2colFn fn = get_im2col_fn();
+    if (!fn) return false;
+    cuuint64_t dims[4] = {static_cast<cuuint64_t>(c), static_cast<cuuint64_t>(w), static_cast<cuuint64_t>(h),
+                          static_cast<cuuint64_t>(n)};
+    cuuint64_t strides[3] = {static_cast<cuuint64_t>(c) * 2, static_cast<cuuint64_t>(w * c) * 2,
+                             static_cast<cuuint64_t>(h * w * c) * 2};
+    const int lower[2] = {-1, -1};   // -padding
+    const int upper[2] = {-1, -1};   // padding - (filter - 1) * dilation
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(ptr), dims, strides, lower, upper, 64, GEMM_BM,
+                    estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
 // 16-bit row-major [rows, cols] tensor, box = [box_rows, 64 cols], 128B swizzle, OOB -> 0
 bool make_map_2d(CUtensorMap* m, const void* ptr, long long rows, long long cols, int box_rows, int opd) {
     EncodeTiledFn fn = get_encode_fn();
@@ -1344,11 +1376,20 @@ namespace usp {
 // C[M,N] = A[M,K] W[N,K]^T + epilogue on raw device pointers (tensor maps are encoded per call): the GEMM entry of the
 // latent decoder (csrc/vae.cu).  Returns a message on failure.
 const char* gemm_raw(int epilogue, const void* a16, const void* w16, const float* bias, const float* resid,
-                     float* out32, void* out16, int M, int N, int K, int operand_dtype, int num_sms, cudaStream_t s) {
+                     float* out32, void* out16, int M, int N, int K, int operand_dtype, int num_sms, cudaStream_t s,
+                     int conv_C, int conv_H, int conv_W) {
     if (!get_encode_fn()) return "cuTensorMapEncodeTiled entry point not found";
     if (gemm_configure() != cudaSuccess) return "gemm_configure failed";
     GemmMaps maps;
-    bool ok = make_map_2d(&maps.a0, a16, M, K, GEMM_BM, operand_dtype);
+    bool ok;
+    if (conv_C > 0) {
+        // implicit GEMM: a16 is the NHWC activation, K = 9 * conv_C
+        if (conv_C % 64 != 0 || K != 9 * conv_C || M % (conv_H * conv_W) != 0 || M % 256 != 0 || operand_dtype != OPD_FP16)
+            return "implicit-GEMM convolution needs C % 64 == 0, K == 9 C, whole images and M % 256 == 0";
+        ok = make_map_im2col(&maps.a0, a16, M / (conv_H * conv_W), conv_H, conv_W, conv_C);
+    } else {
+        ok = make_map_2d(&maps.a0, a16, M, K, GEMM_BM, operand_dtype);
+    }
     maps.a1 = maps.a0;
     ok &= make_map_2d(&maps.b, w16, N, K, gemm_weight_box_rows(), operand_dtype);
     if (out32 != nullptr) {
@@ -1362,6 +1403,7 @@ const char* gemm_raw(int epilogue, const void* a16, const void* w16, const float
     g.M = M; g.N = N; g.K = K; g.K0 = K; g.opd = operand_dtype;
     g.bias = bias; g.resid = resid; g.out32 = out32; g.out16 = out16;
     g.L = 1; g.H = 1;
+    g.conv_C = conv_C; g.conv_H = conv_H; g.conv_W = conv_W;
     cudaError_t e = launch_gemm(epilogue, maps, g, num_sms, s);
     return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }

@@ -150,6 +150,28 @@ __device__ __forceinline__ void tma_load_2d_cg2(const CUtensorMap* m, uint32_t b
         : "memory");
 }
 
+// im2col mode (A operand of a 3x3 convolution straight from the NHWC activation): loads `pixelsPerColumn` consecutive
+// output pixels x `channelsPerPixel` channels of filter tap (woff, hoff); (w, h) is the base pixel = output pixel + the
+// bounding box's lower corner (-padding); pixels outside the image are zero-filled by the TMA unit.
+__device__ __forceinline__ void tma_load_im2col(const CUtensorMap* m, uint64_t* bar, void* dst, int c, int w, int h,
+                                                int n, uint16_t woff, uint16_t hoff) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes "
+        "[%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h), "r"(n),
+          "h"(woff), "h"(hoff)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_im2col_cg2(const CUtensorMap* m, uint32_t bar_cluster_addr, void* dst, int c,
+                                                    int w, int h, int n, uint16_t woff, uint16_t hoff) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.im2col.mbarrier::complete_tx::bytes "
+        "[%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c), "r"(w), "r"(h), "r"(n),
+          "h"(woff), "h"(hoff)
+        : "memory");
+}
+
 // 2-CTA + multicast: the box lands at the same offset in every CTA of cta_mask; each destination's completion is
 // signalled on the barrier at the same offset in the LEADER of that destination's pair (bar_local is this CTA's
 // shared::cta address of the barrier with the peer bit cleared - CUTLASS's Sm100MmaPeerBitMask convention).

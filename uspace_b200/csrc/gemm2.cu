@@ -138,7 +138,12 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
                         if (leader && elect_one()) mbar_arrive(&full_bar[stage]);
                     } else if (elect_one()) {
                         if (leader) mbar_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);
-                        if (NP == 1) {
+                        if (g.conv_C > 0) {      // implicit GEMM (launched with NP == 1 only)
+                            const int cpt = g.conv_C / BK, tap = kb / cpt;
+                            tma_load_im2col_cg2(&tmA0, lead_full, sa, (kb - tap * cpt) * BK, m0 % g.conv_W - 1,
+                                                (m0 / g.conv_W) % g.conv_H - 1, m0 / (g.conv_W * g.conv_H),
+                                                static_cast<uint16_t>(tap % 3), static_cast<uint16_t>(tap / 3));
+                        } else if (NP == 1) {
                             if (kb < nkb0)
                                 tma_load_2d_cg2(&tmA0, lead_full, sa, kb * BK, m0);
                             else
@@ -328,7 +333,7 @@ cudaError_t launch2k(const GemmMaps& maps, const GemmArgs& a, int num_sms, cudaS
     const int n_tiles = ((a.M + 2 * BM - 1) / (2 * BM)) * (a.N / BN);
     GemmArgs a2 = a;
     const int cl4 = gemm_cluster4_mode();
-    if (cl4 && (cl4 == 1 || a.N <= 1024) && (a.N / BN) % 2 == 0 && n_tiles >= num_sms) {
+    if (cl4 && a.conv_C == 0 && (cl4 == 1 || a.N <= 1024) && (a.N / BN) % 2 == 0 && n_tiles >= num_sms) {
         int c4 = max_clusters4<EPI, LONGK>();
         if (c4 > 0) {
             if (n_tiles / 2 < c4) c4 = n_tiles / 2;

@@ -3,16 +3,19 @@
 //
 // Layout: activations are NHWC, fp32 "residual" copies [B*H*W, C] plus fp16 GEMM operands.  Every convolution is a
 // GEMM on the tcgen05 kernels of the U-ViT path (csrc/gemm2.cu / gemm.cu through gemm_raw):
-//   3x3 conv  = im2col (fp16, K ordered (ky, kx, c), optional nearest x2 upsample folded into the gather) x W[Cout, 9C]
+//   3x3 conv  = IMPLICIT GEMM: the A tiles are loaded straight from the fp16 NHWC activation through a TMA im2col
+//               tensor map (128 output pixels x 64 channels of one filter tap per load, padding zero-filled by the
+//               TMA unit) x W[Cout, 9C] with K ordered (ky, kx, c).  conv_in (C = 4) and USP_VAE_IM2COL=explicit
+//               materialise the im2col matrix instead.
 //   1x1 conv  = the fp16 activation itself x W[Cout, Cin]
 // with bias (+ residual for the second conv of a ResnetBlock and for the attention's proj_out) in the GEMM epilogue,
 // which writes the NHWC fp32 result directly (row m = pixel, column n = output channel).  GroupNorm(32, eps 1e-6) +
 // swish produce the next fp16 operand (two-stage deterministic statistics, no atomics).  The single 1024-token
 // attention block is three GEMMs per image (q k^T, softmax rows, P v) - 1 GFLOP of 620.
-// Everything here is either a GEMM (tensor pipe) or a streaming pass (HBM); the im2col matrix is the price of reusing
-// the GEMM kernel unchanged (302 MB per image for the largest layer, written and read once).
+// Everything here is either a GEMM (tensor pipe) or a streaming pass (HBM).
 #include <cuda_fp16.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
@@ -94,6 +97,20 @@ __global__ void im2col_kernel(const __half* __restrict__ in, __half* __restrict_
                 v = *reinterpret_cast<const uint2*>(in + ((static_cast<long long>(b) * Hin + yy / up) * Win + xx / up) * C + c0);
             *reinterpret_cast<uint2*>(A + m * Kp + static_cast<long long>(j) * 4) = v;
         }
+    }
+}
+
+// nearest x2 upsample of an fp16 NHWC tensor (torch.nn.functional.interpolate(scale_factor=2, mode="nearest"))
+__global__ void upsample2_kernel(const __half* __restrict__ in, __half* __restrict__ out, int B, int Hin, int Win, int C) {
+    const int cv = C / 8, H = 2 * Hin, W = 2 * Win;
+    const long long n = static_cast<long long>(B) * H * W * cv;
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const int c8 = static_cast<int>(i % cv);
+        const long long m = i / cv;
+        const int x = static_cast<int>(m % W), y = static_cast<int>((m / W) % H), b = static_cast<int>(m / (static_cast<long long>(W) * H));
+        reinterpret_cast<uint4*>(out)[i] =
+            *reinterpret_cast<const uint4*>(in + ((static_cast<long long>(b) * Hin + y / 2) * Win + x / 2) * C + c8 * 8);
     }
 }
 
@@ -305,6 +322,20 @@ int conv(usp_vae* h, const std::string& p, const __half* in16, int B, int Hin, i
     const int Ci = static_cast<int>(w.shape[1]), ks = static_cast<int>(w.shape[2]);
     const long long M = static_cast<long long>(B) * Hin * up * Win * up;
     const __half* A = in16;
+    // USP_VAE_IM2COL=explicit materialises the im2col matrix instead of loading through a TMA im2col map
+    static const bool explicit_cols = [] { const char* e = getenv("USP_VAE_IM2COL"); return e && e[0] == 'e'; }();
+    if (ks == 3 && Ci % 64 == 0 && M % 256 == 0 && !explicit_cols) {
+        // implicit GEMM: the TMA unit gathers the 3x3 neighbourhood (and zero-fills the padding) while loading A
+        if (up == 2) {
+            upsample2_kernel<<<grid_for(M * (Ci / 8)), VT, 0, s>>>(in16, h->col, B, Hin, Win, Ci);
+            VTRY(h, cudaGetLastError());
+            A = h->col;
+        }
+        const char* e = gemm_raw(epi, A, w.d16, b.bias_pad, resid, out32, out16, static_cast<int>(M), w.Np, w.Kp, OPD_FP16,
+                                 h->num_sms, s, Ci, Hin * up, Win * up);
+        if (e) return vfail(h, USP_ERR_CUDA, "conv " + p + ": " + e);
+        return USP_OK;
+    }
     if (ks == 3) {
         if (Ci % 8 == 0)
             im2col_kernel<8><<<grid_for(M * (w.Kp / 8)), VT, 0, s>>>(in16, h->col, B, Hin, Win, Ci, up, w.Kp);
