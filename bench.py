@@ -52,8 +52,7 @@ def decoder_line(latents, dev):
     """Context, not the headline: the latent -> image decoder (csrc/vae.cu) on the latents the timed run produced."""
     import torch
 
-    from oracle.vae_oracle import flops_per_image
-    from uspace_b200.autoencoder import get_model
+    from uspace_b200.autoencoder import flops_per_image, get_model
     try:
         torch.manual_seed(0)
         vae = get_model().to(dev)
@@ -350,10 +349,10 @@ def main():
 
     if rank == 0:
         pk = peaks()
-        from oracle.uvit_oracle import model_dims
-        d = model_dims(wl["cfg"])
-        D, L = d["D"], d["L"]
-        gemm_flops_img = (2 * d["n_in"] + 1) * 24.0 * L * D * D + d["n_in"] * 4.0 * L * D * D
+        # algorithmic GEMM FLOPs per image per evaluation: blocks + skip_linears
+        D, n_in = wl["cfg"]["embed_dim"], wl["cfg"]["depth"] // 2
+        L = (wl["cfg"]["img_size"] // wl["cfg"]["patch_size"]) ** 2 + (78 if wl["t2i"] else 1)
+        gemm_flops_img = (2 * n_in + 1) * 24.0 * L * D * D + n_in * 4.0 * L * D * D
         gemm_ms = sum(prof[k][0] for k in ("gemm_qkv", "gemm_proj", "gemm_fc1", "gemm_fc2", "gemm_skip"))
         gemm_launches = sum(prof[k][1] for k in ("gemm_qkv", "gemm_proj", "gemm_fc1", "gemm_fc2", "gemm_skip"))
         fwd_ms = sum(v[0] for v in prof.values())

@@ -335,3 +335,5 @@ def test_vae_mirror_state_dict_layout_and_flops():
     with pytest.raises(NotImplementedError):
         FrozenAutoencoderKL(dict(V.DDCONFIG, ch=64))
     assert V.flops_per_image(32) / 1e9 == pytest.approx(622.19, rel=1e-3)      # 0.62 TFLOP per 256^2 image
+    from uspace_b200.autoencoder import flops_per_image
+    assert flops_per_image(32) == V.flops_per_image(32) and flops_per_image(16) == V.flops_per_image(16)

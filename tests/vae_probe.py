@@ -7,7 +7,7 @@ import numpy as np
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from oracle import vae_oracle as V  # noqa: E402
+from oracle import vae_oracle as V  # noqa: E402  (developer probe: torch-library timing of the restatement)
 from tests.golden.cases import vae_latents, vae_state_dict  # noqa: E402
 from uspace_b200.autoencoder import get_model  # noqa: E402
 

@@ -153,6 +153,27 @@ class FrozenAutoencoderKL(nn.Module):
         raise NotImplementedError
 
 
+def flops_per_image(S: int = 32) -> float:
+    """Multiply-add = 2 FLOPs over every convolution and attention product of one decode at latent side S
+    (0.62 TFLOP for the 256^2 models)."""
+    ch, mult, n_blk = DDCONFIG["ch"], DDCONFIG["ch_mult"], DDCONFIG["num_res_blocks"] + 1
+    res, c = S, DDCONFIG["ch"] * DDCONFIG["ch_mult"][-1]
+    f = 2.0 * res * res * 4 * 4 + 2.0 * res * res * 9 * 4 * c + 4 * 2.0 * res * res * 9 * c * c
+    f += 4 * 2.0 * res * res * c * c + 2 * 2.0 * (res * res) ** 2 * c
+    cin = c
+    for lvl in reversed(range(len(mult))):
+        cout = ch * mult[lvl]
+        for _ in range(n_blk):
+            f += 2.0 * res * res * 9 * cin * cout + 2.0 * res * res * 9 * cout * cout
+            if cin != cout:
+                f += 2.0 * res * res * cin * cout
+            cin = cout
+        if lvl != 0:
+            res *= 2
+            f += 2.0 * res * res * 9 * cin * cin
+    return f + 2.0 * res * res * 9 * cin * 3
+
+
 def get_model(pretrained_path=None, scale_factor=0.18215):
     return FrozenAutoencoderKL(DDCONFIG, 4, pretrained_path, scale_factor)
 
