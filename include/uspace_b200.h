@@ -154,6 +154,10 @@ const char* usp_vae_weight_name(const usp_vae* h, int i);
 int usp_vae_set_weight(usp_vae* h, const char* name, const void* data, const int64_t* shape, int ndim);
 int usp_vae_finalize(usp_vae* h, void* stream);      /* packs the convolution weights; synchronises */
 int usp_vae_decode(usp_vae* h, const float* z, float* out, int B, int S, void* stream);
+/* Replaces FrozenAutoencoderKL.encode_moments (libs/autoencoder.py:426-429: Encoder.forward :275-300 + quant_conv):
+ *   x [B, 3, R, R] images in [-1, 1] (R in {128, 256, 384, 512})  ->  moments [B, 8, R/8, R/8] = (mean, logvar);
+ * the caller draws the latent sample (libs/autoencoder.py:431-437). Weight names "encoder.*", "quant_conv.*". */
+int usp_vae_encode_moments(usp_vae* h, const float* x, float* moments, int B, int R, void* stream);
 
 /* Same with HOST buffers: copies z (and context / y / delta_table) host->device, samples, copies z back,
  * and synchronises. This is the end-to-end call bench.py times. */

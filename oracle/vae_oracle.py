@@ -96,3 +96,25 @@ def flops_per_image(S: int = 32) -> float:
             f += 2.0 * res * res * 9 * cin * cin
     f += 2.0 * res * res * 9 * cin * 3
     return f
+
+
+def encoder_forward(sd: Dict[str, Tensor], x: Tensor, prefix: str = "encoder") -> Tensor:
+    """Encoder.forward (libs/autoencoder.py:275-300); Downsample = zero pad (0, 1, 0, 1) + 3x3 stride-2 conv (:65-69)."""
+    n_res = len(DDCONFIG["ch_mult"])
+    h = _conv(x, sd, f"{prefix}.conv_in", 1)
+    for lvl in range(n_res):
+        for blk in range(DDCONFIG["num_res_blocks"]):
+            h = resnet_block(h, sd, f"{prefix}.down.{lvl}.block.{blk}")
+        if lvl != n_res - 1:
+            p = f"{prefix}.down.{lvl}.downsample.conv"
+            h = F.conv2d(F.pad(h, (0, 1, 0, 1)), sd[p + ".weight"], sd[p + ".bias"], stride=2)
+    h = resnet_block(h, sd, f"{prefix}.mid.block_1")
+    h = attn_block(h, sd, f"{prefix}.mid.attn_1")
+    h = resnet_block(h, sd, f"{prefix}.mid.block_2")
+    h = _swish(_gn(h, sd, f"{prefix}.norm_out"))
+    return _conv(h, sd, f"{prefix}.conv_out", 1)
+
+
+def encode_moments(sd: Dict[str, Tensor], x: Tensor) -> Tensor:
+    """FrozenAutoencoderKL.encode_moments (libs/autoencoder.py:426-429): images [B, 3, R, R] -> [B, 8, R/8, R/8]."""
+    return _conv(encoder_forward(sd, x), sd, "quant_conv", 0)

@@ -83,3 +83,23 @@ def vae_latents(name):
     c = VAE_CASES[name]
     g = torch.Generator().manual_seed(c["in_seed"])
     return 0.18215 * 4.0 * torch.randn(c["B"], 4, c["S"], c["S"], generator=g)    # scaled like encoded latents
+
+
+VAE_ENC_CASES = dict(seed=12, vae_enc_small=dict(B=2, R=128, in_seed=31), vae_enc_full=dict(B=1, R=256, in_seed=32))
+
+
+def vae_enc_state_dict():
+    """Mirror Encoder + quant_conv under the golden seed (== the reference's modules under that seed)."""
+    from uspace_b200.autoencoder import DDCONFIG, Encoder
+    torch.manual_seed(VAE_ENC_CASES["seed"])
+    enc = Encoder(**DDCONFIG)
+    qc = torch.nn.Conv2d(8, 8, 1)
+    sd = {f"encoder.{k}": v for k, v in enc.state_dict().items()}
+    sd.update({f"quant_conv.{k}": v for k, v in qc.state_dict().items()})
+    return sd
+
+
+def vae_images(name):
+    c = VAE_ENC_CASES[name]
+    g = torch.Generator().manual_seed(c["in_seed"])
+    return torch.rand(c["B"], 3, c["R"], c["R"], generator=g) * 2.0 - 1.0       # images in [-1, 1]

@@ -815,10 +815,10 @@ _vae = {}
 
 def vae_model_gpu():
     if "m" not in _vae:
-        from tests.golden.cases import vae_state_dict
+        from tests.golden.cases import vae_enc_state_dict, vae_state_dict
         from uspace_b200.autoencoder import get_model
         m = get_model()
-        m.load_state_dict(vae_state_dict())
+        m.load_state_dict({**vae_state_dict(), **vae_enc_state_dict()})
         _vae["m"] = m.to(dev())
     return _vae["m"]
 
@@ -850,3 +850,37 @@ def test_vae_decode_batch_independence_and_chunking():
     assert rel(out[9:11], want) < VAE_TOL
     with pytest.raises(ValueError):
         m.decode(torch.zeros(1, 4, 10, 10, device=dev()))
+
+
+@pytest.mark.parametrize("name", ["vae_enc_small", "vae_enc_full"])
+def test_vae_encode_moments_matches_reference_golden(golden_dir, name):
+    from tests.golden.cases import vae_images
+    m = vae_model_gpu()
+    x = vae_images(name)
+    got = m.encode_moments(x.to(dev()))
+    want = golden(golden_dir, name)["moments"]
+    assert tuple(got.shape) == want.shape and rel(got, want) < VAE_TOL
+    assert torch.equal(m(x.to(dev()), "encode_moments"), got)
+    # sample() (libs/autoencoder.py:431-437): scale * (mean + std * eps) with std = exp(clamp(logvar) / 2)
+    torch.manual_seed(3)
+    z = m.encode(x.to(dev()))
+    torch.manual_seed(3)
+    eps = torch.randn_like(got[:, :4])
+    assert torch.allclose(z, 0.18215 * (got[:, :4] + torch.exp(0.5 * got[:, 4:].clamp(-30, 20)) * eps), atol=1e-6)
+
+
+def test_vae_round_trip_and_chunked_decode():
+    """Image -> moments -> decode on random weights is no identity, but every stage must be finite, batch-independent
+    and chunk-independent (decode_large_batch, dissect_lfm.py:86-98)."""
+    from uspace_b200.autoencoder import decode_large_batch
+    m = vae_model_gpu()
+    g = torch.Generator().manual_seed(9)
+    x = (torch.rand(10, 3, 128, 128, generator=g) * 2 - 1).to(dev())
+    mo = m.encode_moments(x)
+    assert mo.shape == (10, 8, 16, 16) and torch.isfinite(mo).all()
+    assert torch.equal(mo[8:9], m.encode_moments(x[8:9]))                   # second library chunk == batch of one
+    z = 0.18215 * mo[:, :4]
+    img = m.decode(z)
+    assert torch.equal(decode_large_batch(m, z, chunk=3), img)
+    with pytest.raises(ValueError):
+        m.encode_moments(torch.zeros(1, 3, 100, 100, device=dev()))

@@ -319,21 +319,32 @@ def test_vae_mirror_state_dict_layout_and_flops():
     from uspace_b200.autoencoder import FrozenAutoencoderKL, get_model
     m = get_model()
     sd = m.state_dict()
-    assert len(sd) == 140 and sum(v.numel() for v in sd.values()) == 49490179 + 20   # Decoder + post_quant_conv
+    assert len(sd) == 248 and sum(v.numel() for v in sd.values()) == 83653863         # the SD KL-f8 autoencoder
+    dec = {k: v for k, v in sd.items() if k.startswith(("decoder.", "post_quant_conv."))}
+    assert len(dec) == 140 and sum(v.numel() for v in dec.values()) == 49490179 + 20
     assert sd["decoder.up.1.block.0.nin_shortcut.weight"].shape == (256, 512, 1, 1)
     assert sd["decoder.up.3.upsample.conv.weight"].shape == (512, 512, 3, 3)
     assert "decoder.up.0.upsample.conv.weight" not in sd and sd["post_quant_conv.weight"].shape == (4, 4, 1, 1)
-    # a full reference checkpoint (encoder half included) loads; unknown keys do not
-    full = dict(sd, **{"encoder.conv_in.weight": torch.zeros(1), "quant_conv.weight": torch.zeros(1)})
-    m.load_state_dict(full)
+    assert sd["encoder.down.2.downsample.conv.weight"].shape == (512, 512, 3, 3) and sd["quant_conv.weight"].shape == (8, 8, 1, 1)
+    assert sd["encoder.conv_out.weight"].shape == (8, 512, 3, 3) and "encoder.down.3.downsample.conv.weight" not in sd
+    m.load_state_dict(sd)
     with pytest.raises(RuntimeError):
         m.load_state_dict(dict(sd, bogus=torch.zeros(1)))
     with pytest.raises(RuntimeError, match="no CPU"):
         m.decode(torch.zeros(1, 4, 32, 32))
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(RuntimeError, match="no CPU"):
         m.encode(torch.zeros(1, 3, 256, 256))
     with pytest.raises(NotImplementedError):
         FrozenAutoencoderKL(dict(V.DDCONFIG, ch=64))
     assert V.flops_per_image(32) / 1e9 == pytest.approx(622.19, rel=1e-3)      # 0.62 TFLOP per 256^2 image
     from uspace_b200.autoencoder import flops_per_image
     assert flops_per_image(32) == V.flops_per_image(32) and flops_per_image(16) == V.flops_per_image(16)
+
+
+@pytest.mark.parametrize("name", ["vae_enc_small", "vae_enc_full"])
+def test_vae_encoder_oracle_matches_reference_golden(golden_dir, name):
+    from oracle import vae_oracle as V
+    from tests.golden.cases import vae_enc_state_dict, vae_images
+    got = V.encode_moments(vae_enc_state_dict(), vae_images(name))
+    want = load(golden_dir, name)["moments"]
+    assert got.shape == want.shape and rel(got, want) < 5e-6

@@ -1,11 +1,12 @@
-"""Mirror of the reference's latent -> image decoder (libs/autoencoder.py): same constructor keywords, same
-``state_dict`` keys (``decoder.*``, ``post_quant_conv.*``), same ``decode(z)`` call - the step right after the sampling
-path (dissect_lfm.py:86-98 decodes in chunks of 50).
+"""Mirror of the reference's KL autoencoder (libs/autoencoder.py): same constructor keywords, same ``state_dict``
+keys (``encoder.*``, ``decoder.*``, ``quant_conv.*``, ``post_quant_conv.*``), same ``decode(z)`` / ``encode(x)`` /
+``encode_moments(x)`` calls - the steps on either side of the sampling path (dissect_lfm.py:86-98 decodes in chunks
+of 50; real-image editing encodes first, dissect_lfm.py:150-160).
 
 The modules below only HOLD parameters in the reference's layout (so reference checkpoints load unchanged and the
-seeded constructor reproduces the reference initialisation); ``decode`` runs on the CUDA library (csrc/vae.cu: im2col +
-the tcgen05 GEMMs of the U-ViT path, GroupNorm/swish, 1024-token attention).  There is no PyTorch fallback.
-The encoder half (``encode`` / ``encode_moments``) is not built."""
+seeded constructor reproduces the reference initialisation); the convolutions run on the CUDA library (csrc/vae.cu:
+implicit-GEMM convolutions on the tcgen05 kernels of the U-ViT path, GroupNorm/swish, 1024-token attention).  There is
+no PyTorch fallback."""
 from __future__ import annotations
 
 import ctypes as C
@@ -26,6 +27,14 @@ class Upsample(nn.Module):
         self.with_conv = with_conv
         if with_conv:
             self.conv = nn.Conv2d(in_channels, in_channels, kernel_size=3, stride=1, padding=1)
+
+
+class Downsample(nn.Module):
+    def __init__(self, in_channels, with_conv):
+        super().__init__()
+        self.with_conv = with_conv
+        if with_conv:   # asymmetric (0, 1, 0, 1) zero padding is applied by the caller (libs/autoencoder.py:65-69)
+            self.conv = nn.Conv2d(in_channels, in_channels, kernel_size=3, stride=2, padding=0)
 
 
 class ResnetBlock(nn.Module):
@@ -52,6 +61,44 @@ class AttnBlock(nn.Module):
         self.k = nn.Conv2d(in_channels, in_channels, kernel_size=1)
         self.v = nn.Conv2d(in_channels, in_channels, kernel_size=1)
         self.proj_out = nn.Conv2d(in_channels, in_channels, kernel_size=1)
+
+
+class Encoder(nn.Module):
+    """libs/autoencoder.py:209-272 (parameter creation order kept)."""
+
+    def __init__(self, *, ch, out_ch, ch_mult=(1, 2, 4, 8), num_res_blocks, attn_resolutions, dropout=0.0,
+                 resamp_with_conv=True, in_channels, resolution, z_channels, double_z=True, use_linear_attn=False,
+                 attn_type="vanilla", **ignore_kwargs):
+        super().__init__()
+        if use_linear_attn or attn_type != "vanilla" or not resamp_with_conv or not double_z:
+            raise NotImplementedError("only the configuration of libs/autoencoder.py::get_model is built")
+        self.num_resolutions = len(ch_mult)
+        self.conv_in = nn.Conv2d(in_channels, ch, kernel_size=3, stride=1, padding=1)
+        curr_res = resolution
+        in_ch_mult = (1,) + tuple(ch_mult)
+        self.down = nn.ModuleList()
+        block_in = ch
+        for i_level in range(self.num_resolutions):
+            block, attn = nn.ModuleList(), nn.ModuleList()
+            block_in = ch * in_ch_mult[i_level]
+            block_out = ch * ch_mult[i_level]
+            for _ in range(num_res_blocks):
+                block.append(ResnetBlock(in_channels=block_in, out_channels=block_out, temb_channels=0, dropout=dropout))
+                block_in = block_out
+                if curr_res in attn_resolutions:
+                    raise NotImplementedError("attention inside the down path is not used by get_model and not built")
+            down = nn.Module()
+            down.block, down.attn = block, attn
+            if i_level != self.num_resolutions - 1:
+                down.downsample = Downsample(block_in, resamp_with_conv)
+                curr_res = curr_res // 2
+            self.down.append(down)
+        self.mid = nn.Module()
+        self.mid.block_1 = ResnetBlock(in_channels=block_in, out_channels=block_in, temb_channels=0, dropout=dropout)
+        self.mid.attn_1 = AttnBlock(block_in)
+        self.mid.block_2 = ResnetBlock(in_channels=block_in, out_channels=block_in, temb_channels=0, dropout=dropout)
+        self.norm_out = Normalize(block_in)
+        self.conv_out = nn.Conv2d(block_in, 2 * z_channels, kernel_size=3, stride=1, padding=1)
 
 
 class Decoder(nn.Module):
@@ -97,7 +144,7 @@ DDCONFIG = dict(double_z=True, z_channels=4, resolution=256, in_channels=3, out_
 
 
 class FrozenAutoencoderKL(nn.Module):
-    """libs/autoencoder.py:412-460, decoder half.  ``pretrained_path=None`` keeps the random initialisation."""
+    """libs/autoencoder.py:412-460.  ``pretrained_path=None`` keeps the random initialisation."""
 
     def __init__(self, ddconfig=None, embed_dim=4, pretrained_path=None, scale_factor=0.18215):
         super().__init__()
@@ -105,24 +152,20 @@ class FrozenAutoencoderKL(nn.Module):
         if (ddconfig["ch"], list(ddconfig["ch_mult"]), ddconfig["num_res_blocks"], ddconfig["z_channels"],
                 ddconfig["out_ch"]) != (128, [1, 2, 4, 4], 2, 4, 3) or embed_dim != 4:
             raise NotImplementedError("only the Stable-Diffusion KL-f8 decoder of get_model() is built")
+        self.encoder = Encoder(**ddconfig)
         self.decoder = Decoder(**ddconfig)
+        self.quant_conv = nn.Conv2d(2 * ddconfig["z_channels"], 2 * embed_dim, 1)
         self.post_quant_conv = nn.Conv2d(embed_dim, ddconfig["z_channels"], 1)
         self.embed_dim, self.scale_factor = embed_dim, scale_factor
         self._engine = None
         if pretrained_path is not None:
-            m, u = self.load_state_dict(torch.load(pretrained_path, map_location="cpu"), strict=False)
-            assert all(k.startswith(("encoder.", "quant_conv.")) for k in u), u     # encoder half is not held here
-            assert not m, m
+            m, u = self.load_state_dict(torch.load(pretrained_path, map_location="cpu"))
+            assert len(m) == 0 and len(u) == 0
         self.eval().requires_grad_(False)
 
     def load_state_dict(self, state_dict, strict=True, **kw):
         self._engine = None
-        keep = {k: v for k, v in state_dict.items() if k.startswith(("decoder.", "post_quant_conv."))}
-        r = super().load_state_dict(keep, strict=strict, **kw)
-        extra = [k for k in state_dict if k not in keep]
-        if strict and any(not k.startswith(("encoder.", "quant_conv.")) for k in extra):
-            raise RuntimeError(f"unexpected keys {extra[:3]}")
-        return torch.nn.modules.module._IncompatibleKeys(list(r.missing_keys), extra)
+        return super().load_state_dict(state_dict, strict=strict, **kw)
 
     def _apply(self, fn, *a, **k):
         self._engine = None
@@ -140,15 +183,27 @@ class FrozenAutoencoderKL(nn.Module):
     def decode(self, z):
         return self.engine().decode(z)
 
-    def encode(self, x):
-        raise NotImplementedError("the encoder half of the autoencoder is not built")
+    @torch.no_grad()
+    def encode_moments(self, x):
+        """libs/autoencoder.py:426-429: images [B, 3, R, R] -> (mean, logvar) moments [B, 8, R/8, R/8]."""
+        return self.engine().encode_moments(x)
 
-    encode_moments = encode
+    def sample(self, moments):
+        """libs/autoencoder.py:431-437 (elementwise glue; the noise comes from torch's generator like the reference's)."""
+        mean, logvar = torch.chunk(moments, 2, dim=1)
+        logvar = torch.clamp(logvar, -30.0, 20.0)
+        std = torch.exp(0.5 * logvar)
+        return self.scale_factor * (mean + std * torch.randn_like(mean))
+
+    def encode(self, x):
+        return self.sample(self.encode_moments(x))
 
     def forward(self, inputs, fn):
         if fn == "decode":
             return self.decode(inputs)
-        if fn in ("encode", "encode_moments"):
+        if fn == "encode_moments":
+            return self.encode_moments(inputs)
+        if fn == "encode":
             return self.encode(inputs)
         raise NotImplementedError
 
@@ -172,6 +227,11 @@ def flops_per_image(S: int = 32) -> float:
             res *= 2
             f += 2.0 * res * res * 9 * cin * cin
     return f + 2.0 * res * res * 9 * cin * 3
+
+
+def decode_large_batch(autoencoder, batch, chunk: int = 50):
+    """dissect_lfm.py:86-98: decode in chunks of ``chunk`` latents and concatenate."""
+    return torch.cat([autoencoder.decode(batch[i:i + chunk]) for i in range(0, batch.shape[0], chunk)], dim=0)
 
 
 def get_model(pretrained_path=None, scale_factor=0.18215):
@@ -201,6 +261,16 @@ class VaeEngine:
 
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def encode_moments(self, x):
+        if x.dim() != 4 or x.shape[1] != 3 or x.shape[2] != x.shape[3] or x.shape[2] % 128 != 0:
+            raise ValueError(f"images must be [B, 3, R, R] with R % 128 == 0, got {tuple(x.shape)}")
+        x = x.to(self.device, torch.float32).contiguous()
+        B, R = x.shape[0], x.shape[2]
+        out = torch.empty((B, 8, R // 8, R // 8), device=self.device, dtype=torch.float32)
+        _lib.check(self.lib.usp_vae_encode_moments(self.handle, C.c_void_p(x.data_ptr()), C.c_void_p(out.data_ptr()), B, R,
+                                                   self._stream()), self.handle, "usp_vae_encode_moments", vae=True)
+        return out
 
     def decode(self, z):
         if z.dim() != 4 or z.shape[1] != 4 or z.shape[2] != z.shape[3] or z.shape[2] % 4 != 0:

@@ -34,16 +34,17 @@ namespace {
 constexpr int VT = 256;   // threads per block of the streaming kernels
 
 // ---- weights ------------------------------------------------------------------------------------------------
-// conv weight [Co, Ci, kh, kw] fp32 -> fp16 [Np, Kp] with k = (ky*kw + kx)*Ci + ci, zero padded
-__global__ void pack_conv_kernel(const float* __restrict__ w, __half* __restrict__ out, int Co, int Ci, int ks, int Np,
-                                 int Kp) {
+// conv weight [Co, Ci, kh, kw] fp32 -> fp16 [Np, Kp] with k = (ky*kw + kx)*Cip + ci (Cip >= Ci: the activation's
+// channel count after padding, 4 for the encoder's RGB input), zero padded
+__global__ void pack_conv_kernel(const float* __restrict__ w, __half* __restrict__ out, int Co, int Ci, int Cip, int ks,
+                                 int Np, int Kp) {
     const long long n = static_cast<long long>(Np) * Kp;
     const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
     for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
         const int co = static_cast<int>(i / Kp), k = static_cast<int>(i % Kp);
         float v = 0.f;
-        if (co < Co && k < ks * ks * Ci) {
-            const int tap = k / Ci, ci = k % Ci;
+        if (co < Co && k < ks * ks * Cip && k % Cip < Ci) {
+            const int tap = k / Cip, ci = k % Cip;
             v = w[((static_cast<long long>(co) * Ci + ci) * ks + tap / ks) * ks + tap % ks];
         }
         out[i] = __float2half_rn(v);
@@ -97,6 +98,55 @@ __global__ void im2col_kernel(const __half* __restrict__ in, __half* __restrict_
                 v = *reinterpret_cast<const uint2*>(in + ((static_cast<long long>(b) * Hin + yy / up) * Win + xx / up) * C + c0);
             *reinterpret_cast<uint2*>(A + m * Kp + static_cast<long long>(j) * 4) = v;
         }
+    }
+}
+
+// Downsample (libs/autoencoder.py:65-69): zero pad (0, 1, 0, 1), 3x3 conv, stride 2, no padding -> the im2col row of
+// output pixel (y, x) gathers input pixels (2y + ky, 2x + kx), zero beyond the last row / column
+__global__ void im2col_s2_kernel(const __half* __restrict__ in, __half* __restrict__ A, int B, int Hin, int Win, int C) {
+    const int H = Hin / 2, W = Win / 2, cv = C / 8, kv = 9 * cv;
+    const long long n = static_cast<long long>(B) * H * W * kv;
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const long long m = i / kv;
+        const int j = static_cast<int>(i % kv), tap = j / cv, c0 = (j % cv) * 8;
+        const int x = static_cast<int>(m % W), y = static_cast<int>((m / W) % H), b = static_cast<int>(m / (static_cast<long long>(W) * H));
+        const int yy = 2 * y + tap / 3, xx = 2 * x + tap % 3;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (yy < Hin && xx < Win) v = *reinterpret_cast<const uint4*>(in + ((static_cast<long long>(b) * Hin + yy) * Win + xx) * C + c0);
+        reinterpret_cast<uint4*>(A)[i] = v;
+    }
+}
+
+// encoder input: image NCHW fp32 [B, 3, R, R] -> fp16 NHWC with a zero 4th channel
+__global__ void vae_enc_in_kernel(const float* __restrict__ x, __half* __restrict__ out, int B, int HW) {
+    const long long n = static_cast<long long>(B) * HW;
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int b = static_cast<int>(i / HW), p = static_cast<int>(i % HW);
+    __half2 lo = __floats2half2_rn(x[(static_cast<long long>(b) * 3 + 0) * HW + p], x[(static_cast<long long>(b) * 3 + 1) * HW + p]);
+    __half2 hi = __floats2half2_rn(x[(static_cast<long long>(b) * 3 + 2) * HW + p], 0.f);
+    uint2 u;
+    u.x = *reinterpret_cast<uint32_t*>(&lo);
+    u.y = *reinterpret_cast<uint32_t*>(&hi);
+    reinterpret_cast<uint2*>(out)[i] = u;
+}
+// encoder output: conv_out result fp32 NHWC [M, Np] (8 channels) -> quant_conv (1x1, 8 -> 8) -> moments NCHW
+__global__ void vae_enc_out_kernel(const float* __restrict__ h, const float* __restrict__ w, const float* __restrict__ bq,
+                                   float* __restrict__ out, int B, int HW, int Np) {
+    const long long n = static_cast<long long>(B) * HW;
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int b = static_cast<int>(i / HW), p = static_cast<int>(i % HW);
+    float v[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) v[c] = h[i * Np + c];
+#pragma unroll
+    for (int o = 0; o < 8; ++o) {
+        float acc = bq[o];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc = fmaf(w[o * 8 + c], v[c], acc);
+        out[(static_cast<long long>(b) * 8 + o) * HW + p] = acc;
     }
 }
 
@@ -241,7 +291,7 @@ struct VWeight {
     float* d32 = nullptr;
     __half* d16 = nullptr;      // packed GEMM operand (conv weights)
     float* bias_pad = nullptr;  // bias zero-padded to the GEMM's N (conv biases whose Cout is not a multiple of 128)
-    int Np = 0, Kp = 0;
+    int Np = 0, Kp = 0, Cip = 0;
     bool set = false;
 };
 
@@ -319,7 +369,7 @@ int conv(usp_vae* h, const std::string& p, const __half* in16, int B, int Hin, i
          float* out32, __half* out16, int epi, cudaStream_t s) {
     const VWeight& w = W(h, p + ".weight");
     const VWeight& b = W(h, p + ".bias");
-    const int Ci = static_cast<int>(w.shape[1]), ks = static_cast<int>(w.shape[2]);
+    const int Ci = w.Cip, ks = static_cast<int>(w.shape[2]);   // channels of the (padded) activation
     const long long M = static_cast<long long>(B) * Hin * up * Win * up;
     const __half* A = in16;
     // USP_VAE_IM2COL=explicit materialises the im2col matrix instead of loading through a TMA im2col map
@@ -436,6 +486,60 @@ int ensure_workspace(usp_vae* h, int B, int S) {
     return USP_OK;
 }
 
+// Downsample.forward: x fp32 [B, H, H, C] -> y [B, H/2, H/2, C]
+int downsample(usp_vae* h, const std::string& p, const float* x, float* y, int B, int H, int C, cudaStream_t s) {
+    const VWeight& w = W(h, p + ".weight");
+    const VWeight& b = W(h, p + ".bias");
+    cudaError_t e = launch_convert16(x, h->a16, static_cast<long long>(B) * H * H * C, OPD_FP16, s);
+    if (e != cudaSuccess) return vfail(h, USP_ERR_CUDA, std::string("convert16: ") + cudaGetErrorString(e));
+    const long long M = static_cast<long long>(B) * (H / 2) * (H / 2);
+    im2col_s2_kernel<<<grid_for(M * 9 * (C / 8)), VT, 0, s>>>(h->a16, h->col, B, H, H, C);
+    VTRY(h, cudaGetLastError());
+    const char* err = gemm_raw(EPI_BIAS_F32, h->col, w.d16, b.bias_pad, nullptr, y, nullptr, static_cast<int>(M), w.Np, w.Kp,
+                               OPD_FP16, h->num_sms, s);
+    if (err) return vfail(h, USP_ERR_CUDA, "conv " + p + ": " + err);
+    return USP_OK;
+}
+
+// Encoder.forward + quant_conv for a chunk of B images of side R
+int encode_chunk(usp_vae* h, const float* img, float* moments, int B, int R, cudaStream_t s) {
+    int rc;
+    const std::string d = "encoder.";
+    const long long n_in = static_cast<long long>(B) * R * R;
+    vae_enc_in_kernel<<<static_cast<unsigned>((n_in + VT - 1) / VT), VT, 0, s>>>(img, h->a16, B, R * R);
+    VTRY(h, cudaGetLastError());
+    float *x = h->f0, *y = h->f1, *t = h->f2, *r = h->f3;
+    int C = CH, H = R;
+    if ((rc = conv(h, d + "conv_in", h->a16, B, H, H, 1, nullptr, x, nullptr, EPI_BIAS_F32, s))) return rc;
+    for (int lvl = 0; lvl < 4; ++lvl) {
+        const int Co = CH * MULT[lvl];
+        for (int blk = 0; blk < NRES; ++blk) {
+            if ((rc = res_block(h, d + "down." + std::to_string(lvl) + ".block." + std::to_string(blk), x, t, r, y, B, H, C, Co, s)))
+                return rc;
+            std::swap(x, y);
+            C = Co;
+        }
+        if (lvl != 3) {
+            if ((rc = downsample(h, d + "down." + std::to_string(lvl) + ".downsample.conv", x, y, B, H, C, s))) return rc;
+            std::swap(x, y);
+            H /= 2;
+        }
+    }
+    if ((rc = res_block(h, d + "mid.block_1", x, t, r, y, B, H, C, C, s))) return rc;
+    std::swap(x, y);
+    if ((rc = attn_block(h, d + "mid.attn_1", x, y, B, H, C, s))) return rc;
+    std::swap(x, y);
+    if ((rc = res_block(h, d + "mid.block_2", x, t, r, y, B, H, C, C, s))) return rc;
+    std::swap(x, y);
+    if ((rc = group_norm(h, d + "norm_out", x, B, H * H, C, true, h->a16, s))) return rc;
+    if ((rc = conv(h, d + "conv_out", h->a16, B, H, H, 1, nullptr, y, nullptr, EPI_BIAS_F32, s))) return rc;
+    const long long n_out = static_cast<long long>(B) * H * H;
+    vae_enc_out_kernel<<<static_cast<unsigned>((n_out + VT - 1) / VT), VT, 0, s>>>(
+        y, W(h, "quant_conv.weight").d32, W(h, "quant_conv.bias").d32, moments, B, H * H, W(h, d + "conv_out.weight").Np);
+    VTRY(h, cudaGetLastError());
+    return USP_OK;
+}
+
 // Decoder.forward for a chunk of B latents
 int decode_chunk(usp_vae* h, const float* z, float* img, int B, int S, cudaStream_t s) {
     int rc;
@@ -526,6 +630,25 @@ int usp_vae_create(int device, float scale_factor, usp_vae** out) {
     add_norm(h.get(), d + "norm_out", CH);
     add_conv(h.get(), d + "conv_out", CH, 3, 3);
     add_conv(h.get(), "post_quant_conv", 4, 4, 1);
+    // encoder (libs/autoencoder.py:209-272) + quant_conv
+    const std::string e = "encoder.";
+    add_conv(h.get(), e + "conv_in", 3, CH, 3);
+    int ec = CH;
+    for (int lvl = 0; lvl < 4; ++lvl) {
+        const int co = CH * MULT[lvl];
+        for (int blk = 0; blk < NRES; ++blk) {
+            add_res(h.get(), e + "down." + std::to_string(lvl) + ".block." + std::to_string(blk), ec, co);
+            ec = co;
+        }
+        if (lvl != 3) add_conv(h.get(), e + "down." + std::to_string(lvl) + ".downsample.conv", ec, ec, 3);
+    }
+    add_res(h.get(), e + "mid.block_1", ec, ec);
+    add_norm(h.get(), e + "mid.attn_1.norm", ec);
+    for (const char* n : {"q", "k", "v", "proj_out"}) add_conv(h.get(), e + "mid.attn_1." + n, ec, ec, 1);
+    add_res(h.get(), e + "mid.block_2", ec, ec);
+    add_norm(h.get(), e + "norm_out", ec);
+    add_conv(h.get(), e + "conv_out", ec, 8, 3);
+    add_conv(h.get(), "quant_conv", 8, 8, 1);
     *out = h.release();
     return USP_OK;
 }
@@ -572,12 +695,13 @@ int usp_vae_finalize(usp_vae* h, void* stream) {
         if (!w.set) return vfail(h, USP_ERR_STATE, "weight not set: " + w.name);
     for (size_t i = 0; i < h->w.size(); ++i) {
         VWeight& w = h->w[i];
-        if (w.shape.size() != 4 || w.name == "post_quant_conv.weight") continue;
+        if (w.shape.size() != 4 || w.name == "post_quant_conv.weight" || w.name == "quant_conv.weight") continue;
         const int Co = static_cast<int>(w.shape[0]), Ci = static_cast<int>(w.shape[1]), ks = static_cast<int>(w.shape[2]);
+        w.Cip = (Ci + 3) / 4 * 4;            // the RGB input is stored with a zero 4th channel
         w.Np = (Co + 127) / 128 * 128;
-        w.Kp = (ks * ks * Ci + 63) / 64 * 64;
+        w.Kp = (ks * ks * w.Cip + 63) / 64 * 64;
         if (!w.d16) VTRY(h, cudaMalloc(&w.d16, static_cast<size_t>(w.Np) * w.Kp * 2));
-        pack_conv_kernel<<<grid_for(static_cast<long long>(w.Np) * w.Kp), VT, 0, s>>>(w.d32, w.d16, Co, Ci, ks, w.Np, w.Kp);
+        pack_conv_kernel<<<grid_for(static_cast<long long>(w.Np) * w.Kp), VT, 0, s>>>(w.d32, w.d16, Co, Ci, w.Cip, ks, w.Np, w.Kp);
         VTRY(h, cudaGetLastError());
         VWeight& b = h->w[i + 1];     // the bias follows its weight
         if (!b.bias_pad) VTRY(h, cudaMalloc(&b.bias_pad, w.Np * 4));
@@ -604,6 +728,25 @@ int usp_vae_decode(usp_vae* h, const float* z, float* out, int B, int S, void* s
     for (int b0 = 0; b0 < B; b0 += chunk) {
         const int nb = B - b0 < chunk ? B - b0 : chunk;
         rc = decode_chunk(h, z + static_cast<long long>(b0) * 4 * S * S, out + static_cast<long long>(b0) * 3 * 64 * S * S, nb, S, s);
+        if (rc) return rc;
+    }
+    return USP_OK;
+}
+
+int usp_vae_encode_moments(usp_vae* h, const float* x, float* moments, int B, int R, void* stream) {
+    if (!h) return USP_ERR_INVALID;
+    if (!h->finalized) return vfail(h, USP_ERR_STATE, "weights not finalised");
+    if (!x || !moments || B < 1) return vfail(h, USP_ERR_INVALID, "null buffer or empty batch");
+    if (R < 128 || R > 512 || R % 128 != 0)
+        return vfail(h, USP_ERR_INVALID, "image side must be 128, 256, 384 or 512 (latent side R / 8 in {16, 32, 48, 64})");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    VTRY(h, cudaSetDevice(h->device));
+    const int S = R / 8, chunk = S <= 32 ? 8 : 2;
+    int rc = ensure_workspace(h, B < chunk ? B : chunk, S);
+    if (rc) return rc;
+    for (int b0 = 0; b0 < B; b0 += chunk) {
+        const int nb = B - b0 < chunk ? B - b0 : chunk;
+        rc = encode_chunk(h, x + static_cast<long long>(b0) * 3 * R * R, moments + static_cast<long long>(b0) * 8 * S * S, nb, R, s);
         if (rc) return rc;
     }
     return USP_OK;
