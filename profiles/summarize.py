@@ -22,8 +22,9 @@ RAW_METRICS = [
 ]
 
 
-def launches(tag):
-    p = os.path.join(GO, f"{tag}_launches.csv")
+def launches(tag, stem="launches", out="launch_list",
+             what="ONE U-ViT-L velocity evaluation at batch 64"):
+    p = os.path.join(GO, f"{tag}_{stem}.csv")
     if not os.path.exists(p):
         return
     rows = list(csv.reader(open(p)))
@@ -36,8 +37,8 @@ def launches(tag):
             agg.setdefault(r[kn].split("(")[0].replace("void ", "").replace("usp::<unnamed>::", "")[-48:], []).append(
                 float(r[mv].replace(",", "")))
     tot = sum(sum(v) for v in agg.values())
-    with open(os.path.join(OUT, f"{tag}_launch_list.md"), "w") as f:
-        f.write(f"# {tag}: ncu launch list of ONE U-ViT-L velocity evaluation at batch 64 "
+    with open(os.path.join(OUT, f"{tag}_{out}.md"), "w") as f:
+        f.write(f"# {tag}: ncu launch list of {what} "
                 "(`--metrics gpu__time_duration.sum --clock-control none`, cold-cache, serialised: compare shares)\n\n")
         f.write("| kernel | launches | total us | avg us | share |\n|---|---:|---:|---:|---:|\n")
         for k, v in agg.items():
@@ -89,5 +90,6 @@ def rep(tag, name):
 if __name__ == "__main__":
     tag = sys.argv[1]
     launches(tag)
-    for n in ("gemm", "attn"):
+    launches(tag, "vae_launches", "vae_launch_list", "ONE decode of 8 latents through the autoencoder (second call)")
+    for n in ("gemm", "attn", "vae"):
         rep(tag, n)

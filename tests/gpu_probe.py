@@ -284,6 +284,18 @@ def sec_one(lib, opd):
     print("kernels per forward", eng.kernels_per_forward())
 
 
+def sec_vae(lib, opd):
+    """Two decodes of 8 latents through the autoencoder (profile the second one under ncu)."""
+    from uspace_b200.autoencoder import get_model
+    torch.manual_seed(0)
+    m = get_model().to(dev)
+    z = 0.7 * torch.randn(8, 4, 32, 32, device=dev)
+    for _ in range(2):
+        img = m.decode(z)
+    torch.cuda.synchronize()
+    print("decoded", tuple(img.shape), bool(torch.isfinite(img).all()))
+
+
 if __name__ == "__main__":
     lib = _lib.load()
     sec = sys.argv[1]

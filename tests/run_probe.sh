@@ -12,5 +12,10 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm
     -o gpurun_out/${R}_prof_gemm -f python tests/gpu_probe.py one > gpurun_out/${R}_ncu_gemm.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:attention2_kernel -s 21 -c 1 \
     -o gpurun_out/${R}_prof_attn -f python tests/gpu_probe.py one > gpurun_out/${R}_ncu_attn.log 2>&1
+# the decoder's implicit-GEMM convolutions: second decode, three GEMMs from the 128^2 x 256-channel level
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm2_kernel -s 72 -c 3 \
+    -o gpurun_out/${R}_prof_vae -f python tests/gpu_probe.py vae > gpurun_out/${R}_ncu_vae.log 2>&1
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 300 -c 400 --csv \
+    --log-file gpurun_out/${R}_vae_launches.csv python tests/gpu_probe.py vae > gpurun_out/${R}_ncu_vae_launch.log 2>&1
 fi
 cat gpurun_out/${R}_pytest_gpu.log gpurun_out/${R}_smoke.log gpurun_out/${R}_bench.json
