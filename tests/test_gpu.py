@@ -884,3 +884,16 @@ def test_vae_round_trip_and_chunked_decode():
     assert torch.equal(decode_large_batch(m, z, chunk=3), img)
     with pytest.raises(ValueError):
         m.encode_moments(torch.zeros(1, 3, 100, 100, device=dev()))
+
+
+def test_vae_other_resolutions_against_oracle():
+    """The decoder / encoder are resolution-agnostic up to the GEMM shape rules (latent side 16, 32, 48, 64)."""
+    from oracle import vae_oracle as V
+    from tests.golden.cases import vae_enc_state_dict, vae_state_dict
+    m = vae_model_gpu()
+    sd = {k: v.double() for k, v in {**vae_state_dict(), **vae_enc_state_dict()}.items()}
+    g = torch.Generator().manual_seed(17)
+    z = 0.7 * torch.randn(1, 4, 48, 48, generator=g)
+    assert rel(m.decode(z.to(dev())), V.decode(sd, z.double())) < VAE_TOL
+    x = torch.rand(1, 3, 384, 384, generator=g) * 2 - 1
+    assert rel(m.encode_moments(x.to(dev())), V.encode_moments(sd, x.double())) < VAE_TOL
