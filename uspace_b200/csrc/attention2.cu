@@ -154,7 +154,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                 const uint8_t* vbuf = sV + (n & 1) * kv_bytes;
                 mbar_wait(&tail_go, n & 1);
                 mbar_wait(&kv_full[n & 1], (n >> 1) & 1);
-                for (int l = n_qt * QT; l < L; ++l) {
+                for (int l = n_qt * QT; l < ((a.diag & 32) ? 0 : L); ++l) {   // diag 32: skip the tail rows' arithmetic
                     // query row -> fp32 in smem
                     if (tt < HD / 2) {
                         const uint32_t w = reinterpret_cast<const uint32_t*>(a.q16)[(static_cast<long long>(bh) * L + l) * (HD / 2) + tt];

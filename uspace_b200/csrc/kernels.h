@@ -71,7 +71,8 @@ struct AttnArgs {
     const float* vscale;  // optional post-softmax column re-weighting [B, L] (p2p_rescale, tools/utils_t2i.py:196-224):
                           // O = sum_j (p_j * m_j) v_j / sum_j p_j  (no re-normalisation), or nullptr
     const struct StepState* st;  // sampling: apply vscale only while st->attn_on != 0; nullptr: always apply
-    int diag;             // diagnostics (env USP_ATTN_DIAG): 1 = no MUFU, 2 = no softmax arithmetic at all (results invalid)
+    int diag;             // diagnostics (env USP_ATTN_DIAG, results invalid): 1 = no MUFU, 2 = no softmax arithmetic,
+                          // 4 / 8 = no PV / S MMAs (non-pipelined variants), 16 = no TMEM reads, 32 = no tail-row arithmetic
     const void* q16;      // raw pointer to Q [B*H, L, 64] (the SIMT tail-row path reads its query rows directly)
 };
 constexpr int ATTN_MAX_L = 384;
