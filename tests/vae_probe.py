@@ -8,12 +8,12 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from oracle import vae_oracle as V  # noqa: E402  (developer probe: torch-library timing of the restatement)
-from tests.golden.cases import vae_latents, vae_state_dict  # noqa: E402
+from tests.golden.cases import vae_enc_state_dict, vae_latents, vae_state_dict  # noqa: E402
 from uspace_b200.autoencoder import get_model  # noqa: E402
 
 dev = torch.device("cuda:0")
 m = get_model()
-m.load_state_dict(vae_state_dict())
+m.load_state_dict({**vae_state_dict(), **vae_enc_state_dict()})
 m = m.to(dev)
 for name in ("vae_small", "vae_full"):
     g = np.load(os.path.join(os.path.dirname(__file__), "golden", f"{name}.npz"))["decode"]

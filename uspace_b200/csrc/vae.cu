@@ -199,29 +199,35 @@ __global__ void __launch_bounds__(VT) gn_partial_kernel(const float* __restrict_
         part[(static_cast<long long>(b) * chunks + chunk) * 32 + threadIdx.x] = make_double2(a, c);
     }
 }
-// pass 2: (mean, rstd) per (sample, group)
-__global__ void gn_final_kernel(const double2* __restrict__ part, float2* __restrict__ stats, int chunks, double inv_n) {
-    const int b = blockIdx.x, g = threadIdx.x;
-    double a = 0.0, c = 0.0;
-    for (int k = 0; k < chunks; ++k) {
-        const double2 p = part[(static_cast<long long>(b) * chunks + k) * 32 + g];
-        a += p.x;
-        c += p.y;
+// pass 2: every block first folds its sample's partials into (mean, rstd) per group - fixed order, so all blocks and
+// all runs agree - then normalises, applies the affine and optional swish x*sigmoid(x) (libs/autoencoder.py:26-28)
+// and writes fp16.  grid = (blocks per sample, B)
+__global__ void __launch_bounds__(VT) gn_apply_kernel(const float* __restrict__ x, const double2* __restrict__ part,
+                                                      const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                      __half* __restrict__ out, int HW, int C, int chunks, double inv_n,
+                                                      int swish) {
+    __shared__ float2 sh_stats[32];
+    const int b = blockIdx.y;
+    if (threadIdx.x < 32) {
+        double a = 0.0, c = 0.0;
+        for (int k = 0; k < chunks; ++k) {
+            const double2 p = part[(static_cast<long long>(b) * chunks + k) * 32 + threadIdx.x];
+            a += p.x;
+            c += p.y;
+        }
+        const double mean = a * inv_n;
+        const double var = fmax(c * inv_n - mean * mean, 0.0);
+        sh_stats[threadIdx.x] = make_float2(static_cast<float>(mean), static_cast<float>(rsqrt(var + 1e-6)));
     }
-    const double mean = a * inv_n;
-    const double var = fmax(c * inv_n - mean * mean, 0.0);
-    stats[b * 32 + g] = make_float2(static_cast<float>(mean), static_cast<float>(rsqrt(var + 1e-6)));
-}
-// pass 3: normalise, affine, optional swish x*sigmoid(x) (libs/autoencoder.py:26-28), fp16
-__global__ void gn_apply_kernel(const float* __restrict__ x, const float2* __restrict__ stats,
-                                const float* __restrict__ gamma, const float* __restrict__ beta, __half* __restrict__ out,
-                                long long n4, int HW, int C, int swish) {
+    __syncthreads();
     const int qpp = C / 4, cpg = C / 32;
+    const long long n4 = static_cast<long long>(HW) * qpp;          // float4 per sample
+    const long long base = static_cast<long long>(b) * n4;
     const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
-        const int q = static_cast<int>(i % qpp);
-        const int b = static_cast<int>(i / (static_cast<long long>(qpp) * HW));
-        const float2 st = stats[b * 32 + (q * 4) / cpg];
+    for (long long ii = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; ii < n4; ii += stride) {
+        const long long i = base + ii;
+        const int q = static_cast<int>(ii % qpp);
+        const float2 st = sh_stats[(q * 4) / cpg];
         const float4 v = reinterpret_cast<const float4*>(x)[i];
         const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + q);
         const float4 be = __ldg(reinterpret_cast<const float4*>(beta) + q);
@@ -314,7 +320,6 @@ struct usp_vae {
     __half *a16 = nullptr, *col = nullptr, *q16 = nullptr, *k16 = nullptr, *v16 = nullptr, *p16 = nullptr, *vt16 = nullptr;
     float* s32 = nullptr;
     double2* gn_part = nullptr;
-    float2* gn_stats = nullptr;
 };
 
 namespace {
@@ -407,10 +412,12 @@ int group_norm(usp_vae* h, const std::string& p, const float* x, int B, int HW, 
     if (chunks < 1) chunks = 1;
     if (chunks > 64) chunks = 64;
     gn_partial_kernel<<<dim3(chunks, B), VT, 0, s>>>(x, h->gn_part, HW, C, chunks);
-    gn_final_kernel<<<B, 32, 0, s>>>(h->gn_part, h->gn_stats, chunks, 1.0 / (static_cast<double>(HW) * (C / 32)));
-    const long long n4 = static_cast<long long>(B) * HW * C / 4;
-    gn_apply_kernel<<<grid_for(n4), VT, 0, s>>>(x, h->gn_stats, W(h, p + ".weight").d32, W(h, p + ".bias").d32, out, n4, HW, C,
-                                                swish ? 1 : 0);
+    const long long n4 = static_cast<long long>(HW) * C / 4;     // per sample
+    int per_sample = static_cast<int>((n4 + VT * 8 - 1) / (VT * 8));   // ~8 float4 per thread
+    if (per_sample < 1) per_sample = 1;
+    if (per_sample > 1024) per_sample = 1024;
+    gn_apply_kernel<<<dim3(per_sample, B), VT, 0, s>>>(x, h->gn_part, W(h, p + ".weight").d32, W(h, p + ".bias").d32, out, HW, C,
+                                                       chunks, 1.0 / (static_cast<double>(HW) * (C / 32)), swish ? 1 : 0);
     VTRY(h, cudaGetLastError());
     return USP_OK;
 }
@@ -472,7 +479,7 @@ int ensure_workspace(usp_vae* h, int B, int S) {
     const size_t o_a = carve(act * 2), o_col = carve(colb * 2);
     const size_t o_q = carve(B * T * C * 2), o_k = carve(B * T * C * 2), o_v = carve(B * T * C * 2);
     const size_t o_p = carve(T * T * 2), o_vt = carve(T * C * 2), o_s = carve(T * T * 4);
-    const size_t o_gp = carve(static_cast<size_t>(B) * 64 * 32 * sizeof(double2)), o_gs = carve(static_cast<size_t>(B) * 32 * sizeof(float2));
+    const size_t o_gp = carve(static_cast<size_t>(B) * 64 * 32 * sizeof(double2));
     VTRY(h, cudaMalloc(&h->slab, off));
     char* base = static_cast<char*>(h->slab);
     h->f0 = reinterpret_cast<float*>(base + o_f0); h->f1 = reinterpret_cast<float*>(base + o_f1);
@@ -481,7 +488,7 @@ int ensure_workspace(usp_vae* h, int B, int S) {
     h->q16 = reinterpret_cast<__half*>(base + o_q); h->k16 = reinterpret_cast<__half*>(base + o_k);
     h->v16 = reinterpret_cast<__half*>(base + o_v); h->p16 = reinterpret_cast<__half*>(base + o_p);
     h->vt16 = reinterpret_cast<__half*>(base + o_vt); h->s32 = reinterpret_cast<float*>(base + o_s);
-    h->gn_part = reinterpret_cast<double2*>(base + o_gp); h->gn_stats = reinterpret_cast<float2*>(base + o_gs);
+    h->gn_part = reinterpret_cast<double2*>(base + o_gp);
     h->ws_B = B; h->ws_S = S;
     return USP_OK;
 }
