@@ -59,16 +59,20 @@ EncodeIm2colFn get_im2col_fn() {
 }
 // fp16 NHWC activation [n, h, w, c] as the A operand of a 3x3 / stride 1 / pad 1 convolution: 128 output pixels x 64
 // channels per load (the same 128-row x 128-byte swizzled box the plain GEMM stages), padding zero-filled by the TMA
-bool make_map_im2col(CUtensorMap* m, const void* ptr, long long n, long long h, long long w, long long c) {
+bool make_map_im2col(CUtensorMap* m, const void* ptr, long long n, long long h, long long w, long long c, int stride) {
     EncodeIm2colFn fn = get_im2col_fn();
     if (!fn) return false;
     cuuint64_t dims[4] = {static_cast<cuuint64_t>(c), static_cast<cuuint64_t>(w), static_cast<cuuint64_t>(h),
                           static_cast<cuuint64_t>(n)};
     cuuint64_t strides[3] = {static_cast<cuuint64_t>(c) * 2, static_cast<cuuint64_t>(w * c) * 2,
                              static_cast<cuuint64_t>(h * w * c) * 2};
-    const int lower[2] = {-1, -1};   // -padding
-    const int upper[2] = {-1, -1};   // padding - (filter - 1) * dilation
-    cuuint32_t estr[4] = {1, 1, 1, 1};
+    // lower corner = -padding_low, upper corner = padding_high - (filter - 1) * dilation; stride 2 = the Downsample
+    // convolution: no padding before, one zero row / column after, every second base pixel
+    const int lo = stride == 1 ? -1 : 0;
+    const int lower[2] = {lo, lo};
+    const int upper[2] = {-1, -1};
+    const cuuint32_t st = static_cast<cuuint32_t>(stride);
+    cuuint32_t estr[4] = {1, st, st, 1};
     CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(ptr), dims, strides, lower, upper, 64, GEMM_BM,
                     estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -1377,7 +1381,7 @@ namespace usp {
 // latent decoder (csrc/vae.cu).  Returns a message on failure.
 const char* gemm_raw(int epilogue, const void* a16, const void* w16, const float* bias, const float* resid,
                      float* out32, void* out16, int M, int N, int K, int operand_dtype, int num_sms, cudaStream_t s,
-                     int conv_C, int conv_H, int conv_W) {
+                     int conv_C, int conv_H, int conv_W, int conv_stride) {
     if (!get_encode_fn()) return "cuTensorMapEncodeTiled entry point not found";
     if (gemm_configure() != cudaSuccess) return "gemm_configure failed";
     GemmMaps maps;
@@ -1386,7 +1390,9 @@ const char* gemm_raw(int epilogue, const void* a16, const void* w16, const float
         // implicit GEMM: a16 is the NHWC activation, K = 9 * conv_C
         if (conv_C % 64 != 0 || K != 9 * conv_C || M % (conv_H * conv_W) != 0 || M % 256 != 0 || operand_dtype != OPD_FP16)
             return "implicit-GEMM convolution needs C % 64 == 0, K == 9 C, whole images and M % 256 == 0";
-        ok = make_map_im2col(&maps.a0, a16, M / (conv_H * conv_W), conv_H, conv_W, conv_C);
+        if (conv_stride != 1 && conv_stride != 2) return "convolution stride must be 1 or 2";
+        ok = make_map_im2col(&maps.a0, a16, M / (conv_H * conv_W), static_cast<long long>(conv_H) * conv_stride,
+                             static_cast<long long>(conv_W) * conv_stride, conv_C, conv_stride);
     } else {
         ok = make_map_2d(&maps.a0, a16, M, K, GEMM_BM, operand_dtype);
     }
@@ -1404,6 +1410,7 @@ const char* gemm_raw(int epilogue, const void* a16, const void* w16, const float
     g.bias = bias; g.resid = resid; g.out32 = out32; g.out16 = out16;
     g.L = 1; g.H = 1;
     g.conv_C = conv_C; g.conv_H = conv_H; g.conv_W = conv_W;
+    g.conv_stride = conv_stride; g.conv_pad = conv_stride == 1 ? 1 : 0;
     cudaError_t e = launch_gemm(epilogue, maps, g, num_sms, s);
     return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
 }

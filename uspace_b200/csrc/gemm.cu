@@ -100,8 +100,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CU
                         mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
                         if (g.conv_C > 0) {
                             const int cpt = g.conv_C / BK, tap = kb / cpt;
-                            tma_load_im2col(&tmA0, &full_bar[stage], sa, (kb - tap * cpt) * BK, m0 % g.conv_W - 1,
-                                            (m0 / g.conv_W) % g.conv_H - 1, m0 / (g.conv_W * g.conv_H),
+                            tma_load_im2col(&tmA0, &full_bar[stage], sa, (kb - tap * cpt) * BK,
+                                            (m0 % g.conv_W) * g.conv_stride - g.conv_pad,
+                                            ((m0 / g.conv_W) % g.conv_H) * g.conv_stride - g.conv_pad,
+                                            m0 / (g.conv_W * g.conv_H),
                                             static_cast<uint16_t>(tap % 3), static_cast<uint16_t>(tap / 3));
                         } else if (kb < nkb0)
                             tma_load_2d(&tmA0, &full_bar[stage], sa, kb * BK, m0);

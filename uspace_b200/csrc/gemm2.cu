@@ -140,8 +140,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
                         if (leader) mbar_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);
                         if (g.conv_C > 0) {      // implicit GEMM (launched with NP == 1 only)
                             const int cpt = g.conv_C / BK, tap = kb / cpt;
-                            tma_load_im2col_cg2(&tmA0, lead_full, sa, (kb - tap * cpt) * BK, m0 % g.conv_W - 1,
-                                                (m0 / g.conv_W) % g.conv_H - 1, m0 / (g.conv_W * g.conv_H),
+                            tma_load_im2col_cg2(&tmA0, lead_full, sa, (kb - tap * cpt) * BK,
+                                                (m0 % g.conv_W) * g.conv_stride - g.conv_pad,
+                                                ((m0 / g.conv_W) % g.conv_H) * g.conv_stride - g.conv_pad,
+                                                m0 / (g.conv_W * g.conv_H),
                                                 static_cast<uint16_t>(tap % 3), static_cast<uint16_t>(tap / 3));
                         } else if (NP == 1) {
                             if (kb < nkb0)

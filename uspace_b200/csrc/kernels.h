@@ -42,7 +42,8 @@ struct GemmArgs {
     // ---- implicit GEMM for 3x3 / stride 1 / pad 1 convolutions (csrc/vae.cu) ----
     // conv_C > 0: A is the fp16 NHWC activation [*, conv_H, conv_W, conv_C] behind an im2col tensor map (GemmMaps::a0);
     // row m = output pixel, K block kb = channels [(kb % (C/64)) * 64, +64) of filter tap kb / (C/64)
-    int conv_C, conv_H, conv_W;
+    int conv_C, conv_H, conv_W;   // conv_H / conv_W: OUTPUT height / width
+    int conv_stride, conv_pad;    // 1 / 1 (same-size convolution) or 2 / 0 (Downsample: zero pad only at the far edges)
     // producer side (skip / proj / fc2): partial row statistics of the fp32 values it writes, one slot per
     // (row, 128-column group): [M, N/128, 2]
     float* stats_out;
@@ -163,9 +164,10 @@ cudaError_t launch_step(StepState* st, const float* grid, const unsigned char* m
 // GEMM on raw device pointers (api.cu): nullptr on success, else a message
 // conv_C > 0: a16 is an fp16 NHWC activation [M / (conv_H * conv_W), conv_H, conv_W, conv_C] and the product is its
 // 3x3 / stride 1 / pad 1 convolution with W[N, 9 * conv_C] (K ordered (ky, kx, c)), loaded through a TMA im2col map
+// conv_stride == 2: the stride-2 Downsample convolution (input [.., 2 conv_H, 2 conv_W, conv_C], zero padding (0, 1, 0, 1))
 const char* gemm_raw(int epilogue, const void* a16, const void* w16, const float* bias, const float* resid,
                      float* out32, void* out16, int M, int N, int K, int operand_dtype, int num_sms, cudaStream_t s,
-                     int conv_C = 0, int conv_H = 0, int conv_W = 0);
+                     int conv_C = 0, int conv_H = 0, int conv_W = 0, int conv_stride = 1);
 
 // ---- adaptive Dormand-Prince 5(4) (csrc/ode.cu) -------------------------------------------------
 // torchdiffeq's RKAdaptiveStepsizeODESolver restated with the controller on the device: time-like quantities are

@@ -500,10 +500,18 @@ int downsample(usp_vae* h, const std::string& p, const float* x, float* y, int B
     cudaError_t e = launch_convert16(x, h->a16, static_cast<long long>(B) * H * H * C, OPD_FP16, s);
     if (e != cudaSuccess) return vfail(h, USP_ERR_CUDA, std::string("convert16: ") + cudaGetErrorString(e));
     const long long M = static_cast<long long>(B) * (H / 2) * (H / 2);
-    im2col_s2_kernel<<<grid_for(M * 9 * (C / 8)), VT, 0, s>>>(h->a16, h->col, B, H, H, C);
-    VTRY(h, cudaGetLastError());
-    const char* err = gemm_raw(EPI_BIAS_F32, h->col, w.d16, b.bias_pad, nullptr, y, nullptr, static_cast<int>(M), w.Np, w.Kp,
-                               OPD_FP16, h->num_sms, s);
+    static const bool explicit_cols = [] { const char* e = getenv("USP_VAE_IM2COL"); return e && e[0] == 'e'; }();
+    const char* err;
+    if (C % 64 == 0 && M % 256 == 0 && !explicit_cols) {
+        // implicit GEMM with a stride-2 im2col map (every second base pixel, zero row / column at the far edge)
+        err = gemm_raw(EPI_BIAS_F32, h->a16, w.d16, b.bias_pad, nullptr, y, nullptr, static_cast<int>(M), w.Np, w.Kp, OPD_FP16,
+                       h->num_sms, s, C, H / 2, H / 2, 2);
+    } else {
+        im2col_s2_kernel<<<grid_for(M * 9 * (C / 8)), VT, 0, s>>>(h->a16, h->col, B, H, H, C);
+        VTRY(h, cudaGetLastError());
+        err = gemm_raw(EPI_BIAS_F32, h->col, w.d16, b.bias_pad, nullptr, y, nullptr, static_cast<int>(M), w.Np, w.Kp, OPD_FP16,
+                       h->num_sms, s);
+    }
     if (err) return vfail(h, USP_ERR_CUDA, "conv " + p + ": " + err);
     return USP_OK;
 }
