@@ -46,3 +46,15 @@ for dt in (torch.float32, torch.float16):
             V.decode(sdd, z.to(dt))
         torch.cuda.synchronize()
     print(f"torch {dt} B=8: {(time.time() - t) / 3 * 1e3:.1f} ms", flush=True)
+for B in (8, 64):
+    x = (torch.rand(B, 3, 256, 256) * 2 - 1).to(dev)
+    m.encode_moments(x)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+    e0.record()
+    for _ in range(3):
+        m.encode_moments(x)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 3
+    print(f"encode_moments B={B}: {ms:.2f} ms  {B / ms * 1e3:.1f} img/s", flush=True)
