@@ -164,9 +164,17 @@ __global__ void upsample2_kernel(const __half* __restrict__ in, __half* __restri
     }
 }
 
-// ---- GroupNorm(32 groups, eps 1e-6, affine) [+ swish] -> fp16 -------------------------------------------------------
+// ---- GroupNorm(32 groups, eps 1e-6, affine) [+ swish]: fp16 copy of the activation in, fp16 GEMM operand out ----------
+// (every producing GEMM writes the fp16 copy next to its fp32 result; reading 2 instead of 4 bytes twice takes a third
+// off the GroupNorm time, which was 29 % of a decode)
 // pass 1: per (sample, pixel chunk, group) partial sum / sum of squares; a thread always sees the same 4 channels
-__global__ void __launch_bounds__(VT) gn_partial_kernel(const float* __restrict__ x, double2* __restrict__ part, int HW,
+__device__ __forceinline__ float4 ld_half4(const __half* p) {
+    const uint2 u = *reinterpret_cast<const uint2*>(p);
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
+    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+}
+__global__ void __launch_bounds__(VT) gn_partial_kernel(const __half* __restrict__ x, double2* __restrict__ part, int HW,
                                                         int C, int chunks) {
     const int b = blockIdx.y, chunk = blockIdx.x;
     const int qpp = C / 4;                       // float4 per pixel
@@ -177,7 +185,7 @@ __global__ void __launch_bounds__(VT) gn_partial_kernel(const float* __restrict_
     float s = 0.f, ss = 0.f;
     if (sub < ppi) {
         for (int p = p0 + sub; p < p1; p += ppi) {
-            const float4 v = *reinterpret_cast<const float4*>(x + (static_cast<long long>(b) * HW + p) * C + q * 4);
+            const float4 v = ld_half4(x + (static_cast<long long>(b) * HW + p) * C + q * 4);
             s += (v.x + v.y) + (v.z + v.w);
             ss += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
         }
@@ -202,7 +210,7 @@ __global__ void __launch_bounds__(VT) gn_partial_kernel(const float* __restrict_
 // pass 2: every block first folds its sample's partials into (mean, rstd) per group - fixed order, so all blocks and
 // all runs agree - then normalises, applies the affine and optional swish x*sigmoid(x) (libs/autoencoder.py:26-28)
 // and writes fp16.  grid = (blocks per sample, B)
-__global__ void __launch_bounds__(VT) gn_apply_kernel(const float* __restrict__ x, const double2* __restrict__ part,
+__global__ void __launch_bounds__(VT) gn_apply_kernel(const __half* __restrict__ x, const double2* __restrict__ part,
                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
                                                       __half* __restrict__ out, int HW, int C, int chunks, double inv_n,
                                                       int swish) {
@@ -228,7 +236,7 @@ __global__ void __launch_bounds__(VT) gn_apply_kernel(const float* __restrict__ 
         const long long i = base + ii;
         const int q = static_cast<int>(ii % qpp);
         const float2 st = sh_stats[(q * 4) / cpg];
-        const float4 v = reinterpret_cast<const float4*>(x)[i];
+        const float4 v = ld_half4(x + 4 * i);
         const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + q);
         const float4 be = __ldg(reinterpret_cast<const float4*>(beta) + q);
         float y[4] = {(v.x - st.x) * st.y * g.x + be.x, (v.y - st.x) * st.y * g.y + be.y,
@@ -316,7 +324,8 @@ struct usp_vae {
     // workspace for (chunk batch, latent side)
     int ws_B = 0, ws_S = 0;
     void* slab = nullptr;
-    float *f0 = nullptr, *f1 = nullptr, *f2 = nullptr, *f3 = nullptr;   // fp32 NHWC activations
+    float *f0 = nullptr, *f1 = nullptr, *f2 = nullptr;   // fp32 NHWC activations: x, y ping-pong, nin_shortcut result
+    __half *h0 = nullptr, *h1 = nullptr, *t16 = nullptr;  // fp16 copies of x / y, conv1 result
     __half *a16 = nullptr, *col = nullptr, *q16 = nullptr, *k16 = nullptr, *v16 = nullptr, *p16 = nullptr, *vt16 = nullptr;
     float* s32 = nullptr;
     double2* gn_part = nullptr;
@@ -405,8 +414,14 @@ int conv(usp_vae* h, const std::string& p, const __half* in16, int B, int Hin, i
     return USP_OK;
 }
 
-// GroupNorm (+ swish) of fp32 NHWC x [B, HW, C] -> fp16
-int group_norm(usp_vae* h, const std::string& p, const float* x, int B, int HW, int C, bool swish, __half* out,
+// an activation: fp32 NHWC (residual path) + its fp16 copy (GroupNorm / 1x1 conv / resampling input)
+struct Act {
+    float* f;
+    __half* h;
+};
+
+// GroupNorm (+ swish) of the fp16 NHWC copy x [B, HW, C] -> fp16
+int group_norm(usp_vae* h, const std::string& p, const __half* x, int B, int HW, int C, bool swish, __half* out,
                cudaStream_t s) {
     int chunks = HW / 64;
     if (chunks < 1) chunks = 1;
@@ -422,28 +437,26 @@ int group_norm(usp_vae* h, const std::string& p, const float* x, int B, int HW, 
     return USP_OK;
 }
 
-// ResnetBlock.forward (libs/autoencoder.py:114-134, temb is None): x [B, H*W, Ci] fp32 in `x`, result in `y`
-int res_block(usp_vae* h, const std::string& p, const float* x, float* t, float* r, float* y, int B, int H, int Ci, int Co,
-              cudaStream_t s) {
+// ResnetBlock.forward (libs/autoencoder.py:114-134, temb is None): x [B, H*W, Ci] -> y [B, H*W, Co]
+int res_block(usp_vae* h, const std::string& p, Act x, Act y, int B, int H, int Ci, int Co, cudaStream_t s) {
     int rc;
-    if ((rc = group_norm(h, p + ".norm1", x, B, H * H, Ci, true, h->a16, s))) return rc;
-    if ((rc = conv(h, p + ".conv1", h->a16, B, H, H, 1, nullptr, t, nullptr, EPI_BIAS_F32, s))) return rc;
-    const float* resid = x;
+    if ((rc = group_norm(h, p + ".norm1", x.h, B, H * H, Ci, true, h->a16, s))) return rc;
+    // conv1's result only feeds norm2: fp16 is all that is written
+    if ((rc = conv(h, p + ".conv1", h->a16, B, H, H, 1, nullptr, nullptr, h->t16, EPI_BIAS_F32, s))) return rc;
+    const float* resid = x.f;
     if (Ci != Co) {
-        cudaError_t e = launch_convert16(x, h->a16, static_cast<long long>(B) * H * H * Ci, OPD_FP16, s);
-        if (e != cudaSuccess) return vfail(h, USP_ERR_CUDA, std::string("convert16: ") + cudaGetErrorString(e));
-        if ((rc = conv(h, p + ".nin_shortcut", h->a16, B, H, H, 1, nullptr, r, nullptr, EPI_BIAS_F32, s))) return rc;
-        resid = r;
+        if ((rc = conv(h, p + ".nin_shortcut", x.h, B, H, H, 1, nullptr, h->f2, nullptr, EPI_BIAS_F32, s))) return rc;
+        resid = h->f2;
     }
-    if ((rc = group_norm(h, p + ".norm2", t, B, H * H, Co, true, h->a16, s))) return rc;
-    return conv(h, p + ".conv2", h->a16, B, H, H, 1, resid, y, nullptr, EPI_BIAS_RESID, s);
+    if ((rc = group_norm(h, p + ".norm2", h->t16, B, H * H, Co, true, h->a16, s))) return rc;
+    return conv(h, p + ".conv2", h->a16, B, H, H, 1, resid, y.f, y.h, EPI_BIAS_RESID, s);
 }
 
 // AttnBlock.forward (libs/autoencoder.py:171-195): single head over H*W tokens of width C
-int attn_block(usp_vae* h, const std::string& p, const float* x, float* y, int B, int H, int C, cudaStream_t s) {
+int attn_block(usp_vae* h, const std::string& p, Act x, Act y, int B, int H, int C, cudaStream_t s) {
     const int T = H * H;
     int rc;
-    if ((rc = group_norm(h, p + ".norm", x, B, T, C, false, h->a16, s))) return rc;
+    if ((rc = group_norm(h, p + ".norm", x.h, B, T, C, false, h->a16, s))) return rc;
     if ((rc = conv(h, p + ".q", h->a16, B, H, H, 1, nullptr, nullptr, h->q16, EPI_BIAS_F32, s))) return rc;
     if ((rc = conv(h, p + ".k", h->a16, B, H, H, 1, nullptr, nullptr, h->k16, EPI_BIAS_F32, s))) return rc;
     if ((rc = conv(h, p + ".v", h->a16, B, H, H, 1, nullptr, nullptr, h->v16, EPI_BIAS_F32, s))) return rc;
@@ -462,7 +475,7 @@ int attn_block(usp_vae* h, const std::string& p, const float* x, float* y, int B
                      OPD_FP16, h->num_sms, s);
         if (e) return vfail(h, USP_ERR_CUDA, std::string("attention P v: ") + e);
     }
-    return conv(h, p + ".proj_out", h->a16, B, H, H, 1, x, y, nullptr, EPI_BIAS_RESID, s);
+    return conv(h, p + ".proj_out", h->a16, B, H, H, 1, x.f, y.f, y.h, EPI_BIAS_RESID, s);
 }
 
 int ensure_workspace(usp_vae* h, int B, int S) {
@@ -475,7 +488,8 @@ int ensure_workspace(usp_vae* h, int B, int S) {
     const long long T = static_cast<long long>(S) * S, C = 512;
     size_t off = 0;
     auto carve = [&](size_t bytes) { size_t o = off; off = (off + bytes + 1023) / 1024 * 1024; return o; };
-    const size_t o_f0 = carve(act * 4), o_f1 = carve(act * 4), o_f2 = carve(act * 4), o_f3 = carve(act * 4);
+    const size_t o_f0 = carve(act * 4), o_f1 = carve(act * 4), o_f2 = carve(act * 4);
+    const size_t o_h0 = carve(act * 2), o_h1 = carve(act * 2), o_t16 = carve(act * 2);
     const size_t o_a = carve(act * 2), o_col = carve(colb * 2);
     const size_t o_q = carve(B * T * C * 2), o_k = carve(B * T * C * 2), o_v = carve(B * T * C * 2);
     const size_t o_p = carve(T * T * 2), o_vt = carve(T * C * 2), o_s = carve(T * T * 4);
@@ -483,7 +497,9 @@ int ensure_workspace(usp_vae* h, int B, int S) {
     VTRY(h, cudaMalloc(&h->slab, off));
     char* base = static_cast<char*>(h->slab);
     h->f0 = reinterpret_cast<float*>(base + o_f0); h->f1 = reinterpret_cast<float*>(base + o_f1);
-    h->f2 = reinterpret_cast<float*>(base + o_f2); h->f3 = reinterpret_cast<float*>(base + o_f3);
+    h->f2 = reinterpret_cast<float*>(base + o_f2);
+    h->h0 = reinterpret_cast<__half*>(base + o_h0); h->h1 = reinterpret_cast<__half*>(base + o_h1);
+    h->t16 = reinterpret_cast<__half*>(base + o_t16);
     h->a16 = reinterpret_cast<__half*>(base + o_a); h->col = reinterpret_cast<__half*>(base + o_col);
     h->q16 = reinterpret_cast<__half*>(base + o_q); h->k16 = reinterpret_cast<__half*>(base + o_k);
     h->v16 = reinterpret_cast<__half*>(base + o_v); h->p16 = reinterpret_cast<__half*>(base + o_p);
@@ -494,22 +510,20 @@ int ensure_workspace(usp_vae* h, int B, int S) {
 }
 
 // Downsample.forward: x fp32 [B, H, H, C] -> y [B, H/2, H/2, C]
-int downsample(usp_vae* h, const std::string& p, const float* x, float* y, int B, int H, int C, cudaStream_t s) {
+int downsample(usp_vae* h, const std::string& p, Act x, Act y, int B, int H, int C, cudaStream_t s) {
     const VWeight& w = W(h, p + ".weight");
     const VWeight& b = W(h, p + ".bias");
-    cudaError_t e = launch_convert16(x, h->a16, static_cast<long long>(B) * H * H * C, OPD_FP16, s);
-    if (e != cudaSuccess) return vfail(h, USP_ERR_CUDA, std::string("convert16: ") + cudaGetErrorString(e));
     const long long M = static_cast<long long>(B) * (H / 2) * (H / 2);
     static const bool explicit_cols = [] { const char* e = getenv("USP_VAE_IM2COL"); return e && e[0] == 'e'; }();
     const char* err;
     if (C % 64 == 0 && M % 256 == 0 && !explicit_cols) {
         // implicit GEMM with a stride-2 im2col map (every second base pixel, zero row / column at the far edge)
-        err = gemm_raw(EPI_BIAS_F32, h->a16, w.d16, b.bias_pad, nullptr, y, nullptr, static_cast<int>(M), w.Np, w.Kp, OPD_FP16,
+        err = gemm_raw(EPI_BIAS_F32, x.h, w.d16, b.bias_pad, nullptr, y.f, y.h, static_cast<int>(M), w.Np, w.Kp, OPD_FP16,
                        h->num_sms, s, C, H / 2, H / 2, 2);
     } else {
-        im2col_s2_kernel<<<grid_for(M * 9 * (C / 8)), VT, 0, s>>>(h->a16, h->col, B, H, H, C);
+        im2col_s2_kernel<<<grid_for(M * 9 * (C / 8)), VT, 0, s>>>(x.h, h->col, B, H, H, C);
         VTRY(h, cudaGetLastError());
-        err = gemm_raw(EPI_BIAS_F32, h->col, w.d16, b.bias_pad, nullptr, y, nullptr, static_cast<int>(M), w.Np, w.Kp, OPD_FP16,
+        err = gemm_raw(EPI_BIAS_F32, h->col, w.d16, b.bias_pad, nullptr, y.f, y.h, static_cast<int>(M), w.Np, w.Kp, OPD_FP16,
                        h->num_sms, s);
     }
     if (err) return vfail(h, USP_ERR_CUDA, "conv " + p + ": " + err);
@@ -523,13 +537,13 @@ int encode_chunk(usp_vae* h, const float* img, float* moments, int B, int R, cud
     const long long n_in = static_cast<long long>(B) * R * R;
     vae_enc_in_kernel<<<static_cast<unsigned>((n_in + VT - 1) / VT), VT, 0, s>>>(img, h->a16, B, R * R);
     VTRY(h, cudaGetLastError());
-    float *x = h->f0, *y = h->f1, *t = h->f2, *r = h->f3;
+    Act x = {h->f0, h->h0}, y = {h->f1, h->h1};
     int C = CH, H = R;
-    if ((rc = conv(h, d + "conv_in", h->a16, B, H, H, 1, nullptr, x, nullptr, EPI_BIAS_F32, s))) return rc;
+    if ((rc = conv(h, d + "conv_in", h->a16, B, H, H, 1, nullptr, x.f, x.h, EPI_BIAS_F32, s))) return rc;
     for (int lvl = 0; lvl < 4; ++lvl) {
         const int Co = CH * MULT[lvl];
         for (int blk = 0; blk < NRES; ++blk) {
-            if ((rc = res_block(h, d + "down." + std::to_string(lvl) + ".block." + std::to_string(blk), x, t, r, y, B, H, C, Co, s)))
+            if ((rc = res_block(h, d + "down." + std::to_string(lvl) + ".block." + std::to_string(blk), x, y, B, H, C, Co, s)))
                 return rc;
             std::swap(x, y);
             C = Co;
@@ -540,17 +554,17 @@ int encode_chunk(usp_vae* h, const float* img, float* moments, int B, int R, cud
             H /= 2;
         }
     }
-    if ((rc = res_block(h, d + "mid.block_1", x, t, r, y, B, H, C, C, s))) return rc;
+    if ((rc = res_block(h, d + "mid.block_1", x, y, B, H, C, C, s))) return rc;
     std::swap(x, y);
     if ((rc = attn_block(h, d + "mid.attn_1", x, y, B, H, C, s))) return rc;
     std::swap(x, y);
-    if ((rc = res_block(h, d + "mid.block_2", x, t, r, y, B, H, C, C, s))) return rc;
+    if ((rc = res_block(h, d + "mid.block_2", x, y, B, H, C, C, s))) return rc;
     std::swap(x, y);
-    if ((rc = group_norm(h, d + "norm_out", x, B, H * H, C, true, h->a16, s))) return rc;
-    if ((rc = conv(h, d + "conv_out", h->a16, B, H, H, 1, nullptr, y, nullptr, EPI_BIAS_F32, s))) return rc;
+    if ((rc = group_norm(h, d + "norm_out", x.h, B, H * H, C, true, h->a16, s))) return rc;
+    if ((rc = conv(h, d + "conv_out", h->a16, B, H, H, 1, nullptr, y.f, nullptr, EPI_BIAS_F32, s))) return rc;
     const long long n_out = static_cast<long long>(B) * H * H;
     vae_enc_out_kernel<<<static_cast<unsigned>((n_out + VT - 1) / VT), VT, 0, s>>>(
-        y, W(h, "quant_conv.weight").d32, W(h, "quant_conv.bias").d32, moments, B, H * H, W(h, d + "conv_out.weight").Np);
+        y.f, W(h, "quant_conv.weight").d32, W(h, "quant_conv.bias").d32, moments, B, H * H, W(h, d + "conv_out.weight").Np);
     VTRY(h, cudaGetLastError());
     return USP_OK;
 }
@@ -577,38 +591,36 @@ int decode_chunk(usp_vae* h, const float* z, float* img, int B, int S, cudaStrea
                                                                                W(h, "post_quant_conv.bias").d32, h->a16, B, S,
                                                                                1.0f / h->scale);
     VTRY(h, cudaGetLastError());
-    float *x = h->f0, *y = h->f1, *t = h->f2, *r = h->f3;
+    Act x = {h->f0, h->h0}, y = {h->f1, h->h1};
     int C = CH * MULT[3], H = S;
-    if ((rc = conv(h, d + "conv_in", h->a16, B, H, H, 1, nullptr, x, nullptr, EPI_BIAS_F32, s))) return rc;
-    if ((rc = res_block(h, d + "mid.block_1", x, t, r, y, B, H, C, C, s))) return rc;
+    if ((rc = conv(h, d + "conv_in", h->a16, B, H, H, 1, nullptr, x.f, x.h, EPI_BIAS_F32, s))) return rc;
+    if ((rc = res_block(h, d + "mid.block_1", x, y, B, H, C, C, s))) return rc;
     std::swap(x, y);
     if ((rc = attn_block(h, d + "mid.attn_1", x, y, B, H, C, s))) return rc;
     std::swap(x, y);
-    if ((rc = res_block(h, d + "mid.block_2", x, t, r, y, B, H, C, C, s))) return rc;
+    if ((rc = res_block(h, d + "mid.block_2", x, y, B, H, C, C, s))) return rc;
     std::swap(x, y);
     for (int lvl = 3; lvl >= 0; --lvl) {
         const int Co = CH * MULT[lvl];
         for (int blk = 0; blk <= NRES; ++blk) {
             const std::string p = d + "up." + std::to_string(lvl) + ".block." + std::to_string(blk);
-            if ((rc = res_block(h, p, x, t, r, y, B, H, C, Co, s))) return rc;
+            if ((rc = res_block(h, p, x, y, B, H, C, Co, s))) return rc;
             std::swap(x, y);
             C = Co;
         }
         if (lvl != 0) {
             // Upsample: nearest x2 folded into the im2col gather, then the 3x3 conv (libs/autoencoder.py:46-50)
-            cudaError_t e = launch_convert16(x, h->a16, static_cast<long long>(B) * H * H * C, OPD_FP16, s);
-            if (e != cudaSuccess) return vfail(h, USP_ERR_CUDA, std::string("convert16: ") + cudaGetErrorString(e));
-            if ((rc = conv(h, d + "up." + std::to_string(lvl) + ".upsample.conv", h->a16, B, H, H, 2, nullptr, y, nullptr,
+            if ((rc = conv(h, d + "up." + std::to_string(lvl) + ".upsample.conv", x.h, B, H, H, 2, nullptr, y.f, y.h,
                            EPI_BIAS_F32, s)))
                 return rc;
             std::swap(x, y);
             H *= 2;
         }
     }
-    if ((rc = group_norm(h, d + "norm_out", x, B, H * H, C, true, h->a16, s))) return rc;
-    if ((rc = conv(h, d + "conv_out", h->a16, B, H, H, 1, nullptr, y, nullptr, EPI_BIAS_F32, s))) return rc;
+    if ((rc = group_norm(h, d + "norm_out", x.h, B, H * H, C, true, h->a16, s))) return rc;
+    if ((rc = conv(h, d + "conv_out", h->a16, B, H, H, 1, nullptr, y.f, nullptr, EPI_BIAS_F32, s))) return rc;
     const long long n_out = static_cast<long long>(B) * 3 * H * H;
-    vae_out_kernel<<<static_cast<unsigned>((n_out + VT - 1) / VT), VT, 0, s>>>(y, img, B, H * H, W(h, d + "conv_out.weight").Np);
+    vae_out_kernel<<<static_cast<unsigned>((n_out + VT - 1) / VT), VT, 0, s>>>(y.f, img, B, H * H, W(h, d + "conv_out.weight").Np);
     VTRY(h, cudaGetLastError());
     return USP_OK;
 }
