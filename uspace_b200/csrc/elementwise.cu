@@ -147,13 +147,16 @@ __global__ void __launch_bounds__(256) embed_kernel(const EmbedArgs a) {
 template <int V4>  // float4 per lane: D = 128 * V4
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ g,
                                                         const float* __restrict__ bta, uint16_t* __restrict__ out,
-                                                        int M, int opd) {
+                                                        int M, int opd, int reverse) {
     constexpr int D = 128 * V4;
     pdl_wait();
     pdl_launch();
-    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    // rows are visited from the END: the GEMM that produced x wrote its last rows last, and with ~170 MB passing
+    // through the 126 MB L2 during that GEMM those are the rows still resident
+    const int row_fwd = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
-    if (row >= M) return;
+    if (row_fwd >= M) return;
+    const int row = reverse ? M - 1 - row_fwd : row_fwd;
     const float4* xr = reinterpret_cast<const float4*>(x + static_cast<long long>(row) * D);
     float4 v[V4];
     float s = 0.f;
@@ -402,16 +405,21 @@ cudaError_t launch_embed(const EmbedArgs& a, cudaStream_t s) {
 
 cudaError_t launch_layernorm(const float* x, const float* g, const float* b, void* out16, int M, int D, int opd,
                              cudaStream_t s) {
+    static int rev = -1;
+    if (rev < 0) {   // USP_LN_REVERSE=0 restores ascending row order (A/B comparison)
+        const char* e = getenv("USP_LN_REVERSE");
+        rev = e ? atoi(e) : 1;
+    }
     const int rows_per_block = 8;
     const int grid = (M + rows_per_block - 1) / rows_per_block;
     uint16_t* o = reinterpret_cast<uint16_t*>(out16);
     switch (D) {
-        case 256: return launch_pdl(layernorm_kernel<2>, dim3(grid), dim3(256), 0, s, x, g, b, o, M, opd);
-        case 384: return launch_pdl(layernorm_kernel<3>, dim3(grid), dim3(256), 0, s, x, g, b, o, M, opd);
-        case 512: return launch_pdl(layernorm_kernel<4>, dim3(grid), dim3(256), 0, s, x, g, b, o, M, opd);
-        case 768: return launch_pdl(layernorm_kernel<6>, dim3(grid), dim3(256), 0, s, x, g, b, o, M, opd);
-        case 1024: return launch_pdl(layernorm_kernel<8>, dim3(grid), dim3(256), 0, s, x, g, b, o, M, opd);
-        case 1536: return launch_pdl(layernorm_kernel<12>, dim3(grid), dim3(256), 0, s, x, g, b, o, M, opd);
+        case 256: return launch_pdl(layernorm_kernel<2>, dim3(grid), dim3(256), 0, s, x, g, b, o, M, opd, rev);
+        case 384: return launch_pdl(layernorm_kernel<3>, dim3(grid), dim3(256), 0, s, x, g, b, o, M, opd, rev);
+        case 512: return launch_pdl(layernorm_kernel<4>, dim3(grid), dim3(256), 0, s, x, g, b, o, M, opd, rev);
+        case 768: return launch_pdl(layernorm_kernel<6>, dim3(grid), dim3(256), 0, s, x, g, b, o, M, opd, rev);
+        case 1024: return launch_pdl(layernorm_kernel<8>, dim3(grid), dim3(256), 0, s, x, g, b, o, M, opd, rev);
+        case 1536: return launch_pdl(layernorm_kernel<12>, dim3(grid), dim3(256), 0, s, x, g, b, o, M, opd, rev);
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();
