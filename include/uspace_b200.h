@@ -93,6 +93,17 @@ int usp_forward(usp_handle* h, const float* x, const float* t, const float* cont
 int usp_forward_edit(usp_handle* h, const float* x, const float* t, const float* context, const int64_t* y,
                      float* out, int B, const usp_attn_edit* edit, void* stream);
 
+/* usp_forward_edit plus the semantic-direction hook of ONE velocity evaluation, as the reference applies it inside
+ * UViT.forward (libs/uvit.py:313-314 "head": on the latent before patch_embed; :349-350 "tail": on the velocity),
+ * dissect_helper_uvit (libs/dissection.py:115-186):
+ *   delta != NULL      "write_attr" / "write_pca":  x + delta * write_scale, delta [C,S,S] = the row the hook loads from
+ *                      delta_{t:.2f}.npy (the CALLER applies should_edit() and passes NULL when it is false);
+ *   read_out != NULL   "read": the activation at edit_loc [B,C,S,S] (what the hook np.save()s).
+ * delta / read_out are device pointers; edit_loc USP_EDIT_NONE with both NULL is usp_forward_edit. */
+int usp_forward_hook(usp_handle* h, const float* x, const float* t, const float* context, const int64_t* y,
+                     float* out, int B, int edit_loc, const float* delta, float write_scale, float* read_out,
+                     const usp_attn_edit* edit, void* stream);
+
 /* Replaces odeint(func, z, [t0,t1], method, options=dict(step_size)) as called by CNF.decode (t0=0,t1=1) and
  * CNF.encode (t0=1,t1=0) (flow_matching.py:118-125,140-147): torchdiffeq fixed-grid semantics, one CUDA graph
  * per step replayed on `stream`.  z is updated in place.

@@ -47,6 +47,7 @@ _SIGNATURES = {
     "usp_weight_name": (C.c_char_p, [_vp, _i]),
     "usp_forward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "usp_forward_edit": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, C.POINTER(UspAttnEdit), _vp]),
+    "usp_forward_hook": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _f, _vp, C.POINTER(UspAttnEdit), _vp]),
     "usp_sample_edit": (_i, [_vp, _vp, _vp, _vp, _i, _f, _f, _f, _i, _vp, _f, _f, _i, C.POINTER(UspAttnEdit), _vp]),
     "usp_sample": (_i, [_vp, _vp, _vp, _vp, _i, _f, _f, _f, _i, _vp, _f, _f, _i, _vp]),
     "usp_sample_adaptive": (_i, [_vp, _vp, _vp, _vp, _i, _f, _f, _i, C.c_double, C.c_double, _vp, _i, _f, _f, _i,

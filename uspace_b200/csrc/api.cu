@@ -378,6 +378,7 @@ struct FwdIO {
     const float* delta;     // edit table or nullptr
     int edit_loc;
     const float* sscale;    // per-sample write_scale [B] (scale sweep) or nullptr
+    float hook_scale;       // plain forward (st == nullptr): write_scale for row 0 of `delta`
     float* trace;           // "read" dump [n_grid, B, C, S, S] at edit_loc or nullptr
     const float* colscale;  // attention column weights [B, L] or nullptr (p2p edit)
     uint64_t block_mask;    // blocks the attention edit applies to
@@ -469,6 +470,7 @@ int enqueue_forward(usp_handle* h, Plan* p, const FwdIO& io, cudaStream_t s) {
     ea.freqs = h->freqs;
     ea.delta = io.edit_loc == USP_EDIT_HEAD ? io.delta : nullptr;
     ea.sscale = io.sscale;
+    ea.hook_scale = io.hook_scale;
     ea.trace = io.edit_loc == USP_EDIT_HEAD ? io.trace : nullptr;
     ea.out32 = p->x32;
     ea.opd = opd;
@@ -588,6 +590,7 @@ int enqueue_forward(usp_handle* h, Plan* p, const FwdIO& io, cudaStream_t s) {
     fa.cb = h->i_fb >= 0 ? h->w[h->i_fb].d32 : nullptr;
     fa.delta = io.edit_loc == USP_EDIT_TAIL ? io.delta : nullptr;
     fa.sscale = io.sscale;
+    fa.hook_scale = io.hook_scale;
     fa.trace = io.edit_loc == USP_EDIT_TAIL ? io.trace : nullptr;
     fa.st = io.st; fa.base = io.base; fa.aux = io.aux; fa.vstore = io.vstore; fa.acc2 = io.acc2; fa.out = io.out;
     fa.m1 = io.m1; fa.m2 = io.m2;
@@ -826,9 +829,21 @@ int usp_forward(usp_handle* h, const float* x, const float* t, const float* cont
 
 int usp_forward_edit(usp_handle* h, const float* x, const float* t, const float* context, const int64_t* y,
                      float* out, int B, const usp_attn_edit* edit, void* stream) {
+    return usp_forward_hook(h, x, t, context, y, out, B, USP_EDIT_NONE, nullptr, 0.f, nullptr, edit, stream);
+}
+
+int usp_forward_hook(usp_handle* h, const float* x, const float* t, const float* context, const int64_t* y,
+                     float* out, int B, int edit_loc, const float* delta, float write_scale, float* read_out,
+                     const usp_attn_edit* edit, void* stream) {
     int rc = check_ready(h, B);
     if (rc) return rc;
     if (!x || !t || !out) return fail(h, USP_ERR_INVALID, "null tensor");
+    if (edit_loc != USP_EDIT_NONE && edit_loc != USP_EDIT_HEAD && edit_loc != USP_EDIT_TAIL)
+        return fail(h, USP_ERR_INVALID, "edit_loc must be none, head or tail (\"mid\" is broken in the reference)");
+    if (edit_loc == USP_EDIT_NONE && (delta != nullptr || read_out != nullptr))
+        return fail(h, USP_ERR_INVALID, "delta / read_out need edit_loc head or tail");
+    if (delta != nullptr && read_out != nullptr)
+        return fail(h, USP_ERR_INVALID, "the hook either writes (delta) or reads (read_out), not both");
     if ((h->cfg.num_clip_token > 0) != (context != nullptr))
         return fail(h, USP_ERR_INVALID, "context must be given exactly for the t2i model");
     if ((y != nullptr) != (h->cfg.num_classes > 0))
@@ -847,6 +862,7 @@ int usp_forward_edit(usp_handle* h, const float* x, const float* t, const float*
     memset(&io, 0, sizeof(io));
     io.x = x; io.tvec = t; io.y = reinterpret_cast<const long long*>(y); io.has_ctx = context != nullptr;
     io.out = out; io.m1 = 1.f;
+    io.edit_loc = edit_loc; io.delta = delta; io.hook_scale = write_scale; io.trace = read_out;
     if (edit != nullptr && edit->colscale != nullptr) {
         CUDA_TRY(h, cudaMemcpyAsync(p->colscale, edit->colscale, static_cast<size_t>(B) * h->L * 4, cudaMemcpyDefault, s));
         io.colscale = p->colscale;

@@ -52,13 +52,15 @@ __global__ void __launch_bounds__(256) embed_kernel(const EmbedArgs a) {
             const int p2 = f % p;
             const int idx = (c * S + ph * p + p1) * S + pw * p + p2;
             float v = a.x[static_cast<long long>(b) * C * S * S + idx];
-            if (a.delta != nullptr && a.st != nullptr) {
-                float sc = a.st->edit;
+            // sampling: row / scale of the current step; plain forward with a hook (usp_forward_hook): row 0
+            const int didx = a.st ? a.st->didx : 0;
+            if (a.delta != nullptr) {
+                float sc = a.st ? a.st->edit : a.hook_scale;
                 if (sc != 0.f && a.sscale != nullptr) sc = a.sscale[b];
-                if (sc != 0.f) v += a.delta[static_cast<long long>(a.st->didx) * C * S * S + idx] * sc;
+                if (sc != 0.f) v += a.delta[static_cast<long long>(didx) * C * S * S + idx] * sc;
             }
-            if (a.trace != nullptr && a.st != nullptr)   // dissect_name="read" (libs/dissection.py:126-136)
-                a.trace[(static_cast<long long>(a.st->didx) * a.B + b) * C * S * S + idx] = v;
+            if (a.trace != nullptr)   // dissect_name="read" (libs/dissection.py:126-136)
+                a.trace[(static_cast<long long>(didx) * a.B + b) * C * S * S + idx] = v;
             feat[tk][f] = v;
         }
     }
@@ -289,12 +291,13 @@ __global__ void __launch_bounds__(256) final_kernel(const FinalArgs a) {
         v = pf[((yh / p) * gw + (xw / p)) * P + ((yh % p) * p + (xw % p)) * C + co];
     }
     const int chw = static_cast<int>(i % (static_cast<long long>(C) * S * S));
-    if (a.delta != nullptr && a.st != nullptr) {
-        float sc = a.st->edit;
+    const int didx = a.st ? a.st->didx : 0;   // plain forward with a hook (usp_forward_hook): row 0
+    if (a.delta != nullptr) {
+        float sc = a.st ? a.st->edit : a.hook_scale;
         if (sc != 0.f && a.sscale != nullptr) sc = a.sscale[b];
-        if (sc != 0.f) v += a.delta[static_cast<long long>(a.st->didx) * C * S * S + chw] * sc;
+        if (sc != 0.f) v += a.delta[static_cast<long long>(didx) * C * S * S + chw] * sc;
     }
-    if (a.trace != nullptr && a.st != nullptr) a.trace[static_cast<long long>(a.st->didx) * n + i] = v;
+    if (a.trace != nullptr) a.trace[static_cast<long long>(didx) * n + i] = v;
     if (a.st == nullptr) {
         a.out[i] = v;
         return;

@@ -109,6 +109,7 @@ struct EmbedArgs {
     const float* delta;    // head edit table [nsteps+1, C*S*S] or nullptr
     const float* sscale;   // optional per-sample write_scale [B] (scale sweep); nullptr: st->edit for every sample
     float* trace;          // optional "read" dump at edit_loc head: trace[st->didx][B,C,S,S] = the latent as the net sees it
+    float hook_scale;      // plain forward (st == nullptr): write_scale applied with row 0 of `delta` (usp_forward_hook)
     float* out32;          // [B*L, D]
     void* out16;           // optional un-normalised 16-bit copy [B*L, D] (folded-LayerNorm path)
     float* stats;          // optional [B*L, 8, 2] partial row statistics (one slot per warp of the block)
@@ -139,6 +140,7 @@ struct FinalArgs {
     const float* sscale;   // optional per-sample write_scale [B] (scale sweep)
     float* trace;          // optional "read" dump at edit_loc tail: trace[st->didx][B,C,S,S] = the velocity
     const StepState* st;   // nullptr for a plain forward
+    float hook_scale;      // plain forward (st == nullptr): write_scale applied with row 0 of `delta` (usp_forward_hook)
     const float* base;     // ODE: state the update starts from
     const float* aux;      // a stored derivative combination (Heun stage 2: k1), or nullptr
     float* vstore;         // running combination 1: vstore = vs_a * v + vs_b * vstore (Heun stage 1: k1), or nullptr

@@ -101,7 +101,11 @@ class Engine:
                              float(attn_edit.get("t_edit", float("inf"))))
         return e, cs
 
-    def forward(self, x, t, y=None, context=None, attn_edit=None) -> torch.Tensor:
+    def forward(self, x, t, y=None, context=None, attn_edit=None, edit_loc=None, delta=None, write_scale=0.0,
+                read=False):
+        """One velocity evaluation.  ``edit_loc`` "head" / "tail" with ``delta`` [C,S,S] adds ``delta * write_scale`` to
+        the latent before the embedding / to the velocity (libs/uvit.py:313-314,349-350); with ``read=True`` the call
+        returns (out, activation at edit_loc) instead (the hook's "read" mode, libs/dissection.py:126-136)."""
         self._check_latent(x)
         B = x.shape[0]
         x = x.to(self.device, torch.float32).contiguous()
@@ -110,12 +114,18 @@ class Engine:
             y = y.to(self.device, torch.int64).contiguous()
         if context is not None:
             context = context.to(self.device, torch.float32).contiguous()
+        if delta is not None:
+            delta = torch.as_tensor(delta).to(self.device, torch.float32).contiguous()
+            if tuple(delta.shape[-3:]) != (self.C, self.S, self.S) or delta.numel() != self.C * self.S * self.S:
+                raise ValueError(f"delta must be [{self.C},{self.S},{self.S}], got {tuple(delta.shape)}")
         out = torch.empty_like(x)
+        trace = torch.empty_like(x) if read else None
         edit, _keep = self._attn_edit(attn_edit, B)
-        _lib.check(self.lib.usp_forward_edit(self.handle, _ptr(x), _ptr(t), _ptr(context), _ptr(y), _ptr(out), B,
+        _lib.check(self.lib.usp_forward_hook(self.handle, _ptr(x), _ptr(t), _ptr(context), _ptr(y), _ptr(out), B,
+                                             _lib.EDIT_LOC[edit_loc], _ptr(delta), float(write_scale), _ptr(trace),
                                              C.byref(edit) if edit is not None else None, self._stream()),
                    self.handle, "usp_forward")
-        return out
+        return (out, trace) if read else out
 
     def sample(self, z, t0=0.0, t1=1.0, step_size=0.02, method="euler", y=None, context=None, delta_table=None,
                write_scale=0.0, t_edit=0.0, edit_loc=None, attn_edit=None) -> torch.Tensor:

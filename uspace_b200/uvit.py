@@ -204,16 +204,51 @@ class UViT(_UViTBase):
         if self.num_classes > 0:
             self.label_emb = nn.Embedding(self.num_classes, self.embed_dim)
 
+    def _hook(self, timesteps, kwargs):
+        """What dissect_helper_uvit (libs/dissection.py:115-186) would do inside this call (libs/uvit.py:313-314 head,
+        :349-350 tail): -> (edit_loc, delta [C,S,S] | None, write_scale, read_path | None).  The hook keys on
+        f"{timesteps[0].item():.2f}" (one host sync per call, like the reference); CNF.decode / encode of this package
+        pre-gather the whole table instead and never come through here."""
+        loc = kwargs.get("edit_loc")
+        if loc == "mid":
+            raise NotImplementedError("edit_loc='mid' is broken in the reference for U-ViT and is not built")
+        if loc not in ("head", "tail") or kwargs.get("dissect_task") != "uspace_uvit":
+            return None, None, 0.0, None
+        from .flow_matching import _read_delta, should_edit
+        import os
+        name = kwargs.get("dissect_name")
+        digit = f"{timesteps.reshape(-1)[0].item():.2f}"
+        if name == "read":
+            root = kwargs.get("read_path_root")
+            os.makedirs(root, exist_ok=True)
+            return loc, None, 0.0, os.path.join(root, f"{kwargs['batch_id']}_{digit}")
+        if name not in ("write_attr", "write_pca"):
+            raise ValueError(f"dissect_name should be read or write, here is {name}")
+        if not should_edit(digit, kwargs.get("t_edit")):
+            return None, None, 0.0, None
+        root = kwargs.get("write_path_root")
+        if name == "write_attr":
+            delta = _read_delta(os.path.join(root, f"delta_{digit}.npy"), kwargs.get("ith_attr"))
+        else:
+            delta = _read_delta(os.path.join(root, f"pca{kwargs.get('pca_n')}_{digit}.npy"), kwargs.get("ith_component"))
+        return loc, torch.from_numpy(delta.astype("float32")), float(kwargs.get("write_scale")), None
+
     def forward(self, x, timesteps, y=None, **kwargs):
         # kwargs.get: the reference indexes kwargs["edit_loc"] (libs/uvit.py:313) and raises KeyError without it;
-        # accepting its absence is a strict superset.  Edits are applied by CNF (the sampler owns the step index).
+        # accepting its absence is a strict superset.
         if self._wants_autograd(x):
             tok = self.patch_embed.proj(x).flatten(2).transpose(1, 2)
             tok = torch.cat((self._time_token(timesteps), tok), dim=1)
             if y is not None:
                 tok = torch.cat((self.label_emb(y).unsqueeze(1), tok), dim=1)
             return self._trunk_autograd(tok), None
-        return self.engine().forward(x, timesteps, y=y), None
+        loc, delta, ws, read_path = self._hook(timesteps, kwargs)
+        if read_path is not None:
+            import numpy as np
+            out, act = self.engine().forward(x, timesteps, y=y, edit_loc=loc, read=True)
+            np.save(read_path, act.cpu().numpy())
+            return out, None
+        return self.engine().forward(x, timesteps, y=y, edit_loc=loc, delta=delta, write_scale=ws), None
 
 
 class UViTT2I(_UViTBase):
