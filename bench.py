@@ -341,22 +341,48 @@ def main():
     h2d = zh_src.numel() * 4 + (ctx_h.numel() * 4 if ctx_h is not None else 0) + (delta.numel() * 4 if delta is not None else 0)
     d2h = zh.numel() * 4
 
-    # ---- per-kernel-class device time of one velocity evaluation (events between launches) ----
-    t_half = torch.full((Bl,), 0.5, device=dev)
-    eng.profile_forward(z_dev, t_half, context=ctx_dev)
-    prof = eng.profile_forward(z_dev, t_half, context=ctx_dev)
+    # ---- per-kernel-class device time of one velocity evaluation: events between launches, mean over 12 evaluations
+    #      enqueued back to back right after the timed loops (the GPU is still at the power-capped clock of the run) ----
+    t_half = torch.full((Bl * n_rep,), 0.5, device=dev)
+    z_prof = z_dev if n_rep == 1 else z_dev.repeat_interleave(n_rep, 0)
+    prof = eng.profile_forward(z_prof, t_half, context=ctx_dev, warmup=2, reps=12)
     torch.cuda.synchronize()
 
     if rank == 0:
         pk = peaks()
-        # algorithmic GEMM FLOPs per image per evaluation: blocks + skip_linears
         D, n_in = wl["cfg"]["embed_dim"], wl["cfg"]["depth"] // 2
+        Hd = int(D * wl["cfg"]["mlp_ratio"])
         L = (wl["cfg"]["img_size"] // wl["cfg"]["patch_size"]) ** 2 + (78 if wl["t2i"] else 1)
-        gemm_flops_img = (2 * n_in + 1) * 24.0 * L * D * D + n_in * 4.0 * L * D * D
-        gemm_ms = sum(prof[k][0] for k in ("gemm_qkv", "gemm_proj", "gemm_fc1", "gemm_fc2", "gemm_skip"))
-        gemm_launches = sum(prof[k][1] for k in ("gemm_qkv", "gemm_proj", "gemm_fc1", "gemm_fc2", "gemm_skip"))
+        M = Bl * n_rep * L
+        # algorithmic FLOPs / bytes (16-bit operands in, result out; fp32 residual in+out where the epilogue has one)
+        # of ONE launch of each GEMM class
+        shapes = {"gemm_qkv": (3 * D, D, 2 * M * 3 * D), "gemm_proj": (D, D, 8 * M * D + 2 * M * D),
+                  "gemm_fc1": (Hd, D, 2 * M * Hd), "gemm_fc2": (D, Hd, 8 * M * D + 2 * M * D),
+                  "gemm_skip": (D, 2 * D, 4 * M * D + 2 * M * D)}
+        classes = {}
+        for k, (N, K, out_bytes) in shapes.items():
+            ms_k, n_k = prof[k]
+            if n_k == 0:
+                continue
+            fl = 2.0 * M * N * K
+            by = 2.0 * M * K + 2.0 * N * K + out_bytes
+            classes[k] = {"launches": n_k, "avg_launch_ms": ms_k / n_k, "flops_per_launch": fl, "algorithmic_bytes": by,
+                          "tflops": fl / (ms_k / n_k * 1e-3) / 1e12}
+        dom = max(classes, key=lambda k: prof[k][0])          # the class with the largest share of the evaluation
+        gemm_ms = sum(prof[k][0] for k in classes)
+        gemm_flops = sum(c["flops_per_launch"] * c["launches"] for c in classes.values())
         fwd_ms = sum(v[0] for v in prof.values())
-        achieved = gemm_flops_img * Bl / (gemm_ms * 1e-3) / 1e12
+        achieved = classes[dom]["tflops"]
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")   # written by profiles/summarize.py from the ncu capture
+        if os.path.exists(tpath) and args.workload == "c2" and Bl == 64:
+            tj = json.load(open(tpath))
+            if dom in tj.get("kernels", {}):
+                traffic = tj["kernels"][dom]["dram_bytes"]
+                classes[dom]["traffic_source"] = tj.get("source")
+        kernel_names = {"gemm_qkv": "gemm2_kernel<EPI_QKV>", "gemm_proj": "gemm2_kernel<EPI_BIAS_RESID> (proj)",
+                        "gemm_fc1": "gemm2_kernel<EPI_BIAS_GELU> (fc1 + erf-GELU)",
+                        "gemm_fc2": "gemm2_kernel<EPI_BIAS_RESID, LONGK> (fc2)", "gemm_skip": "gemm2_kernel<EPI_BIAS_F32> (skip_linear)"}
         flops_img = eng.flops_per_forward()
         sec = ms_total * 1e-3
         value = Bg * n_rep * args.steps / sec
@@ -374,19 +400,23 @@ def main():
             "e2e": {"value": Bg * n_rep * args.steps / e2e_s, "unit": "images/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "matches_device_path": same},
             "gpu_launches": args.steps * (n_grid - 1) * nfe_per_step * (eng.kernels_per_forward() + 1),
-            "roofline": {"bound": "tensor", "kernel": "usp::gemm2_kernel<EPI,LONGK,NP> (2-CTA tcgen05 GEMM: all five U-ViT linears of one velocity evaluation)",
-                         "note": "the kernel itself is limited by SM<->L2 delivery at its 256x256 pair tile (~1530 TFLOP/s without "
-                                 "epilogue traffic, the same ceiling cuBLAS shows); see profiles/r01f_gemm_traffic_experiments.md",
+            "roofline": {"bound": "tensor", "kernel": "usp::" + kernel_names[dom] + ": the dominant kernel of the step (2-CTA tcgen05 GEMM)",
                          "achieved": achieved, "peak": pk["sustained"], "unit": "TFLOP/s", "frac": achieved / pk["sustained"],
-                         "peak_kind": f"bf16_tflops_sustained of {pk['src']} (kernel timed inside a long step); burst {pk['burst']}",
-                         "launches": gemm_launches, "avg_launch_ms": gemm_ms / max(1, gemm_launches),
-                         "share_of_forward": gemm_ms / fwd_ms,
-                         # DRAM read+write bytes per GEMM launch (mean over the 94 launches of one evaluation) from the
-                         # `ncu --set full` capture profiles/r01f_ncu_gemm.md (qkv 94.6, proj 121.6, fc1 128.6,
-                         # fc2 278.4 MB measured; skip_linear 140 MB estimated); algorithmic operand+result bytes: 193.5 MB
-                         "traffic": 154.1e6 if (args.workload == "c2" and Bl == 64) else None,
-                         "algorithmic_bytes": 193.5e6 if (args.workload == "c2" and Bl == 64) else None},
+                         "frac_burst": achieved / pk["burst"],
+                         "peak_kind": f"bf16_tflops_sustained of {pk['src']} (kernel timed inside a long run at the power cap); burst {pk['burst']}",
+                         "launches": classes[dom]["launches"], "avg_launch_ms": classes[dom]["avg_launch_ms"],
+                         "share_of_forward": prof[dom][0] / fwd_ms,
+                         "how": "CUDA events between launches on the launching stream, mean over 12 evaluations enqueued back "
+                                "to back right after the timed loops",
+                         "traffic": traffic, "algorithmic_bytes": classes[dom]["algorithmic_bytes"],
+                         "all_gemms": {"tflops": gemm_flops / (gemm_ms * 1e-3) / 1e12,
+                                       "frac": gemm_flops / (gemm_ms * 1e-3) / 1e12 / pk["sustained"],
+                                       "frac_burst": gemm_flops / (gemm_ms * 1e-3) / 1e12 / pk["burst"],
+                                       "share_of_forward": gemm_ms / fwd_ms},
+                         "classes": {k: {"tflops": round(c["tflops"], 1), "avg_launch_us": round(c["avg_launch_ms"] * 1e3, 2),
+                                         "launches": c["launches"]} for k, c in classes.items()}},
             "kernel_ms_per_forward": {k: round(v[0], 4) for k, v in prof.items()},
+            "ms_per_forward": {"in_graph": ms_total / args.steps / nfe, "eager_with_events": fwd_ms},
             "clocks": clocks, "finite": finite,
         }
         if world == 1 and not args.no_cpu_baseline:

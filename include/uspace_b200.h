@@ -34,7 +34,8 @@ typedef enum usp_status {
     USP_ERR_INVALID = -1,      /* bad argument / unsupported configuration */
     USP_ERR_CUDA = -2,         /* a CUDA runtime / driver call failed       */
     USP_ERR_STATE = -3,        /* weights missing or not finalised          */
-    USP_ERR_UNSUPPORTED = -4   /* configuration outside the built path      */
+    USP_ERR_UNSUPPORTED = -4,  /* configuration outside the built path      */
+    USP_ERR_NONFINITE = -5     /* a velocity evaluation produced inf / NaN  */
 } usp_status;
 
 /* Mirrors the constructor keywords of libs/uvit.py:183-202 and libs/uvit_t2i.py:193-211. */
@@ -175,6 +176,11 @@ int usp_vae_encode_moments(usp_vae* h, const float* x, float* moments, int B, in
 int usp_sample_host(usp_handle* h, float* z_host, const float* context_host, const int64_t* y_host, int B, float t0,
                     float t1, float step_size, int method, const float* delta_table_host, float write_scale,
                     float t_edit, int edit_loc);
+/* fp16 tensor-core operands saturate at 65504: a checkpoint whose activations exceed that yields inf / NaN velocities.
+ * Every velocity evaluation checks its output on the device; this reads and clears the sticky flag (*flag = 1 if any
+ * evaluation since the last read was non-finite). SYNCHRONISES `stream`. usp_sample_host checks it itself and returns
+ * USP_ERR_NONFINITE; bf16 operands (usp_config.operand_dtype = 0) have the fp32 exponent range. */
+int usp_nonfinite(usp_handle* h, int* flag, void* stream);
 /* Number of grid points torchdiffeq builds for (t0, t1, step_size): ceil(|t1-t0|/step + 1). */
 int usp_grid_size(float t0, float t1, float step_size);
 /* Writes the grid itself (host memory, fp32) into out[0..cap); returns the number of points or 0 on error. */
@@ -192,6 +198,10 @@ int usp_last_forward_ms(usp_handle* h, float* ms);  /* device time of the most r
 #define USP_NUM_KERNEL_CLASSES 10
 int usp_profile_forward(usp_handle* h, const float* x, const float* t, const float* context, const int64_t* y,
                         float* out, int B, float* class_ms, int* class_launches, void* stream);
+/* The same over `warmup` untimed + `reps` timed evaluations enqueued back to back (no host synchronisation in between,
+ * so the GPU holds the clock / power state of a long run); class_ms / class_launches are per evaluation (mean). */
+int usp_profile_forward_n(usp_handle* h, const float* x, const float* t, const float* context, const int64_t* y,
+                          float* out, int B, int warmup, int reps, float* class_ms, int* class_launches, void* stream);
 
 /* Kernel-level entry points (parity tests and micro-benchmarks call the kernels through the ABI).
  * All pointers are device pointers; a16/w16/q/k/v/out16 hold 16-bit operands of type `operand_dtype`. */

@@ -62,6 +62,29 @@ def rep(tag, name):
                     i = h.index(m)
                     f.write(f"| {m} | {r[i]} | {rows[1][i]} |\n")
             f.write("\n")
+    if name == "gemm":
+        # per-launch DRAM traffic of each GEMM class, read by bench.py for `roofline.traffic` (U-ViT-L, batch 64)
+        import json
+        import re
+        cls = {"0": "gemm_qkv", "1": "gemm_fc1", "3": "gemm_skip"}
+        kern = {}
+        for r in rows[2:]:
+            m = re.search(r"gemm2_kernel<\(?(?:int\))?(\d), \(?(?:bool\))?(\d)", r[h.index("Kernel Name")])
+            if not m:
+                continue
+            c = cls.get(m.group(1)) or ("gemm_fc2" if m.group(2) == "1" else "gemm_proj")
+
+            def val(metric):
+                i = h.index(metric)
+                v = float(r[i].replace(",", ""))
+                u = rows[1][i].lower()
+                return v * {"mbyte": 1e6, "gbyte": 1e9, "kbyte": 1e3, "byte": 1.0}.get(u, 1.0)
+            kern[c] = {"dram_bytes": val("dram__bytes_read.sum") + val("dram__bytes_write.sum"),
+                       "time_us": float(r[h.index("gpu__time_duration.sum")].replace(",", "")),
+                       "tensor_active_pct": float(r[h.index("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active")])}
+        with open(os.path.join(OUT, "ncu_traffic.json"), "w") as f:
+            json.dump({"source": f"profiles/{tag}_ncu_gemm.md (ncu --set full --clock-control none, U-ViT-L batch 64, one launch each)",
+                       "kernels": kern}, f, indent=1)
     src = subprocess.run(["ncu", "-i", p, "--page", "source", "--csv"], capture_output=True, text=True).stdout
     ks, cur = [], None
     for r in csv.reader(src.splitlines()):

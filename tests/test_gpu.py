@@ -77,7 +77,9 @@ def model(name, opd="fp16"):
     ("qkv", 16448, 3072, 1024, 1024), ("bias_gelu", 10688, 4096, 1024, 1024), ("bias_resid", 16448, 1024, 4096, 4096),
     ("bias_f32", 10688, 1024, 2048, 1024),
     ("bias_resid", 514, 1024, 4096, 4096), ("bias_resid", 16448, 1024, 1024, 1024),
-    ("bias_f32", 16448, 1024, 2048, 1024), ("qkv", 10688, 3072, 1024, 1024)])
+    ("bias_f32", 16448, 1024, 2048, 1024), ("qkv", 10688, 3072, 1024, 1024),
+    # BASELINE configs[2] (t2i-L, batch 128): M = 128 * 334 = 42752
+    ("bias_gelu", 42752, 4096, 1024, 1024), ("bias_resid", 42752, 1024, 4096, 4096), ("qkv", 42752, 3072, 1024, 1024)])
 def test_gemm_epilogues(lib, opd, epi, M, N, K, K0):
     td, L = TD[opd], (334 if M % 334 == 0 else 257)
     g = torch.Generator().manual_seed(M + N + K)
@@ -122,7 +124,8 @@ def test_gemm_epilogues(lib, opd, epi, M, N, K, K0):
 
 @pytest.mark.parametrize("opd", ["fp16", "bf16"])
 @pytest.mark.parametrize("B,H,L", [(1, 1, 17), (1, 1, 128), (1, 2, 256), (2, 8, 257), (3, 4, 258), (2, 16, 334),
-                                   (1, 1, 384), (64, 16, 257)])
+                                   (1, 1, 384), (64, 16, 257), (128, 16, 334), (3, 2, 288), (2, 2, 320), (2, 3, 352),
+                                   (5, 16, 129), (2, 4, 64), (1, 3, 1)])
 def test_attention(lib, opd, B, H, L):
     td = TD[opd]
     g = torch.Generator().manual_seed(B * 1000 + L)
@@ -361,6 +364,130 @@ def test_library_mask_follows_should_edit():
     want = O.sample(sd, case["cfg"], x.double(), 0.0, 1.0, 0.2, "euler", delta_table=table.double(), write_scale=2.0,
                     t_edit=0.4, edit_loc="head")
     assert rel(got, want) < 1e-3
+
+
+@pytest.mark.parametrize("loc", ["head", "tail"])
+def test_module_call_applies_the_edit_hook_like_the_reference(golden_dir, tmp_path, loc):
+    """nnet(x, t, y, **config.dissection) itself (libs/uvit.py:313-314,349-350 -> dissect_helper_uvit): the velocity
+    the reference module returned with edit_loc head / tail, write_attr."""
+    case = CASES["tiny_uncond"]
+    e = case["edit"]
+    g = golden(golden_dir, "tiny_uncond")
+    m = model("tiny_uncond")
+    x, _, _, _ = build_inputs(case)
+    np.save(tmp_path / f"delta_{e['t']:.2f}.npy", g["edit_delta"])
+    kw = dict(dissect_task="uspace_uvit", dissect_name="write_attr", write_path_root=str(tmp_path),
+              ith_attr=e["ith_attr"], t_edit=e["t_edit"], write_scale=e["write_scale"], edit_loc=loc, batch_id=0)
+    t = torch.full((x.shape[0],), e["t"], device=dev())
+    with torch.no_grad():
+        got = m(x.to(dev()), t, None, **kw)[0]
+        plain = m(x.to(dev()), t, None, edit_loc=None)[0]
+        # t > t_edit: should_edit() is false, no file is touched (libs/dissection.py:21-34)
+        late = m(x.to(dev()), torch.full_like(t, 0.9), None, **kw)[0]
+        late_plain = m(x.to(dev()), torch.full_like(t, 0.9), None, edit_loc=None)[0]
+    assert rel(got, g[f"edit_{loc}"]) < 2e-3
+    assert rel(plain, g[f"edit_{loc}"]) > 1e-2
+    assert torch.equal(late, late_plain)
+    # "read": the hook dumps the activation at edit_loc as {batch_id}_{t:.2f}.npy (libs/dissection.py:126-136)
+    rd = dict(kw, dissect_name="read", read_path_root=str(tmp_path / "read"))
+    with torch.no_grad():
+        out = m(x.to(dev()), t, None, **rd)[0]
+    dumped = np.load(tmp_path / "read" / f"0_{e['t']:.2f}.npy")
+    assert torch.equal(out, plain)
+    want = x.numpy() if loc == "head" else plain.cpu().numpy()
+    assert np.array_equal(dumped, want)
+    with pytest.raises(ValueError):
+        m(x.to(dev()), t, None, **dict(kw, dissect_name="bogus"))
+    with pytest.raises(NotImplementedError):
+        m(x.to(dev()), t, None, **dict(kw, edit_loc="mid"))
+
+
+# ---- the BASELINE configurations as whole trajectories against the oracle (fp32 FAST mode: the same torch CPU calls
+#      the reference makes; about a minute of host time each) -------------------------------------------------------
+def _oracle_fast(fn):
+    O.FAST = True
+    try:
+        return fn()
+    finally:
+        O.FAST = False
+
+
+@pytest.mark.parametrize("method,nfe", [("euler", 50), ("heun", 100)])
+def test_uvit_large_50_step_trajectory_against_oracle(method, nfe):
+    """BASELINE configs[1] (50 Euler steps) and the Heun variant of configs[3], U-ViT-L, two images: the final latents
+    against the CPU oracle driving the same 50-interval grid (flow_matching.py:130-151)."""
+    case = CASES["large_uncond"]
+    m = model("large_uncond")
+    sd = {k: v.cpu() for k, v in m.state_dict().items()}
+    z = parallel.global_noise(2)
+    want = _oracle_fast(lambda: O.sample(sd, case["cfg"], z, 0.0, 1.0, 0.02, method))
+    got = m.engine().sample(z.to(dev()), 0.0, 1.0, 0.02, method)
+    assert len(O.fixed_grid(0.0, 1.0, 0.02)) == 51
+    assert rel(got, want) < 1e-3
+
+
+def test_t2i_large_trajectory_against_oracle():
+    """BASELINE configs[2] model (t2i U-ViT-L, 77 context tokens, L = 334): 10 Euler steps, two images."""
+    case = CASES["large_t2i"]
+    m = model("large_t2i")
+    sd = {k: v.cpu() for k, v in m.state_dict().items()}
+    z = parallel.global_noise(2)
+    ctx = torch.randn(2, 77, 768, generator=torch.Generator().manual_seed(1231))
+    want = _oracle_fast(lambda: O.sample(sd, case["cfg"], z, 0.0, 1.0, 0.1, "euler", context=ctx))
+    got = m.engine().sample(z.to(dev()), 0.0, 1.0, 0.1, "euler", context=ctx.to(dev()))
+    assert rel(got, want) < 1e-3
+
+
+def test_fp16_operand_range_scaled_weights():
+    """fp16 tensor-core operands saturate at 65504.  A checkpoint whose MLP hidden activations exceed that must either
+    stay within tolerance or fail loudly - never return silently wrong numbers.  The library's contract: GELU outputs
+    beyond the fp16 range make the forward non-finite (inf -> NaN through fc2 / LayerNorm), which the caller can test
+    with one isfinite(); with bf16 operands (8 exponent bits) the same weights stay finite and within the bf16 bound."""
+    case = CASES["tiny_uncond"]
+    x, t, _, _ = build_inputs(case)
+    torch.manual_seed(case["seed"])
+    sd = UViT(**case["cfg"]).state_dict()
+    # 1) large but representable: |fc1 output| ~ 2e3 (100 x the random-init scale) - still exact to tolerance
+    sd_ok = {k: (v * 100.0 if k.endswith("mlp.fc1.weight") else v * (0.01 if k.endswith("mlp.fc2.weight") else 1.0))
+             for k, v in sd.items()}
+    m = UViT(**case["cfg"]).eval()
+    m.load_state_dict(sd_ok)
+    m = m.to(dev())
+    with torch.no_grad():
+        got = m(x.to(dev()), t.to(dev()))[0]
+    want = O.uvit_forward(sd_ok, case["cfg"], x, t)
+    hidden_max = max((O.layer_norm(torch.randn(4, 256), sd_ok["in_blocks.0.norm2.weight"], sd_ok["in_blocks.0.norm2.bias"])
+                      @ sd_ok["in_blocks.0.mlp.fc1.weight"].T).abs().max().item(), 0.0)
+    assert hidden_max > 50.0
+    assert torch.isfinite(got).all() and rel(got, want) < 1.5e-3
+    # 2) beyond the fp16 range: hidden |x| > 7e4
+    sd_big = {k: (v * 4000.0 if k.endswith("mlp.fc1.weight") else v * (2.5e-4 if k.endswith("mlp.fc2.weight") else 1.0))
+              for k, v in sd.items()}
+    want = O.uvit_forward(sd_big, case["cfg"], x, t)
+    assert torch.isfinite(want).all()
+    m16 = UViT(**case["cfg"]).eval()
+    m16.load_state_dict(sd_big)
+    m16 = m16.to(dev())
+    with torch.no_grad():
+        got16 = m16(x.to(dev()), t.to(dev()))[0]
+    overflowed = m16.engine().nonfinite()          # the library's own sticky flag (usp_nonfinite)
+    assert overflowed == (not torch.isfinite(got16).all().item())
+    assert overflowed or rel(got16, want) < 1.5e-3  # loud or right, never quietly wrong
+    if overflowed:
+        kw = dict(dissect_name="none", solver_kwargs=dict(solver="fixed", solver_fix="euler", solver_fix_step=0.5))
+        with pytest.raises(FloatingPointError, match="fp16"):
+            CNF(m16).decode(x.to(dev()), y=None, **kw)
+        zh = x.clone().pin_memory()
+        with pytest.raises(RuntimeError, match="inf / NaN"):
+            m16.engine().sample_host(zh, 0.0, 1.0, 0.5, "euler")
+    assert not m.engine().nonfinite()
+    mb = UViT(**case["cfg"]).eval()
+    mb.operand_dtype = "bf16"
+    mb.load_state_dict(sd_big)
+    mb = mb.to(dev())
+    with torch.no_grad():
+        gotb = mb(x.to(dev()), t.to(dev()))[0]
+    assert torch.isfinite(gotb).all() and rel(gotb, want) < 1.2e-2
 
 
 def test_encode_decode_round_trip_full_size_model():
@@ -766,6 +893,26 @@ def test_rk4_with_grid_point_edit_and_attention_rule():
     assert rel(want, no_mid) > 5e-3
     with pytest.raises(RuntimeError, match="read mode"):
         m.engine().sample_read(x.to(dev()), 0.0, 1.0, 0.5, "rk4", context=ctx, edit_loc="tail")
+
+
+def test_cnf_rejects_write_edits_under_midpoint_and_rk4(tmp_path):
+    """The reference's hook keys on f"{t:.2f}" at every evaluation (libs/dissection.py:120), in-between stages of
+    midpoint / rk4 included; the CNF mirror's table is keyed by grid point, so it refuses rather than diverge."""
+    m = model("tiny_uncond")
+    x, _, _, _ = build_inputs(CASES["tiny_uncond"])
+    for t in ("0.25", "0.50"):
+        np.save(tmp_path / f"delta_{t}.npy", np.zeros((2, 4, 32, 32), np.float32))
+    for method in ("midpoint", "rk4"):
+        kw = dict(dissect_task="uspace_uvit", dissect_name="write_attr", write_path_root=str(tmp_path), ith_attr=1,
+                  t_edit=0.5, write_scale=1.0, edit_loc="tail",
+                  solver_kwargs=dict(solver="fixed", solver_fix=method, solver_fix_step=0.25))
+        with pytest.raises(NotImplementedError, match="write edits"):
+            CNF(m).decode(x.to(dev()), y=None, **kw)
+    # torchdiffeq's name for the two-stage Heun
+    kw = dict(dissect_name="none", solver_kwargs=dict(solver="fixed", solver_fix="heun2", solver_fix_step=0.25))
+    a = CNF(m).decode(x.to(dev()), y=None, **kw)
+    b = m.engine().sample(x.to(dev()), 0.0, 1.0, 0.25, "heun")
+    assert torch.equal(a, b)
 
 
 def test_scale_sweep_full_size_model_bit_exact():

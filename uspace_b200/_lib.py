@@ -55,6 +55,7 @@ _SIGNATURES = {
     "usp_sample_sweep": (_i, [_vp, _vp, _vp, _vp, _vp, _i, C.POINTER(_f), _i, _f, _f, _f, _i, _vp, _f, _i, _vp]),
     "usp_sample_read": (_i, [_vp, _vp, _vp, _vp, _i, _f, _f, _f, _i, _i, _vp, _vp]),
     "usp_sample_host": (_i, [_vp, _vp, _vp, _vp, _i, _f, _f, _f, _i, _vp, _f, _f, _i]),
+    "usp_nonfinite": (_i, [_vp, C.POINTER(_i), _vp]),
     "usp_grid_size": (_i, [_f, _f, _f]),
     "usp_time_grid": (_i, [_f, _f, _f, C.POINTER(_f), _i]),
     "usp_workspace_bytes": (C.c_size_t, [_vp, _i]),
@@ -62,6 +63,7 @@ _SIGNATURES = {
     "usp_flops_per_forward": (C.c_double, [_vp]),
     "usp_last_forward_ms": (_i, [_vp, C.POINTER(_f)]),
     "usp_profile_forward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, C.POINTER(_f), C.POINTER(_i), _vp]),
+    "usp_profile_forward_n": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, C.POINTER(_f), C.POINTER(_i), _vp]),
     "usp_vae_create": (_i, [_i, _f, C.POINTER(_vp)]),
     "usp_vae_destroy": (None, [_vp]),
     "usp_vae_last_error": (C.c_char_p, [_vp]),

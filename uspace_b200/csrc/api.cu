@@ -199,6 +199,7 @@ struct usp_handle {
     cudaStream_t cap_stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     RkState* rs_host = nullptr;   // pinned mirror of the adaptive solver's device state
+    int* nonfinite = nullptr;     // device flag set by final_kernel when a velocity is inf / NaN (sticky until read)
     bool ev_valid = false;
     int kernels_per_forward = 0;
     std::string err;
@@ -592,6 +593,7 @@ int enqueue_forward(usp_handle* h, Plan* p, const FwdIO& io, cudaStream_t s) {
     fa.sscale = io.sscale;
     fa.hook_scale = io.hook_scale;
     fa.trace = io.edit_loc == USP_EDIT_TAIL ? io.trace : nullptr;
+    fa.nonfinite = h->nonfinite;
     fa.st = io.st; fa.base = io.base; fa.aux = io.aux; fa.vstore = io.vstore; fa.acc2 = io.acc2; fa.out = io.out;
     fa.m1 = io.m1; fa.m2 = io.m2;
     fa.vs_a = io.vs_a; fa.vs_b = io.vs_b; fa.a2_a = io.a2_a; fa.a2_b = io.a2_b;
@@ -724,6 +726,8 @@ int usp_create(const usp_config* cfg, int device, usp_handle** out) {
         }
         CUDA_TRY(nullptr, cudaMalloc(&h->freqs, half * 4));
         CUDA_TRY(nullptr, cudaMemcpy(h->freqs, f.data(), half * 4, cudaMemcpyHostToDevice));
+        CUDA_TRY(nullptr, cudaMalloc(&h->nonfinite, 4));
+        CUDA_TRY(nullptr, cudaMemset(h->nonfinite, 0, 4));
     }
     CUDA_TRY(nullptr, cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
     CUDA_TRY(nullptr, cudaEventCreate(&h->ev0));
@@ -755,6 +759,7 @@ void usp_destroy(usp_handle* h) {
         cudaFree(b.fc1_d);
     }
     cudaFree(h->freqs);
+    cudaFree(h->nonfinite);
     if (h->rs_host) cudaFreeHost(h->rs_host);
     if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -877,18 +882,27 @@ int usp_forward_hook(usp_handle* h, const float* x, const float* t, const float*
 
 int usp_profile_forward(usp_handle* h, const float* x, const float* t, const float* context, const int64_t* y,
                         float* out, int B, float* class_ms, int* class_launches, void* stream) {
-    if (!h || !class_ms || !class_launches) return USP_ERR_INVALID;
-    h->profiling = true;
+    return usp_profile_forward_n(h, x, t, context, y, out, B, 0, 1, class_ms, class_launches, stream);
+}
+
+int usp_profile_forward_n(usp_handle* h, const float* x, const float* t, const float* context, const int64_t* y,
+                          float* out, int B, int warmup, int reps, float* class_ms, int* class_launches, void* stream) {
+    if (!h || !class_ms || !class_launches || reps < 1 || warmup < 0) return USP_ERR_INVALID;
+    for (int i = 0; i < USP_NUM_KERNEL_CLASSES; ++i) { class_ms[i] = 0.f; class_launches[i] = 0; }
+    int rc = USP_OK;
+    // back to back, no host synchronisation in between: the GPU stays at the clock / power state of a long run
+    for (int i = 0; i < warmup && rc == USP_OK; ++i) rc = usp_forward(h, x, t, context, y, out, B, stream);
     h->prof_ev.clear();
     h->prof_cls.clear();
-    int rc = usp_forward(h, x, t, context, y, out, B, stream);
+    h->profiling = true;
+    for (int i = 0; i < reps && rc == USP_OK; ++i) rc = usp_forward(h, x, t, context, y, out, B, stream);
     h->profiling = false;
     if (rc == USP_OK) {
         cudaError_t e = cudaStreamSynchronize(static_cast<cudaStream_t>(stream));
         if (e != cudaSuccess) rc = fail(h, USP_ERR_CUDA, std::string("profile sync: ") + cudaGetErrorString(e));
     }
-    for (int i = 0; i < USP_NUM_KERNEL_CLASSES; ++i) { class_ms[i] = 0.f; class_launches[i] = 0; }
     if (rc == USP_OK) {
+        // every evaluation ends with a class -1 mark: an interval belongs to the class of the mark that opens it
         for (size_t i = 0; i + 1 < h->prof_ev.size(); ++i) {
             const int c = h->prof_cls[i];
             if (c < 0 || c >= USP_NUM_KERNEL_CLASSES) continue;
@@ -896,6 +910,10 @@ int usp_profile_forward(usp_handle* h, const float* x, const float* t, const flo
             cudaEventElapsedTime(&ms, h->prof_ev[i], h->prof_ev[i + 1]);
             class_ms[c] += ms;
             class_launches[c] += (c == 8 || c == 9) ? 2 : 1;
+        }
+        for (int i = 0; i < USP_NUM_KERNEL_CLASSES; ++i) {   // per evaluation
+            class_ms[i] /= static_cast<float>(reps);
+            class_launches[i] /= reps;
         }
     }
     for (auto e : h->prof_ev) cudaEventDestroy(e);
@@ -1338,6 +1356,22 @@ int usp_sample_host(usp_handle* h, float* z_host, const float* context_host, con
     rc = usp_sample(h, z_host, ctx_dev, y_host, B, t0, t1, step_size, method, delta_table_host, write_scale, t_edit,
                     edit_loc, s);
     if (rc) return rc;
+    int flag = 0;
+    rc = usp_nonfinite(h, &flag, s);   // synchronises
+    if (rc) return rc;
+    if (flag)
+        return fail(h, USP_ERR_NONFINITE,
+                    "a velocity evaluation produced inf / NaN (activations beyond the fp16 operand range?): "
+                    "use operand_dtype bf16 for this checkpoint");
+    return USP_OK;
+}
+
+int usp_nonfinite(usp_handle* h, int* flag, void* stream) {
+    if (!h || !flag) return USP_ERR_INVALID;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    CUDA_TRY(h, cudaMemcpyAsync(flag, h->nonfinite, 4, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(h, cudaMemsetAsync(h->nonfinite, 0, 4, s));
     CUDA_TRY(h, cudaStreamSynchronize(s));
     return USP_OK;
 }

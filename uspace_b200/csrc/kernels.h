@@ -145,6 +145,7 @@ struct FinalArgs {
     const float* aux;      // a stored derivative combination (Heun stage 2: k1), or nullptr
     float* vstore;         // running combination 1: vstore = vs_a * v + vs_b * vstore (Heun stage 1: k1), or nullptr
     float* acc2;           // running combination 2: acc2 = a2_a * v + a2_b * acc2 (rk4: k1 + 3 k2 + 3 k3), or nullptr
+    int* nonfinite;        // sticky flag: set to 1 when a velocity is inf / NaN (fp16 operand overflow upstream)
     float* out;            // forward: v;  ODE: base + dt*(m1*v + m2*aux), aux read BEFORE the combinations are updated
     float m1, m2;
     float vs_a, vs_b, a2_a, a2_b;

@@ -235,8 +235,9 @@ class Engine:
                    "usp_sample_host")
         return z_host
 
-    def profile_forward(self, x, t, y=None, context=None):
-        """One eager forward with an event between launches -> {kernel class: (ms, launches)}."""
+    def profile_forward(self, x, t, y=None, context=None, warmup=0, reps=1):
+        """Eager forwards with an event between launches -> {kernel class: (ms, launches)} per evaluation (mean over
+        ``reps`` evaluations enqueued back to back after ``warmup`` untimed ones)."""
         B = x.shape[0]
         x = x.to(self.device, torch.float32).contiguous()
         t = t.to(self.device, torch.float32).expand(B).contiguous()
@@ -244,9 +245,17 @@ class Engine:
         n = len(_lib.KERNEL_CLASSES)
         ms = (C.c_float * n)()
         cnt = (C.c_int * n)()
-        _lib.check(self.lib.usp_profile_forward(self.handle, _ptr(x), _ptr(t), _ptr(context), _ptr(y), _ptr(out), B,
-                                                ms, cnt, self._stream()), self.handle, "usp_profile_forward")
+        _lib.check(self.lib.usp_profile_forward_n(self.handle, _ptr(x), _ptr(t), _ptr(context), _ptr(y), _ptr(out), B,
+                                                  int(warmup), int(reps), ms, cnt, self._stream()),
+                   self.handle, "usp_profile_forward_n")
         return {k: (ms[i], cnt[i]) for i, k in enumerate(_lib.KERNEL_CLASSES)}
+
+    def nonfinite(self) -> bool:
+        """True if any velocity evaluation since the last call produced inf / NaN (fp16 operand overflow); reads and
+        clears the device flag, synchronising the current stream."""
+        flag = C.c_int(0)
+        _lib.check(self.lib.usp_nonfinite(self.handle, C.byref(flag), self._stream()), self.handle, "usp_nonfinite")
+        return bool(flag.value)
 
     # ---- introspection ---------------------------------------------------------------------------
     def last_ms(self) -> float:

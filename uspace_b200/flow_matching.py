@@ -23,7 +23,7 @@ from torch import Tensor
 
 from .engine import time_grid
 
-_FIXED_METHODS = ("euler", "heun", "midpoint", "rk4")
+_FIXED_METHODS = ("euler", "heun", "heun2", "midpoint", "rk4")   # "heun2" is torchdiffeq's name for the 2-stage Heun
 _ADAPTIVE_METHODS = ("dopri5", "bosh3", "adaptive_heun")
 _RTOL = 1e-5   # flow_matching.py:11-12
 _ATOL = 1e-5
@@ -80,10 +80,13 @@ def build_delta_table(grid, shape, **kwargs):
     return torch.from_numpy(table), loc
 
 
-def build_delta_digits(shape, n_rows: int = 101, **kwargs):
+def build_delta_digits(shape, n_rows: int = 101, missing=None, **kwargs):
     """The same edit for a solver whose evaluation times are not known in advance: row i holds what the hook would
-    load for timestep_digit f"{i/100:.2f}" (libs/dissection.py:139-183).  Files that do not exist give a zero row (the
-    reference raises FileNotFoundError if the solver ever evaluates there).  Returns (table, edit_loc) or (None, None)."""
+    load for timestep_digit f"{i/100:.2f}" (libs/dissection.py:139-183).  The reference raises FileNotFoundError when
+    the solver evaluates at a digit without a file; an adaptive solver's evaluation times are not known here, so a
+    missing file gives a zero row, its digit is appended to ``missing`` (reported in ``CNF.last_solver_stats`` with a
+    one-time warning), and a root without ANY matching file raises FileNotFoundError like the reference would.
+    Returns (table, edit_loc) or (None, None)."""
     name = kwargs.get("dissect_name")
     if kwargs.get("dissect_task") != "uspace_uvit" or name in (None, "none"):
         return None, None
@@ -98,13 +101,26 @@ def build_delta_digits(shape, n_rows: int = 101, **kwargs):
         return None, None
     root = kwargs["write_path_root"]
     table = np.zeros((n_rows,) + tuple(shape), dtype=np.float32)
+    wanted = n_missing = 0
     for i in range(n_rows):
         digit = f"{i / 100:.2f}"
         if not should_edit(digit, kwargs.get("t_edit")):
             continue
         path = os.path.join(root, f"delta_{digit}.npy" if name == "write_attr" else f"pca{kwargs.get('pca_n')}_{digit}.npy")
+        wanted += 1
         if os.path.exists(path):
             table[i] = _read_delta(path, kwargs.get("ith_attr") if name == "write_attr" else kwargs.get("ith_component"))
+        elif missing is not None:
+            missing.append(digit)
+        else:
+            n_missing += 1
+    n_missing += len(missing) if missing is not None else 0
+    if wanted and n_missing == wanted:
+        raise FileNotFoundError(f"no delta / pca file for any edited timestep under {root!r}")
+    if n_missing:
+        import warnings
+        warnings.warn(f"uspace_b200: {n_missing} of {wanted} edited timestep digits have no file under {root!r}; the "
+                      "edit is skipped there (the reference raises FileNotFoundError if the solver evaluates at one)")
     return torch.from_numpy(table), loc
 
 
@@ -151,9 +167,20 @@ def build_attn_edit(B: int, L: int, **kwargs):
 
 
 class _CNFBase(nn.Module):
+    # decode / encode end with one 4-byte read of the library's non-finite flag (a stream synchronisation) and raise
+    # when a velocity evaluation overflowed the fp16 operand range; set False to keep the call fully asynchronous
+    check_overflow = True
+
     def __init__(self, net):
         super().__init__()
         self.net = net
+
+    def _checked(self, engine, out: Tensor) -> Tensor:
+        if self.check_overflow and engine.nonfinite():
+            raise FloatingPointError(
+                "uspace_b200: a velocity evaluation produced inf / NaN - activations of this checkpoint exceed the "
+                "fp16 tensor-core operand range (65504); set net.operand_dtype = 'bf16'")
+        return out
 
     def _call_net(self, x, t, cond, **kwargs):
         raise NotImplementedError
@@ -194,7 +221,8 @@ class _CNFBase(nn.Module):
     def _fixed_kwargs(sk):
         if sk["solver_fix"] not in _FIXED_METHODS:
             raise NotImplementedError(f"solver_fix={sk['solver_fix']!r}: built methods are {_FIXED_METHODS}")
-        return dict(method=sk["solver_fix"], rtol=_RTOL, atol=_ATOL, options=dict(step_size=float(sk["solver_fix_step"])))
+        method = "heun" if sk["solver_fix"] == "heun2" else sk["solver_fix"]
+        return dict(method=method, rtol=_RTOL, atol=_ATOL, options=dict(step_size=float(sk["solver_fix_step"])))
 
     def training_losses(self, x, cond, sigma_min, **kwargs):
         """flow_matching.py:88-100 (runs the differentiable PyTorch graph of the mirror module)."""
@@ -224,17 +252,28 @@ class _CNFBase(nn.Module):
             table, loc = build_delta_table(time_grid(t0, t1, h), z.shape[1:], **kwargs) if dissect else (None, None)
             ws = float(kwargs.get("write_scale") or 0.0) if table is not None else 0.0
             # rows where should_edit() is false are zero, so the library's own mask can stay wide open
-            return engine.sample(z, t0, t1, h, ode_kwargs["method"], delta_table=table, write_scale=ws,
-                                 t_edit=float("inf"), edit_loc=loc, attn_edit=attn, **self._cond_kw(cond))
+            if table is not None and ode_kwargs["method"] in ("midpoint", "rk4"):
+                # the reference's hook keys on f"{t:.2f}" at EVERY evaluation, so midpoint / rk4 would load (or fail to
+                # find) delta files for their in-between stage times; the library's table is keyed by grid point only
+                raise NotImplementedError(
+                    f"write edits under solver_fix={ode_kwargs['method']!r}: the stages between grid points have no "
+                    "row in the grid-keyed delta table (use euler / heun, or an adaptive solver)")
+            return self._checked(engine, engine.sample(z, t0, t1, h, ode_kwargs["method"], delta_table=table,
+                                                       write_scale=ws, t_edit=float("inf"), edit_loc=loc,
+                                                       attn_edit=attn, **self._cond_kw(cond)))
         if ode_kwargs["method"] not in _ADAPTIVE_METHODS:
             raise NotImplementedError(f"method={ode_kwargs['method']!r}")
-        table, loc = build_delta_digits(z.shape[1:], **kwargs) if dissect else (None, None)
+        missing = []
+        table, loc = build_delta_digits(z.shape[1:], missing=missing, **kwargs) if dissect else (None, None)
+        self._missing_digits = missing
         ws = float(kwargs.get("write_scale") or 0.0) if table is not None else 0.0
         self.last_solver_stats = {}
-        return engine.sample_adaptive(z, t0, t1, ode_kwargs["rtol"], ode_kwargs["atol"], delta_digits=table,
-                                      write_scale=ws, t_edit=float("inf"), edit_loc=loc, attn_edit=attn,
-                                      stats=self.last_solver_stats, method=ode_kwargs["method"],
-                                      **self._cond_kw(cond))
+        if table is not None:
+            self.last_solver_stats["delta_rows_missing"] = self._missing_digits
+        return self._checked(engine, engine.sample_adaptive(
+            z, t0, t1, ode_kwargs["rtol"], ode_kwargs["atol"], delta_digits=table, write_scale=ws,
+            t_edit=float("inf"), edit_loc=loc, attn_edit=attn, stats=self.last_solver_stats,
+            method=ode_kwargs["method"], **self._cond_kw(cond)))
 
     def _integrate_read(self, engine, z, cond, t0, t1, ode_kwargs, **kwargs) -> Tensor:
         """dissect_name="read" (libs/dissection.py:126-136): np.save(f"{read_path_root}/{batch_id}_{t:.2f}", x) for the
