@@ -2,7 +2,7 @@
 # Developer GPU session (run under gpurun): tests, smoke, bench, ncu launch list + full captures.
 mkdir -p gpurun_out
 R=${R:-r01}
-(timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -15) > gpurun_out/${R}_pytest_gpu.log
+(timeout 1800 python -m pytest tests -x -q -m gpu --durations=8 2>&1 | tail -15) > gpurun_out/${R}_pytest_gpu.log
 (timeout 300 python __graft_entry__.py smoke 2>&1 | tail -3) > gpurun_out/${R}_smoke.log
 (timeout 600 python bench.py 2>&1 | tail -1) > gpurun_out/${R}_bench.json
 if [ "${NCU:-1}" = "1" ]; then

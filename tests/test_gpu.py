@@ -396,10 +396,11 @@ def test_module_call_applies_the_edit_hook_like_the_reference(golden_dir, tmp_pa
     assert torch.equal(out, plain)
     want = x.numpy() if loc == "head" else plain.cpu().numpy()
     assert np.array_equal(dumped, want)
-    with pytest.raises(ValueError):
-        m(x.to(dev()), t, None, **dict(kw, dissect_name="bogus"))
-    with pytest.raises(NotImplementedError):
-        m(x.to(dev()), t, None, **dict(kw, edit_loc="mid"))
+    with torch.no_grad():
+        with pytest.raises(ValueError):
+            m(x.to(dev()), t, None, **dict(kw, dissect_name="bogus"))
+        with pytest.raises(NotImplementedError):
+            m(x.to(dev()), t, None, **dict(kw, edit_loc="mid"))
 
 
 # ---- the BASELINE configurations as whole trajectories against the oracle (fp32 FAST mode: the same torch CPU calls
