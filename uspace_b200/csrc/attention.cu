@@ -250,12 +250,17 @@ cudaError_t attention2_configure();
 bool attention2_supported(const AttnArgs& a);
 cudaError_t launch_attention2(const CUtensorMap& q, const CUtensorMap& k, const CUtensorMap& v, const AttnArgs& a,
                               int num_sms, cudaStream_t s);
+cudaError_t attention3_configure();
+bool attention3_supported(const AttnArgs& a);
+cudaError_t launch_attention3(const CUtensorMap& q, const CUtensorMap& k, const CUtensorMap& v, const AttnArgs& a,
+                              int num_sms, cudaStream_t s);
 
 cudaError_t attention_configure() {
     static bool done = false;
     if (done) return cudaSuccess;
     cudaError_t e = cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_SMEM);
     if (e == cudaSuccess) e = attention2_configure();
+    if (e == cudaSuccess) e = attention3_configure();
     if (e == cudaSuccess) done = true;
     return e;
 }
@@ -274,6 +279,8 @@ cudaError_t launch_attention(const CUtensorMap& q, const CUtensorMap& k, const C
                              cudaStream_t s) {
     if (a.L < 1 || a.L > ATTN_MAX_L || a.D != a.H * HD) return cudaErrorInvalidValue;
     // the column re-weighting (p2p) hook lives in the persistent kernel only
+    // default: two tiles in flight (attention3.cu); USP_ATTN_V3=0 / USP_ATTN_V1=1 select the older kernels
+    if (!force_v1() && attention3_supported(a)) return launch_attention3(q, k, v, a, a.num_sms, s);
     if (a.vscale != nullptr && (force_v1() || !attention2_supported(a))) return cudaErrorNotSupported;
     if (!force_v1() && attention2_supported(a)) return launch_attention2(q, k, v, a, a.num_sms, s);
     dim3 grid((a.L + QT - 1) / QT, a.B * a.H);

@@ -6,24 +6,24 @@
 
 namespace usp {
 
-// exact-erf GELU (nn.GELU() default, libs/timm.py:101-108).  erf via Abramowitz-Stegun 7.1.26
-// (|abs err| <= 1.5e-7, far below the 16-bit rounding of the stored activation); 2 MUFU + ~12 FMA-class ops,
-// about half the instruction count of erff(), which matters because fc1's epilogue is issue-bound.
+// exact-erf GELU (nn.GELU() default, libs/timm.py:101-108) as  gelu(v) = max(v, 0) - |v| * Phi(-|v|)  with
+// Phi(-a) = 0.5 erfc(a / sqrt2) = 2^q(a): q is the degree-5 minimax fit of log2(0.5 erfc(a / sqrt2)) on [0, 5.5]
+// (weighted by a * Phi(-a), the sensitivity of the result); its leading coefficient is negative, so 2^q(a) keeps
+// decaying beyond the fitted range and no clamp is needed.  |abs err| <= 1.4e-6 for every finite v (checked on a
+// 5e-5 grid over [-60, 60] against scipy's erf in fp64, coefficients rounded to fp32) - far below the 16-bit
+// rounding of the stored activation.  1 MUFU + 7 FMA-class ops: the Abramowitz-Stegun form used before
+// (2 MUFU + ~14 ops) made fc1's epilogue longer than its main loop (MUFU alone: 2 x 128 x 8 clk x 2 warps per
+// scheduler = 4096 clk per tile = the tile's MMA time).
 __device__ __forceinline__ float gelu_erf_fast(float v) {
-    const float x = fabsf(v) * 0.70710678118654752440f;
-    float t;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, x, 1.0f)));
-    float p = fmaf(1.061405429f, t, -1.453152027f);
-    p = fmaf(p, t, 1.421413741f);
-    p = fmaf(p, t, -0.284496736f);
-    p = fmaf(p, t, 0.254829592f);
-    p *= t;
+    const float a = fabsf(v);
+    float q = fmaf(-0.0003865355101879686f, a, 0.006509846542030573f);
+    q = fmaf(q, a, -0.050480134785175323f);
+    q = fmaf(q, a, -0.46135035157203674f);
+    q = fmaf(q, a, -1.1502251625061035f);
+    q = fmaf(q, a, -1.0001084804534912f);
     float e;
-    const float a = -x * x * 1.44269504088896340736f;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(a));
-    const float erf_abs = fmaf(-p, e, 1.0f);      // erf(|v|/sqrt2)
-    const float hv = 0.5f * v;
-    return fmaf(fabsf(hv), erf_abs, hv);          // 0.5*v*(1 + sign(v)*erf_abs) == hv + |hv|*erf_abs
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(q));
+    return fmaf(-a, e, fmaxf(v, 0.f));
 }
 
 __device__ __forceinline__ uint32_t pack16(int opd, float a, float b) {
