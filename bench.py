@@ -222,6 +222,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch override")
     ap.add_argument("--operand", default="fp16", choices=["fp16", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--fuse-ln", type=int, default=-1, help="override usp_config.fuse_layernorm (0 / 1)")
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
     if args.batch:
@@ -248,6 +249,8 @@ def main():
     torch.manual_seed(0)
     model = (UViTT2I if wl["t2i"] else UViT)(**wl["cfg"]).eval()
     model.operand_dtype = args.operand
+    if args.fuse_ln >= 0:
+        model.fuse_layernorm = bool(args.fuse_ln)
     model = model.to(dev)
     eng = model.engine()
     Bl = wl["batch"]

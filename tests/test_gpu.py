@@ -139,6 +139,22 @@ def test_attention(lib, opd, B, H, L):
     assert rel(out.float(), want) < (6e-4 if opd == "fp16" else 5e-3)
 
 
+@pytest.mark.parametrize("B,H,L,scale", [(2, 4, 257, 6.0), (3, 16, 334, 5.0), (64, 16, 257, 4.0), (2, 2, 200, 8.0)])
+def test_attention_large_scores_running_max(lib, B, H, L, scale):
+    """Scores whose block maxima differ by far more than 2^8: the lazy running-maximum path of attention3.cu (O rescaled
+    in TMEM between key blocks) against fp32 SDPA (libs/uvit.py:95)."""
+    g = torch.Generator().manual_seed(7 * B + L)
+    q = (scale * torch.randn(B * H, L, 64, generator=g)).to(dev()).half()
+    k, v = (torch.randn(B * H, L, 64, generator=g).to(dev()).half() for _ in range(2))
+    out = torch.zeros(B * L, H * 64, device=dev(), dtype=torch.float16)
+    _lib.check(lib.usp_op_attention(P(q), P(k), P(v), P(out), B, H, L, _lib.OPERAND["fp16"], stream()))
+    torch.cuda.synchronize()
+    ref = torch.nn.functional.scaled_dot_product_attention(q.float(), k.float(), v.float())
+    want = ref.view(B, H, L, 64).permute(0, 2, 1, 3).reshape(B * L, H * 64)
+    assert torch.isfinite(out).all()
+    assert rel(out.float(), want) < 6e-4
+
+
 def test_attention_rejects_long_sequences(lib):
     q = torch.zeros(1, 385, 64, device=dev(), dtype=torch.float16)
     assert lib.usp_op_attention(P(q), P(q), P(q), P(q), 1, 1, 385, 1, stream()) != 0

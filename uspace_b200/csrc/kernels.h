@@ -75,6 +75,7 @@ struct AttnArgs {
     int diag;             // diagnostics (env USP_ATTN_DIAG, results invalid): 1 = no MUFU, 2 = no softmax arithmetic,
                           // 4 / 8 = no PV / S MMAs (non-pipelined variants), 16 = no TMEM reads, 32 = no tail-row arithmetic
     const void* q16;      // raw pointer to Q [B*H, L, 64] (the SIMT tail-row path reads its query rows directly)
+    unsigned long long* trace;   // debugging (env USP_ATTN_TRACE=<file>): per-role event timeline of CTA 0, else nullptr
 };
 constexpr int ATTN_MAX_L = 384;
 // tensor maps: q = [planes, L, 64] with 128-row boxes; k, v = same tensors with attn_kv_box_rows(L)-row boxes
