@@ -455,6 +455,12 @@ attention3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
             const uint64_t qdesc = qdesc0 + gq * (QTILE_BYTES / 16);
             const uint64_t kdesc_item = kdesc0 + (n & 1) * (kv_bytes / 16);
             const uint64_t vdesc_item = vdesc0 + (n & 1) * (kv_bytes / 16);
+            // the slot's next tile g + 2 = (item n2, tile t2), Q buffer gq2
+            const int g2 = g + 2;
+            int n2 = n, t2 = t + 2;
+            while (t2 >= n_qt) { t2 -= n_qt; ++n2; }
+            const int gq2 = gq + 2 >= NQ ? gq + 2 - NQ : gq + 2;
+            bool next_issued = false;
             for (int kb = 0; kb < nkb; ++kb, ++b) {
                 const int woff_next = woff == 2 * KSTEP ? 0 : woff + KSTEP;
                 const bool last = kb == nkb - 1;
@@ -470,8 +476,22 @@ attention3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                 mbar_wait(&s_free[s], b & 1);
                 tc_fence_after();
                 USP_TR(2 + s, 10);
-                if (!last) issue_s(t_slot + woff_next, qdesc, kdesc_next, idesc_next);
-                else if (g + NQ < n_tiles) load_q(g + NQ, n3, t3);
+                if (!last) {
+                    issue_s(t_slot + woff_next, qdesc, kdesc_next, idesc_next);
+                } else {
+                    // The next tile's first block goes out right here as well (its window is the rotation's next one: it
+                    // overlaps neither P(b) nor anything unread) - provided its Q tile and K/V have landed; a blocking wait
+                    // at this point would hold back PV(b).  Otherwise it is issued behind PV(b) below.
+                    if (g2 < n_tiles &&
+                        __all_sync(0xffffffffu, mbar_test_wait(&q_full[gq2], (g2 / NQ) & 1) &&
+                                                    mbar_test_wait(&kv_full[n2 & 1], (n2 >> 1) & 1))) {
+                        tc_fence_after();
+                        issue_s(t_slot + woff_next, qdesc0 + gq2 * (QTILE_BYTES / 16), kdesc0 + (n2 & 1) * (kv_bytes / 16),
+                                idesc_full);
+                        next_issued = true;
+                    }
+                    if (g + NQ < n_tiles) load_q(g + NQ, n3, t3);
+                }
                 USP_TR(2 + s, 11);
                 // ---- P(b) is published: O += P V ----
                 mbar_wait(&p_bar[s][b & 1], (b >> 1) & 1);
@@ -495,12 +515,9 @@ attention3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                 USP_TR(2 + s, 13);
                 woff = woff_next;
             }
-            // next tile of this slot: g + 2
-            g += 2;
-            t += 2;
-            while (t >= n_qt) { t -= n_qt; ++n; }
-            gq = gq + 2 >= NQ ? gq + 2 - NQ : gq + 2;
-            if (g < n_tiles) {
+            // next tile of this slot
+            g = g2; n = n2; t = t2; gq = gq2;
+            if (g < n_tiles && !next_issued) {
                 mbar_wait(&q_full[gq], (g / NQ) & 1);
                 mbar_wait(&kv_full[n & 1], (n >> 1) & 1);
                 tc_fence_after();
@@ -526,6 +543,67 @@ attention3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         const int all_secs = ((n_tiles + 1) / 2) * nkb;
         const bool lock = (a.diag & 64) == 0;   // diag 64: no ping-pong lock around the exponential sections (A/B comparison)
         if (lock && s == 1) asm volatile("bar.arrive 4, 256;" ::: "memory");   // warpgroup 0 goes first
+        // Read-out of a finished tile: O / sum -> out16.  It is DEFERRED to right after the next tile's first block has
+        // been published: by then PV of the tile's last block has long retired (no wait), and the ~1.5k cycles of
+        // TMEM loads / scaling / stores run while the other warpgroup holds its exponential turn instead of stalling the
+        // alternation at every tile end.  The MMA warp holds PV(next tile, block 0) back until o_free.
+        auto read_out = [&](int p_jt, int p_bh, int p_t, bool p_row_ok, bool p_warp_ok, float p_sum) {
+            const int l0 = p_t * QT + lg * 32;
+            if (lg == 0) USP_TR(s, 6);
+            mbar_wait(&bar_o[s], p_jt & 1);
+            tc_fence_after();
+            if (lg == 0) USP_TR(s, 7);
+            if (p_warp_ok) {
+                uint32_t o[2][32];
+                tmem_ld32(t_o, o[0]);
+                tmem_ld32(t_o + 32, o[1]);
+                tmem_ld_wait();
+                tc_fence_before();
+                mbar_arrive(&o_free[s]);
+                const float inv = 1.0f / p_sum;
+                uint16_t* op = reinterpret_cast<uint16_t*>(a.out16) +
+                               (static_cast<long long>(p_bh / a.H) * L + l0 + lane) * a.D + (p_bh % a.H) * HD;
+                uint8_t* stg = sStage + warp * 4096;
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                    uint32_t u[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        u[j] = Op16<OPD>::pack(__uint_as_float(o[hh][2 * j]) * inv, __uint_as_float(o[hh][2 * j + 1]) * inv);
+                    if (staged) {
+                        // own row (128 B) into the warp's staging tile, 16-byte units XOR-swizzled by (row & 7)
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            *reinterpret_cast<uint4*>(stg + lane * 128 + (((hh * 4 + q) ^ (lane & 7)) << 4)) =
+                                make_uint4(u[4 * q], u[4 * q + 1], u[4 * q + 2], u[4 * q + 3]);
+                    } else if (p_row_ok) {
+                        st_global_v8_b32(op + hh * 32, u);
+                        st_global_v8_b32(op + hh * 32 + 16, u + 8);
+                    }
+                }
+                if (staged) {
+                    __syncwarp();
+                    // 8 lanes per row: every store instruction writes 4 complete 128-byte rows
+                    uint8_t* ob = reinterpret_cast<uint8_t*>(a.out16) +
+                                  ((static_cast<long long>(p_bh / a.H) * L + l0) * a.D + (p_bh % a.H) * HD) * 2 + (lane & 7) * 16;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int rr = 4 * i + (lane >> 3);
+                        const uint4 v = *reinterpret_cast<const uint4*>(stg + rr * 128 + (((lane & 7) ^ (rr & 7)) << 4));
+                        if (l0 + rr < L) *reinterpret_cast<uint4*>(ob + static_cast<long long>(rr) * a.D * 2) = v;
+                    }
+                    __syncwarp();
+                }
+                if (lg == 0) USP_TR(s, 8);
+            } else {
+                tc_fence_before();
+                mbar_arrive(&o_free[s]);
+            }
+        };
+        bool have_prev = false;
+        int p_jt = 0, p_bh = 0, p_t = 0;
+        bool p_row_ok = false, p_warp_ok = false;
+        float p_sum = 1.f;
         for (int g = s; g < n_tiles; g += 2, ++jt) {
             const int n = g / n_qt, t = g - n * n_qt;
             const int bh = static_cast<int>(blockIdx.x) + n * static_cast<int>(gridDim.x);
@@ -542,7 +620,11 @@ attention3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                 const int vcnt = (L - key0) < len ? (L - key0) : len;   // valid keys of this block (>= 1)
                 const uint32_t t_s = t_slot + KSTEP * (ks % 3);
                 if (lg == 0) USP_TR(s, 0);
-                mbar_wait(&bar_s[s], ks & 1);
+                if (a.diag & 128) {     // experiment: non-suspending poll
+                    while (!mbar_test_wait(&bar_s[s], ks & 1)) {}
+                } else {
+                    mbar_wait(&bar_s[s], ks & 1);
+                }
                 tc_fence_after();
                 if (lg == 0) USP_TR(s, 1);
                 if (warp_ok) {
@@ -569,59 +651,15 @@ attention3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                 }
                 tc_fence_before();
                 mbar_arrive(&p_bar[s][ks & 1]);
-            }
-            // ---- read-out: O / sum -> out16 ----
-            if (lg == 0) USP_TR(s, 6);
-            mbar_wait(&bar_o[s], jt & 1);
-            tc_fence_after();
-            if (lg == 0) USP_TR(s, 7);
-            if (warp_ok) {
-                uint32_t o[2][32];
-                tmem_ld32(t_o, o[0]);
-                tmem_ld32(t_o + 32, o[1]);
-                tmem_ld_wait();
-                tc_fence_before();
-                mbar_arrive(&o_free[s]);
-                const float inv = 1.0f / sum;
-                uint16_t* op = reinterpret_cast<uint16_t*>(a.out16) +
-                               (static_cast<long long>(bh / a.H) * L + l) * a.D + (bh % a.H) * HD;
-                uint8_t* stg = sStage + warp * 4096;
-#pragma unroll
-                for (int hh = 0; hh < 2; ++hh) {
-                    uint32_t u[16];
-#pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        u[j] = Op16<OPD>::pack(__uint_as_float(o[hh][2 * j]) * inv, __uint_as_float(o[hh][2 * j + 1]) * inv);
-                    if (staged) {
-                        // own row (128 B) into the warp's staging tile, 16-byte units XOR-swizzled by (row & 7)
-#pragma unroll
-                        for (int q = 0; q < 4; ++q)
-                            *reinterpret_cast<uint4*>(stg + lane * 128 + (((hh * 4 + q) ^ (lane & 7)) << 4)) =
-                                make_uint4(u[4 * q], u[4 * q + 1], u[4 * q + 2], u[4 * q + 3]);
-                    } else if (row_ok) {
-                        st_global_v8_b32(op + hh * 32, u);
-                        st_global_v8_b32(op + hh * 32 + 16, u + 8);
-                    }
+                if (kb == 0 && have_prev) {
+                    read_out(p_jt, p_bh, p_t, p_row_ok, p_warp_ok, p_sum);
+                    have_prev = false;
                 }
-                if (staged) {
-                    __syncwarp();
-                    // 8 lanes per row: every store instruction writes 4 complete 128-byte rows
-                    const int l0 = t * QT + lg * 32;
-                    uint8_t* ob = reinterpret_cast<uint8_t*>(a.out16) +
-                                  ((static_cast<long long>(bh / a.H) * L + l0) * a.D + (bh % a.H) * HD) * 2 + (lane & 7) * 16;
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int rr = 4 * i + (lane >> 3);
-                        const uint4 v = *reinterpret_cast<const uint4*>(stg + rr * 128 + (((lane & 7) ^ (rr & 7)) << 4));
-                        if (l0 + rr < L) *reinterpret_cast<uint4*>(ob + static_cast<long long>(rr) * a.D * 2) = v;
-                    }
-                    __syncwarp();
-                }
-            } else {
-                tc_fence_before();
-                mbar_arrive(&o_free[s]);
             }
+            have_prev = true;
+            p_jt = jt; p_bh = bh; p_t = t; p_row_ok = row_ok; p_warp_ok = warp_ok; p_sum = sum;
         }
+        if (have_prev) read_out(p_jt, p_bh, p_t, p_row_ok, p_warp_ok, p_sum);
         for (int i = my_secs; lock && i < all_secs; ++i) {     // empty sections: keep the alternation going for the other warpgroup
             if (s == 0) asm volatile("bar.sync 4, 256;\n\tbar.arrive 5, 256;" ::: "memory");
             else asm volatile("bar.sync 5, 256;\n\tbar.arrive 4, 256;" ::: "memory");
