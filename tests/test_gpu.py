@@ -477,8 +477,11 @@ def test_fp16_operand_range_scaled_weights():
                       @ sd_ok["in_blocks.0.mlp.fc1.weight"].T).abs().max().item(), 0.0)
     assert hidden_max > 50.0
     assert torch.isfinite(got).all() and rel(got, want) < 1.5e-3
-    # 2) beyond the fp16 range: hidden |x| > 7e4
-    sd_big = {k: (v * 4000.0 if k.endswith("mlp.fc1.weight") else v * (2.5e-4 if k.endswith("mlp.fc2.weight") else 1.0))
+    # 2) beyond the fp16 range: fc1 pre-activations ~ N(0, (2.6e4)^2), i.e. GELU outputs far above 65504 in every block
+    #    (fc2 is scaled back so that the fp32 oracle stays finite; its fp16 copy underflows, which no longer matters:
+    #    the run must be flagged.  A 4000x scale - used by an earlier version of this test - does NOT overflow (hidden
+    #    maximum ~6e3) and only measures the fp16-subnormal rounding of the shrunken fc2 weights, 1.8e-3.)
+    sd_big = {k: (v * 8.0e4 if k.endswith("mlp.fc1.weight") else v * (1.25e-5 if k.endswith("mlp.fc2.weight") else 1.0))
               for k, v in sd.items()}
     want = O.uvit_forward(sd_big, case["cfg"], x, t)
     assert torch.isfinite(want).all()
@@ -489,7 +492,7 @@ def test_fp16_operand_range_scaled_weights():
         got16 = m16(x.to(dev()), t.to(dev()))[0]
     overflowed = m16.engine().nonfinite()          # the library's own sticky flag (usp_nonfinite)
     assert overflowed == (not torch.isfinite(got16).all().item())
-    assert overflowed or rel(got16, want) < 1.5e-3  # loud or right, never quietly wrong
+    assert overflowed                                 # loud, never quietly wrong
     if overflowed:
         kw = dict(dissect_name="none", solver_kwargs=dict(solver="fixed", solver_fix="euler", solver_fix_step=0.5))
         with pytest.raises(FloatingPointError, match="fp16"):

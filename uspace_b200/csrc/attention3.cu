@@ -41,9 +41,10 @@ namespace {
 
 constexpr int HD = 64;
 constexpr int QT = 128;
-constexpr int THREADS = 384;            // 2 softmax warpgroups + 2 MMA-issue warps + 2 loader / tail-row warps
+constexpr int THREADS = 512;            // 2 softmax warpgroups | 2 MMA-issue warps + loader warp | 4 tail-row warps
 constexpr int MMA_WARP0 = 8;            // warps 8, 9: MMA issue (and Q loads) of slot 0, 1
-constexpr int TAIL_WARP0 = 10;          // warps 10, 11: K/V loads, leftover query rows
+constexpr int LOAD_WARP = 10;           // warp 10: K/V loads (warp 11 idle)
+constexpr int TAIL_WARP0 = 12;          // warps 12-15: leftover query rows on CUDA cores
 constexpr int QTILE_BYTES = QT * HD * 2;   // 16 KiB
 constexpr int NQ = 3;                   // Q tile buffers
 constexpr int KBMAX = 96;               // keys per score block = fp32 score registers per softmax thread
@@ -53,9 +54,9 @@ constexpr int MAX_L3 = 336;
 constexpr int TMEM_COLS = 512;
 constexpr int SLOT_COLS = 256;
 constexpr int O_OFF = 192;
-constexpr int TAIL_MAX = 0;             // leftover query rows handled on CUDA cores (0: they run as a masked third tile)
-constexpr int TAIL_THREADS = 64;        // warps 10-11
-constexpr int TAIL_KEYS = 5;            // keys per tail thread (L <= 320 whenever there are tail rows)
+constexpr int TAIL_MAX = 2;             // leftover query rows handled on CUDA cores (more run as a masked extra tile)
+constexpr int TAIL_THREADS = 128;       // warps 12-15
+constexpr int TAIL_KEYS = 3;            // keys per tail thread (L <= 258 whenever there are tail rows: MAX_L3 = 336)
 constexpr float RESCALE_LOG2 = 8.0f;    // lazy running-maximum update threshold (log2 domain)
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -117,7 +118,7 @@ constexpr int TRACE_N = 2048;
     } while (0)
 
 constexpr int STAGE_BYTES = 8 * 4096;
-constexpr int MAX_DYN_SMEM = 232448 - 2048;     // opt-in limit minus static shared memory
+constexpr int MAX_DYN_SMEM = 232448 - 3072;     // opt-in limit minus static shared memory
 __host__ __device__ inline bool stage_fits(int L16) {
     return NQ * QTILE_BYTES + 4 * L16 * 128 + 1024 + STAGE_BYTES <= MAX_DYN_SMEM;
 }
@@ -229,7 +230,7 @@ attention3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 
     __shared__ __align__(8) uint64_t q_full[NQ], kv_full[2], kv_free[2], bar_s[2], s_free[2], p_bar[2][2], bar_pv[2],
         bar_o[2], o_free[2];
-    __shared__ float t_q[HD], t_p[MAX_L3 + 16], t_red[2][2], t_o[2][HD];
+    __shared__ float t_q[HD], t_p[MAX_L3 + 16], t_red[2][4], t_o[4][HD];
     __shared__ uint32_t tmem_base_smem;
 
     const int warp = threadIdx.x >> 5;
@@ -261,7 +262,7 @@ attention3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         for (int i = 0; i < NQ; ++i) mbar_init(&q_full[i], 1);
         for (int i = 0; i < 2; ++i) {
             mbar_init(&kv_full[i], 1);
-            mbar_init(&kv_free[i], n_qt);      // one commit per tile of the item (its last PV)
+            mbar_init(&kv_free[i], n_qt + (tail_simt ? 1 : 0));   // one commit per tile (its last PV) + the tail warps
             mbar_init(&bar_s[i], 1);
             mbar_init(&s_free[i], QT);
             mbar_init(&p_bar[i][0], QT);      // P(b) arrives on p_bar[slot][b & 1]: a warp that runs one block ahead of its
@@ -282,28 +283,14 @@ attention3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     pdl_launch();
 
     if (warp >= TAIL_WARP0) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
-        // ============ warps 10-11: K/V loads (one elected thread) + the leftover query rows on CUDA cores ============
-        const int tt = threadIdx.x - TAIL_WARP0 * 32;   // 0..63
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
+        // ============ warps 12-15: the leftover query rows (L = 257 / 258) on CUDA cores, from the resident K/V tiles ======
+        // (as a masked third MMA tile they cost a whole tile's chain of hand-offs per item: 66 us against 45 at L = 256)
+        const int tt = threadIdx.x - TAIL_WARP0 * 32;   // 0..127
         const float c2 = 0.125f * 1.44269504088896340736f;
-        auto issue_kv = [&](int m) {      // K/V of this CTA's item m into buffer m & 1 (thread tt == 0 only)
-            const int nb = m & 1;
-            const int bh = static_cast<int>(blockIdx.x) + m * static_cast<int>(gridDim.x);
-            mbar_expect_tx(&kv_full[nb], 2 * kv_bytes);
-            for (int c = 0; c < 2; ++c) {
-                tma_load_3d(&tmK, &kv_full[nb], sK + nb * kv_bytes + c * hrows * 128, 0, c * hrows, bh);
-                tma_load_3d(&tmV, &kv_full[nb], sV + nb * kv_bytes + c * hrows * 128, 0, c * hrows, bh);
-            }
-        };
-        if (tt == 0) {
-            tma_prefetch_desc(&tmK);
-            tma_prefetch_desc(&tmV);
-            if (my_items > 0) issue_kv(0);
-            if (my_items > 1) issue_kv(1);
-        }
-        for (int n = 0; n < my_items; ++n) {
+        for (int n = 0; tail_simt && n < my_items; ++n) {
             const int bh = static_cast<int>(blockIdx.x) + n * static_cast<int>(gridDim.x);
-            if (tail_simt) {
+            {
                 const float* cs = (EDIT && a.vscale != nullptr && (a.st == nullptr || a.st->attn_on != 0))
                                       ? a.vscale + static_cast<long long>(bh / a.H) * L : nullptr;   // p2p column weights
                 const uint8_t* kbuf = sK + (n & 1) * kv_bytes;
@@ -316,7 +303,7 @@ attention3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                         t_q[2 * tt] = f.x;
                         t_q[2 * tt + 1] = f.y;
                     }
-                    asm volatile("bar.sync 2, 64;" ::: "memory");
+                    asm volatile("bar.sync 2, 128;" ::: "memory");
                     // scores for keys tt, tt+64, ... (log2 domain)
                     float x[TAIL_KEYS];
                     float mx = -INFINITY;
@@ -345,8 +332,8 @@ attention3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
                     if (lane == 0) t_red[0][warp - TAIL_WARP0] = mx;
-                    asm volatile("bar.sync 2, 64;" ::: "memory");
-                    mx = fmaxf(t_red[0][0], t_red[0][1]);
+                    asm volatile("bar.sync 2, 128;" ::: "memory");
+                    mx = fmaxf(fmaxf(t_red[0][0], t_red[0][1]), fmaxf(t_red[0][2], t_red[0][3]));
                     float sum = 0.f;
 #pragma unroll
                     for (int i = 0; i < TAIL_KEYS; ++i) {
@@ -364,12 +351,12 @@ attention3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
                     if (lane == 0) t_red[1][warp - TAIL_WARP0] = sum;
-                    asm volatile("bar.sync 2, 64;" ::: "memory");
-                    const float inv = 1.0f / (t_red[1][0] + t_red[1][1]);
-                    // O[d] = sum_j p_j V[j][d]: thread = (pair of d, every other key)
+                    asm volatile("bar.sync 2, 128;" ::: "memory");
+                    const float inv = 1.0f / ((t_red[1][0] + t_red[1][1]) + (t_red[1][2] + t_red[1][3]));
+                    // O[d] = sum_j p_j V[j][d]: thread = (pair of d, every fourth key)
                     const int dp = tt & 31, seg = tt >> 5;
                     float o0 = 0.f, o1 = 0.f;
-                    for (int j = seg; j < L; j += 2) {
+                    for (int j = seg; j < L; j += 4) {
                         const uint8_t* vrow = vbuf + (j >> 3) * 1024 + (j & 7) * 128;
                         const uint32_t w = *reinterpret_cast<const uint32_t*>(vrow + ((((dp >> 2) ^ (j & 7))) << 4) + (dp & 3) * 4);
                         const float2 f = Op16<OPD>::unpack(w);
@@ -379,23 +366,38 @@ attention3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                     }
                     t_o[seg][2 * dp] = o0;
                     t_o[seg][2 * dp + 1] = o1;
-                    asm volatile("bar.sync 2, 64;" ::: "memory");
+                    asm volatile("bar.sync 2, 128;" ::: "memory");
                     if (tt < HD / 2) {
-                        const float r0 = (t_o[0][2 * tt] + t_o[1][2 * tt]) * inv;
-                        const float r1 = (t_o[0][2 * tt + 1] + t_o[1][2 * tt + 1]) * inv;
+                        const float r0 = ((t_o[0][2 * tt] + t_o[1][2 * tt]) + (t_o[2][2 * tt] + t_o[3][2 * tt])) * inv;
+                        const float r1 = ((t_o[0][2 * tt + 1] + t_o[1][2 * tt + 1]) + (t_o[2][2 * tt + 1] + t_o[3][2 * tt + 1])) * inv;
                         reinterpret_cast<uint32_t*>(a.out16)[((static_cast<long long>(bh / a.H) * L + l) * a.D + (bh % a.H) * HD) / 2 + tt] =
                             Op16<OPD>::pack(r0, r1);
                     }
-                    asm volatile("bar.sync 2, 64;" ::: "memory");   // t_q / t_p / t_o are reused by the next row
+                    asm volatile("bar.sync 2, 128;" ::: "memory");   // t_q / t_p / t_o are reused by the next row
                 }
-                asm volatile("bar.sync 2, 64;" ::: "memory");       // every tail thread has left this K/V buffer
+                asm volatile("bar.sync 2, 128;" ::: "memory");       // every tail thread has left this K/V buffer
             }
-            // buffer n & 1 is refilled with item n + 2 once the item's MMAs have retired (kv_free: one commit per tile)
-            if (tt == 0 && n + 2 < my_items) {
-                mbar_wait(&kv_free[n & 1], (n >> 1) & 1);
-                issue_kv(n + 2);
+            if (tt == 0) mbar_arrive(&kv_free[n & 1]);     // (the barrier above: every tail thread has left the buffer)
+        }
+    } else if (warp >= LOAD_WARP) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
+        // ============ warp 10: K/V loads (one lane) ============
+        if (warp == LOAD_WARP && lane == 0) {
+            tma_prefetch_desc(&tmK);
+            tma_prefetch_desc(&tmV);
+            for (int m = 0; m < my_items; ++m) {
+                const int nb = m & 1;
+                const int bh = static_cast<int>(blockIdx.x) + m * static_cast<int>(gridDim.x);
+                // buffer m & 1 was last used by item m - 2: its MMAs have retired and its tail rows are done
+                if (m >= 2) mbar_wait(&kv_free[nb], ((m >> 1) - 1) & 1);
+                mbar_expect_tx(&kv_full[nb], 2 * kv_bytes);
+                for (int c = 0; c < 2; ++c) {
+                    tma_load_3d(&tmK, &kv_full[nb], sK + nb * kv_bytes + c * hrows * 128, 0, c * hrows, bh);
+                    tma_load_3d(&tmV, &kv_full[nb], sV + nb * kv_bytes + c * hrows * 128, 0, c * hrows, bh);
+                }
             }
         }
+        __syncwarp();
     } else if (warp >= MMA_WARP0) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
         // ============ warps 8 / 9: MMA issue for slot 0 / 1 (+ the Q tile loads); warp-uniform, one elected lane acts =====
@@ -526,7 +528,7 @@ attention3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         }
     } else {
         // ===================== softmax / output warps: one thread per query row, warpgroup = slot =====================
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 176;");
         const int s = warp >> 2;
         const int lg = warp & 3;
         const int row = lg * 32 + lane;
