@@ -148,6 +148,62 @@ def cpu_port_forward_time(cfg, t2i, B, max_seconds=25.0, warmup=1, reps=3):
     return statistics.median(times), len(times)
 
 
+_STAGED_NETS = {}
+
+
+def staged_reference_forward_time(cfg, t2i, B, max_seconds=25.0, warmup=1, reps=3):
+    """Times the reference's OWN module (libs.uvit.UViT / libs.uvit_t2i.UViT from baseline/_ref, staged unmodified by
+    baseline/stage_reference.py) for one velocity evaluation at batch B on the host cores.  Returns None when the
+    staged copy is absent or cannot be imported here (then the oracle port is timed instead)."""
+    import importlib
+    import types
+
+    import torch
+    ref_root = os.path.join(os.path.dirname(os.path.abspath(__file__)), "baseline", "_ref")
+    if not os.path.exists(os.path.join(ref_root, "libs", "uvit.py")):
+        return None
+    try:
+        if ref_root not in sys.path:
+            sys.path.insert(0, ref_root)
+        if "IPython" not in sys.modules:      # tools.ptp_utils imports it for notebook display only
+            ip, ipd = types.ModuleType("IPython"), types.ModuleType("IPython.display")
+            ipd.display = lambda *a, **k: None
+            ip.display = ipd
+            sys.modules["IPython"], sys.modules["IPython.display"] = ip, ipd
+        import contextlib
+        key = ("t2i" if t2i else "uvit", json.dumps(cfg, sort_keys=True, default=str))
+        net = _STAGED_NETS.get(key)
+        if net is None:
+            with contextlib.redirect_stdout(sys.stderr):     # the reference modules print at import time
+                mod = importlib.import_module("libs.uvit_t2i" if t2i else "libs.uvit")
+            torch.set_num_threads(os.cpu_count() or 1)
+            torch.manual_seed(0)
+            net = mod.UViT(**cfg).eval()
+            _STAGED_NETS[key] = net
+    except Exception as ex:  # missing third-party dependency of the t2i closure, ...
+        sys.stderr.write(f"bench: staged reference not importable ({type(ex).__name__}: {str(ex)[:100]}); timing the port\n")
+        return None
+    g = torch.Generator().manual_seed(1230)
+    x = torch.randn(B, 4, 32, 32, generator=g)
+    t = torch.full((B,), 0.5)
+    ctx = torch.randn(B, 77, 768, generator=g) if t2i else None
+    y = torch.zeros(B, dtype=torch.long) if (not t2i and cfg.get("num_classes", -1) > 0) else None
+    times = []
+    with torch.no_grad():
+        def fwd():
+            return net(x, t, ctx) if t2i else net(x, t, y, edit_loc=None)
+        for _ in range(warmup):
+            fwd()
+        t_start = time.perf_counter()
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            fwd()
+            times.append(time.perf_counter() - t0)
+            if time.perf_counter() - t_start > max_seconds:
+                break
+    return statistics.median(times), len(times)
+
+
 def torch_eager_on_gpu(wl, dev, nfe):
     """Context only (not the product, not the reference arm): the reference's algorithm as plain torch-eager library
     calls on the same B200 (fp32 as shipped - Attention.forward forces .float(), libs/uvit.py:93 - and bf16 autocast),
@@ -185,7 +241,8 @@ def torch_eager_on_gpu(wl, dev, nfe):
 
 
 def run_reference(args, wl):
-    """Reference arm: the reference algorithm on the host cores (oracle port), bounded sample per step."""
+    """Reference arm: the reference's own modules (baseline/_ref, staged by baseline/stage_reference.py) on the host
+    cores, bounded sample per step; the oracle port only when the staged copy is missing / not importable."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -194,8 +251,13 @@ def run_reference(args, wl):
     Bs = 8
     cores = os.cpu_count() or 1
     sec = []
+    kind = "reference"
     for i in range(args.warmup + args.steps):
-        tf, _ = cpu_port_forward_time(wl["cfg"], wl["t2i"], Bs, max_seconds=60, warmup=0, reps=1)
+        r = staged_reference_forward_time(wl["cfg"], wl["t2i"], Bs, max_seconds=60, warmup=0, reps=1) if kind == "reference" else None
+        if r is None:
+            kind = "port"
+            r = cpu_port_forward_time(wl["cfg"], wl["t2i"], Bs, max_seconds=60, warmup=0, reps=1)
+        tf = r[0]
         if i >= args.warmup:
             sec.append(tf)
     tf = sum(sec) / len(sec)
@@ -206,8 +268,10 @@ def run_reference(args, wl):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": tf * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
         "config": {"workload": wl["name"], "nfe": nfe, "sample": sample},
-        "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample,
-                         "torch_threads": torch.get_num_threads()},
+        "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": kind, "sample": sample,
+                         "torch_threads": torch.get_num_threads(),
+                         "what": ("libs.uvit.UViT.forward of the staged, unmodified reference (baseline/_ref)" if kind == "reference"
+                                  else "oracle/uvit_oracle.py in FAST mode (staged reference absent)")},
         "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -423,10 +487,14 @@ def main():
             "clocks": clocks, "finite": finite,
         }
         if world == 1 and not args.no_cpu_baseline:
-            tf, n = cpu_port_forward_time(wl["cfg"], wl["t2i"], 8)
-            res["cpu_baseline"] = {"value": 8 / (tf * nfe), "unit": "images/s", "cores": os.cpu_count(), "kind": "port",
-                                   "sample": f"{n} velocity evaluations at batch 8 on the host cores (torch fp32 oracle), "
-                                             f"images/s = 8/(t_fwd*{nfe}) extrapolated from per-forward time"}
+            r = staged_reference_forward_time(wl["cfg"], wl["t2i"], 8)
+            kind = "reference" if r is not None else "port"
+            tf, n = r if r is not None else cpu_port_forward_time(wl["cfg"], wl["t2i"], 8)
+            res["cpu_baseline"] = {"value": 8 / (tf * nfe), "unit": "images/s", "cores": os.cpu_count(), "kind": kind,
+                                   "sample": f"{n} velocity evaluations at batch 8 on the host cores ("
+                                             + ("the staged reference's own libs.uvit.UViT, torch fp32 eager" if kind == "reference"
+                                                else "torch fp32 oracle port")
+                                             + f"), images/s = 8/(t_fwd*{nfe}) extrapolated from per-forward time"}
         if world == 1 and not args.no_cpu_baseline:
             res["torch_eager_b200"] = torch_eager_on_gpu(wl, dev, nfe)
             res["decoder"] = decoder_line(out[:Bl] if not scales else out[:Bl], dev)
