@@ -26,9 +26,20 @@
 // The exponential sections of the two warpgroups strictly alternate (named barriers, FA3-style ping-pong): one
 // warpgroup owns the MUFU pipe while the other one loads its next scores and takes the row maxima.
 //
-// K and V of an item are TMA-loaded once (double-buffered across items), Q tiles rotate through 3 buffers (two in
-// flight + one prefetched).  The 1-2 leftover query rows of L = 257 / 258 are computed by the otherwise idle warps
-// 10-11 on CUDA cores from the resident K/V tiles (as in v2).
+// K and V of an item are TMA-loaded once by a loader warp (double-buffered across items), Q tiles rotate through 3
+// buffers (two in flight + one prefetched).  The 1-2 leftover query rows of L = 257 / 258 are computed by four
+// otherwise idle warps (12-15) on CUDA cores from the resident K/V tiles; as a masked third MMA tile they cost a whole
+// tile's chain of hand-offs per item (66 us against 45 us at L = 256), on CUDA cores 6 us.
+//
+// What was tried on the way (event traces with USP_ATTN_TRACE, ncu r02c-r02e; all at (64,16,L=256/257), isolated):
+//   one 144-key block in place, S(q+1) behind PV(q), polling control warp ........ 64.8 us (v2: 66.5)
+//   + staggered 96-key windows, MMA warp per slot, compile-time block bodies ....... 47 us at L = 256
+//   + exponential sections strictly alternating (named barriers) ................... 44.6 us (per-scheduler or
+//     per-warpgroup MUFU mutexes instead: 46.6 / 51.2 us - the alternation, not the exclusion, is what helps)
+//   two threads per row (16 softmax warps, row maximum exchanged through smem) ..... 58 us - slower, not kept
+// Every phase of a warpgroup's chain is latency-bound (TMEM load of 96 columns ~400 cycles = 128 B/clk/SM, maxima
+// 250, exponentials 950, hand-offs ~500 per block, read-out ~1700 per tile): 12k cycles per item against a MUFU floor
+// of 4.4k.
 #include <stdio.h>
 #include <stdlib.h>
 
@@ -108,14 +119,19 @@ __device__ __forceinline__ uint64_t umma_desc_v_mn(uint32_t saddr) {
     return d;
 }
 
-// event timeline of CTA 0 (USP_ATTN_TRACE): role r = 0 / 1 softmax thread 0 of slot 0 / 1, 2 / 3 MMA warp of slot 0 / 1
+// event timeline of CTA 0 (build with -DUSP_ATTN_TRACE_BUILD, run with USP_ATTN_TRACE=<file>): role r = 0 / 1 softmax
+// thread 0 of slot 0 / 1, 2 / 3 MMA warp of slot 0 / 1.  Compiled out by default: the checks sit on the hand-off paths.
 constexpr int TRACE_N = 2048;
+#ifdef USP_ATTN_TRACE_BUILD
 #define USP_TR(role, tag)                                                                              \
     do {                                                                                               \
         if (a.trace != nullptr && blockIdx.x == 0 && lane == 0 && tr_i < TRACE_N)                      \
             a.trace[(role) * TRACE_N + tr_i++] = (static_cast<unsigned long long>(tag) << 48) |        \
                                                  (static_cast<unsigned long long>(clock64()) & 0xffffffffffffull); \
     } while (0)
+#else
+#define USP_TR(role, tag) do { } while (0)
+#endif
 
 constexpr int STAGE_BYTES = 8 * 4096;
 constexpr int MAX_DYN_SMEM = 232448 - 3072;     // opt-in limit minus static shared memory
@@ -236,6 +252,7 @@ attention3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     int tr_i = 0;
+    (void)tr_i;
     const int L = a.L;
     const int L16 = (L + 15) & ~15;
     const int hrows = L16 / 2;              // K / V arrive as two TMA boxes of L16/2 rows (multiple of 8)
@@ -380,7 +397,7 @@ attention3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
             if (tt == 0) mbar_arrive(&kv_free[n & 1]);     // (the barrier above: every tail thread has left the buffer)
         }
     } else if (warp >= LOAD_WARP) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
         // ============ warp 10: K/V loads (one lane) ============
         if (warp == LOAD_WARP && lane == 0) {
             tma_prefetch_desc(&tmK);
@@ -399,7 +416,7 @@ attention3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         }
         __syncwarp();
     } else if (warp >= MMA_WARP0) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
         // ============ warps 8 / 9: MMA issue for slot 0 / 1 (+ the Q tile loads); warp-uniform, one elected lane acts =====
         // Per slot the softmax warpgroup's events come in a fixed order - S(0) loaded, P(0) published, S(1) loaded, ... -
         // so the issuer is a straight sequence of blocking waits (no polling): S(b+1) goes out the moment S(b) sits in
@@ -528,7 +545,7 @@ attention3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         }
     } else {
         // ===================== softmax / output warps: one thread per query row, warpgroup = slot =====================
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 176;");
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 168;");
         const int s = warp >> 2;
         const int lg = warp & 3;
         const int row = lg * 32 + lane;
