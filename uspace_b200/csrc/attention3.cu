@@ -202,7 +202,19 @@ __device__ __forceinline__ void softmax_block(uint32_t t_s, uint32_t t_o, int vc
     }
     const float mxs = m_ref * c2;
     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-    // optional ping-pong: the exponential sections of the two warpgroups alternate (named barriers 4 / 5)
+    // exponents x = s c2 - m c2 in place, BEFORE the turn is taken: ptxas otherwise hoists these 16 NC FFMAs to the head
+    // of the exponential section, where the MUFU pipe idles behind them while the other warpgroup waits for the turn
+    // (the empty asm pins the values to this point)
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) r[c * 16 + j] = __float_as_uint(fmaf(__uint_as_float(r[c * 16 + j]), c2, -mxs));
+        asm volatile("" : "+r"(r[c * 16]), "+r"(r[c * 16 + 1]), "+r"(r[c * 16 + 2]), "+r"(r[c * 16 + 3]), "+r"(r[c * 16 + 4]),
+                          "+r"(r[c * 16 + 5]), "+r"(r[c * 16 + 6]), "+r"(r[c * 16 + 7]), "+r"(r[c * 16 + 8]), "+r"(r[c * 16 + 9]),
+                          "+r"(r[c * 16 + 10]), "+r"(r[c * 16 + 11]), "+r"(r[c * 16 + 12]), "+r"(r[c * 16 + 13]),
+                          "+r"(r[c * 16 + 14]), "+r"(r[c * 16 + 15]));
+    }
+    // ping-pong: the exponential sections of the two warpgroups alternate (named barriers 4 / 5)
     if (lock_slot == 0) asm volatile("bar.sync 4, 256;" ::: "memory");
     else if (lock_slot == 1) asm volatile("bar.sync 5, 256;" ::: "memory");
 #pragma unroll
@@ -210,10 +222,10 @@ __device__ __forceinline__ void softmax_block(uint32_t t_s, uint32_t t_o, int vc
         uint32_t w[8];
 #pragma unroll
         for (int j = 0; j < 8; j += 2) {
-            const float p0 = ex2_approx(fmaf(__uint_as_float(r[c * 16 + 2 * j]), c2, -mxs));
-            const float p1 = ex2_approx(fmaf(__uint_as_float(r[c * 16 + 2 * j + 1]), c2, -mxs));
-            const float p2 = ex2_approx(fmaf(__uint_as_float(r[c * 16 + 2 * j + 2]), c2, -mxs));
-            const float p3 = ex2_approx(fmaf(__uint_as_float(r[c * 16 + 2 * j + 3]), c2, -mxs));
+            const float p0 = ex2_approx(__uint_as_float(r[c * 16 + 2 * j]));
+            const float p1 = ex2_approx(__uint_as_float(r[c * 16 + 2 * j + 1]));
+            const float p2 = ex2_approx(__uint_as_float(r[c * 16 + 2 * j + 2]));
+            const float p3 = ex2_approx(__uint_as_float(r[c * 16 + 2 * j + 3]));
             s0 += p0;
             s1 += p1;
             s2 += p2;
@@ -312,7 +324,7 @@ attention3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                                       ? a.vscale + static_cast<long long>(bh / a.H) * L : nullptr;   // p2p column weights
                 const uint8_t* kbuf = sK + (n & 1) * kv_bytes;
                 const uint8_t* vbuf = sV + (n & 1) * kv_bytes;
-                mbar_wait(&kv_full[n & 1], (n >> 1) & 1);
+                mbar_wait_idle(&kv_full[n & 1], (n >> 1) & 1);     // (a whole item away: back off between polls)
                 for (int l = n_qt * QT; l < ((a.diag & 32) ? 0 : L); ++l) {   // diag 32: skip the tail rows' arithmetic
                     if (tt < HD / 2) {
                         const uint32_t w = reinterpret_cast<const uint32_t*>(a.q16)[(static_cast<long long>(bh) * L + l) * (HD / 2) + tt];
@@ -406,7 +418,7 @@ attention3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                 const int nb = m & 1;
                 const int bh = static_cast<int>(blockIdx.x) + m * static_cast<int>(gridDim.x);
                 // buffer m & 1 was last used by item m - 2: its MMAs have retired and its tail rows are done
-                if (m >= 2) mbar_wait(&kv_free[nb], ((m >> 1) - 1) & 1);
+                if (m >= 2) mbar_wait_idle(&kv_free[nb], ((m >> 1) - 1) & 1);
                 mbar_expect_tx(&kv_full[nb], 2 * kv_bytes);
                 for (int c = 0; c < 2; ++c) {
                     tma_load_3d(&tmK, &kv_full[nb], sK + nb * kv_bytes + c * hrows * 128, 0, c * hrows, bh);
