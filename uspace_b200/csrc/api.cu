@@ -223,6 +223,23 @@ int fail(usp_handle* h, int code, const std::string& msg) {
             return fail(h, USP_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));     \
     } while (0)
 
+// Every ABI entry point runs on the handle's device and leaves the caller's current device as it found it (a model on
+// cuda:1 used from a process whose current device is cuda:0 must not change torch's current device).
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int device) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != device) ok = cudaSetDevice(device) == cudaSuccess;
+    }
+    ~DeviceGuard() {
+        int cur = -1;
+        if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+    }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
 int add_weight(usp_handle* h, const std::string& name, std::vector<int64_t> shape, bool gemm) {
     Weight w;
     w.name = name;
@@ -672,7 +689,8 @@ int usp_create(const usp_config* cfg, int device, usp_handle** out) {
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return fail(nullptr, USP_ERR_CUDA, "device query failed");
     if (prop.major != 10)
         return fail(nullptr, USP_ERR_UNSUPPORTED, "uspace_b200 kernels are built for sm_100a (Blackwell B200) only");
-    if (cudaSetDevice(device) != cudaSuccess) return fail(nullptr, USP_ERR_CUDA, "cudaSetDevice failed");
+    DeviceGuard dev_guard(device);
+    if (!dev_guard.ok) return fail(nullptr, USP_ERR_CUDA, "cudaSetDevice failed");
     if (!get_encode_fn()) return fail(nullptr, USP_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
 
     std::unique_ptr<usp_handle> h(new usp_handle());
@@ -741,7 +759,7 @@ int usp_create(const usp_config* cfg, int device, usp_handle** out) {
 
 void usp_destroy(usp_handle* h) {
     if (!h) return;
-    cudaSetDevice(h->device);
+    DeviceGuard dev_guard(h->device);
     for (auto& kv : h->plans) {
         for (auto& g : kv.second->graphs) cudaGraphExecDestroy(g.second);
         cudaFree(kv.second->slab);
@@ -781,7 +799,11 @@ int usp_set_weight(usp_handle* h, const char* name, const void* data, const int6
     bool same = static_cast<int>(w.shape.size()) == ndim;
     for (int i = 0; same && i < ndim; ++i) same = w.shape[i] == shape[i];
     if (!same) return fail(h, USP_ERR_INVALID, std::string("shape mismatch for ") + name);
-    CUDA_TRY(h, cudaSetDevice(h->device));
+    DeviceGuard dev_guard(h->device);
+    if (!dev_guard.ok) return fail(h, USP_ERR_CUDA, "cudaSetDevice failed");
+    // Set-up time call.  The source may be a live CUDA parameter written on non-blocking side streams (optimizer / EMA
+    // updates), and an earlier sampling may still be reading the old copy: order against everything on the device.
+    CUDA_TRY(h, cudaDeviceSynchronize());
     CUDA_TRY(h, cudaMemcpy(w.d32, data, w.numel * 4, cudaMemcpyDefault));
     w.set = true;
     h->finalized = false;
@@ -791,7 +813,8 @@ int usp_set_weight(usp_handle* h, const char* name, const void* data, const int6
 int usp_finalize_weights(usp_handle* h, void* stream) {
     if (!h) return USP_ERR_INVALID;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    CUDA_TRY(h, cudaSetDevice(h->device));
+    DeviceGuard dev_guard(h->device);
+    if (!dev_guard.ok) return fail(h, USP_ERR_CUDA, "cudaSetDevice failed");
     for (auto& w : h->w)
         if (!w.set) return fail(h, USP_ERR_STATE, "weight never set: " + w.name);
     if (h->fuse_ln) {
@@ -854,7 +877,8 @@ int usp_forward_hook(usp_handle* h, const float* x, const float* t, const float*
     if ((y != nullptr) != (h->cfg.num_classes > 0))
         return fail(h, USP_ERR_INVALID, "y must be given exactly for the class-conditional model (num_classes > 0)");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    CUDA_TRY(h, cudaSetDevice(h->device));
+    DeviceGuard dev_guard(h->device);
+    if (!dev_guard.ok) return fail(h, USP_ERR_CUDA, "cudaSetDevice failed");
     Plan* p = nullptr;
     rc = get_plan(h, B, &p);
     if (rc) return rc;
@@ -970,7 +994,8 @@ int sample_impl(usp_handle* h, const float* z_in, float* z, const float* context
     const int n = build_grid(t0, t1, step_size, &grid);
     if (n < 2) return fail(h, USP_ERR_INVALID, "bad time grid (t0 == t1, step_size <= 0 or more than 4096 points)");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    CUDA_TRY(h, cudaSetDevice(h->device));
+    DeviceGuard dev_guard(h->device);
+    if (!dev_guard.ok) return fail(h, USP_ERR_CUDA, "cudaSetDevice failed");
     Plan* p = nullptr;
     rc = get_plan(h, B, &p);
     if (rc) return rc;
@@ -1196,7 +1221,8 @@ int usp_sample_adaptive(usp_handle* h, float* z, const float* context, const int
         return fail(h, USP_ERR_INVALID, "need rtol > 0, atol >= 0 and t0 != t1");
     if (max_steps <= 0) max_steps = 1 << 20;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    CUDA_TRY(h, cudaSetDevice(h->device));
+    DeviceGuard dev_guard(h->device);
+    if (!dev_guard.ok) return fail(h, USP_ERR_CUDA, "cudaSetDevice failed");
     Plan* p = nullptr;
     rc = get_plan(h, B, &p);
     if (rc) return rc;
@@ -1339,7 +1365,8 @@ int usp_sample_host(usp_handle* h, float* z_host, const float* context_host, con
                     float t_edit, int edit_loc) {
     int rc = check_ready(h, B);
     if (rc) return rc;
-    CUDA_TRY(h, cudaSetDevice(h->device));
+    DeviceGuard dev_guard(h->device);
+    if (!dev_guard.ok) return fail(h, USP_ERR_CUDA, "cudaSetDevice failed");
     Plan* p = nullptr;
     rc = get_plan(h, B, &p);
     if (rc) return rc;
@@ -1369,7 +1396,8 @@ int usp_sample_host(usp_handle* h, float* z_host, const float* context_host, con
 int usp_nonfinite(usp_handle* h, int* flag, void* stream) {
     if (!h || !flag) return USP_ERR_INVALID;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    CUDA_TRY(h, cudaSetDevice(h->device));
+    DeviceGuard dev_guard(h->device);
+    if (!dev_guard.ok) return fail(h, USP_ERR_CUDA, "cudaSetDevice failed");
     CUDA_TRY(h, cudaMemcpyAsync(flag, h->nonfinite, 4, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(h, cudaMemsetAsync(h->nonfinite, 0, 4, s));
     CUDA_TRY(h, cudaStreamSynchronize(s));

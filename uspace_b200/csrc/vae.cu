@@ -484,7 +484,13 @@ int ensure_workspace(usp_vae* h, int B, int S) {
     h->slab = nullptr;
     const long long px = static_cast<long long>(S) * 8 * S * 8;                 // output pixels per image
     const long long act = static_cast<long long>(B) * px * 256;                 // largest activation: 256 channels at full size
-    const long long colb = static_cast<long long>(B) * px * 2304;               // largest im2col: 9 * 256 at full size
+    // scratch shared by the nearest-x2 upsampled operand (256 channels at full size) and the explicit im2col matrices:
+    // only conv_in (K = 36 padded to 64) is materialised on the default implicit-GEMM path, so 9 * 256 columns are
+    // reserved only for the USP_VAE_IM2COL=explicit fallback (4.8 GB less at 16 images per pass)
+    static const bool explicit_ws = [] { const char* e = getenv("USP_VAE_IM2COL"); return e && e[0] == 'e'; }();
+    // (the implicit path needs M % 256 == 0 at every level; the coarsest one has B * S * S rows)
+    const bool all_implicit = !explicit_ws && (static_cast<long long>(B) * S * S) % 256 == 0;
+    const long long colb = static_cast<long long>(B) * px * (all_implicit ? 256 : 2304);
     const long long T = static_cast<long long>(S) * S, C = 512;
     size_t off = 0;
     auto carve = [&](size_t bytes) { size_t o = off; off = (off + bytes + 1023) / 1024 * 1024; return o; };
