@@ -37,6 +37,13 @@
 //   + exponential sections strictly alternating (named barriers) ................... 44.6 us (per-scheduler or
 //     per-warpgroup MUFU mutexes instead: 46.6 / 51.2 us - the alternation, not the exclusion, is what helps)
 //   two threads per row (16 softmax warps, row maximum exchanged through smem) ..... 58 us - slower, not kept
+//   read-out by four dedicated warps (12-15) instead of the softmax warpgroups ..... 41.6 us at L = 256, 128 us at
+//     L = 334 (from 45.9 / 136) but 60 us at L = 257 (from 54): the two slots' read-outs serialise behind the leftover
+//     rows; as a hybrid (dedicated warps only when there are no leftover rows) 44.9 / 55.9 / 134.4 - not kept
+//   640 threads (own warpgroups for read-out and leftover rows) .................... 51.5 us: setmaxnreg only
+//     redistributes the CTA's LAUNCH allocation (640 x 96 = 61440 registers; asking for more in total hangs), which
+//     leaves the softmax threads 144 registers and spills
+//   one mbarrier arrival per warp (lane 0 behind __syncwarp) instead of per thread .. no change (48.8 vs 48.4 us)
 // Every phase of a warpgroup's chain is latency-bound (TMEM load of 96 columns ~400 cycles = 128 B/clk/SM, maxima
 // 250, exponentials 950, hand-offs ~500 per block, read-out ~1700 per tile): 12k cycles per item against a MUFU floor
 // of 4.4k.
