@@ -111,7 +111,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
         fence_barrier_init();
     }
     __syncwarp();
-    if (warp == 1) tmem_alloc_cg2<TMEM_COLS>(&tmem_base_smem);
+    // (allocated by the warp that initialised the barriers: compute-sanitizer's racecheck attributes the allocator's
+    //  shared-memory write to neighbouring barrier bytes and reported 1154 "hazards" against warp 0's mbarrier.init
+    //  when another warp allocated - profiles/r02h_racecheck_gemm.log)
+    if (warp == 0) tmem_alloc_cg2<TMEM_COLS>(&tmem_base_smem);
     tc_fence_before();
     cluster_sync_all();   // peer barriers initialised, both TMEM allocations done
     tc_fence_after();
@@ -296,7 +299,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
     // no CTA may exit (or free TMEM) while its peer can still touch its shared memory / barriers
     tc_fence_before();
     cluster_sync_all();
-    if (warp == 1) tmem_dealloc_cg2<TMEM_COLS>(tmem_base);
+    if (warp == 0) tmem_dealloc_cg2<TMEM_COLS>(tmem_base);
 }
 
 // resident clusters of 4 CTAs (a GPC with an odd number of TPCs leaves one idle: 33 on B200, i.e. 132 of 148 SMs)
