@@ -274,23 +274,23 @@ def test_attention_edit_from_reference_kwargs():
 def test_hot_kernels_do_not_spill(tmp_path):
     """ptxas must keep the tensor-core kernels spill-free: a hook added to the attention softmax loop once spilled
     448 B and ran the kernel 3x slower without failing any parity test.  (The p2p-edit instantiations of the attention
-    kernel, attention2_kernel<*, true>, are allowed to spill: they are not on the headline path.)"""
+    kernels, attention2_kernel<*, true> / attention3_kernel<*, true>, are allowed to spill: they are not on the headline path.)"""
     import shutil
     import subprocess
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         pytest.skip("nvcc not available")
     csrc = os.path.join(ROOT, "uspace_b200", "csrc")
-    for src in ("gemm2.cu", "attention2.cu"):
+    for src in ("gemm2.cu", "attention2.cu", "attention3.cu"):
         r = subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-Xptxas", "-v",
                             "-c", os.path.join(csrc, src), "-o", str(tmp_path / (src + ".o"))],
                            capture_output=True, text=True, timeout=600)
         assert r.returncode == 0, r.stderr[-2000:]
         entries = re.findall(r"Compiling entry function '(\S+)'.*?(\d+) bytes stack frame, (\d+) bytes spill stores",
                              r.stderr + r.stdout, flags=re.S)
-        assert len(entries) >= 6, src
+        assert len(entries) >= (4 if src == "attention3.cu" else 6), src
         for name, stack, spill in entries:
-            if "attention2_kernelILi" in name and "ELb1E" in name:
+            if ("attention2_kernelILi" in name or "attention3_kernelILi" in name) and "ELb1E" in name:
                 continue
             assert int(spill) == 0 and int(stack) == 0, (src, name, stack, spill)
 
