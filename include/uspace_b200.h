@@ -55,6 +55,8 @@ typedef struct usp_config {
     int32_t skip;            /* out-blocks carry skip_linear              */
     int32_t operand_dtype;   /* tensor-core operand type: 0 bf16, 1 fp16  */
     int32_t fuse_layernorm;  /* 1: fold norm1/norm2 into the qkv / fc1 GEMMs (no LayerNorm kernels) */
+    int32_t mlp_time_embed;  /* 1: time token = Linear(4D->D)(SiLU(Linear(D->4D)(sinusoid))) (libs/uvit.py:215-223);
+                                weights "time_embed.0.{weight,bias}", "time_embed.2.{weight,bias}"                  */
 } usp_config;
 
 /* Post-softmax attention column re-weighting ("p2p_rescale": tools/utils_t2i.py:196-224,265-296, called from

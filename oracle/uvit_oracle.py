@@ -201,7 +201,12 @@ def uvit_forward(sd: Dict[str, Tensor], cfg: dict, x: Tensor, t: Tensor, y: Opti
     pidx = patchify_index(C, S, p)
     feats = x.reshape(B, C * S * S)[:, pidx.reshape(-1)].reshape(B, d["n_patch"], d["P"])
     tok = feats @ sd["patch_embed.proj.weight"].reshape(D, d["P"]).T + sd["patch_embed.proj.bias"]
-    time_tok = timestep_embedding(t.to(dt), D)[:, None, :]
+    time_tok = timestep_embedding(t.to(dt), D)
+    if "time_embed.0.weight" in sd:       # mlp_time_embed=True: Linear -> SiLU -> Linear (libs/uvit.py:215-223, :320)
+        hid = time_tok @ sd["time_embed.0.weight"].T + sd["time_embed.0.bias"]
+        hid = hid * torch.sigmoid(hid)
+        time_tok = hid @ sd["time_embed.2.weight"].T + sd["time_embed.2.bias"]
+    time_tok = time_tok[:, None, :]
     if d["n_ctx"]:
         ctx = context.to(dt) @ sd["context_embed.weight"].T + sd["context_embed.bias"]
         h = torch.cat([time_tok, ctx, tok], dim=1)

@@ -21,6 +21,11 @@ CASES = {
                      euler_steps=4,
                      # dissect_lfm_t2i.py "p2p" mode: post-softmax re-weighting of context-token columns
                      p2p=dict(t=0.3, t_edit=0.4, block_id=[1, 3], multiplier=[2.0, -1.5], ids=[[3, 4], [10]])),
+    # mlp_time_embed=True (libs/uvit.py:215-223; no shipped config sets it): class-conditional, forward + Euler loop
+    "tiny_time_mlp": dict(cfg=dict(_TINY, num_classes=10, mlp_time_embed=True), t2i=False, seed=4, B=2, in_seed=11,
+                          euler_steps=3),
+    "tiny_t2i_time_mlp": dict(cfg=dict(_TINY, clip_dim=768, num_clip_token=77, mlp_time_embed=True), t2i=True, seed=5,
+                              B=2, in_seed=12, euler_steps=None),
     # configs/lfm_cm256_uvit_large.py:42-56 and configs/lfm_mmcelebahq256_uvit_large.py:43-58, one image
     "large_uncond": dict(cfg=dict(_L, num_classes=-1), t2i=False, seed=0, B=1, in_seed=1230, euler_steps=None),
     "large_t2i": dict(cfg=dict(_L, clip_dim=768, num_clip_token=77), t2i=True, seed=0, B=1, in_seed=1231,

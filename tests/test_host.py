@@ -74,8 +74,10 @@ def test_config_mapping():
     assert (c.clip_dim, c.num_clip_token, c.num_classes, c.operand_dtype) == (768, 77, 0, 0)
     c = config_from_kwargs(CASES["tiny_class"]["cfg"])
     assert (c.num_classes, c.clip_dim, c.num_clip_token, c.operand_dtype) == (10, 0, 0, 1)
-    with pytest.raises(NotImplementedError):
-        config_from_kwargs(dict(CASES["tiny_uncond"]["cfg"], mlp_time_embed=True))
+    assert c.mlp_time_embed == 0
+    assert config_from_kwargs(CASES["tiny_time_mlp"]["cfg"]).mlp_time_embed == 1
+    # qk_scale is accepted and without effect, like the reference's flash-attention path (libs/uvit.py:95)
+    config_from_kwargs(dict(CASES["tiny_uncond"]["cfg"], qk_scale=0.2))
 
 
 # ---- module mirrors ----------------------------------------------------------------------------------

@@ -22,7 +22,7 @@ EPI = {"qkv": 0, "bias_gelu": 1, "bias_resid": 2, "bias_f32": 3}
 class UspConfig(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "img_size", "patch_size", "in_chans", "embed_dim", "depth", "num_heads", "mlp_hidden", "num_classes",
-        "clip_dim", "num_clip_token", "qkv_bias", "conv", "skip", "operand_dtype", "fuse_layernorm")]
+        "clip_dim", "num_clip_token", "qkv_bias", "conv", "skip", "operand_dtype", "fuse_layernorm", "mlp_time_embed")]
 
 
 class UspAttnEdit(C.Structure):

@@ -161,6 +161,7 @@ struct Plan {
     float* colscale = nullptr;      // [B, L] attention column weights (p2p edit)
     unsigned char* amask = nullptr; // per grid point: attention edit active
     float* sscale = nullptr;        // [B] per-sample write_scale (usp_sample_sweep)
+    float *t_sincos = nullptr, *t_hidden = nullptr, *t_tok = nullptr;   // mlp_time_embed scratch: [B,D], [B,4D], [B,D]
     float* rk_k = nullptr;          // [RK_STAGES][B,C,S,S] stage derivatives of the adaptive solver
     RkState* rs = nullptr;
     double* rk_partials = nullptr;  // [2][RK_MAX_PARTIALS]
@@ -190,6 +191,7 @@ struct usp_handle {
     std::vector<Weight> w;
     std::map<std::string, int> widx;
     std::vector<BlockW> blocks;
+    int i_tw1 = -1, i_tb1 = -1, i_tw2 = -1, i_tb2 = -1;   // mlp_time_embed (time_embed.0 / time_embed.2)
     int i_pos = -1, i_pew = -1, i_peb = -1, i_label = -1, i_ctxw = -1, i_ctxb = -1, i_nw = -1, i_nb = -1,
         i_dw = -1, i_db = -1, i_fw = -1, i_fb = -1;
     float* freqs = nullptr;
@@ -325,6 +327,10 @@ int get_plan(usp_handle* h, int B, Plan** out) {
                  o_cs = carve(static_cast<size_t>(B) * L * 4), o_rkk = carve(RK_STAGES * zel * 4),
                  o_rs = carve(sizeof(RkState)), o_rkp = carve(2 * RK_MAX_PARTIALS * 8),
                  o_ss = carve(static_cast<size_t>(B) * 4);
+    const bool tmlp = h->cfg.mlp_time_embed != 0;
+    const size_t o_tsc = carve(tmlp ? static_cast<size_t>(B) * D * 4 : 16),
+                 o_thid = carve(tmlp ? static_cast<size_t>(B) * 4 * D * 4 : 16),
+                 o_ttok = carve(tmlp ? static_cast<size_t>(B) * D * 4 : 16);
     p->bytes = off;
     CUDA_TRY(h, cudaMalloc(&p->slab, off));
     CUDA_TRY(h, cudaMemset(p->slab, 0, off));
@@ -355,6 +361,9 @@ int get_plan(usp_handle* h, int B, Plan** out) {
     p->amask = reinterpret_cast<unsigned char*>(base + o_amask);
     p->colscale = reinterpret_cast<float*>(base + o_cs);
     p->sscale = reinterpret_cast<float*>(base + o_ss);
+    p->t_sincos = reinterpret_cast<float*>(base + o_tsc);
+    p->t_hidden = reinterpret_cast<float*>(base + o_thid);
+    p->t_tok = reinterpret_cast<float*>(base + o_ttok);
     p->rk_k = reinterpret_cast<float*>(base + o_rkk);
     p->rs = reinterpret_cast<RkState*>(base + o_rs);
     p->rk_partials = reinterpret_cast<double*>(base + o_rkp);
@@ -496,6 +505,18 @@ int enqueue_forward(usp_handle* h, Plan* p, const FwdIO& io, cudaStream_t s) {
     ea.B = B; ea.C = h->cfg.in_chans; ea.S = h->cfg.img_size; ea.p = h->cfg.patch_size; ea.D = D; ea.L = L;
     ea.n_ctx = h->cfg.num_clip_token; ea.has_label = (h->cfg.num_classes > 0 && io.y != nullptr) ? 1 : 0;
     prof_mark(h, 0, s);
+    if (h->cfg.mlp_time_embed) {
+        // time token through time_embed (libs/uvit.py:320): one row for the shared ODE time, B rows for a forward
+        TimeMlpArgs ta;
+        memset(&ta, 0, sizeof(ta));
+        ta.tvec = io.tvec; ta.st = io.st; ta.freqs = h->freqs;
+        ta.w1 = h->w[h->i_tw1].d32; ta.b1 = h->w[h->i_tb1].d32; ta.w2 = h->w[h->i_tw2].d32; ta.b2 = h->w[h->i_tb2].d32;
+        ta.sincos = p->t_sincos; ta.hidden = p->t_hidden; ta.ttok = p->t_tok;
+        ta.rows = io.st ? 1 : B; ta.D = D;
+        KTRY(launch_time_mlp(ta, s));
+        nk += 2;
+        ea.ttok = p->t_tok;
+    }
     KTRY(launch_embed(ea, s));
 
     const CUtensorMap* xprev = nullptr;  // 16-bit copy of the previous block's output
@@ -712,6 +733,12 @@ int usp_create(const usp_config* cfg, int device, usp_handle** out) {
     h->i_pos = add_weight(h.get(), "pos_embed", {1, h->L, D}, false);
     h->i_pew = add_weight(h.get(), "patch_embed.proj.weight", {D, c.in_chans, c.patch_size, c.patch_size}, false);
     h->i_peb = add_weight(h.get(), "patch_embed.proj.bias", {D}, false);
+    if (c.mlp_time_embed) {
+        h->i_tw1 = add_weight(h.get(), "time_embed.0.weight", {4 * D, D}, false);
+        h->i_tb1 = add_weight(h.get(), "time_embed.0.bias", {4 * D}, false);
+        h->i_tw2 = add_weight(h.get(), "time_embed.2.weight", {D, 4 * D}, false);
+        h->i_tb2 = add_weight(h.get(), "time_embed.2.bias", {D}, false);
+    }
     if (c.num_classes > 0) h->i_label = add_weight(h.get(), "label_emb.weight", {c.num_classes, D}, false);
     if (c.num_clip_token > 0) {
         h->i_ctxw = add_weight(h.get(), "context_embed.weight", {D, c.clip_dim}, true);

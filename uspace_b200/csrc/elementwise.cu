@@ -92,6 +92,8 @@ __global__ void __launch_bounds__(256) embed_kernel(const EmbedArgs a) {
             float v;
             if (a.has_label && l == 0) {
                 v = a.label[a.y[b] * D + d];
+            } else if (l == t_tok && a.ttok != nullptr) {
+                v = a.ttok[static_cast<long long>(a.st ? 0 : b) * D + d];    // mlp_time_embed: from launch_time_mlp
             } else if (l == t_tok) {
                 const float t = a.st ? a.st->t : a.tvec[b];
                 const int half = D / 2;
@@ -401,6 +403,67 @@ __global__ void step_kernel(StepState* st, const float* __restrict__ grid, const
 }
 
 }  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// mlp_time_embed: sinusoid -> Linear(D, 4D) -> SiLU -> Linear(4D, D)   (libs/uvit.py:215-223, :320)
+// Three small fp32 launches; one warp per output neuron, the weight row read once and reused for every row of t.
+// ------------------------------------------------------------------------------------------------
+namespace {
+__global__ void time_sincos_kernel(const TimeMlpArgs a) {
+    const int half = a.D / 2;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.rows * a.D; i += gridDim.x * blockDim.x) {
+        const int n = i / a.D, d = i - n * a.D;
+        const float t = a.st ? a.st->t : a.tvec[n];
+        float v = 0.f;
+        if (d < half) v = cosf(t * a.freqs[d]);
+        else if (d < 2 * half) v = sinf(t * a.freqs[d - half]);
+        a.sincos[i] = v;
+    }
+}
+
+template <bool SILU>
+__global__ void __launch_bounds__(256) small_linear_kernel(const float* __restrict__ in, const float* __restrict__ w,
+                                                           const float* __restrict__ bias, float* __restrict__ out,
+                                                           int rows, int K, int N) {
+    const int j = blockIdx.x * 8 + (threadIdx.x >> 5);     // output neuron of this warp
+    const int lane = threadIdx.x & 31;
+    if (j >= N) return;
+    const float* wr = w + static_cast<long long>(j) * K;
+    for (int n0 = 0; n0 < rows; n0 += 4) {                  // four rows of t per pass over the weight row
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int k = lane * 4; k < K; k += 128) {
+            const float4 w4 = __ldg(reinterpret_cast<const float4*>(wr + k));
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                if (n0 + r < rows) {
+                    const float4 x4 = *reinterpret_cast<const float4*>(in + static_cast<long long>(n0 + r) * K + k);
+                    acc[r] = fmaf(w4.x, x4.x, fmaf(w4.y, x4.y, fmaf(w4.z, x4.z, fmaf(w4.w, x4.w, acc[r]))));
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], o);
+            if (lane == 0 && n0 + r < rows) {
+                float v = acc[r] + bias[j];
+                if (SILU) v = v / (1.0f + expf(-v));
+                out[static_cast<long long>(n0 + r) * N + j] = v;
+            }
+        }
+    }
+}
+
+}  // namespace
+
+cudaError_t launch_time_mlp(const TimeMlpArgs& a, cudaStream_t s) {
+    if (a.D % 4 != 0) return cudaErrorInvalidValue;
+    const int n = a.rows * a.D;
+    time_sincos_kernel<<<(n + 255) / 256, 256, 0, s>>>(a);
+    small_linear_kernel<true><<<(4 * a.D + 7) / 8, 256, 0, s>>>(a.sincos, a.w1, a.b1, a.hidden, a.rows, a.D, 4 * a.D);
+    small_linear_kernel<false><<<(a.D + 7) / 8, 256, 0, s>>>(a.hidden, a.w2, a.b2, a.ttok, a.rows, 4 * a.D, a.D);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_embed(const EmbedArgs& a, cudaStream_t s) {
     if (a.C * a.p * a.p > 64) return cudaErrorInvalidValue;

@@ -107,6 +107,7 @@ struct EmbedArgs {
     const float* pos;      // [L, D]
     const float* label;    // label_emb.weight [num_classes, D] or nullptr
     const float* freqs;    // [D/2]
+    const float* ttok;     // mlp_time_embed: the time token(s) [1 or B, D] computed by launch_time_mlp, else nullptr
     const float* delta;    // head edit table [nsteps+1, C*S*S] or nullptr
     const float* sscale;   // optional per-sample write_scale [B] (scale sweep); nullptr: st->edit for every sample
     float* trace;          // optional "read" dump at edit_loc head: trace[st->didx][B,C,S,S] = the latent as the net sees it
@@ -118,6 +119,24 @@ struct EmbedArgs {
     int B, C, S, p, D, L, n_ctx, has_label;
 };
 cudaError_t launch_embed(const EmbedArgs& a, cudaStream_t s);
+
+// mlp_time_embed (libs/uvit.py:215-223, :320): ttok[n] = W2 silu(W1 temb(t_n) + b1) + b2 for n < rows, where
+// temb is the sinusoidal timestep embedding and t_n = st->t (rows == 1, sampling) or tvec[n] (forward).
+// `sincos` [rows, D] and `hidden` [rows, 4D] are scratch.  fp32 throughout (B x 8 D^2 MACs: not a hot kernel).
+struct TimeMlpArgs {
+    const float* tvec;
+    const StepState* st;
+    const float* freqs;    // [D/2]
+    const float* w1;       // [4D, D]
+    const float* b1;       // [4D]
+    const float* w2;       // [D, 4D]
+    const float* b2;       // [D]
+    float* sincos;
+    float* hidden;
+    float* ttok;           // [rows, D]
+    int rows, D;
+};
+cudaError_t launch_time_mlp(const TimeMlpArgs& a, cudaStream_t s);
 
 cudaError_t launch_layernorm(const float* x, const float* g, const float* b, void* out16, int M, int D, int opd,
                              cudaStream_t s);

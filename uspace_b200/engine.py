@@ -16,10 +16,6 @@ def _ptr(t: Optional[torch.Tensor]):
 
 def config_from_kwargs(kw: dict, operand_dtype: str = "fp16", fuse_layernorm: bool = False) -> _lib.UspConfig:
     """Map the reference ctor kwargs (libs/uvit.py:183-202, libs/uvit_t2i.py:193-211) to usp_config."""
-    if kw.get("mlp_time_embed", False):
-        raise NotImplementedError("mlp_time_embed=True is not used by any reference config and is not built")
-    if kw.get("qk_scale") is not None:
-        raise NotImplementedError("qk_scale override is not built (reference configs use head_dim**-0.5)")
     t2i = "clip_dim" in kw or "num_clip_token" in kw
     c = _lib.UspConfig()
     c.img_size = kw.get("img_size", 224)
@@ -37,6 +33,7 @@ def config_from_kwargs(kw: dict, operand_dtype: str = "fp16", fuse_layernorm: bo
     c.skip = int(bool(kw.get("skip", True)))
     c.operand_dtype = _lib.OPERAND[operand_dtype]
     c.fuse_layernorm = int(bool(fuse_layernorm))
+    c.mlp_time_embed = int(bool(kw.get("mlp_time_embed", False)))
     return c
 
 

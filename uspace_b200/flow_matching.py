@@ -243,6 +243,9 @@ class _CNFBase(nn.Module):
         if isinstance(self, CNFT2I):
             attn = build_attn_edit(z.shape[0], engine.cfg.num_clip_token + 1 + (engine.S // engine.cfg.patch_size) ** 2,
                                    **kwargs)
+            if attn is not None and getattr(net, "qk_scale", None) is not None:
+                raise NotImplementedError("attention editing with a qk_scale override is not built "
+                                          "(the editing branch of libs/uvit_t2i.py:96-107 would use it)")
         dissect = self.is_dissection_mode(kwargs)
         reading = dissect and kwargs.get("dissect_task") == "uspace_uvit" and kwargs.get("dissect_name") == "read"
         if reading:

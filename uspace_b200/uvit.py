@@ -81,14 +81,14 @@ class _UViTBase(nn.Module):
 
     def _build(self, img_size, patch_size, in_chans, embed_dim, depth, num_heads, mlp_ratio, qkv_bias,
                mlp_time_embed, conv, skip, extras):
-        if mlp_time_embed:
-            raise NotImplementedError("mlp_time_embed=True is not used by any reference config and is not built")
         self.embed_dim = self.num_features = embed_dim
         self.in_chans = in_chans
         self.extras = extras
         self.patch_embed = _PatchEmbed(patch_size, in_chans, embed_dim)
         num_patches = (img_size // patch_size) ** 2
-        self.time_embed = nn.Identity()
+        # libs/uvit.py:215-223 (same construction order as the reference: the seeded initialisation must match)
+        self.time_embed = (nn.Sequential(nn.Linear(embed_dim, 4 * embed_dim), nn.SiLU(), nn.Linear(4 * embed_dim, embed_dim))
+                           if mlp_time_embed else nn.Identity())
         self._ctor_extra()
         self.pos_embed = nn.Parameter(torch.zeros(1, self.extras + num_patches, embed_dim))
         mk = lambda s: _Block(embed_dim, num_heads, mlp_ratio, qkv_bias, s)
@@ -176,7 +176,7 @@ class _UViTBase(nn.Module):
         half = self.embed_dim // 2
         freqs = torch.exp(-math.log(10000) * torch.arange(half, dtype=torch.float32) / half).to(timesteps.device)
         args = timesteps[:, None].float() * freqs[None]
-        return torch.cat([torch.cos(args), torch.sin(args)], dim=-1).unsqueeze(1)
+        return self.time_embed(torch.cat([torch.cos(args), torch.sin(args)], dim=-1)).unsqueeze(1)
 
     @staticmethod
     def _wants_autograd(x):
@@ -191,12 +191,14 @@ class UViT(_UViTBase):
                  num_classes=-1, use_checkpoint=False, conv=True, skip=True, use_latent1d=0,
                  latent_1d_pooling=False):
         super().__init__()
-        if qk_scale is not None:
-            raise NotImplementedError("qk_scale override is not built")
+        # qk_scale: accepted and WITHOUT EFFECT, exactly like the reference as it runs - libs/uvit.py:79 stores it in
+        # Attention.scale, but with torch >= 2.0 ATTENTION_MODE is "flash" and F.scaled_dot_product_attention
+        # (libs/uvit.py:95) always uses head_dim ** -0.5; only the dead "math" branch (:109) reads self.scale.
+        self.qk_scale = qk_scale
         self.num_classes = num_classes
         self._ctor_kwargs = dict(img_size=img_size, patch_size=patch_size, in_chans=in_chans, embed_dim=embed_dim,
                                  depth=depth, num_heads=num_heads, mlp_ratio=mlp_ratio, qkv_bias=qkv_bias,
-                                 num_classes=num_classes, conv=conv, skip=skip)
+                                 num_classes=num_classes, conv=conv, skip=skip, mlp_time_embed=mlp_time_embed)
         self._build(img_size, patch_size, in_chans, embed_dim, depth, num_heads, mlp_ratio, qkv_bias,
                     mlp_time_embed, conv, skip, extras=2 if num_classes > 0 else 1)
 
@@ -258,12 +260,14 @@ class UViTT2I(_UViTBase):
                  mlp_ratio=4.0, qkv_bias=False, qk_scale=None, norm_layer=nn.LayerNorm, mlp_time_embed=False,
                  use_checkpoint=False, clip_dim=768, num_clip_token=77, conv=True, skip=True, use_latent1d=False):
         super().__init__()
-        if qk_scale is not None:
-            raise NotImplementedError("qk_scale override is not built")
+        # qk_scale: without effect on the plain forward (flash path, libs/uvit_t2i.py:118-122, as in libs/uvit.py); the
+        # reference reads it only in the attention-editing branch (:96-107), which is rejected below when it is set.
+        self.qk_scale = qk_scale
         self._clip = (clip_dim, num_clip_token)
         self._ctor_kwargs = dict(img_size=img_size, patch_size=patch_size, in_chans=in_chans, embed_dim=embed_dim,
                                  depth=depth, num_heads=num_heads, mlp_ratio=mlp_ratio, qkv_bias=qkv_bias,
-                                 clip_dim=clip_dim, num_clip_token=num_clip_token, conv=conv, skip=skip)
+                                 clip_dim=clip_dim, num_clip_token=num_clip_token, conv=conv, skip=skip,
+                                 mlp_time_embed=mlp_time_embed)
         self._build(img_size, patch_size, in_chans, embed_dim, depth, num_heads, mlp_ratio, qkv_bias,
                     mlp_time_embed, conv, skip, extras=1 + num_clip_token)
 
@@ -280,6 +284,9 @@ class UViTT2I(_UViTBase):
             # the reference's attention-editing branch (libs/uvit_t2i.py:91-107): active for t <= t_edit in decode
             from .flow_matching import build_attn_edit
             attn = build_attn_edit(x.shape[0], self.pos_embed.shape[1], **kwargs)
+            if attn is not None and self.qk_scale is not None:
+                raise NotImplementedError("attention editing with a qk_scale override is not built "
+                                          "(the editing branch of libs/uvit_t2i.py:96-107 would use it)")
             if attn is not None and not float(f"{timesteps[0].item():.2f}") <= attn["t_edit"]:
                 attn = None
         return self.engine().forward(x, timesteps, context=context, attn_edit=attn), None
