@@ -153,6 +153,16 @@ int usp_sample_adaptive(usp_handle* h, float* z, const float* context, const int
                         int method, double rtol, double atol, const float* delta_digits, int n_rows, float write_scale,
                         float t_edit, int edit_loc, const usp_attn_edit* attn, int max_steps,
                         usp_adaptive_stats* stats, void* stream);
+/* dissect_name="read" (libs/dissection.py:126-136) under an adaptive solver: the same integration, and every velocity
+ * evaluation - the two of the starting-step search and rejected attempts included, like the reference's hook inside
+ * the net - dumps the activation at edit_loc (head: the latent the net sees, tail: the velocity) into its own row
+ * trace[i] ([trace_cap][B,C,S,S] fp32, host or device) and its model time into times[i]; *n_evals receives the number
+ * of evaluations (USP_ERR_STATE if it exceeds trace_cap; the first trace_cap rows are still returned). The caller
+ * writes {batch_id}_{times[i]:.2f}.npy in evaluation order, so that a later evaluation at the same digit overwrites the
+ * file as in the reference. */
+int usp_sample_adaptive_read(usp_handle* h, float* z, const float* context, const int64_t* y, int B, float t0, float t1,
+                             int method, double rtol, double atol, int edit_loc, float* trace, float* times, int trace_cap,
+                             int* n_evals, int max_steps, usp_adaptive_stats* stats, void* stream);
 /* ---- latent -> image decoder -------------------------------------------------------------------------------------
  * Replaces FrozenAutoencoderKL.decode (libs/autoencoder.py:446-450: z / scale_factor -> post_quant_conv -> Decoder),
  * the call dissect_lfm.py:86-98 / train_lfm.py make on every batch of sampled latents. Only the configuration of

@@ -445,7 +445,8 @@ def sample_adaptive(sd: Dict[str, Tensor], cfg: dict, z: Tensor, t0: float = 0.0
                     atol: float = 1e-5, y: Optional[Tensor] = None, context: Optional[Tensor] = None,
                     delta_digits: Optional[Tensor] = None, write_scale: float = 0.0, t_edit: float = 0.0,
                     edit_loc: Optional[str] = None, attn_colscale: Optional[Tensor] = None, attn_blocks=None,
-                    attn_t_edit: float = 0.0, stats: Optional[dict] = None, method: str = "dopri5") -> Tensor:
+                    attn_t_edit: float = 0.0, stats: Optional[dict] = None, method: str = "dopri5",
+                    read_trace: Optional[dict] = None) -> Tensor:
     """CNF.decode with an adaptive method.  delta_digits[i] is the row delta_{i/100:.2f}.npy would supply; the model
     sees the time rounded to fp32, like the reference's fp32 stage times."""
     def func(t: float, x: Tensor) -> Tensor:
@@ -458,7 +459,14 @@ def sample_adaptive(sd: Dict[str, Tensor], cfg: dict, z: Tensor, t0: float = 0.0
                 hd, td = (dlt, None) if edit_loc == "head" else (None, dlt)
         cs = attn_colscale if (attn_colscale is not None and float(f"{tf:.2f}") <= attn_t_edit) else None
         tt = torch.full((x.shape[0],), tf, dtype=torch.float32)
-        return uvit_forward(sd, cfg, x, tt, y=y, context=context, head_delta=hd, tail_delta=td,
-                            attn_colscale=cs, attn_blocks=attn_blocks)
+        # dissect_name="read" (libs/dissection.py:126-136): np.save(f"{batch_id}_{t:.2f}", x) at every evaluation - the
+        # file of a digit is overwritten by later evaluations at the same digit; read_trace["%.2f"] plays the file
+        if read_trace is not None and edit_loc == "head":
+            read_trace[f"{tf:.2f}"] = x.detach().clone()
+        v = uvit_forward(sd, cfg, x, tt, y=y, context=context, head_delta=hd, tail_delta=td,
+                         attn_colscale=cs, attn_blocks=attn_blocks)
+        if read_trace is not None and edit_loc == "tail":
+            read_trace[f"{tf:.2f}"] = v.detach().clone()
+        return v
 
     return odeint_dopri5(func, z, t0, t1, rtol, atol, stats=stats, method=method)

@@ -728,6 +728,43 @@ def test_cnf_default_adaptive_and_fixadp_against_oracle(tmp_path):
     assert rel(got.double().cpu() - plain, want - plain) < 3e-2
 
 
+@pytest.mark.parametrize("loc", ["head", "tail"])
+def test_cnf_read_under_adaptive_solver_against_oracle(tmp_path, loc):
+    """dissect_name="read" with solver="adaptive" (libs/dissection.py:126-136 runs under any solver): one
+    {batch_id}_{t:.2f}.npy per evaluation digit, the last evaluation at a digit wins.  The oracle replays dopri5 with
+    the same hook.  The two controllers need not take the same steps (at rtol = 1e-5 the embedded error estimate of
+    the 16-bit path carries its rounding noise), so the digit sets are compared where they overlap: the rows of common
+    digits must agree up to the solution's own tolerance plus the drift of x over the difference of the two evaluation
+    times inside one digit."""
+    case = CASES["tiny_uncond"]
+    m = model("tiny_uncond")
+    x = build_inputs(case)[0][:2]
+    sd = {k: v.cpu().double() for k, v in m.state_dict().items()}
+    cnf = CNF(m)
+    root = tmp_path / "dump"
+    kw = dict(dissect_task="uspace_uvit", dissect_name="read", read_path_root=str(root), batch_id=3, edit_loc=loc,
+              t_edit=1.0, write_scale=0.0, solver_kwargs=dict(solver="adaptive", solver_adaptive="dopri5"))
+    got = cnf.decode(x.to(dev()), y=None, **kw)
+    trace = {}
+    want = O.sample_adaptive(sd, case["cfg"], x.double(), 0.0, 1.0, 1e-5, 1e-5, edit_loc=loc, read_trace=trace)
+    assert rel(got, want) < 1e-3
+    files = sorted(os.listdir(root))
+    assert all(f.startswith("3_") and f.endswith(".npy") for f in files)
+    digits_got = [f[len("3_"):-len(".npy")] for f in files]
+    assert "0.00" in digits_got and 5 <= len(digits_got) <= cnf.last_solver_stats["nfe"]
+    common = sorted(set(digits_got) & set(trace))
+    assert "0.00" in common and len(common) >= 3, (digits_got, sorted(trace))
+    for d in digits_got:
+        assert np.load(root / f"3_{d}.npy").shape == (2, 4, 32, 32)
+    # (torchdiffeq does not clip the last step to t1: evaluation times beyond 1.00 are dumped like any other.)
+    # Inside a digit the two evaluation times differ by up to 0.01
+    for d in common:
+        row = torch.from_numpy(np.load(root / f"3_{d}.npy"))
+        assert rel(row, trace[d]) < 5e-2, (d, rel(row, trace[d]))
+    if loc == "head":       # no later evaluation prints "0.00" here: the file holds what the net saw near t0
+        assert rel(torch.from_numpy(np.load(root / "3_0.00.npy")), trace["0.00"]) < 1e-4
+
+
 def test_adaptive_agrees_with_fine_fixed_grid_on_north_star_model():
     """Size-independent property on U-ViT-L: dopri5(1e-5) and Heun(h = 0.01) integrate the same field."""
     m = model("large_uncond")

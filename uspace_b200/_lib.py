@@ -52,6 +52,8 @@ _SIGNATURES = {
     "usp_sample": (_i, [_vp, _vp, _vp, _vp, _i, _f, _f, _f, _i, _vp, _f, _f, _i, _vp]),
     "usp_sample_adaptive": (_i, [_vp, _vp, _vp, _vp, _i, _f, _f, _i, C.c_double, C.c_double, _vp, _i, _f, _f, _i,
                                  C.POINTER(UspAttnEdit), _i, C.POINTER(UspAdaptiveStats), _vp]),
+    "usp_sample_adaptive_read": (_i, [_vp, _vp, _vp, _vp, _i, _f, _f, _i, C.c_double, C.c_double, _i, _vp, _vp, _i,
+                                      C.POINTER(_i), _i, C.POINTER(UspAdaptiveStats), _vp]),
     "usp_sample_sweep": (_i, [_vp, _vp, _vp, _vp, _vp, _i, C.POINTER(_f), _i, _f, _f, _f, _i, _vp, _f, _i, _vp]),
     "usp_sample_read": (_i, [_vp, _vp, _vp, _vp, _i, _f, _f, _f, _i, _i, _vp, _vp]),
     "usp_sample_host": (_i, [_vp, _vp, _vp, _vp, _i, _f, _f, _f, _i, _vp, _f, _f, _i]),

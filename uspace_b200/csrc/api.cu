@@ -1224,10 +1224,18 @@ int usp_sample_sweep(usp_handle* h, const float* z, float* out, const float* con
                        t_edit, edit_loc, nullptr, nullptr, stream);
 }
 
-int usp_sample_adaptive(usp_handle* h, float* z, const float* context, const int64_t* y, int B, float t0, float t1,
-                        int method, double rtol, double atol, const float* delta_digits, int n_rows, float write_scale,
-                        float t_edit, int edit_loc, const usp_attn_edit* attn, int max_steps,
-                        usp_adaptive_stats* stats, void* stream) {
+}  // extern "C"
+
+namespace {
+// usp_sample_adaptive, and with trace_out its "read" variant: every velocity evaluation (the two of the starting-step
+// search and rejected attempts included, like the reference's hook inside the net) dumps the activation at edit_loc
+// into its own row, and its model time into times_out; the caller names the files by "%.2f" of the time in evaluation
+// order (libs/dissection.py:126-136: later evaluations at the same digit overwrite the file).
+int sample_adaptive_impl(usp_handle* h, float* z, const float* context, const int64_t* y, int B, float t0, float t1,
+                         int method, double rtol, double atol, const float* delta_digits, int n_rows, float write_scale,
+                         float t_edit, int edit_loc, const usp_attn_edit* attn, int max_steps,
+                         usp_adaptive_stats* stats, float* trace_out, float* times_out, int trace_cap, int* n_evals_out,
+                         void* stream) {
     int rc = check_ready(h, B);
     if (rc) return rc;
     if (!z) return fail(h, USP_ERR_INVALID, "null latent");
@@ -1237,9 +1245,14 @@ int usp_sample_adaptive(usp_handle* h, float* z, const float* context, const int
         return fail(h, USP_ERR_INVALID, "y must be given exactly for the class-conditional model (num_classes > 0)");
     if (edit_loc != USP_EDIT_NONE && edit_loc != USP_EDIT_HEAD && edit_loc != USP_EDIT_TAIL)
         return fail(h, USP_ERR_INVALID, "edit_loc must be none, head or tail (\"mid\" is broken in the reference)");
-    if ((edit_loc != USP_EDIT_NONE) != (delta_digits != nullptr))
+    const bool reading = trace_out != nullptr;
+    if (reading && (times_out == nullptr || n_evals_out == nullptr || trace_cap < 1 || delta_digits != nullptr ||
+                    edit_loc == USP_EDIT_NONE))
+        return fail(h, USP_ERR_INVALID, "read mode needs trace / times / count buffers, an edit_loc and no delta table");
+    if (!reading && (edit_loc != USP_EDIT_NONE) != (delta_digits != nullptr))
         return fail(h, USP_ERR_INVALID, "delta_digits must be given exactly when edit_loc is head or tail");
     if (delta_digits && (n_rows < 1 || n_rows > RK_DIGITS)) return fail(h, USP_ERR_INVALID, "n_rows must be in [1, 128]");
+    if (reading) n_rows = 0;
     if (method < USP_METHOD_DOPRI5 || method > USP_METHOD_ADAPTIVE_HEUN)
         return fail(h, USP_ERR_INVALID, "unknown adaptive method (dopri5, bosh3, adaptive_heun)");
     const int rkm = method - USP_METHOD_DOPRI5;
@@ -1264,10 +1277,29 @@ int usp_sample_adaptive(usp_handle* h, float* z, const float* context, const int
     std::vector<unsigned char> emask(RK_DIGITS, 0), amask(RK_DIGITS, 0);
     for (int i = 0; i < RK_DIGITS; ++i) {
         bool zero = false;
-        if (edit_loc != USP_EDIT_NONE) emask[i] = (digit_leq(i / 100.0, t_edit, &zero) && !zero && i < n_rows) ? 1 : 0;
+        if (edit_loc != USP_EDIT_NONE && !reading)
+            emask[i] = (digit_leq(i / 100.0, t_edit, &zero) && !zero && i < n_rows) ? 1 : 0;
         if (use_attn) amask[i] = digit_leq(i / 100.0, attn->t_edit, nullptr) ? 1 : 0;
     }
-    if (edit_loc != USP_EDIT_NONE) {
+    float* times_dev = nullptr;
+    int* count_dev = nullptr;
+    if (reading) {
+        // [trace_cap][B,C,S,S] rows, then the evaluation times and the evaluation counter
+        const size_t tbytes = static_cast<size_t>(trace_cap) * zbytes + static_cast<size_t>(trace_cap) * 4 + 16;
+        if (p->trace_cap < tbytes) {
+            for (auto& g : p->graphs) cudaGraphExecDestroy(g.second);
+            p->graphs.clear();
+            if (p->trace) CUDA_TRY(h, cudaFree(p->trace));
+            p->trace = nullptr;
+            p->trace_cap = 0;
+            CUDA_TRY(h, cudaMalloc(&p->trace, tbytes));
+            p->trace_cap = tbytes;
+        }
+        times_dev = reinterpret_cast<float*>(reinterpret_cast<char*>(p->trace) + static_cast<size_t>(trace_cap) * zbytes);
+        count_dev = reinterpret_cast<int*>(times_dev + trace_cap);
+        CUDA_TRY(h, cudaMemsetAsync(p->trace, 0, tbytes, s));
+    }
+    if (edit_loc != USP_EDIT_NONE && !reading) {
         const size_t dbytes = static_cast<size_t>(n_rows) * C * S * S * 4;
         if (p->delta_cap < dbytes) {
             for (auto& g : p->graphs) cudaGraphExecDestroy(g.second);
@@ -1289,7 +1321,8 @@ int usp_sample_adaptive(usp_handle* h, float* z, const float* context, const int
     memset(&rs0, 0, sizeof(rs0));
     rs0.s0 = static_cast<double>(sign) * static_cast<double>(t0);
     rs0.s_end = static_cast<double>(sign) * static_cast<double>(t1);
-    rs0.rtol = rtol; rs0.atol = atol; rs0.sign = sign; rs0.write_scale = write_scale; rs0.n_rows = delta_digits ? n_rows : 0;
+    rs0.rtol = rtol; rs0.atol = atol; rs0.sign = sign; rs0.write_scale = write_scale;
+    rs0.n_rows = delta_digits ? n_rows : 0;
     // pageable source: the copy is staged before the call returns, so the stack object may go out of scope
     CUDA_TRY(h, cudaMemcpyAsync(p->rs, &rs0, sizeof(rs0), cudaMemcpyHostToDevice, s));
     CUDA_TRY(h, cudaMemcpyAsync(p->z, z, zbytes, cudaMemcpyDefault, s));
@@ -1303,11 +1336,13 @@ int usp_sample_adaptive(usp_handle* h, float* z, const float* context, const int
     memset(&ra, 0, sizeof(ra));
     ra.rs = p->rs; ra.st = p->st; ra.y0 = p->z; ra.k = p->rk_k; ra.ytmp = p->ztmp; ra.out = p->z;
     ra.partials = p->rk_partials; ra.emask = p->mask; ra.amask = p->amask; ra.n = zel; ra.method = rkm;
+    ra.eval_times = times_dev; ra.eval_count = count_dev; ra.eval_cap = trace_cap;
     auto velocity = [&](const float* x, int stage, cudaStream_t cs) -> int {
         FwdIO io;
         memset(&io, 0, sizeof(io));
         io.x = x; io.st = p->st; io.y = y ? p->y : nullptr; io.has_ctx = context != nullptr;
-        io.delta = edit_loc != USP_EDIT_NONE ? p->delta : nullptr; io.edit_loc = edit_loc;
+        io.delta = (edit_loc != USP_EDIT_NONE && !reading) ? p->delta : nullptr; io.edit_loc = edit_loc;
+        io.trace = reading ? p->trace : nullptr;
         if (use_attn) { io.colscale = p->colscale; io.block_mask = attn->block_mask; }
         io.out = p->rk_k + static_cast<long long>(stage) * zel; io.m1 = sign;   // base == nullptr: k = sign * v
         return enqueue_forward(h, p, io, cs);
@@ -1328,7 +1363,8 @@ int usp_sample_adaptive(usp_handle* h, float* z, const float* context, const int
     RK_TRY(launch_rk_control(ra, 1, s));
 
     const std::pair<int, uint64_t> key(method | (edit_loc << 3) | ((y ? 1 : 0) << 5) | ((use_attn ? 1 : 0) << 6) |
-                                           ((sign < 0.f ? 1 : 0) << 7),
+                                           ((sign < 0.f ? 1 : 0) << 7) | ((reading ? 1 : 0) << 9) |
+                                           (reading ? (trace_cap << 10) : 0),
                                        use_attn ? attn->block_mask : 0);
     auto git = p->graphs.find(key);
     if (git == p->graphs.end()) {
@@ -1381,10 +1417,41 @@ int usp_sample_adaptive(usp_handle* h, float* z, const float* context, const int
         stats->last_dt = last_dt;
     }
     CUDA_TRY(h, cudaMemcpyAsync(z, p->z, zbytes, cudaMemcpyDefault, s));
+    int n_evals = 0;
+    if (reading) {
+        CUDA_TRY(h, cudaMemcpyAsync(&n_evals, count_dev, 4, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(h, cudaStreamSynchronize(s));
+        *n_evals_out = n_evals;
+        const int rows = n_evals < trace_cap ? n_evals : trace_cap;
+        CUDA_TRY(h, cudaMemcpyAsync(trace_out, p->trace, static_cast<size_t>(rows) * zbytes, cudaMemcpyDefault, s));
+        CUDA_TRY(h, cudaMemcpyAsync(times_out, times_dev, static_cast<size_t>(rows) * 4, cudaMemcpyDefault, s));
+    }
     CUDA_TRY(h, cudaEventRecord(h->ev1, s));
     CUDA_TRY(h, cudaStreamSynchronize(s));
     h->ev_valid = true;
+    if (reading && n_evals > trace_cap)
+        return fail(h, USP_ERR_STATE, "adaptive read: more velocity evaluations than trace rows (raise trace_cap)");
     return USP_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int usp_sample_adaptive(usp_handle* h, float* z, const float* context, const int64_t* y, int B, float t0, float t1,
+                        int method, double rtol, double atol, const float* delta_digits, int n_rows, float write_scale,
+                        float t_edit, int edit_loc, const usp_attn_edit* attn, int max_steps,
+                        usp_adaptive_stats* stats, void* stream) {
+    return sample_adaptive_impl(h, z, context, y, B, t0, t1, method, rtol, atol, delta_digits, n_rows, write_scale, t_edit,
+                                edit_loc, attn, max_steps, stats, nullptr, nullptr, 0, nullptr, stream);
+}
+
+int usp_sample_adaptive_read(usp_handle* h, float* z, const float* context, const int64_t* y, int B, float t0, float t1,
+                             int method, double rtol, double atol, int edit_loc, float* trace, float* times, int trace_cap,
+                             int* n_evals, int max_steps, usp_adaptive_stats* stats, void* stream) {
+    if (!trace || !times || !n_evals) return fail(h, USP_ERR_INVALID, "null trace / times / n_evals buffer");
+    if (trace_cap < 1 || trace_cap > 4096) return fail(h, USP_ERR_INVALID, "trace_cap must be in [1, 4096]");
+    return sample_adaptive_impl(h, z, context, y, B, t0, t1, method, rtol, atol, nullptr, 0, 0.f, 0.f, edit_loc, nullptr,
+                                max_steps, stats, trace, times, trace_cap, n_evals, stream);
 }
 
 int usp_sample_host(usp_handle* h, float* z_host, const float* context_host, const int64_t* y_host, int B, float t0,

@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(256) embed_kernel(const EmbedArgs a) {
                 if (sc != 0.f && a.sscale != nullptr) sc = a.sscale[b];
                 if (sc != 0.f) v += a.delta[static_cast<long long>(didx) * C * S * S + idx] * sc;
             }
-            if (a.trace != nullptr)   // dissect_name="read" (libs/dissection.py:126-136)
+            if (a.trace != nullptr && didx >= 0)   // dissect_name="read" (libs/dissection.py:126-136)
                 a.trace[(static_cast<long long>(didx) * a.B + b) * C * S * S + idx] = v;
             feat[tk][f] = v;
         }
@@ -302,7 +302,7 @@ __global__ void __launch_bounds__(256) final_kernel(const FinalArgs a) {
         if (sc != 0.f && a.sscale != nullptr) sc = a.sscale[b];
         if (sc != 0.f) v += a.delta[static_cast<long long>(didx) * C * S * S + chw] * sc;
     }
-    if (a.trace != nullptr) a.trace[static_cast<long long>(didx) * n + i] = v;
+    if (a.trace != nullptr && didx >= 0) a.trace[static_cast<long long>(didx) * n + i] = v;
     if (a.st == nullptr) {
         a.out[i] = v;
         return;

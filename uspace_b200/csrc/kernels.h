@@ -229,6 +229,9 @@ struct RkArgs {
     double* partials;          // [2][RK_MAX_PARTIALS]
     const unsigned char* emask;   // [RK_DIGITS] write-edit active for digit i
     const unsigned char* amask;   // [RK_DIGITS] attention edit active for digit i
+    float* eval_times;            // "read" mode: model time of the i-th velocity evaluation (row i of the trace), or nullptr
+    int* eval_count;              // ... and the number of evaluations so far
+    int eval_cap;                 // rows of the trace
     long long n;
     int method;                // RkMethod
 };

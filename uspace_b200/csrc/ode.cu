@@ -82,6 +82,14 @@ __device__ void set_stage_time(const RkArgs& a, float s_stage) {
     const int idx = static_cast<int>(rint(static_cast<double>(t) * 100.0));
     const bool in = idx >= 0 && idx < RK_DIGITS;
     st->didx = in && idx < rs->n_rows ? idx : 0;
+    if (a.eval_times != nullptr) {
+        // "read": this evaluation dumps into its own trace row (the host names the files by "%.2f" of the time, in
+        // evaluation order, so that later evaluations overwrite earlier ones like the reference's np.save does)
+        const int c = *a.eval_count;
+        st->didx = c < a.eval_cap ? c : -1;      // -1: no room, nothing is written; the host reports the overflow
+        if (c < a.eval_cap) a.eval_times[c] = t;
+        *a.eval_count = c + 1;
+    }
     st->edit = (in && idx < rs->n_rows && a.emask[idx]) ? rs->write_scale : 0.f;
     st->attn_on = in ? a.amask[idx] : 0;
 }

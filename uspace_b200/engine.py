@@ -178,6 +178,31 @@ class Engine:
                          last_dt=st.last_dt)
         return zz
 
+    def sample_adaptive_read(self, z, t0=0.0, t1=1.0, rtol=1e-5, atol=1e-5, y=None, context=None, edit_loc="tail",
+                             max_steps=0, stats=None, method="dopri5", trace_cap=128):
+        """dissect_name="read" under an adaptive solver: returns (result, trace [n_evals, B, C, S, S], times [n_evals]):
+        the activation at ``edit_loc`` and the model time of every velocity evaluation, in evaluation order."""
+        self._check_latent(z)
+        B = z.shape[0]
+        zz = z.to(self.device, torch.float32).contiguous().clone()
+        if y is not None:
+            y = y.to(self.device, torch.int64).contiguous()
+        if context is not None:
+            context = context.to(self.device, torch.float32).contiguous()
+        trace = torch.zeros(trace_cap, B, self.C, self.S, self.S, device=self.device, dtype=torch.float32)
+        times = torch.zeros(trace_cap, dtype=torch.float32)        # host
+        n_evals = C.c_int(0)
+        st = _lib.UspAdaptiveStats()
+        _lib.check(self.lib.usp_sample_adaptive_read(self.handle, _ptr(zz), _ptr(context), _ptr(y), B, t0, t1,
+                                                     _lib.ADAPTIVE_METHOD[method], rtol, atol, _lib.EDIT_LOC[edit_loc],
+                                                     _ptr(trace), _ptr(times), int(trace_cap), C.byref(n_evals),
+                                                     int(max_steps), C.byref(st), self._stream()),
+                   self.handle, "usp_sample_adaptive_read")
+        if stats is not None:
+            stats.update(n_accept=st.n_accept, n_reject=st.n_reject, nfe=st.nfe, last_ratio=st.last_ratio,
+                         last_dt=st.last_dt)
+        return zz, trace[:n_evals.value], times[:n_evals.value]
+
     def sample_sweep(self, z, write_scales, t0=0.0, t1=1.0, step_size=0.02, method="euler", y=None, context=None,
                      delta_table=None, t_edit=0.0, edit_loc="tail") -> torch.Tensor:
         """All ``write_scales`` of the semantic-direction sweep in one batch: returns [B, len(write_scales), C, S, S]."""

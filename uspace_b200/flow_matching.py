@@ -281,11 +281,27 @@ class _CNFBase(nn.Module):
     def _integrate_read(self, engine, z, cond, t0, t1, ode_kwargs, **kwargs) -> Tensor:
         """dissect_name="read" (libs/dissection.py:126-136): np.save(f"{read_path_root}/{batch_id}_{t:.2f}", x) for the
         activation x at edit_loc of every evaluation - gathered on the device, written after the last step."""
-        if "options" not in ode_kwargs:
-            raise NotImplementedError("dissect_name='read' under an adaptive solver is not built")
         loc = kwargs.get("edit_loc")
         if loc == "mid":
             raise NotImplementedError("edit_loc='mid' is broken in the reference for U-ViT and is not built")
+        if "options" not in ode_kwargs:
+            # adaptive solver: the evaluation times are the solver's; one file per "%.2f" digit, the last evaluation that
+            # printed the digit wins (the reference overwrites {batch_id}_{digit}.npy the same way)
+            self.last_solver_stats = {}
+            kw = dict(rtol=ode_kwargs["rtol"], atol=ode_kwargs["atol"], method=ode_kwargs.get("method", "dopri5"),
+                      stats=self.last_solver_stats, **self._cond_kw(cond))
+            if loc not in ("head", "tail"):
+                return engine.sample_adaptive(z, t0, t1, **kw)
+            out, trace, times = engine.sample_adaptive_read(z, t0, t1, edit_loc=loc, **kw)
+            root = kwargs.get("read_path_root")
+            os.makedirs(root, exist_ok=True)
+            last = {}                                   # digit -> last evaluation that printed it
+            for i, t in enumerate(times.tolist()):
+                last[f"{t:.2f}"] = i
+            host = trace.cpu().numpy()
+            for digit, i in last.items():
+                np.save(os.path.join(root, f"{kwargs['batch_id']}_{digit}"), host[i])
+            return out
         h, method = ode_kwargs["options"]["step_size"], ode_kwargs["method"]
         if loc not in ("head", "tail"):     # the hook is never reached: a plain integration
             return engine.sample(z, t0, t1, h, method, **self._cond_kw(cond))
