@@ -44,6 +44,7 @@
 //     redistributes the CTA's LAUNCH allocation (640 x 96 = 61440 registers; asking for more in total hangs), which
 //     leaves the softmax threads 144 registers and spills
 //   one mbarrier arrival per warp (lane 0 behind __syncwarp) instead of per thread .. no change (48.8 vs 48.4 us)
+//   handing the exponential turn over 1-4 chunks before the end of a section ........ no change (49.3-50.2 vs 49.6 us)
 //   THREE tiles in flight (48-key blocks, 3 x 160 TMEM columns, 640 threads, turns in a ring of three) ..... 57.5 us at
 //     L = 256, 60.3 us at L = 257 against 46.8 / 54.0 in the same run: twice the hand-offs per tile cost more than the
 //     third warpgroup's slack buys (and 104 registers per softmax thread spill)
