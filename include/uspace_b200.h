@@ -176,6 +176,13 @@ const char* usp_vae_last_error(const usp_vae* h);   /* h may be NULL: message of
 int usp_vae_num_weights(const usp_vae* h);
 const char* usp_vae_weight_name(const usp_vae* h, int i);
 int usp_vae_set_weight(usp_vae* h, const char* name, const void* data, const int64_t* shape, int ndim);
+/* Operand precision of every GEMM in the autoencoder; call before usp_vae_finalize (changing it un-finalises).
+ * FP16X3 (default): operands split into hi + lo fp16 parts, three products folded into one GEMM over 3x the K
+ * (~1e-5 against the fp64 oracle); FP16: one product (3x less tensor work, ~2e-3: the precision of the TF32
+ * convolutions the reference runs by default on a GPU). */
+#define USP_VAE_PRECISION_FP16 0
+#define USP_VAE_PRECISION_FP16X3 1
+int usp_vae_set_precision(usp_vae* h, int mode);
 int usp_vae_finalize(usp_vae* h, void* stream);      /* packs the convolution weights; synchronises */
 int usp_vae_decode(usp_vae* h, const float* z, float* out, int B, int S, void* stream);
 /* Replaces FrozenAutoencoderKL.encode_moments (libs/autoencoder.py:426-429: Encoder.forward :275-300 + quant_conv):

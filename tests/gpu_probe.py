@@ -296,6 +296,38 @@ def sec_vae(lib, opd):
     print("decoded", tuple(img.shape), bool(torch.isfinite(img).all()))
 
 
+def sec_vaeprec(lib, opd):
+    """Error against the reference goldens and decode / encode time per image for both operand precisions."""
+    import numpy as np
+    from tests.golden.cases import vae_enc_state_dict, vae_images, vae_latents, vae_state_dict
+    from uspace_b200.autoencoder import get_model
+    gd = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    rel = lambda a, b: ((a.double().cpu() - b.double()).abs().max() / b.double().abs().max()).item()
+    for prec in ("fp16", "fp16x3"):
+        m = get_model(precision=prec)
+        m.load_state_dict({**vae_state_dict(), **vae_enc_state_dict()})
+        m = m.to(dev)
+        for name in ("vae_small", "vae_full"):
+            want = torch.from_numpy(np.load(os.path.join(gd, name + ".npz"))["decode"])
+            print(prec, name, "decode rel err %.3e" % rel(m.decode(vae_latents(name).to(dev)), want), flush=True)
+        for name in ("vae_enc_small", "vae_enc_full"):
+            want = torch.from_numpy(np.load(os.path.join(gd, name + ".npz"))["moments"])
+            print(prec, name, "moments rel err %.3e" % rel(m.encode_moments(vae_images(name).to(dev)), want), flush=True)
+        z = 0.7 * torch.randn(64, 4, 32, 32, device=dev)
+        x = torch.rand(64, 3, 256, 256, device=dev) * 2 - 1
+        for fn, inp, what in ((m.decode, z, "decode"), (m.encode_moments, x, "encode")):
+            fn(inp)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn(inp)
+            e1.record()
+            torch.cuda.synchronize()
+            print(prec, what, "%.3f ms per image (64 images, 256^2)" % (e0.elapsed_time(e1) / 64), flush=True)
+        del m
+        torch.cuda.empty_cache()
+
+
 if __name__ == "__main__":
     lib = _lib.load()
     sec = sys.argv[1]

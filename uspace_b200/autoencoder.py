@@ -143,11 +143,20 @@ DDCONFIG = dict(double_z=True, z_channels=4, resolution=256, in_channels=3, out_
                 num_res_blocks=2, attn_resolutions=[], dropout=0.0)
 
 
+# GEMM operand precision (include/uspace_b200.h USP_VAE_PRECISION_*): "fp16x3" splits every operand into hi + lo fp16
+# parts (three products in one GEMM, ~1e-5 against fp64); "fp16" is one product: 3x less tensor work at ~2e-3, the
+# precision of the TF32 convolutions the reference's torch modules run by default on a GPU.
+PRECISIONS = {"fp16": 0, "fp16x3": 1}
+
+
 class FrozenAutoencoderKL(nn.Module):
     """libs/autoencoder.py:412-460.  ``pretrained_path=None`` keeps the random initialisation."""
 
-    def __init__(self, ddconfig=None, embed_dim=4, pretrained_path=None, scale_factor=0.18215):
+    def __init__(self, ddconfig=None, embed_dim=4, pretrained_path=None, scale_factor=0.18215, precision="fp16x3"):
         super().__init__()
+        if precision not in PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(PRECISIONS)}")
+        self.precision = precision
         ddconfig = dict(DDCONFIG if ddconfig is None else ddconfig)
         if (ddconfig["ch"], list(ddconfig["ch_mult"]), ddconfig["num_res_blocks"], ddconfig["z_channels"],
                 ddconfig["out_ch"]) != (128, [1, 2, 4, 4], 2, 4, 3) or embed_dim != 4:
@@ -176,7 +185,7 @@ class FrozenAutoencoderKL(nn.Module):
         if dev.type != "cuda":
             raise RuntimeError("uspace_b200: the decoder runs on a CUDA (sm_100a) device only; there is no CPU fallback")
         if self._engine is None:
-            self._engine = VaeEngine(dev, self.state_dict(), self.scale_factor)
+            self._engine = VaeEngine(dev, self.state_dict(), self.scale_factor, self.precision)
         return self._engine
 
     @torch.no_grad()
@@ -234,14 +243,14 @@ def decode_large_batch(autoencoder, batch, chunk: int = 50):
     return torch.cat([autoencoder.decode(batch[i:i + chunk]) for i in range(0, batch.shape[0], chunk)], dim=0)
 
 
-def get_model(pretrained_path=None, scale_factor=0.18215):
-    return FrozenAutoencoderKL(DDCONFIG, 4, pretrained_path, scale_factor)
+def get_model(pretrained_path=None, scale_factor=0.18215, precision="fp16x3"):
+    return FrozenAutoencoderKL(DDCONFIG, 4, pretrained_path, scale_factor, precision)
 
 
 class VaeEngine:
     """Owner of a ``usp_vae`` handle (C ABI): weights in the reference's state_dict layout, decode on the current stream."""
 
-    def __init__(self, device, state_dict, scale_factor):
+    def __init__(self, device, state_dict, scale_factor, precision="fp16x3"):
         self.lib = _lib.load()
         self.device = device
         self.handle = C.c_void_p()
@@ -257,6 +266,8 @@ class VaeEngine:
             shape = (C.c_int64 * t.dim())(*t.shape)
             _lib.check(self.lib.usp_vae_set_weight(self.handle, k.encode(), C.c_void_p(t.data_ptr()), shape, t.dim()),
                        self.handle, f"usp_vae_set_weight({k})", vae=True)
+        _lib.check(self.lib.usp_vae_set_precision(self.handle, PRECISIONS[precision]), self.handle, "usp_vae_set_precision",
+                   vae=True)
         _lib.check(self.lib.usp_vae_finalize(self.handle, self._stream()), self.handle, "usp_vae_finalize", vae=True)
 
     def _stream(self):
