@@ -26,6 +26,10 @@ CASES = {
                           euler_steps=3),
     "tiny_t2i_time_mlp": dict(cfg=dict(_TINY, clip_dim=768, num_clip_token=77, mlp_time_embed=True), t2i=True, seed=5,
                               B=2, in_seed=12, euler_steps=None),
+    # 64x64 latents (a 512^2 image, datasets.py:244-245): 1024 patches + the time token = 1025 tokens, beyond one
+    # 384-key attention pass
+    "tiny_long": dict(cfg=dict(_TINY, img_size=64, depth=2, num_classes=-1), t2i=False, seed=6, B=2, in_seed=13,
+                      euler_steps=2),
     # configs/lfm_cm256_uvit_large.py:42-56 and configs/lfm_mmcelebahq256_uvit_large.py:43-58, one image
     "large_uncond": dict(cfg=dict(_L, num_classes=-1), t2i=False, seed=0, B=1, in_seed=1230, euler_steps=None),
     "large_t2i": dict(cfg=dict(_L, clip_dim=768, num_clip_token=77), t2i=True, seed=0, B=1, in_seed=1231,

@@ -256,7 +256,7 @@ def sec_attnperf(lib, opd):
     """Stand-alone timing of the attention kernel at the U-ViT-L shapes."""
     td = TD[opd]
     s = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-    for (B, H, L) in [(64, 16, 256), (64, 16, 257), (128, 16, 334)] if not os.environ.get("USP_ATTN_TRACE") else [(64, 16, 256)]:
+    for (B, H, L) in [(64, 16, 256), (64, 16, 257), (128, 16, 334), (16, 16, 1025)] if not os.environ.get("USP_ATTN_TRACE") else [(64, 16, 256)]:
         q, k, v = (torch.randn(B * H, L, 64, device=dev).to(td) for _ in range(3))
         out = torch.zeros(B * L, H * 64, device=dev, dtype=td)
         for _ in range(3):

@@ -125,7 +125,10 @@ def test_gemm_epilogues(lib, opd, epi, M, N, K, K0):
 @pytest.mark.parametrize("opd", ["fp16", "bf16"])
 @pytest.mark.parametrize("B,H,L", [(1, 1, 17), (1, 1, 128), (1, 2, 256), (2, 8, 257), (3, 4, 258), (2, 16, 334),
                                    (1, 1, 384), (64, 16, 257), (128, 16, 334), (3, 2, 288), (2, 2, 320), (2, 3, 352),
-                                   (5, 16, 129), (2, 4, 64), (1, 3, 1)])
+                                   (5, 16, 129), (2, 4, 64), (1, 3, 1),
+                                   # beyond one 384-key pass: key passes with a running maximum (attention.cu);
+                                   # 1025 = a 512^2 image's 1024 patches + the time token
+                                   (2, 3, 385), (1, 2, 400), (2, 4, 768), (1, 16, 1025), (1, 1, 1153), (1, 2, 2049)])
 def test_attention(lib, opd, B, H, L):
     td = TD[opd]
     g = torch.Generator().manual_seed(B * 1000 + L)
@@ -139,7 +142,8 @@ def test_attention(lib, opd, B, H, L):
     assert rel(out.float(), want) < (6e-4 if opd == "fp16" else 5e-3)
 
 
-@pytest.mark.parametrize("B,H,L,scale", [(2, 4, 257, 6.0), (3, 16, 334, 5.0), (64, 16, 257, 4.0), (2, 2, 200, 8.0)])
+@pytest.mark.parametrize("B,H,L,scale", [(2, 4, 257, 6.0), (3, 16, 334, 5.0), (64, 16, 257, 4.0), (2, 2, 200, 8.0),
+                                         (2, 2, 1025, 6.0), (1, 3, 800, 8.0)])
 def test_attention_large_scores_running_max(lib, B, H, L, scale):
     """Scores whose block maxima differ by far more than 2^8: the lazy running-maximum path of attention3.cu (O rescaled
     in TMEM between key blocks) against fp32 SDPA (libs/uvit.py:95)."""
@@ -155,9 +159,9 @@ def test_attention_large_scores_running_max(lib, B, H, L, scale):
     assert rel(out.float(), want) < 6e-4
 
 
-def test_attention_rejects_long_sequences(lib):
-    q = torch.zeros(1, 385, 64, device=dev(), dtype=torch.float16)
-    assert lib.usp_op_attention(P(q), P(q), P(q), P(q), 1, 1, 385, 1, stream()) != 0
+def test_attention_rejects_sequences_beyond_its_limit(lib):
+    q = torch.zeros(1, 16385, 64, device=dev(), dtype=torch.float16)
+    assert lib.usp_op_attention(P(q), P(q), P(q), P(q), 1, 1, 16385, 1, stream()) != 0
 
 
 @pytest.mark.parametrize("M,D", [(7, 256), (514, 512), (16448, 1024)])
@@ -285,7 +289,7 @@ def test_load_state_dict_repacks_weights():
 FIXED = dict(dissect_name="none", solver_kwargs=dict(solver="fixed", solver_fix="euler", solver_fix_step=0.2))
 
 
-@pytest.mark.parametrize("name", ["tiny_uncond", "tiny_t2i"])
+@pytest.mark.parametrize("name", ["tiny_uncond", "tiny_t2i", "tiny_long"])
 def test_decode_matches_reference_driven_euler_golden(golden_dir, name):
     case = CASES[name]
     m = model(name)

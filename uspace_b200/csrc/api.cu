@@ -727,7 +727,7 @@ int usp_create(const usp_config* cfg, int device, usp_handle** out) {
     h->n_in = c.depth / 2;
     h->n_blocks = 2 * h->n_in + 1;
     h->fuse_ln = c.fuse_layernorm != 0 && h->D % 256 == 0 && h->Hd % 256 == 0;
-    if (h->L > ATTN_MAX_L) return fail(nullptr, USP_ERR_UNSUPPORTED, "sequence length above 384 tokens is not built");
+    if (h->L > ATTN_LONG_MAX_L) return fail(nullptr, USP_ERR_UNSUPPORTED, "sequence length above 16384 tokens is not built");
 
     const int64_t D = h->D;
     h->i_pos = add_weight(h.get(), "pos_embed", {1, h->L, D}, false);
