@@ -252,6 +252,49 @@ def sec_gemmperf(lib, opd):
         print(f"gemmperf {epi:10s} N={N} K={K}: rc={rc} {us:7.1f} us  {2.0 * M * N * K / us / 1e6:7.1f} TFLOP/s", flush=True)
 
 
+def sec_gemmsustained(lib, opd):
+    """Power-capped regime: each U-ViT-L GEMM shape back to back for ~2 s (0.5 s warm-up + 1.5 s timed), this library's
+    fused-epilogue kernel against torch.matmul (cuBLAS, plain 16-bit output, no epilogue) on the same operands."""
+    td = TD[opd]
+    M, D = 16448, 1024
+    shapes = [("qkv", 3 * D, D, D), ("bias_resid", D, D, D), ("bias_gelu", 4 * D, D, D),
+              ("bias_resid", D, 4 * D, 4 * D), ("bias_f32", D, 2 * D, D)]
+    s = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def sustained(fn, est_us):
+        n_warm, n = max(int(0.5e6 / est_us), 10), max(int(1.5e6 / est_us), 20)
+        for _ in range(n_warm):
+            fn()
+        e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n * 1e3
+
+    for epi, N, K, K0 in shapes:
+        a0 = torch.randn(M, K0, device=dev).to(td)
+        a1 = torch.randn(M, K - K0, device=dev).to(td) if K0 < K else None
+        a_full = a0 if a1 is None else torch.cat([a0, a1], 1).contiguous()
+        w = (torch.randn(N, K, device=dev) * 0.05).to(td)
+        bias = torch.randn(N, device=dev)
+        x32 = torch.randn(M, N, device=dev) if epi in ("bias_resid", "bias_f32") else None
+        o16 = torch.empty(M, N, device=dev, dtype=td)
+        H = D // 64 if epi == "qkv" else 1
+        mine = lambda: lib.usp_op_gemm(_lib.EPI[epi], P(a0), P(a1), P(w), None if epi == "qkv" else P(bias),
+                                       P(x32) if epi == "bias_resid" else None, P(x32),
+                                       P(o16) if epi in ("qkv", "bias_gelu", "bias_resid") else None, M, N, K, K0, 257, H,
+                                       _lib.OPERAND[opd], s)
+        wt = w.t()
+        ref = lambda: torch.matmul(a_full, wt, out=o16)
+        fl = 2.0 * M * N * K
+        us_m = sustained(mine, 100.0)
+        us_r = sustained(ref, 100.0)
+        print(f"gemmsustained {epi:10s} N={N} K={K}: this {us_m:7.1f} us {fl / us_m / 1e6:7.1f} TFLOP/s | "
+              f"torch.matmul {us_r:7.1f} us {fl / us_r / 1e6:7.1f} TFLOP/s", flush=True)
+
+
 def sec_attnperf(lib, opd):
     """Stand-alone timing of the attention kernel at the U-ViT-L shapes."""
     td = TD[opd]
