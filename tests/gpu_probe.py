@@ -313,6 +313,20 @@ def sec_attnperf(lib, opd):
         torch.cuda.synchronize()
         us = e0.elapsed_time(e1) / 20 * 1e3
         print(f"attnperf B{B} H{H} L{L}: rc={rc} {us:7.1f} us  {4.0 * B * H * L * L * 64 / us / 1e6:7.1f} TFLOP/s", flush=True)
+        if os.environ.get("USP_ATTN_TRACE"):
+            continue
+        # the library kernel the reference would run (libs/uvit.py:95), same operands in its [B, H, L, 64] layout
+        q4, k4, v4 = (t.view(B, H, L, 64) for t in (q, k, v))
+        for _ in range(3):
+            torch.nn.functional.scaled_dot_product_attention(q4, k4, v4)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(20):
+            torch.nn.functional.scaled_dot_product_attention(q4, k4, v4)
+        e1.record()
+        torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) / 20 * 1e3
+        print(f"attnperf B{B} H{H} L{L}: torch SDPA {us:7.1f} us  {4.0 * B * H * L * L * 64 / us / 1e6:7.1f} TFLOP/s", flush=True)
 
 
 def sec_one(lib, opd):
