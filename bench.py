@@ -66,9 +66,12 @@ def decoder_line(latents, dev):
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 2
-        return {"images_per_s": z.shape[0] / ms * 1e3, "batch": z.shape[0], "ms": ms,
-                "achieved_tflops": flops_per_image(32) * z.shape[0] / ms / 1e9, "finite": bool(torch.isfinite(img).all().item()),
-                "note": "FrozenAutoencoderKL.decode, random-init weights; follows sampling in the reference's pipeline"}
+        alg = flops_per_image(32) * z.shape[0] / ms / 1e9
+        return {"images_per_s": z.shape[0] / ms * 1e3, "batch": z.shape[0], "ms": ms, "precision": vae.precision,
+                "achieved_tflops": alg, "issued_tflops": alg * (3 if vae.precision == "fp16x3" else 1),
+                "finite": bool(torch.isfinite(img).all().item()),
+                "note": "FrozenAutoencoderKL.decode, random-init weights; follows sampling in the reference's pipeline; "
+                        "fp16x3 = split hi + lo operands, three products per GEMM (achieved counts the algorithm's FLOPs once)"}
     except Exception as e:   # context only: never fail the headline line
         return {"error": str(e)[:200]}
 
