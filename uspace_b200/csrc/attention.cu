@@ -6,7 +6,8 @@
 // libs/uvit_t2i.py:91-107): O = softmax(Q K^T * hd^-0.5) V, no mask, no dropout, head_dim 64.
 //
 // One CTA per (128-query tile, sample*head).  Up to 384 keys the full score row fits in TMEM (L16 <= 384 fp32
-// columns) and there is no online-softmax rescaling; longer sequences repeat the sequence below per pass of 384 keys:
+// columns) and there is no online-softmax rescaling; longer sequences repeat the sequence below per pass of 160 keys
+// (two CTAs per SM, see AttnCfg):
 // the softmax warps keep a running row maximum m and sum l, multiply the O accumulator in TMEM by 2^(m_old - m_new)
 // (tcgen05.ld / st) once the previous P V has completed, and the next P V accumulates on top.  K of pass j+1 is
 // fetched while pass j's softmax runs; V and P buffers are reused after pass j's P V.
@@ -31,15 +32,22 @@ constexpr int QT = 128;                       // query rows per CTA
 constexpr int ATTN_THREADS = 288;          // 8 softmax warps + 1 control warp
 constexpr int CTRL_WARP = 8;
 constexpr int TILE16K = 128 * HD * 2;         // one 128-row x 64-col 16-bit tile
-constexpr int MAX_KCH = ATTN_MAX_L / 128;     // 3 row chunks of K / V
-constexpr int MAX_PCH = ATTN_MAX_L / 64;      // 6 column chunks of P
-constexpr int SQ_OFF = 0;
-constexpr int SK_OFF = SQ_OFF + TILE16K;
-constexpr int SV_OFF = SK_OFF + MAX_KCH * TILE16K;
-constexpr int SP_OFF = SV_OFF + MAX_KCH * TILE16K;
-constexpr int ATTN_SMEM = SP_OFF + MAX_PCH * TILE16K + 1024;
-constexpr int O_COL = 384;
-constexpr int ATTN_TMEM_COLS = 512;
+// Shared / tensor memory of one CTA as a function of the keys per pass.  PASS = 384 (whole rows, L <= 384): 209 KB and all
+// 512 TMEM columns, one CTA per SM.  PASS = 160 (longer sequences): 105 KB and 256 columns, so TWO CTAs share an SM and
+// one's softmax runs under the other's MMAs and loads - the passes of a single CTA are strictly serial.
+template <int PASS>
+struct AttnCfg {
+    static constexpr int KV_BYTES = PASS * HD * 2;                 // K (or V) rows of one pass, 128 B each
+    static constexpr int PCH = (PASS + 63) / 64;                   // 64-key column chunks of P
+    static constexpr int SQ_OFF = 0;
+    static constexpr int SK_OFF = SQ_OFF + TILE16K;
+    static constexpr int SV_OFF = SK_OFF + KV_BYTES;
+    static constexpr int SP_OFF = SV_OFF + KV_BYTES;
+    static constexpr int SMEM = SP_OFF + PCH * TILE16K + 1024;
+    static constexpr int O_COL = PASS;
+    static constexpr int TMEM_COLS = PASS + HD <= 256 ? 256 : 512;
+    static_assert(KV_BYTES % 1024 == 0 && PASS % 32 == 0 && PASS + HD <= 512, "pass size");
+};
 
 // V tile as the B operand in MN-major form: rows are keys (K dim), 64 head-dim elements contiguous per row
 // (128 B, swizzled), 8-key groups 1024 B apart (SBO).  One 64-wide MN atom, so LBO is unused.
@@ -72,7 +80,8 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
 }
 __device__ __forceinline__ void tmem_st_wait32() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-__global__ void __launch_bounds__(ATTN_THREADS, 1)
+template <int PASS>
+__global__ void __launch_bounds__(ATTN_THREADS, (PASS + HD <= 256) ? 2 : 1)
 attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                  const __grid_constant__ CUtensorMap tmV, const AttnArgs a) {
     extern __shared__ uint8_t smem_raw[];
@@ -86,11 +95,16 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const int lane = threadIdx.x & 31;
     const int qt = blockIdx.x;
     const int bh = blockIdx.y;
+    using Cfg = AttnCfg<PASS>;
+    constexpr int SQ_OFF = Cfg::SQ_OFF, SK_OFF = Cfg::SK_OFF, SV_OFF = Cfg::SV_OFF, SP_OFF = Cfg::SP_OFF;
+    constexpr int O_COL = Cfg::O_COL, ATTN_TMEM_COLS = Cfg::TMEM_COLS;
     const int L = a.L;
-    // key passes: one pass of L keys up to ATTN_MAX_L, passes of ATTN_MAX_L keys beyond (the last one partial)
-    const int n_pass = (L + ATTN_MAX_L - 1) / ATTN_MAX_L;
-    // K / V arrive as two TMA boxes per pass (attn_kv_box_rows(L) rows each; rows beyond L are zero-filled)
+    // key passes: one pass of L keys when they fit, passes of PASS keys otherwise (the last one partial)
+    const int n_pass = (L + PASS - 1) / PASS;
+    // K / V arrive as n_box TMA boxes of attn_kv_box_rows(L) rows per pass (rows beyond L are zero-filled): two half-row
+    // boxes up to ATTN_MAX_L keys, one box of ATTN_LONG_PASS rows beyond
     const int hrows = attn_kv_box_rows(L);
+    const int n_box = L > ATTN_MAX_L ? 1 : 2;
 
     if (threadIdx.x == 0) {
         mbar_init(&bar_qk, 1);
@@ -117,19 +131,19 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             const int fmt = a.opd == OPD_FP16 ? 0 : 1;
             const uint64_t qdesc = umma_desc_sw128(smem_u32(smem + SQ_OFF));
             const uint32_t idesc_o = umma_idesc(fmt, QT, HD, 0, 1);
-            mbar_expect_tx(&bar_qk, TILE16K + 2 * hrows * 128);
+            mbar_expect_tx(&bar_qk, TILE16K + n_box * hrows * 128);
             tma_load_3d(&tmQ, &bar_qk, smem + SQ_OFF, 0, qt * QT, bh);
-            for (int c = 0; c < 2; ++c)
+            for (int c = 0; c < n_box; ++c)
                 tma_load_3d(&tmK, &bar_qk, smem + SK_OFF + c * hrows * 128, 0, c * hrows, bh);
             for (int j = 0; j < n_pass; ++j) {
                 const uint32_t ph = j & 1;
-                const int k0 = j * ATTN_MAX_L;
-                const int Lp = (L - k0) < ATTN_MAX_L ? (L - k0) : ATTN_MAX_L;
+                const int k0 = j * PASS;
+                const int Lp = (L - k0) < PASS ? (L - k0) : PASS;
                 const int Lp16 = (Lp + 15) & ~15;
                 // V of this pass: its buffer is free once the previous pass's P V has completed
                 if (j > 0) mbar_wait(&bar_o, (j - 1) & 1);
-                mbar_expect_tx(&bar_v, 2 * hrows * 128);
-                for (int c = 0; c < 2; ++c)
+                mbar_expect_tx(&bar_v, n_box * hrows * 128);
+                for (int c = 0; c < n_box; ++c)
                     tma_load_3d(&tmV, &bar_v, smem + SV_OFF + c * hrows * 128, 0, k0 + c * hrows, bh);
                 // ---- S = Q K^T (the softmax warps released the S columns when they published the previous P) ----
                 mbar_wait(&bar_qk, ph);
@@ -146,9 +160,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                 if (j + 1 < n_pass) {
                     // K of the next pass while this pass's softmax runs
                     mbar_wait(&bar_s, ph);
-                    mbar_expect_tx(&bar_qk, 2 * hrows * 128);
-                    for (int c = 0; c < 2; ++c)
-                        tma_load_3d(&tmK, &bar_qk, smem + SK_OFF + c * hrows * 128, 0, k0 + ATTN_MAX_L + c * hrows, bh);
+                    mbar_expect_tx(&bar_qk, n_box * hrows * 128);
+                    for (int c = 0; c < n_box; ++c)
+                        tma_load_3d(&tmK, &bar_qk, smem + SK_OFF + c * hrows * 128, 0, k0 + PASS + c * hrows, bh);
                 }
                 // ---- O (+)= P V ----
                 mbar_wait(&bar_v, ph);
@@ -181,8 +195,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 
         for (int j = 0; j < n_pass; ++j) {
             const uint32_t ph = j & 1;
-            const int k0 = j * ATTN_MAX_L;
-            const int Lp = (L - k0) < ATTN_MAX_L ? (L - k0) : ATTN_MAX_L;
+            const int k0 = j * PASS;
+            const int Lp = (L - k0) < PASS ? (L - k0) : PASS;
             const int nch = (Lp + 31) / 32;
             const int c_lo = part == 0 ? 0 : (nch + 1) / 2;
             const int c_hi = part == 0 ? (nch + 1) / 2 : nch;
@@ -318,7 +332,11 @@ cudaError_t launch_attention3(const CUtensorMap& q, const CUtensorMap& k, const 
 cudaError_t attention_configure() {
     static bool done = false;
     if (done) return cudaSuccess;
-    cudaError_t e = cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(attention_kernel<ATTN_MAX_L>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         AttnCfg<ATTN_MAX_L>::SMEM);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(attention_kernel<ATTN_LONG_PASS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 AttnCfg<ATTN_LONG_PASS>::SMEM);
     if (e == cudaSuccess) e = attention2_configure();
     if (e == cudaSuccess) e = attention3_configure();
     if (e == cudaSuccess) done = true;
@@ -344,7 +362,9 @@ cudaError_t launch_attention(const CUtensorMap& q, const CUtensorMap& k, const C
     if (a.vscale != nullptr && (force_v1() || !attention2_supported(a))) return cudaErrorNotSupported;
     if (!force_v1() && attention2_supported(a)) return launch_attention2(q, k, v, a, a.num_sms, s);
     dim3 grid((a.L + QT - 1) / QT, a.B * a.H);
-    return launch_pdl(attention_kernel, grid, dim3(ATTN_THREADS), ATTN_SMEM, s, q, k, v, a);
+    if (a.L > ATTN_MAX_L)
+        return launch_pdl(attention_kernel<ATTN_LONG_PASS>, grid, dim3(ATTN_THREADS), AttnCfg<ATTN_LONG_PASS>::SMEM, s, q, k, v, a);
+    return launch_pdl(attention_kernel<ATTN_MAX_L>, grid, dim3(ATTN_THREADS), AttnCfg<ATTN_MAX_L>::SMEM, s, q, k, v, a);
 }
 
 }  // namespace usp

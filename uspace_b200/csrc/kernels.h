@@ -78,9 +78,10 @@ struct AttnArgs {
     unsigned long long* trace;   // debugging (env USP_ATTN_TRACE=<file>): per-role event timeline of CTA 0, else nullptr
 };
 constexpr int ATTN_MAX_L = 384;          // keys per pass of attention_kernel (whole rows up to here)
-constexpr int ATTN_LONG_MAX_L = 16384;   // sequence length limit (key passes of ATTN_MAX_L beyond ATTN_MAX_L)
+constexpr int ATTN_LONG_MAX_L = 16384;   // sequence length limit (key passes of ATTN_LONG_PASS beyond ATTN_MAX_L)
+constexpr int ATTN_LONG_PASS = 160;      // keys per pass of the long-sequence kernel (two CTAs per SM)
 // tensor maps: q = [planes, L, 64] with 128-row boxes; k, v = same tensors with attn_kv_box_rows(L)-row boxes
-__host__ __device__ inline int attn_kv_box_rows(int L) { return L > ATTN_MAX_L ? ATTN_MAX_L / 2 : ((L + 15) & ~15) / 2; }
+__host__ __device__ inline int attn_kv_box_rows(int L) { return L > ATTN_MAX_L ? ATTN_LONG_PASS : ((L + 15) & ~15) / 2; }
 cudaError_t launch_attention(const CUtensorMap& q, const CUtensorMap& k, const CUtensorMap& v,
                              const AttnArgs& args, cudaStream_t s);
 
