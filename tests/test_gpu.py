@@ -1046,6 +1046,18 @@ def test_vae_fp16_operand_mode_against_reference_golden(golden_dir):
     with pytest.raises(ValueError):
         from uspace_b200.autoencoder import get_model
         get_model(precision="fp8")
+    # C ABI: an unknown mode is rejected, and switching the mode un-finalises the handle (weights are packed per mode)
+    eng = m.engine()
+    assert eng.lib.usp_vae_set_precision(eng.handle, 7) != 0
+    assert b"precision" in eng.lib.usp_vae_last_error(eng.handle)
+    assert eng.lib.usp_vae_set_precision(eng.handle, 1) == 0
+    out = torch.empty(1, 3, 128, 128, device=dev())
+    assert eng.lib.usp_vae_decode(eng.handle, P(z[:1].contiguous()), P(out), 1, 16, stream()) != 0      # not finalised
+    assert eng.lib.usp_vae_finalize(eng.handle, stream()) == 0
+    assert eng.lib.usp_vae_decode(eng.handle, P(z[:1].contiguous()), P(out), 1, 16, stream()) == 0
+    torch.cuda.synchronize()
+    assert torch.equal(out, vae_model_gpu().decode(z[:1]))
+    _vae.pop("fp16")                                             # that handle now runs the split mode
 
 
 @pytest.mark.parametrize("name", ["vae_small", "vae_full"])
