@@ -45,6 +45,9 @@
 //     leaves the softmax threads 144 registers and spills
 //   one mbarrier arrival per warp (lane 0 behind __syncwarp) instead of per thread .. no change (48.8 vs 48.4 us)
 //   handing the exponential turn over 1-4 chunks before the end of a section ........ no change (49.3-50.2 vs 49.6 us)
+//   a quarter / half of the exponentials on the FMA pipe (Cody-Waite + degree-3 polynomial, 9 instructions each;
+//     parity green) ................................................................... 54.3 -> 57.7 / 64.8 us at L = 257:
+//     the kernel is issue- and latency-bound (45 % issue slots, 35 % MUFU pipe in ncu), not MUFU-bound
 //   THREE tiles in flight (48-key blocks, 3 x 160 TMEM columns, 640 threads, turns in a ring of three) ..... 57.5 us at
 //     L = 256, 60.3 us at L = 257 against 46.8 / 54.0 in the same run: twice the hand-offs per tile cost more than the
 //     third warpgroup's slack buys (and 104 registers per softmax thread spill)
