@@ -66,6 +66,65 @@ __global__ void __launch_bounds__(256) embed_kernel(const EmbedArgs a) {
     }
     __syncthreads();
 
+    if (!EXTRA && P == 16 && (D & 3) == 0) {
+        // every reference config (patch 2, 4 channels): four consecutive output channels per thread - 128-bit position
+        // loads and stores, the four W rows in registers, one set of broadcast feature reads for four outputs.  The
+        // arithmetic per output (fma chain over f = 0..15, + bias, + pos) is the scalar path's, so the bits are too.
+        for (int d0 = threadIdx.x * 4; d0 < D; d0 += blockDim.x * 4) {
+            float wr[4][16];
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float4 w4 = __ldg(reinterpret_cast<const float4*>(a.w + static_cast<long long>(d0 + k) * 16) + q);
+                    wr[k][4 * q] = w4.x; wr[k][4 * q + 1] = w4.y; wr[k][4 * q + 2] = w4.z; wr[k][4 * q + 3] = w4.w;
+                }
+            const float4 bias4 = *reinterpret_cast<const float4*>(a.bias + d0);
+#pragma unroll 4
+            for (int i = 0; i < EMB_TOK; ++i) {
+                const int l = l0 + i;
+                if (l >= l1) break;
+                const float4 pos4 = __ldg(reinterpret_cast<const float4*>(a.pos + static_cast<long long>(l) * D + d0));
+                float v[4];
+                if (l >= first_patch) {
+                    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float4 f4 = *reinterpret_cast<const float4*>(&feat[i][4 * q]);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            acc[k] = fmaf(wr[k][4 * q], f4.x, acc[k]);
+                            acc[k] = fmaf(wr[k][4 * q + 1], f4.y, acc[k]);
+                            acc[k] = fmaf(wr[k][4 * q + 2], f4.z, acc[k]);
+                            acc[k] = fmaf(wr[k][4 * q + 3], f4.w, acc[k]);
+                        }
+                    }
+                    v[0] = acc[0] + bias4.x; v[1] = acc[1] + bias4.y; v[2] = acc[2] + bias4.z; v[3] = acc[3] + bias4.w;
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int d = d0 + k;
+                        if (a.has_label && l == 0) {
+                            v[k] = a.label[a.y[b] * D + d];
+                        } else if (l == t_tok && a.ttok != nullptr) {
+                            v[k] = a.ttok[static_cast<long long>(a.st ? 0 : b) * D + d];
+                        } else if (l == t_tok) {
+                            const float t = a.st ? a.st->t : a.tvec[b];
+                            const int half = D / 2;
+                            v[k] = 0.f;
+                            if (d < half) v[k] = cosf(t * a.freqs[d]);
+                            else if (d < 2 * half) v[k] = sinf(t * a.freqs[d - half]);
+                        } else {
+                            v[k] = a.ctxemb[(static_cast<long long>(b) * a.n_ctx + (l - t_tok - 1)) * D + d];
+                        }
+                    }
+                }
+                *reinterpret_cast<float4*>(a.out32 + (static_cast<long long>(b) * a.L + l) * D + d0) =
+                    make_float4(v[0] + pos4.x, v[1] + pos4.y, v[2] + pos4.z, v[3] + pos4.w);
+            }
+        }
+        return;
+    }
     float st1[EMB_TOK], st2[EMB_TOK];   // this thread's partial row statistics (folded-LayerNorm path)
 #pragma unroll
     for (int i = 0; i < EMB_TOK; ++i) st1[i] = st2[i] = 0.f;
@@ -202,53 +261,67 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
 // head: final LayerNorm + decoder_pred Linear(D -> P) on the patch tokens only (libs/uvit.py:342-345), fp32 SIMT
 // (P = 16: 0.03 % of the FLOPs, kept exact).  One warp per patch token.
 // ------------------------------------------------------------------------------------------------
+constexpr int HEAD_TOK = 2;   // patch tokens per warp: every decoder_pred weight vector read feeds both (the 64 KB of
+                              // weights per token, re-read from L1 for each of 16 k tokens, bound the kernel)
 template <int V4>
 __global__ void __launch_bounds__(256) head_kernel(const HeadArgs a) {
     constexpr int D = 128 * V4;
     pdl_wait();
     pdl_launch();
     const int n_patch = a.L - a.extras;
-    const int tok = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int n_tok = a.B * n_patch;
+    const int tok0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * HEAD_TOK;
     const int lane = threadIdx.x & 31;
-    if (tok >= a.B * n_patch) return;
-    const int b = tok / n_patch, pi = tok % n_patch;
-    const float4* xr =
-        reinterpret_cast<const float4*>(a.x32 + (static_cast<long long>(b) * a.L + a.extras + pi) * D);
-    float4 v[V4];
-    float s = 0.f;
+    if (tok0 >= n_tok) return;
+    float4 v[HEAD_TOK][V4];
 #pragma unroll
-    for (int i = 0; i < V4; ++i) {
-        v[i] = xr[i * 32 + lane];
-        s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
-    }
-    const float mean = warp_sum(s) * (1.0f / D);
-    float q = 0.f;
+    for (int t = 0; t < HEAD_TOK; ++t) {
+        const int tok = tok0 + t < n_tok ? tok0 + t : n_tok - 1;   // a trailing odd token is computed twice, stored once
+        const int b = tok / n_patch, pi = tok % n_patch;
+        const float4* xr =
+            reinterpret_cast<const float4*>(a.x32 + (static_cast<long long>(b) * a.L + a.extras + pi) * D);
+        float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < V4; ++i) {
-        const float a0 = v[i].x - mean, a1 = v[i].y - mean, a2 = v[i].z - mean, a3 = v[i].w - mean;
-        q += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
-    }
-    const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + 1e-5f);
+        for (int i = 0; i < V4; ++i) {
+            v[t][i] = xr[i * 32 + lane];
+            s += (v[t][i].x + v[t][i].y) + (v[t][i].z + v[t][i].w);
+        }
+        const float mean = warp_sum(s) * (1.0f / D);
+        float q = 0.f;
 #pragma unroll
-    for (int i = 0; i < V4; ++i) {
-        const float4 gg = __ldg(reinterpret_cast<const float4*>(a.ng) + i * 32 + lane);
-        const float4 bb = __ldg(reinterpret_cast<const float4*>(a.nb) + i * 32 + lane);
-        v[i].x = (v[i].x - mean) * rstd * gg.x + bb.x;
-        v[i].y = (v[i].y - mean) * rstd * gg.y + bb.y;
-        v[i].z = (v[i].z - mean) * rstd * gg.z + bb.z;
-        v[i].w = (v[i].w - mean) * rstd * gg.w + bb.w;
+        for (int i = 0; i < V4; ++i) {
+            const float a0 = v[t][i].x - mean, a1 = v[t][i].y - mean, a2 = v[t][i].z - mean, a3 = v[t][i].w - mean;
+            q += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
+        }
+        const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + 1e-5f);
+#pragma unroll
+        for (int i = 0; i < V4; ++i) {
+            const float4 gg = __ldg(reinterpret_cast<const float4*>(a.ng) + i * 32 + lane);
+            const float4 bb = __ldg(reinterpret_cast<const float4*>(a.nb) + i * 32 + lane);
+            v[t][i].x = (v[t][i].x - mean) * rstd * gg.x + bb.x;
+            v[t][i].y = (v[t][i].y - mean) * rstd * gg.y + bb.y;
+            v[t][i].z = (v[t][i].z - mean) * rstd * gg.z + bb.z;
+            v[t][i].w = (v[t][i].w - mean) * rstd * gg.w + bb.w;
+        }
     }
-    float* o = a.pf + static_cast<long long>(tok) * a.P;
     for (int j = 0; j < a.P; ++j) {
         const float4* wr = reinterpret_cast<const float4*>(a.w + static_cast<long long>(j) * D);
-        float acc = 0.f;
+        float acc[HEAD_TOK];
+#pragma unroll
+        for (int t = 0; t < HEAD_TOK; ++t) acc[t] = 0.f;
 #pragma unroll
         for (int i = 0; i < V4; ++i) {
             const float4 w4 = __ldg(wr + i * 32 + lane);
-            acc += (v[i].x * w4.x + v[i].y * w4.y) + (v[i].z * w4.z + v[i].w * w4.w);
+#pragma unroll
+            for (int t = 0; t < HEAD_TOK; ++t)
+                acc[t] += (v[t][i].x * w4.x + v[t][i].y * w4.y) + (v[t][i].z * w4.z + v[t][i].w * w4.w);
         }
-        acc = warp_sum(acc);
-        if (lane == 0) o[j] = acc + a.bias[j];
+        const float bj = a.bias[j];
+#pragma unroll
+        for (int t = 0; t < HEAD_TOK; ++t) {
+            const float r = warp_sum(acc[t]);
+            if (lane == 0 && tok0 + t < n_tok) a.pf[static_cast<long long>(tok0 + t) * a.P + j] = r + bj;
+        }
     }
 }
 
@@ -496,7 +569,7 @@ cudaError_t launch_layernorm(const float* x, const float* g, const float* b, voi
 
 cudaError_t launch_head(const HeadArgs& a, cudaStream_t s) {
     const int n_tok = a.B * (a.L - a.extras);
-    const int grid = (n_tok + 7) / 8;
+    const int grid = (n_tok + 8 * HEAD_TOK - 1) / (8 * HEAD_TOK);
     switch (a.D) {
         case 256: return launch_pdl(head_kernel<2>, dim3(grid), dim3(256), 0, s, a);
         case 384: return launch_pdl(head_kernel<3>, dim3(grid), dim3(256), 0, s, a);
