@@ -184,6 +184,10 @@ int usp_vae_set_weight(usp_vae* h, const char* name, const void* data, const int
 #define USP_VAE_PRECISION_FP16X3 1
 int usp_vae_set_precision(usp_vae* h, int mode);
 int usp_vae_finalize(usp_vae* h, void* stream);      /* packs the convolution weights; synchronises */
+/* The activation workspace is sized by the first decode / encode (chunks of <= 16 images) and kept between calls:
+ * its current size, and a way to hand it back (synchronises the device; the next call allocates again). */
+size_t usp_vae_workspace_bytes(const usp_vae* h);
+int usp_vae_release_workspace(usp_vae* h);
 int usp_vae_decode(usp_vae* h, const float* z, float* out, int B, int S, void* stream);
 /* Replaces FrozenAutoencoderKL.encode_moments (libs/autoencoder.py:426-429: Encoder.forward :275-300 + quant_conv):
  *   x [B, 3, R, R] images in [-1, 1] (R in {128, 256, 384, 512})  ->  moments [B, 8, R/8, R/8] = (mean, logvar);

@@ -1119,6 +1119,12 @@ def test_vae_round_trip_and_chunked_decode():
     z = 0.18215 * mo[:, :4]
     img = m.decode(z)
     assert torch.equal(decode_large_batch(m, z, chunk=3), img)
+    # the workspace is kept between calls, can be handed back, and comes back on demand
+    eng = m.engine()
+    assert eng.workspace_bytes() > 0
+    eng.release_workspace()
+    assert eng.workspace_bytes() == 0
+    assert torch.equal(m.decode(z[:2]), img[:2]) and eng.workspace_bytes() > 0
     with pytest.raises(ValueError):
         m.encode_moments(torch.zeros(1, 3, 100, 100, device=dev()))
 

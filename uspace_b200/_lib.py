@@ -74,6 +74,8 @@ _SIGNATURES = {
     "usp_vae_set_weight": (_i, [_vp, C.c_char_p, _vp, C.POINTER(_i64), _i]),
     "usp_vae_set_precision": (_i, [_vp, _i]),
     "usp_vae_finalize": (_i, [_vp, _vp]),
+    "usp_vae_workspace_bytes": (C.c_size_t, [_vp]),
+    "usp_vae_release_workspace": (_i, [_vp]),
     "usp_vae_decode": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
     "usp_vae_encode_moments": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
     "usp_op_convert16": (_i, [_vp, _vp, _i64, _i, _vp]),

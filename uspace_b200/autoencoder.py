@@ -293,6 +293,13 @@ class VaeEngine:
                                            self._stream()), self.handle, "usp_vae_decode", vae=True)
         return out
 
+    def workspace_bytes(self):
+        return int(self.lib.usp_vae_workspace_bytes(self.handle))
+
+    def release_workspace(self):
+        """Hand the activation slab back to the driver (synchronises); the next decode / encode allocates it again."""
+        _lib.check(self.lib.usp_vae_release_workspace(self.handle), self.handle, "usp_vae_release_workspace", vae=True)
+
     def close(self):
         if getattr(self, "handle", None):
             self.lib.usp_vae_destroy(self.handle)

@@ -386,6 +386,7 @@ struct usp_vae {
     std::string err;
     // workspace for (chunk batch, latent side)
     int ws_B = 0, ws_S = 0;
+    size_t ws_bytes = 0;
     void* slab = nullptr;
     float *f0 = nullptr, *f1 = nullptr, *f2 = nullptr;   // fp32 NHWC activations: x, y ping-pong, nin_shortcut result
     float *f3 = nullptr;                                  // split mode: conv1 result (GroupNorm reads fp32 there)
@@ -616,6 +617,7 @@ int ensure_workspace(usp_vae* h, int B, int S) {
     const size_t o_v32 = carve(split ? B * T * C * 4 : 0), o_vt32 = carve(split ? T * C * 4 : 0);
     const size_t o_gp = carve(static_cast<size_t>(B) * 64 * 32 * sizeof(double2));
     VTRY(h, cudaMalloc(&h->slab, off));
+    h->ws_bytes = off;
     char* base = static_cast<char*>(h->slab);
     h->f0 = reinterpret_cast<float*>(base + o_f0); h->f1 = reinterpret_cast<float*>(base + o_f1);
     h->f2 = reinterpret_cast<float*>(base + o_f2);
@@ -863,6 +865,20 @@ int usp_vae_set_weight(usp_vae* h, const char* name, const void* data, const int
     h->finalized = false;
     return USP_OK;
 }
+
+// The activation slab (about 0.47 GB per image of the chunk in the split mode at 256^2) stays allocated between calls;
+// a caller that alternates the decoder with a memory-hungry phase can hand it back.  The next call re-allocates.
+int usp_vae_release_workspace(usp_vae* h) {
+    if (!h) return USP_ERR_INVALID;
+    VTRY(h, cudaSetDevice(h->device));
+    VTRY(h, cudaDeviceSynchronize());        // a decode enqueued on any stream may still be using it
+    if (h->slab) VTRY(h, cudaFree(h->slab));
+    h->slab = nullptr;
+    h->ws_B = 0;
+    h->ws_bytes = 0;
+    return USP_OK;
+}
+size_t usp_vae_workspace_bytes(const usp_vae* h) { return h ? h->ws_bytes : 0; }
 
 int usp_vae_set_precision(usp_vae* h, int mode) {
     if (!h) return USP_ERR_INVALID;
