@@ -74,7 +74,6 @@ constexpr int QTILE_BYTES = QT * HD * 2;   // 16 KiB
 constexpr int NQ = 3;                   // Q tile buffers
 constexpr int KBMAX = 96;               // keys per score block = fp32 score registers per softmax thread
 constexpr int KSTEP = KBMAX / 2;        // window offset step between consecutive blocks
-constexpr int NCH = KBMAX / 16;
 constexpr int MAX_L3 = 336;
 constexpr int TMEM_COLS = 512;
 constexpr int SLOT_COLS = 256;
@@ -577,7 +576,6 @@ attention3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         const int row = lg * 32 + lane;
         const uint32_t t_slot = tmem_base + (static_cast<uint32_t>(lg * 32) << 16) + s * SLOT_COLS;
         const uint32_t t_o = t_slot + O_OFF;
-        const float c2 = 0.125f * 1.44269504088896340736f;  // hd^-0.5 * log2(e)
         int ks = 0;       // score blocks consumed by this slot
         int jt = 0;       // tiles finished by this slot
         // Ping-pong: the exponential sections of the two warpgroups strictly alternate (named barriers 4 / 5, FA3
