@@ -122,7 +122,7 @@ def build(cfg, opd, t2i=False):
     torch.manual_seed(0)
     m = (UViTT2I if t2i else UViT)(**cfg).eval()
     m.operand_dtype = opd
-    m.fuse_layernorm = os.environ.get("USP_FUSE", "0") == "1"
+    m.fuse_layernorm = os.environ.get("USP_FUSE", "1") == "1"    # the default: LayerNorm folded into the GEMMs
     return m
 
 

@@ -230,20 +230,26 @@ def test_forward_matches_reference_golden(golden_dir, name, opd):
 
 
 @pytest.mark.parametrize("name", ["small16_uncond", "tiny_class", "tiny_t2i", "large_uncond"])
-def test_forward_with_layernorm_folded_into_gemms(golden_dir, name):
-    """usp_config.fuse_layernorm: norm1 / norm2 applied algebraically in the qkv / fc1 epilogues."""
+def test_forward_with_stand_alone_layernorm_kernels(golden_dir, name):
+    """usp_config.fuse_layernorm = 0: norm1 / norm2 as LayerNorm launches of their own instead of the default fold
+    into the qkv / fc1 GEMMs (gamma in the weights, rstd and the folded bias in the epilogue)."""
     case = CASES[name]
     m = build_model(case, UViT, UViTT2I)
-    m.fuse_layernorm = True
+    assert m.fuse_layernorm is True
+    m.fuse_layernorm = False
     m = m.to(dev())
     x, t, y, ctx = build_inputs(case)
     with torch.no_grad():
         if case["t2i"]:
             out = m(x.to(dev()), t.to(dev()), context=ctx.to(dev()))[0]
+            ref = model(name)(x.to(dev()), t.to(dev()), context=ctx.to(dev()))[0]
         else:
             out = m(x.to(dev()), t.to(dev()), y if y is None else y.to(dev()))[0]
-    assert m.engine().kernels_per_forward() < model(name).engine().kernels_per_forward()  # no LayerNorm launches
-    assert rel(out, golden(golden_dir, name)["forward"]) < 1e-3
+            ref = model(name)(x.to(dev()), t.to(dev()), y if y is None else y.to(dev()))[0]
+    assert m.engine().kernels_per_forward() > model(name).engine().kernels_per_forward()  # the LayerNorm launches
+    want = golden(golden_dir, name)["forward"]
+    assert rel(out, want) < 1e-3 and rel(ref, want) < 1e-3
+    assert not torch.equal(out, ref)                       # two different computations of the same function
 
 
 def test_forward_meets_1e3_on_north_star_model(golden_dir):

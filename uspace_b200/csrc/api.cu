@@ -197,6 +197,8 @@ struct usp_handle {
     float* freqs = nullptr;
     bool finalized = false;
     bool fuse_ln = false;   // cfg.fuse_layernorm and every GEMM shape is served by the pair kernel
+    bool ln_centre = true;  // folded weights with their row mean removed: the epilogue needs rstd and d only
+                            // (USP_LN_CENTRE=0: keep the mean term, A/B comparison)
     std::map<int, std::unique_ptr<Plan>> plans;
     cudaStream_t cap_stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -548,7 +550,7 @@ int enqueue_forward(usp_handle* h, Plan* p, const FwdIO& io, cudaStream_t s) {
         if (fuse) {
             // norm1 folded into the qkv GEMM: A = un-normalised 16-bit x, epilogue applies rstd / mean / beta
             LnUse ln;
-            ln.stats = p->stats; ln.np = cur_np; ln.c = bw.qkv_c; ln.d = bw.qkv_d;
+            ln.stats = p->stats; ln.np = cur_np; ln.c = h->ln_centre ? nullptr : bw.qkv_c; ln.d = bw.qkv_d;
             prof_mark(h, 2, s);
             rc = run_gemm(h, EPI_QKV, *cur16, nullptr, h->w[bw.qkvw], nullptr, nullptr, nullptr, p->qkv16, M, 3 * D, D,
                           D, s, &ln);
@@ -578,7 +580,7 @@ int enqueue_forward(usp_handle* h, Plan* p, const FwdIO& io, cudaStream_t s) {
         if (rc) return rc;
         if (fuse) {
             LnUse ln;
-            ln.stats = p->stats; ln.np = gemm_np; ln.c = bw.fc1_c; ln.d = bw.fc1_d;
+            ln.stats = p->stats; ln.np = gemm_np; ln.c = h->ln_centre ? nullptr : bw.fc1_c; ln.d = bw.fc1_d;
             prof_mark(h, 5, s);
             rc = run_gemm(h, EPI_BIAS_GELU, p->m_xp, nullptr, h->w[bw.fc1w], nullptr, nullptr, nullptr, p->m16, M, Hd,
                           D, D, s, &ln);
@@ -727,6 +729,10 @@ int usp_create(const usp_config* cfg, int device, usp_handle** out) {
     h->n_in = c.depth / 2;
     h->n_blocks = 2 * h->n_in + 1;
     h->fuse_ln = c.fuse_layernorm != 0 && h->D % 256 == 0 && h->Hd % 256 == 0;
+    {
+        const char* e = getenv("USP_LN_CENTRE");
+        h->ln_centre = !(e && e[0] == '0');
+    }
     if (h->L > ATTN_LONG_MAX_L) return fail(nullptr, USP_ERR_UNSUPPORTED, "sequence length above 16384 tokens is not built");
 
     const int64_t D = h->D;
@@ -856,9 +862,10 @@ int usp_finalize_weights(usp_handle* h, void* stream) {
             }
             CUDA_TRY(h, launch_fold_ln(h->w[b.qkvw].d32, h->w[b.n1w].d32, h->w[b.n1b].d32,
                                        b.qkvb >= 0 ? h->w[b.qkvb].d32 : nullptr, h->w[b.qkvw].d16, b.qkv_c, b.qkv_d,
-                                       3 * D, D, h->cfg.operand_dtype, s));
+                                       3 * D, D, h->cfg.operand_dtype, s, h->ln_centre ? 1 : 0));
             CUDA_TRY(h, launch_fold_ln(h->w[b.fc1w].d32, h->w[b.n2w].d32, h->w[b.n2b].d32, h->w[b.fc1b].d32,
-                                       h->w[b.fc1w].d16, b.fc1_c, b.fc1_d, Hd, D, h->cfg.operand_dtype, s));
+                                       h->w[b.fc1w].d16, b.fc1_c, b.fc1_d, Hd, D, h->cfg.operand_dtype, s,
+                                       h->ln_centre ? 1 : 0));
         }
     }
     for (auto& w : h->w) {

@@ -66,7 +66,11 @@ __global__ void __launch_bounds__(256) embed_kernel(const EmbedArgs a) {
     }
     __syncthreads();
 
-    if (!EXTRA && P == 16 && (D & 3) == 0) {
+    float st1[EMB_TOK], st2[EMB_TOK];   // this thread's partial row statistics (folded-LayerNorm path)
+#pragma unroll
+    for (int i = 0; i < EMB_TOK; ++i) st1[i] = st2[i] = 0.f;
+    const bool fast = P == 16 && (D & 3) == 0;
+    if (fast) {
         // every reference config (patch 2, 4 channels): four consecutive output channels per thread - 128-bit position
         // loads and stores, the four W rows in registers, one set of broadcast feature reads for four outputs.  The
         // arithmetic per output (fma chain over f = 0..15, + bias, + pos) is the scalar path's, so the bits are too.
@@ -119,16 +123,23 @@ __global__ void __launch_bounds__(256) embed_kernel(const EmbedArgs a) {
                         }
                     }
                 }
-                *reinterpret_cast<float4*>(a.out32 + (static_cast<long long>(b) * a.L + l) * D + d0) =
-                    make_float4(v[0] + pos4.x, v[1] + pos4.y, v[2] + pos4.z, v[3] + pos4.w);
+                const float4 o4 = make_float4(v[0] + pos4.x, v[1] + pos4.y, v[2] + pos4.z, v[3] + pos4.w);
+                *reinterpret_cast<float4*>(a.out32 + (static_cast<long long>(b) * a.L + l) * D + d0) = o4;
+                if (EXTRA && a.out16 != nullptr) {
+                    uint2 u;
+                    u.x = a.opd == OPD_FP16 ? Op16<OPD_FP16>::pack(o4.x, o4.y) : Op16<OPD_BF16>::pack(o4.x, o4.y);
+                    u.y = a.opd == OPD_FP16 ? Op16<OPD_FP16>::pack(o4.z, o4.w) : Op16<OPD_BF16>::pack(o4.z, o4.w);
+                    *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(a.out16) +
+                                              (static_cast<long long>(b) * a.L + l) * D + d0) = u;
+                }
+                if (EXTRA) {
+                    st1[i] += (o4.x + o4.y) + (o4.z + o4.w);
+                    st2[i] += (o4.x * o4.x + o4.y * o4.y) + (o4.z * o4.z + o4.w * o4.w);
+                }
             }
         }
-        return;
     }
-    float st1[EMB_TOK], st2[EMB_TOK];   // this thread's partial row statistics (folded-LayerNorm path)
-#pragma unroll
-    for (int i = 0; i < EMB_TOK; ++i) st1[i] = st2[i] = 0.f;
-    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    for (int d = threadIdx.x; !fast && d < D; d += blockDim.x) {
         const float* wrow = a.w + static_cast<long long>(d) * P;
         const float bias = a.bias[d];
         // P == 16 (patch 2, 4 channels: every reference config): keep this row of W in registers, read once as
@@ -401,16 +412,30 @@ __global__ void convert16_kernel(const float* __restrict__ in, uint16_t* __restr
         out[i] = opd == OPD_FP16 ? Op16<OPD_FP16>::one(in[i]) : Op16<OPD_BF16>::one(in[i]);
 }
 
-// one block per output row n of W[N,K]
+// one block per output row n of W[N,K]: W'[n,k] = W[n,k] gamma[k], optionally CENTRED (its row mean removed, so that
+// sum_k x[k] W'[n,k] no longer contains the row mean of x and the epilogue needs rstd and d only), rounded to 16 bits;
+// c[n] = sum_k of the rounded row (what the mean multiplies: ~0 when centred), d[n] = sum_k beta[k] W[n,k] + bias[n]
 __global__ void __launch_bounds__(256) fold_ln_kernel(const float* __restrict__ W, const float* __restrict__ gamma,
                                                       const float* __restrict__ beta, const float* __restrict__ bias,
                                                       uint16_t* __restrict__ w16, float* __restrict__ c,
-                                                      float* __restrict__ d, int K, int opd) {
+                                                      float* __restrict__ d, int K, int opd, int centre) {
     const int n = blockIdx.x;
+    __shared__ float sc[8], sd[8], sm[8];
+    float wmean = 0.f;
+    if (centre) {
+        float ms = 0.f;
+        for (int k = threadIdx.x; k < K; k += blockDim.x) ms += W[static_cast<long long>(n) * K + k] * gamma[k];
+        ms = warp_sum(ms);
+        if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = ms;
+        __syncthreads();
+        float a = 0.f;
+        for (int i = 0; i < 8; ++i) a += sm[i];
+        wmean = a / static_cast<float>(K);
+    }
     float cs = 0.f, ds = 0.f;
     for (int k = threadIdx.x; k < K; k += blockDim.x) {
         const float w = W[static_cast<long long>(n) * K + k];
-        const float wg = w * gamma[k];
+        const float wg = w * gamma[k] - wmean;
         float wr;
         uint16_t h;
         if (opd == OPD_FP16) {
@@ -424,7 +449,6 @@ __global__ void __launch_bounds__(256) fold_ln_kernel(const float* __restrict__ 
         cs += wr;
         ds = fmaf(beta[k], w, ds);
     }
-    __shared__ float sc[8], sd[8];
     cs = warp_sum(cs);
     ds = warp_sum(ds);
     if ((threadIdx.x & 31) == 0) {
@@ -596,8 +620,8 @@ cudaError_t launch_convert16(const float* in, void* out16, long long n, int opd,
 }
 
 cudaError_t launch_fold_ln(const float* W, const float* gamma, const float* beta, const float* bias, void* w16,
-                           float* c, float* d, int N, int K, int opd, cudaStream_t s) {
-    fold_ln_kernel<<<N, 256, 0, s>>>(W, gamma, beta, bias, reinterpret_cast<uint16_t*>(w16), c, d, K, opd);
+                           float* c, float* d, int N, int K, int opd, cudaStream_t s, int centre) {
+    fold_ln_kernel<<<N, 256, 0, s>>>(W, gamma, beta, bias, reinterpret_cast<uint16_t*>(w16), c, d, K, opd, centre);
     return cudaGetLastError();
 }
 

@@ -82,7 +82,17 @@ __device__ __forceinline__ void epi_math(const GemmArgs& g, EpiRow& row, int n, 
                                          const float4* resid, float* v) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-    if (g.ln_stats != nullptr) {
+    if (g.ln_stats != nullptr && g.ln_c == nullptr) {
+        // centred folded weights (zero row sums): the mean term is gone, rstd and the folded bias remain
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+            const float4 d4 = __ldg(reinterpret_cast<const float4*>(g.ln_d + n + j));
+            v[j] = fmaf(row.rstd, v[j], d4.x);
+            v[j + 1] = fmaf(row.rstd, v[j + 1], d4.y);
+            v[j + 2] = fmaf(row.rstd, v[j + 2], d4.z);
+            v[j + 3] = fmaf(row.rstd, v[j + 3], d4.w);
+        }
+    } else if (g.ln_stats != nullptr) {
         const float nm = -row.mean;
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {

@@ -179,7 +179,7 @@ cudaError_t launch_convert16(const float* in, void* out16, long long n, int opd,
 // Fold a LayerNorm into the Linear that consumes it: w16[n,k] = round16(W[n,k] * gamma[k]),
 // c[n] = sum_k w16[n,k], d[n] = sum_k beta[k] * W[n,k] (+ bias[n])
 cudaError_t launch_fold_ln(const float* W, const float* gamma, const float* beta, const float* bias, void* w16,
-                           float* c, float* d, int N, int K, int opd, cudaStream_t s);
+                           float* c, float* d, int N, int K, int opd, cudaStream_t s, int centre = 0);
 // stage 0: start interval `next` (t = grid[next]) and advance; stage 1: a stage at the interval's end (t = grid[cur+1]);
 // stage 2: a stage inside the interval, t = grid[cur] + frac * dt - no grid row, so no write edit; the attention edit
 // follows its "%.2f" rule against st->attn_t_edit

@@ -14,7 +14,7 @@ def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
-def config_from_kwargs(kw: dict, operand_dtype: str = "fp16", fuse_layernorm: bool = False) -> _lib.UspConfig:
+def config_from_kwargs(kw: dict, operand_dtype: str = "fp16", fuse_layernorm: bool = True) -> _lib.UspConfig:
     """Map the reference ctor kwargs (libs/uvit.py:183-202, libs/uvit_t2i.py:193-211) to usp_config."""
     t2i = "clip_dim" in kw or "num_clip_token" in kw
     c = _lib.UspConfig()
@@ -39,7 +39,7 @@ def config_from_kwargs(kw: dict, operand_dtype: str = "fp16", fuse_layernorm: bo
 
 class Engine:
     def __init__(self, ctor_kwargs: dict, device: torch.device, operand_dtype: str = "fp16",
-                 fuse_layernorm: bool = False):
+                 fuse_layernorm: bool = True):
         if device.type != "cuda":
             raise RuntimeError("uspace_b200 runs on CUDA (sm_100a) only; there is no CPU path")
         self.lib = _lib.load()
