@@ -202,7 +202,10 @@ int usp_sample_host(usp_handle* h, float* z_host, const float* context_host, con
 /* fp16 tensor-core operands saturate at 65504: a checkpoint whose activations exceed that yields inf / NaN velocities.
  * Every velocity evaluation checks its output on the device; this reads and clears the sticky flag (*flag = 1 if any
  * evaluation since the last read was non-finite). SYNCHRONISES `stream`. usp_sample_host checks it itself and returns
- * USP_ERR_NONFINITE; bf16 operands (usp_config.operand_dtype = 0) have the fp32 exponent range. */
+ * USP_ERR_NONFINITE; bf16 operands (usp_config.operand_dtype = 0) have the fp32 exponent range.
+ * *flag is a bit set: 1 = a non-finite velocity; 2 = (fuse_layernorm) a token whose mean exceeded 4 standard deviations
+ * reached a folded LayerNorm - its 16-bit un-normalised operand loses log2(|mean| / std) bits there, use
+ * fuse_layernorm = 0 for such a checkpoint. */
 int usp_nonfinite(usp_handle* h, int* flag, void* stream);
 /* Number of grid points torchdiffeq builds for (t0, t1, step_size): ceil(|t1-t0|/step + 1). */
 int usp_grid_size(float t0, float t1, float step_size);

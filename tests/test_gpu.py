@@ -520,6 +520,37 @@ def test_fp16_operand_range_scaled_weights():
     assert torch.isfinite(gotb).all() and rel(gotb, want) < 1.2e-2
 
 
+def test_folded_layernorm_flags_tokens_far_from_zero_mean():
+    """The default fold feeds the GEMMs fp16(x) instead of fp16(LN(x)): harmless while a token's mean is of the order of
+    its standard deviation (every golden), lossy when the whole token is shifted.  A residual stream pushed to
+    mean = 40 std must raise the library's flag (CNF.decode turns it into an exception); the stand-alone LayerNorm
+    kernels (fuse_layernorm = False) stay within tolerance on the same weights and raise nothing."""
+    case = CASES["tiny_uncond"]
+    sd = {k: v.clone() for k, v in build_model(case, UViT, UViTT2I).state_dict().items()}
+    sd["pos_embed"] = sd["pos_embed"] + 40.0
+    x, t, _, _ = build_inputs(case)
+    want = O.uvit_forward(sd, case["cfg"], x, t)
+    fold = UViT(**case["cfg"]).eval()
+    fold.load_state_dict(sd)
+    fold = fold.to(dev())
+    with torch.no_grad():
+        got_fold = fold(x.to(dev()), t.to(dev()))[0]
+    assert fold.engine().status_flags() & 2
+    kw = dict(dissect_name="none", solver_kwargs=dict(solver="fixed", solver_fix="euler", solver_fix_step=0.5))
+    with pytest.raises(FloatingPointError, match="fuse_layernorm"):
+        CNF(fold).decode(x.to(dev()), y=None, **kw)
+    plain = UViT(**case["cfg"]).eval()
+    plain.fuse_layernorm = False
+    plain.load_state_dict(sd)
+    plain = plain.to(dev())
+    with torch.no_grad():
+        got_plain = plain(x.to(dev()), t.to(dev()))[0]
+    assert plain.engine().status_flags() == 0
+    assert rel(got_plain, want) < 1e-3
+    assert rel(got_fold, want) > rel(got_plain, want)        # the loss the flag announces is real
+    assert model("tiny_uncond").engine().status_flags() == 0  # and ordinary weights never raise it
+
+
 def test_encode_decode_round_trip_full_size_model():
     """Size-independent property at the north-star model: decode(encode(x)) returns to x up to O(h) Euler error,
     and the error shrinks with the step (flow_matching.py vis_reversible idea, dissect_lfm.py:171-195)."""

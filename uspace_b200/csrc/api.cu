@@ -468,6 +468,7 @@ int run_gemm(usp_handle* h, int epi, const CUtensorMap& a0, const CUtensorMap* a
     if (ln) {
         g.ln_stats = ln->stats; g.ln_np = ln->np; g.ln_c = ln->c; g.ln_d = ln->d;
         g.ln_inv_d = 1.0f / static_cast<float>(h->D);
+        g.ln_flag = ln->stats != nullptr ? h->nonfinite : nullptr;
         g.stats_out = ln->stats_out;
     }
     cudaError_t e = launch_gemm(epi, maps, g, h->num_sms, s);
@@ -1487,10 +1488,14 @@ int usp_sample_host(usp_handle* h, float* z_host, const float* context_host, con
     int flag = 0;
     rc = usp_nonfinite(h, &flag, s);   // synchronises
     if (rc) return rc;
-    if (flag)
+    if (flag & 1)
         return fail(h, USP_ERR_NONFINITE,
                     "a velocity evaluation produced inf / NaN (activations beyond the fp16 operand range?): "
                     "use operand_dtype bf16 for this checkpoint");
+    if (flag & 2)
+        return fail(h, USP_ERR_NONFINITE,
+                    "folded LayerNorm: a token's mean exceeded 4 standard deviations, the 16-bit operand loses precision "
+                    "there: create the handle with fuse_layernorm = 0 for this checkpoint");
     return USP_OK;
 }
 

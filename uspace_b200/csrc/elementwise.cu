@@ -378,7 +378,7 @@ __global__ void __launch_bounds__(256) final_kernel(const FinalArgs a) {
     }
     // an MLP hidden activation beyond the fp16 operand range turns into inf and reaches every output of its sample
     // as NaN (fc2 -> LayerNorm -> attention): one check here sees any overflow of the whole evaluation
-    if (a.nonfinite != nullptr && !isfinite(v)) *a.nonfinite = 1;
+    if (a.nonfinite != nullptr && !isfinite(v)) atomicOr(a.nonfinite, 1);
     const int chw = static_cast<int>(i % (static_cast<long long>(C) * S * S));
     const int didx = a.st ? a.st->didx : 0;   // plain forward with a hook (usp_forward_hook): row 0
     if (a.delta != nullptr) {

@@ -58,6 +58,7 @@ __device__ __forceinline__ EpiRow epi_row(const GemmArgs& g, int epi, int m) {
         r.mean = a * g.ln_inv_d;
         const float var = fmaxf(b * g.ln_inv_d - r.mean * r.mean, 0.f);
         r.rstd = rsqrtf(var + 1e-5f);
+        if (g.ln_flag != nullptr && r.mean * r.mean > 16.f * (var + 1e-5f)) atomicOr(g.ln_flag, 2);
     }
     if (epi == EPI_QKV) {
         const int b = m / g.L;

@@ -39,6 +39,8 @@ struct GemmArgs {
     const float* ln_d;     // [N]
     int ln_np;             // partials per row
     float ln_inv_d;        // 1 / embed_dim
+    int* ln_flag;          // status word (usp_nonfinite): bit 2 is raised when a row's |mean| exceeds 4 standard deviations,
+                           // i.e. the 16-bit rounding of the un-normalised operand starts to cost precision
     // ---- implicit GEMM for 3x3 / stride 1 / pad 1 convolutions (csrc/vae.cu) ----
     // conv_C > 0: A is the fp16 NHWC activation [*, conv_H, conv_W, conv_C] behind an im2col tensor map (GemmMaps::a0);
     // row m = output pixel, K block kb = channels [(kb % (C/64)) * 64, +64) of filter tap kb / (C/64)

@@ -275,9 +275,14 @@ class Engine:
     def nonfinite(self) -> bool:
         """True if any velocity evaluation since the last call produced inf / NaN (fp16 operand overflow); reads and
         clears the device flag, synchronising the current stream."""
+        return bool(self.status_flags() & 1)
+
+    def status_flags(self) -> int:
+        """Reads and clears the device status word (synchronises): bit 1 = a non-finite velocity, bit 2 = a token whose
+        mean exceeded 4 standard deviations reached a folded LayerNorm (precision loss in its 16-bit operand)."""
         flag = C.c_int(0)
         _lib.check(self.lib.usp_nonfinite(self.handle, C.byref(flag), self._stream()), self.handle, "usp_nonfinite")
-        return bool(flag.value)
+        return int(flag.value)
 
     # ---- introspection ---------------------------------------------------------------------------
     def last_ms(self) -> float:

@@ -176,10 +176,15 @@ class _CNFBase(nn.Module):
         self.net = net
 
     def _checked(self, engine, out: Tensor) -> Tensor:
-        if self.check_overflow and engine.nonfinite():
+        flags = engine.status_flags() if self.check_overflow else 0
+        if flags & 1:
             raise FloatingPointError(
                 "uspace_b200: a velocity evaluation produced inf / NaN - activations of this checkpoint exceed the "
                 "fp16 tensor-core operand range (65504); set net.operand_dtype = 'bf16'")
+        if flags & 2:
+            raise FloatingPointError(
+                "uspace_b200: a token's mean exceeded 4 standard deviations at a folded LayerNorm, where the 16-bit "
+                "operand loses precision; set net.fuse_layernorm = False for this checkpoint")
         return out
 
     def _call_net(self, x, t, cond, **kwargs):
