@@ -252,6 +252,32 @@ def test_forward_with_stand_alone_layernorm_kernels(golden_dir, name):
     assert not torch.equal(out, ref)                       # two different computations of the same function
 
 
+@pytest.mark.parametrize("embed_dim,heads,fold", [(384, 6, False), (768, 12, True), (1536, 24, True)])
+def test_forward_other_widths_against_oracle(embed_dim, heads, fold):
+    """Widths no reference config uses but the constructor accepts: 768 / 1536 take the folded-LayerNorm pair-kernel
+    path, 384 (not a multiple of 256) falls back to stand-alone LayerNorm and the 128-wide GEMM tiles."""
+    cfg = dict(CASES["tiny_class"]["cfg"], embed_dim=embed_dim, num_heads=heads, depth=2)
+    torch.manual_seed(21)
+    m = UViT(**cfg).eval()
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    g = torch.Generator().manual_seed(22)
+    x, t = torch.randn(3, 4, 32, 32, generator=g), torch.rand(3, generator=g)
+    y = torch.randint(0, 10, (3,), generator=g)
+    want = O.uvit_forward(sd, cfg, x, t, y=y)
+    m = m.to(dev())
+    with torch.no_grad():
+        got = m(x.to(dev()), t.to(dev()), y.to(dev()))[0]
+    assert rel(got, want) < 1e-3
+    plain = UViT(**cfg).eval()
+    plain.fuse_layernorm = False
+    plain.load_state_dict(sd)
+    plain = plain.to(dev())
+    with torch.no_grad():
+        plain(x.to(dev()), t.to(dev()), y.to(dev()))
+    # the fold removes the LayerNorm launches only where every GEMM shape is served by the pair kernel
+    assert (m.engine().kernels_per_forward() < plain.engine().kernels_per_forward()) == fold
+
+
 def test_forward_meets_1e3_on_north_star_model(golden_dir):
     for name in ("large_uncond", "large_t2i", "small16_uncond"):
         case = CASES[name]
