@@ -76,6 +76,9 @@ def test_config_mapping():
     assert (c.num_classes, c.clip_dim, c.num_clip_token, c.operand_dtype) == (10, 0, 0, 1)
     assert c.mlp_time_embed == 0
     assert config_from_kwargs(CASES["tiny_time_mlp"]["cfg"]).mlp_time_embed == 1
+    # LayerNorm is folded into the GEMMs unless the module says otherwise
+    assert c.fuse_layernorm == 1 and config_from_kwargs(CASES["tiny_class"]["cfg"], fuse_layernorm=False).fuse_layernorm == 0
+    assert get_nnet("uvit", **CASES["tiny_uncond"]["cfg"]).fuse_layernorm is True
     # qk_scale is accepted and without effect, like the reference's flash-attention path (libs/uvit.py:95)
     config_from_kwargs(dict(CASES["tiny_uncond"]["cfg"], qk_scale=0.2))
 
